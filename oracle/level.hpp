@@ -1,0 +1,491 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT PATH.
+//
+// oracle/level.hpp: CPU restatement of the reference's L3/L4 orchestration
+// for ONE refinement level made of several boxes:
+//   IntegratorContext (scratch + per-direction flux arrays, ghost fill, BCs),
+//   FluxMethodAdapter / ForwardIntegrator / Reconstruction (tile loops),
+//   DimensionalSplitLevelIntegrator + split methods, and the RunSimulation
+//   step loop with its CFL-retry.
+// Citations are relative to /root/reference.
+#pragma once
+#include "patch.hpp"
+
+#include <cfloat>
+#include <functional>
+#include <optional>
+
+namespace fvso {
+
+enum BaseKind { kHllemLarrouturou = 0, kHllem = 1, kHllEinfeldt = 2, kGodunovExact = 3 };
+enum ReconKind { kFirstOrder = 0, kMusclHancock = 1 };
+enum LimiterKind { kNoLimiter = 0, kMinMod = 1, kVanLeer = 2 };
+enum BcKind { kTransmissive = 0, kReflective = 1 };
+enum SplitKind { kGodunovSplitting = 0, kStrangSplitting = 1, kStrangSplittingLumped = 2 };
+
+struct MethodSpec {
+  int base{kHllemLarrouturou};
+  int recon{kMusclHancock};
+  int limiter{kVanLeer};
+  int stencil_width() const { return recon == kMusclHancock ? 2 : 1; }
+};
+
+struct BoundaryCondition {
+  int dir;
+  int side;
+  int kind;
+};
+
+// Calls f(method_object) with the statically typed flux method that
+// corresponds to the runtime MethodSpec.
+template <int D, typename F>
+void with_method(const MethodSpec& ms, const PerfectGasEq& eq, F&& f) {
+  auto with_base = [&](auto wrap) {
+    switch (ms.base) {
+    case kHllemLarrouturou: wrap(Hllem<D, true>(eq)); break;
+    case kHllem: wrap(Hllem<D, false>(eq)); break;
+    case kHllEinfeldt: wrap(HllEinfeldt<A8, D>(eq)); break;
+    case kGodunovExact: wrap(GodunovExact<D>(eq)); break;
+    default: throw std::runtime_error("unknown base method");
+    }
+  };
+  if (ms.recon == kFirstOrder) {
+    with_base([&](auto base) { f(base); });
+  } else {
+    with_base([&](auto base) {
+      using Base = decltype(base);
+      switch (ms.limiter) {
+      case kNoLimiter: f(MusclHancock<Base, NoLimiter>(eq)); break;
+      case kMinMod: f(MusclHancock<Base, MinMod>(eq)); break;
+      case kVanLeer: f(MusclHancock<Base, VanLeer>(eq)); break;
+      default: throw std::runtime_error("unknown limiter");
+      }
+    });
+  }
+}
+
+struct TimeStepTooLarge {
+  double dt;
+};
+
+struct Level {
+  int rank{1};
+  Box domain;
+  double dx[3]{1, 1, 1};
+  bool periodic[3]{false, false, false};
+  std::vector<Box> boxes;
+  // include/fub/AMReX/IntegratorContext.hpp:52-54
+  int scratch_gcw{4};
+  int flux_gcw{2};
+  int regrid_frequency{1};
+  std::vector<Fab> scratch;
+  std::vector<Fab> fluxes[3];
+  std::vector<BoundaryCondition> bcs;
+  PerfectGasEq eq;
+  MethodSpec method;
+  long cycles{0};
+  double time_point{0.0};
+
+  int ncomp() const { return rank + 4; }
+  int ncons() const { return rank + 2; }
+
+  // src/AMReX/IntegratorContext.cpp:303-324
+  void allocate() {
+    scratch.resize(boxes.size());
+    for (int d = 0; d < 3; ++d) fluxes[d].clear();
+    for (int d = 0; d < rank; ++d) fluxes[d].resize(boxes.size());
+    for (size_t b = 0; b < boxes.size(); ++b) {
+      scratch[b].define(grow_all(boxes[b], rank, scratch_gcw), ncomp());
+      for (int d = 0; d < rank; ++d) {
+        Box fb = surrounding_nodes(boxes[b], d);
+        for (int e = 0; e < rank; ++e) {
+          fb = grow(fb, e, e == d ? flux_gcw : scratch_gcw);
+        }
+        fluxes[d][b].define(fb, ncons());
+      }
+    }
+  }
+
+  // -------------------------------------------------------------------------
+  // AMReX: FabArray::FillBoundary(periodicity) -- every ghost cell that lies
+  // inside the valid box of another fab (or of a periodic image) is copied.
+  void FillBoundary() {
+    std::vector<std::array<int, 3>> shifts;
+    int r[3];
+    for (int d = 0; d < 3; ++d) r[d] = (d < rank && periodic[d]) ? 1 : 0;
+    for (int sz = -r[2]; sz <= r[2]; ++sz)
+      for (int sy = -r[1]; sy <= r[1]; ++sy)
+        for (int sx = -r[0]; sx <= r[0]; ++sx)
+          shifts.push_back({sx * int(domain.len(0)), sy * int(domain.len(1)),
+                            sz * int(domain.len(2))});
+    // Copy from a snapshot-free source is fine: sources are valid cells,
+    // destinations are ghost cells, the two sets are disjoint.
+    for (size_t i = 0; i < boxes.size(); ++i) {
+      Fab& dst = scratch[i];
+      for (size_t j = 0; j < boxes.size(); ++j) {
+        const Fab& src = scratch[j];
+        for (const auto& s : shifts) {
+          if (i == j && s[0] == 0 && s[1] == 0 && s[2] == 0) continue;
+          Box image = boxes[j];
+          for (int d = 0; d < 3; ++d) image = shift(image, d, s[d]);
+          const Box region = intersect(dst.box, image);
+          if (!region.ok()) continue;
+          for (int c = 0; c < ncomp(); ++c)
+            for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+              for (int j2 = region.lo[1]; j2 <= region.hi[1]; ++j2)
+                for (int i2 = region.lo[0]; i2 <= region.hi[0]; ++i2)
+                  dst(i2, j2, k, c) = src(i2 - s[0], j2 - s[1], k - s[2], c);
+        }
+      }
+    }
+  }
+
+  // AMReX: Geometry::growNonPeriodicDomain
+  Box GrowNonPeriodicDomain(int ngrow) const {
+    Box b = domain;
+    for (int d = 0; d < rank; ++d) {
+      if (!periodic[d]) b = grow(b, d, ngrow);
+    }
+    return b;
+  }
+
+  // src/AMReX/boundary_condition/TransmissiveBoundary.cpp:60-93
+  void FillTransmissive(const BoundaryCondition& bc) {
+    const int idir = bc.dir;
+    if (periodic[idir]) return;
+    const int ngrow = scratch_gcw;
+    Box slab = GrowNonPeriodicDomain(ngrow);
+    if (bc.side == 0) {
+      slab.hi[idir] = domain.lo[idir] - 1;
+    } else {
+      slab.lo[idir] = domain.hi[idir] + 1;
+    }
+    if (!slab.ok()) return;
+    const int boundary = bc.side == 0 ? domain.lo[idir] : domain.hi[idir];
+    for (Fab& fab : scratch) {
+      const Box fill = intersect(fab.box, slab);
+      if (!fill.ok()) continue;
+      for (int c = 0; c < ncomp(); ++c)
+        for (int k = fill.lo[2]; k <= fill.hi[2]; ++k)
+          for (int j = fill.lo[1]; j <= fill.hi[1]; ++j)
+            for (int i = fill.lo[0]; i <= fill.hi[0]; ++i) {
+              int src[3] = {i, j, k};
+              src[idir] = boundary; // MapToSrc :31-43
+              fab(i, j, k, c) = fab(src[0], src[1], src[2], c);
+            }
+    }
+  }
+
+  // include/fub/AMReX/boundary_condition/ReflectiveBoundary.hpp:67-94,
+  // include/fub/boundary_condition/ReflectiveBoundary.hpp:57-70,
+  // src/boundary_condition/ReflectiveBoundary.cpp:24-36,
+  // src/equations/PerfectGas.cpp:266-300.
+  // AMReX: complementIn(grown, domain) = boxDiff, which peels slabs from the
+  // highest dimension down: the slab of dimension d spans the full grown
+  // extent in dimensions < d and only the domain extent in dimensions > d.
+  void FillReflective(const BoundaryCondition& bc) {
+    const int d = bc.dir;
+    if (periodic[d]) return; // no ghost slab outside a periodic direction
+    const int ngrow = scratch_gcw;
+    Box slab = GrowNonPeriodicDomain(ngrow);
+    for (int e = d + 1; e < rank; ++e) {
+      slab.lo[e] = domain.lo[e];
+      slab.hi[e] = domain.hi[e];
+    }
+    if (bc.side == 0) {
+      slab.hi[d] = domain.lo[d] - 1;
+    } else {
+      slab.lo[d] = domain.hi[d] + 1;
+    }
+    if (!slab.ok()) return;
+    for (Fab& fab : scratch) {
+      const Box fill = intersect(fab.box, slab);
+      if (!fill.ok()) continue;
+      for (int k = fill.lo[2]; k <= fill.hi[2]; ++k)
+        for (int j = fill.lo[1]; j <= fill.hi[1]; ++j)
+          for (int i = fill.lo[0]; i <= fill.hi[0]; ++i) {
+            int idx[3] = {i, j, k};
+            int src[3] = {i, j, k};
+            if (bc.side == 0) {
+              const int distance = (fill.hi[d] + 1) - idx[d];
+              src[d] = idx[d] + 2 * distance - 1;
+            } else {
+              const int distance = idx[d] - (fill.lo[d] - 1);
+              src[d] = idx[d] - 2 * distance + 1;
+            }
+            for (int c = 0; c < ncomp(); ++c) {
+              double v = fab(src[0], src[1], src[2], c);
+              // m - 2 (m . e_d) e_d  ==  -m_d exactly
+              if (c == 1 + d) v = v - 2 * (v * 1.0 * 1.0);
+              fab(i, j, k, c) = v;
+            }
+          }
+    }
+  }
+
+  void ApplyBc(const BoundaryCondition& bc) {
+    if (bc.kind == kTransmissive) {
+      FillTransmissive(bc);
+    } else {
+      FillReflective(bc);
+    }
+  }
+
+  // src/AMReX/IntegratorContext.cpp:347-359 + BoundarySet.cpp:35-41
+  void ApplyBoundaryCondition(int dir) {
+    for (const BoundaryCondition& bc : bcs) {
+      if (bc.dir == dir) ApplyBc(bc);
+    }
+  }
+
+  // src/AMReX/IntegratorContext.cpp:422-444: FillPatchSingleLevel with the
+  // scratch as its own source = FillBoundary + physical BC functor (all BCs
+  // of the BoundarySet in order, BoundarySet.cpp:26-32).
+  void FillGhostLayerSingleLevel() {
+    FillBoundary();
+    for (const BoundaryCondition& bc : bcs) ApplyBc(bc);
+  }
+
+  // -------------------------------------------------------------------------
+  struct TileRef {
+    size_t fab;
+    Tile tile;
+  };
+  std::vector<TileRef> Tiles(const int tile_size[3], int nodal_dir) const {
+    std::vector<TileRef> out;
+    for (size_t b = 0; b < boxes.size(); ++b) {
+      std::vector<Tile> ts;
+      int ngrow[3];
+      for (int d = 0; d < 3; ++d) {
+        ngrow[d] = (nodal_dir >= 0 && d == nodal_dir) ? flux_gcw : scratch_gcw;
+      }
+      build_tiles(ts, boxes[b], rank, tile_size, ngrow, nodal_dir);
+      for (const Tile& t : ts) out.push_back({b, t});
+    }
+    return out;
+  }
+
+  // include/fub/AMReX/FluxMethodAdapter.hpp:69-114 (tile size 1024000,8,8;
+  // growntilebox; min starts at DBL_MAX)
+  template <int D> double ComputeStableDtD(int dir) const {
+    const int tile_size[3] = {1024000, 8, 8};
+    const std::vector<TileRef> tiles = Tiles(tile_size, -1);
+    const double dxd = dx[dir];
+    double min_dt = std::numeric_limits<double>::max();
+    with_method<D>(method, eq, [&](const auto& m) {
+#pragma omp parallel for schedule(dynamic) reduction(min : min_dt)
+      for (size_t t = 0; t < tiles.size(); ++t) {
+        const double dt = fvso::ComputeStableDt(m, scratch[tiles[t].fab],
+                                          tiles[t].tile.grown, dxd, dir);
+        min_dt = std::min(min_dt, dt);
+      }
+    });
+    return min_dt;
+  }
+  double ComputeStableDt(int dir) const {
+    switch (rank) {
+    case 1: return ComputeStableDtD<1>(dir);
+    case 2: return ComputeStableDtD<2>(dir);
+    default: return ComputeStableDtD<3>(dir);
+    }
+  }
+
+  // include/fub/AMReX/FluxMethodAdapter.hpp:120-150 (ForEachFab tiles
+  // 1024000,16,32 over the face-centred flux MultiFab)
+  template <int D> void ComputeNumericFluxesD(double dt, int dir) {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, dir);
+    const double dxd = dx[dir];
+    const int w = method.stencil_width();
+    with_method<D>(method, eq, [&](const auto& m) {
+#pragma omp parallel for schedule(dynamic)
+      for (size_t t = 0; t < tiles.size(); ++t) {
+        const size_t b = tiles[t].fab;
+        Box cells, faces;
+        GetCellsAndFacesInStencilRange(cells, faces, scratch[b].box,
+                                       tiles[t].tile.grown, w, dir);
+        fvso::ComputeNumericFluxes(m, fluxes[dir][b], faces, scratch[b], dt, dxd,
+                             dir);
+      }
+    });
+  }
+  void ComputeNumericFluxes_(double dt, int dir) {
+    switch (rank) {
+    case 1: ComputeNumericFluxesD<1>(dt, dir); break;
+    case 2: ComputeNumericFluxesD<2>(dt, dir); break;
+    default: ComputeNumericFluxesD<3>(dt, dir); break;
+    }
+  }
+
+  // src/AMReX/TimeIntegrator.cpp:29-67
+  void UpdateConservatively_(double dt, int dir) {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, -1);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      const size_t b = tiles[t].fab;
+      const Box all_faces = surrounding_nodes(tiles[t].tile.grown, dir);
+      const Box flux_box = intersect(all_faces, fluxes[dir][b].box);
+      const Box cell_box = enclosed_cells(flux_box, dir);
+      fvso::UpdateConservatively(scratch[b], scratch[b], fluxes[dir][b], cell_box,
+                           ncons(), dt, dx[dir], dir);
+    }
+  }
+
+  // include/fub/AMReX/Reconstruction.hpp:44-60
+  void CompleteFromCons_() {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, -1);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      const size_t b = tiles[t].fab;
+      switch (rank) {
+      case 1: CompleteFromConsBox<1>(eq, scratch[b], tiles[t].tile.grown); break;
+      case 2: CompleteFromConsBox<2>(eq, scratch[b], tiles[t].tile.grown); break;
+      default: CompleteFromConsBox<3>(eq, scratch[b], tiles[t].tile.grown); break;
+      }
+    }
+  }
+
+  // -------------------------------------------------------------------------
+  // include/fub/solver/DimensionalSplitLevelIntegrator.hpp:204-219
+  double ComputeStableDtAllDirections() const {
+    double min_dt = std::numeric_limits<double>::max();
+    for (int d = 0; d < rank; ++d) {
+      min_dt = std::min(min_dt, ComputeStableDt(d));
+    }
+    return min_dt;
+  }
+
+  using AdvanceFn = std::function<std::optional<TimeStepTooLarge>(double)>;
+
+  // src/split_method/{Godunov,Strang,StrangLumped}Splitting.cpp and the
+  // recursion in include/fub/split_method/SplittingMethod.hpp:53-75
+  static std::optional<TimeStepTooLarge>
+  Split2(int kind, double dt, const AdvanceFn& a1, const AdvanceFn& a2) {
+    if (kind == kGodunovSplitting) {
+      if (auto r = a1(dt)) return r;
+      return a2(dt);
+    } else if (kind == kStrangSplitting) {
+      if (auto r = a1(0.5 * dt)) return r;
+      if (auto r = a2(0.5 * dt)) return r;
+      if (auto r = a2(0.5 * dt)) return r;
+      return a1(0.5 * dt);
+    } else {
+      if (auto r = a1(0.5 * dt)) return r;
+      if (auto r = a2(dt)) return r;
+      return a1(0.5 * dt);
+    }
+  }
+  static std::optional<TimeStepTooLarge>
+  Split3(int kind, double dt, const AdvanceFn& a1, const AdvanceFn& a2,
+         const AdvanceFn& a3) {
+    if (kind == kStrangSplitting) {
+      // StrangSplitting.cpp:44-69 overrides the three-operator case
+      if (auto r = a1(0.5 * dt)) return r;
+      if (auto r = a2(0.5 * dt)) return r;
+      if (auto r = a3(0.5 * dt)) return r;
+      if (auto r = a3(0.5 * dt)) return r;
+      if (auto r = a2(0.5 * dt)) return r;
+      return a1(0.5 * dt);
+    }
+    // SplittingMethod.hpp:53-60: Advance(dt, a1, [a2, a3 recursively])
+    AdvanceFn inner = [&](double t) { return Split2(kind, t, a2, a3); };
+    return Split2(kind, dt, a1, inner);
+  }
+
+  // include/fub/solver/DimensionalSplitLevelIntegrator.hpp:221-276
+  std::optional<TimeStepTooLarge>
+  AdvanceLevelNonRecursively(double dt, int split_kind,
+                             std::vector<double>* sweep_dts = nullptr) {
+    // MakeSplitDirections, include/fub/split_method/SplittingMethod.hpp:115-126
+    // (single level: subcycle = {0, 1})
+    const int is_odd = int(cycles % 2);
+    int dirs[3];
+    for (int i = 0; i < rank; ++i) dirs[i] = is_odd ? (rank - 1 - i) : i;
+    int counts[3] = {0, 0, 0};
+    auto make = [&](int slot) -> AdvanceFn {
+      const int dir = dirs[slot];
+      return [this, dir, slot, &counts,
+              sweep_dts](double split_dt) -> std::optional<TimeStepTooLarge> {
+        if (counts[slot] > 0) {
+          ApplyBoundaryCondition(dir);
+        }
+        counts[slot] += 1;
+        const double level_dt = ComputeStableDt(dir); // MinAll: one process
+        if (sweep_dts) sweep_dts->push_back(level_dt);
+        if (level_dt < split_dt) {
+          return TimeStepTooLarge{level_dt};
+        }
+        ComputeNumericFluxes_(split_dt, dir);
+        UpdateConservatively_(split_dt, dir);
+        CompleteFromCons_();
+        return std::nullopt;
+      };
+    };
+    if (rank == 1) {
+      return make(0)(dt);
+    } else if (rank == 2) {
+      return Split2(split_kind, dt, make(0), make(1));
+    }
+    return Split3(split_kind, dt, make(0), make(1), make(2));
+  }
+
+  // include/fub/solver/SubcycleFineFirstSolver.hpp:114-193 for one level:
+  // AdvanceLevelNonRecursively, cycles += 1, time += dt
+  // (src/AMReX/IntegratorContext.cpp:653-676), then the ghost refill every
+  // `regrid_frequency` cycles (:177-192).
+  std::optional<TimeStepTooLarge>
+  AdvanceHierarchy(double dt, int split_kind,
+                   std::vector<double>* sweep_dts = nullptr) {
+    if (auto r = AdvanceLevelNonRecursively(dt, split_kind, sweep_dts)) {
+      return r;
+    }
+    cycles += 1;
+    time_point = time_point + dt;
+    if (cycles % regrid_frequency == 0) {
+      FillGhostLayerSingleLevel();
+    }
+    return std::nullopt;
+  }
+};
+
+struct RunOptions {
+  double cfl{0.8};
+  double final_time{1.0};
+  long max_cycles{-1};
+  double smallest_time_step_size{1e-12};
+  int split_kind{kStrangSplitting};
+};
+
+// include/fub/RunSimulation.hpp:83-191 without output: stable dt -> limited
+// dt -> AdvanceHierarchy -> on TimeStepTooLarge restore the backup and retry
+// with the failure dt.
+inline int RunSimulation(Level& level, const RunOptions& opt,
+                         std::vector<double>* dt_sequence,
+                         std::vector<double>* sweep_dts = nullptr) {
+  const double eps = opt.smallest_time_step_size;
+  Level backup = level;
+  std::optional<double> failure_dt;
+  int retries = 0;
+  while (level.time_point + eps < opt.final_time &&
+         (opt.max_cycles < 0 || level.cycles < opt.max_cycles)) {
+    const double stable_dt =
+        failure_dt ? *failure_dt : level.ComputeStableDtAllDirections();
+    const double limited_dt =
+        std::min(opt.final_time - level.time_point, opt.cfl * stable_dt);
+    auto result = level.AdvanceHierarchy(limited_dt, opt.split_kind, sweep_dts);
+    if (result) {
+      failure_dt = result->dt;
+      level = backup;
+      ++retries;
+      if (retries > 100) throw std::runtime_error("too many CFL retries");
+    } else {
+      if (dt_sequence) dt_sequence->push_back(limited_dt);
+      failure_dt.reset();
+      backup = level;
+    }
+  }
+  return retries;
+}
+
+} // namespace fvso

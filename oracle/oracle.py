@@ -1,0 +1,225 @@
+"""TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT PATH.
+
+ctypes binding of the CPU oracle (oracle/liboracle.so).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# enums shared with include/fvs_b200.h (same numeric values)
+BASE_HLLEM_LARROUTUROU, BASE_HLLEM, BASE_HLL_EINFELDT, BASE_GODUNOV_EXACT = 0, 1, 2, 3
+RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK = 0, 1
+LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
+BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
+SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.fvso_last_error.restype = C.c_char_p
+        L.fvso_level_create.restype = C.c_void_p
+        L.fvso_level_scratch.restype = C.POINTER(C.c_double)
+        L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
+        L.fvso_level_cycles.restype = C.c_long
+        L.fvso_level_time.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _ia(x):
+    return (C.c_int * len(x))(*[int(v) for v in x])
+
+
+def _da(x):
+    return (C.c_double * len(x))(*[float(v) for v in x])
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check(rc):
+    if rc < 0:
+        raise RuntimeError(lib().fvso_last_error().decode())
+    return rc
+
+
+def pad3(v, fill=0):
+    v = list(v)
+    return v + [fill] * (3 - len(v))
+
+
+class Level:
+    """One refinement level of several boxes on the CPU oracle."""
+
+    def __init__(self, rank, domain_lo, domain_hi, dx, boxes, scratch_gcw=4,
+                 flux_gcw=2, periodic=(0, 0, 0), gamma=1.4):
+        self.rank = rank
+        self.boxes = [(pad3(lo), pad3(hi)) for lo, hi in boxes]
+        lo = [v for b in self.boxes for v in b[0]]
+        hi = [v for b in self.boxes for v in b[1]]
+        self.h = C.c_void_p(lib().fvso_level_create(
+            rank, _ia(pad3(domain_lo)), _ia(pad3(domain_hi)), _da(pad3(dx, 1.0)),
+            _ia(pad3(periodic)), len(self.boxes), _ia(lo), _ia(hi),
+            scratch_gcw, flux_gcw, C.c_double(gamma)))
+        self.ncomp = rank + 4
+        self.ncons = rank + 2
+
+    def __del__(self):
+        try:
+            lib().fvso_level_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_method(self, base, recon, limiter):
+        lib().fvso_level_set_method(self.h, base, recon, limiter)
+
+    def add_bc(self, direction, side, kind):
+        lib().fvso_level_add_bc(self.h, direction, side, kind)
+
+    def set_regrid_frequency(self, f):
+        lib().fvso_level_set_regrid_frequency(self.h, f)
+
+    def set_cycles(self, cycles, time_point=0.0):
+        lib().fvso_level_set_cycles(self.h, C.c_long(cycles), C.c_double(time_point))
+
+    @property
+    def cycles(self):
+        return lib().fvso_level_cycles(self.h)
+
+    @property
+    def time_point(self):
+        return lib().fvso_level_time(self.h)
+
+    def _view(self, ptr, lo, hi, nc):
+        shape = (nc, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+        n = int(np.prod(shape))
+        arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape)
+        return arr, list(lo), list(hi)
+
+    def scratch(self, box):
+        """numpy view [comp, z, y, x] of the scratch fab (with ghosts)."""
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        p = lib().fvso_level_scratch(self.h, box, lo, hi, C.byref(nc))
+        return self._view(p, lo, hi, nc.value)
+
+    def fluxes(self, box, direction):
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        p = lib().fvso_level_fluxes(self.h, box, direction, lo, hi, C.byref(nc))
+        return self._view(p, lo, hi, nc.value)
+
+    def fill_ghost_layer(self):
+        _check(lib().fvso_fill_ghost_layer(self.h))
+
+    def fill_boundary(self):
+        _check(lib().fvso_fill_boundary(self.h))
+
+    def apply_boundary_condition(self, direction):
+        _check(lib().fvso_apply_boundary_condition(self.h, direction))
+
+    def compute_stable_dt(self, direction):
+        out = C.c_double()
+        _check(lib().fvso_compute_stable_dt(self.h, direction, C.byref(out)))
+        return out.value
+
+    def compute_numeric_fluxes(self, dt, direction):
+        _check(lib().fvso_compute_numeric_fluxes(self.h, C.c_double(dt), direction))
+
+    def update_conservatively(self, dt, direction):
+        _check(lib().fvso_update_conservatively(self.h, C.c_double(dt), direction))
+
+    def complete_from_cons(self):
+        _check(lib().fvso_complete_from_cons(self.h))
+
+    def sweep(self, dt, direction):
+        _check(lib().fvso_sweep(self.h, C.c_double(dt), direction))
+
+    def advance_hierarchy(self, dt, split):
+        """Returns (ok, failure_dt, sweep_dts)."""
+        too = C.c_double()
+        buf = (C.c_double * 16)()
+        n = C.c_int(16)
+        rc = _check(lib().fvso_advance_hierarchy(self.h, C.c_double(dt), split,
+                                                 C.byref(too), buf, C.byref(n)))
+        return rc == 0, too.value, [buf[i] for i in range(min(n.value, 16))]
+
+    def run(self, cfl, final_time, max_cycles, split):
+        cap = max(int(max_cycles), 1) if max_cycles >= 0 else 100000
+        buf = np.zeros(cap)
+        retries = C.c_int()
+        n = _check(lib().fvso_run(self.h, C.c_double(cfl), C.c_double(final_time),
+                                  C.c_long(max_cycles), split, _dp(buf), cap,
+                                  C.byref(retries)))
+        return buf[:n].copy(), retries.value
+
+
+def update_conservatively(prev, flux, dt, dx):
+    prev = np.ascontiguousarray(prev, dtype=np.float64)
+    flux = np.ascontiguousarray(flux, dtype=np.float64)
+    out = np.full_like(prev, np.nan)
+    lib().fvso_unit_update_conservatively(_dp(out), _dp(prev), _dp(flux),
+                                          len(prev), C.c_double(dt), C.c_double(dx))
+    return out
+
+
+def complete_from_cons(rank, cons, gamma=1.4):
+    cons = np.ascontiguousarray(cons, dtype=np.float64)
+    out = np.zeros(rank + 4)
+    lib().fvso_unit_complete_from_cons(rank, C.c_double(gamma), _dp(cons), _dp(out))
+    return out
+
+
+def numeric_flux(rank, base, recon, limiter, states, dt, dx, direction, gamma=1.4):
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.zeros(rank + 2)
+    _check(lib().fvso_unit_numeric_flux(rank, C.c_double(gamma), base, recon, limiter,
+                                        _dp(states), C.c_double(dt), C.c_double(dx),
+                                        direction, _dp(out)))
+    return out
+
+
+def numeric_flux_scalar_hll(rank, recon, limiter, states, dt, dx, direction, gamma=1.4):
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.zeros(rank + 2)
+    _check(lib().fvso_unit_numeric_flux_scalar_hll(rank, C.c_double(gamma), recon,
+                                                   limiter, _dp(states), C.c_double(dt),
+                                                   C.c_double(dx), direction, _dp(out)))
+    return out
+
+
+def exact_riemann(rank, left, right, direction=0, gamma=1.4):
+    left = np.ascontiguousarray(left, dtype=np.float64)
+    right = np.ascontiguousarray(right, dtype=np.float64)
+    pu = np.zeros(2)
+    sol = np.zeros(rank + 4)
+    _check(lib().fvso_unit_exact_riemann(rank, C.c_double(gamma), _dp(left), _dp(right),
+                                         direction, _dp(pu), _dp(sol)))
+    return pu, sol
+
+
+def tiles(rank, lo, hi, tile_size, ngrow, nodal_dir=-1):
+    cap = 4096
+    buf = (C.c_int * (12 * cap))()
+    n = lib().fvso_unit_tiles(rank, _ia(pad3(lo)), _ia(pad3(hi)), _ia(pad3(tile_size, 1)),
+                              _ia(pad3(ngrow)), nodal_dir, buf, cap)
+    out = []
+    for t in range(n):
+        v = [buf[12 * t + i] for i in range(12)]
+        out.append((v[0:3], v[3:6], v[6:9], v[9:12]))
+    return out

@@ -1,0 +1,197 @@
+"""Pins the CPU oracle against the reference's own unit tests.
+
+Each test names the reference test it restates (paths relative to
+/root/reference).  These run without a GPU.
+"""
+import math
+
+import numpy as np
+import pytest
+
+GAMMA = 1.4
+
+
+def complete(orc, rank, rho, mom, energy):
+    return orc.complete_from_cons(rank, [rho, *mom, energy])
+
+
+# --- tests/test.HyperbolicSplitPatchIntegrator.cpp:37-102 --------------------
+def test_update_1_cell(oracle):
+    out = oracle.update_conservatively([1.0], [0.3, 0.4], 1.0, 1.0)
+    assert out[0] == pytest.approx(0.9)
+    # exactly what prev + dt/dx (fL - fR) gives in IEEE arithmetic
+    assert out[0] == 1.0 + 1.0 * (0.3 - 0.4)
+
+
+def test_update_8_cells(oracle):
+    prev = np.ones(8)
+    flux = np.array([0.3, 0.4, -0.2, 0.0, 0.1, 0.2, 0.0, 0.0, 0.0])
+    out = oracle.update_conservatively(prev, flux, 1.0, 1.0)
+    for i in range(8):
+        assert out[i] == pytest.approx(prev[i] + flux[i] - flux[i + 1])
+        assert out[i] == prev[i] + 1.0 * (flux[i] - flux[i + 1])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 15, 16, 17, 64])
+def test_update_widths(oracle, n):
+    # tests/benchmark/HyperbolicSplitPatchIntegrator.cpp:14-76 widths, tails
+    rng = np.random.default_rng(1234)
+    prev = rng.random(n)
+    flux = rng.random(n + 1)
+    out = oracle.update_conservatively(prev, flux, 0.37, 0.0125)
+    lam = 0.37 / 0.0125
+    ref = prev + lam * (flux[:-1] - flux[1:])
+    assert np.array_equal(out, ref)
+
+
+# --- tests/test.simd_FluxMethod.cpp:54-105 -----------------------------------
+def test_simd_single_state_muscl_hll(oracle):
+    orc = oracle
+    s0 = complete(orc, 2, 1.0, [0.0, 0.0], 2.0)
+    s2 = complete(orc, 2, 1.0, [0.0, 0.0], 1.0)
+    states = np.concatenate([s0, s0, s2, s2])
+    # MusclHancockMethod(equation, hll): default limiter MinMod
+    scalar = orc.numeric_flux_scalar_hll(2, orc.RECON_MUSCL_HANCOCK, orc.LIMITER_MINMOD,
+                                         states, 1.0, 1.0, 0)
+    array = orc.numeric_flux(2, orc.BASE_HLL_EINFELDT, orc.RECON_MUSCL_HANCOCK,
+                             orc.LIMITER_MINMOD, states, 1.0, 1.0, 0)
+    assert np.array_equal(scalar, array)
+    assert np.all(np.isfinite(array))
+    # physical sanity: equal densities at rest -> no mass flux; the pressure
+    # jump gives positive x-momentum and energy flux
+    assert array[0] == 0.0 and array[1] > 0.0 and array[3] > 0.0
+
+
+# --- tests/test.simd_FluxMethod.cpp:40-52,107-186 ------------------------------
+def _init_states(orc, nx, ny, gx, gy, dx):
+    # InitializeStates: rho=1, m=0, E = 1 + 0.5 sin(x^2 + y^2); x = i dx
+    st = {}
+    for j in range(-gy, ny + gy):
+        for i in range(-gx, nx + gx):
+            x, y = i * dx, j * dx
+            st[(i, j)] = complete(orc, 2, 1.0, [0.0, 0.0], 1.0 + 0.5 * math.sin(x * x + y * y))
+    return st
+
+
+@pytest.mark.parametrize("direction", [0, 1])
+def test_hll_patch_scalar_equals_simd(oracle, direction):
+    orc = oracle
+    dx = 0.0125
+    gx, gy = (1, 0) if direction == 0 else (0, 1)
+    st = _init_states(orc, 16, 16, gx, gy, dx)
+    # array path through the level machinery (16x16 box, 1 ghost in `direction`)
+    lvl = orc.Level(2, [0, 0], [15, 15], [dx, dx], [([0, 0], [15, 15])],
+                    scratch_gcw=1, flux_gcw=0)
+    lvl.set_method(orc.BASE_HLL_EINFELDT, orc.RECON_FIRST_ORDER, orc.LIMITER_NONE)
+    arr, lo, hi = lvl.scratch(0)
+    for j in range(lo[1], hi[1] + 1):
+        for i in range(lo[0], hi[0] + 1):
+            x, y = i * dx, j * dx
+            arr[:, 0, j - lo[1], i - lo[0]] = complete(
+                orc, 2, 1.0, [0.0, 0.0], 1.0 + 0.5 * math.sin(x * x + y * y))
+    dt = lvl.compute_stable_dt(direction)
+    assert 0.0 < dt < 1.0
+    lvl.compute_numeric_fluxes(dt, direction)
+    flux, flo, fhi = lvl.fluxes(0, direction)
+    # scalar path face by face
+    for j in range(0, 16 + (direction == 1)):
+        for i in range(0, 16 + (direction == 0)):
+            left = st[(i - 1, j)] if direction == 0 else st[(i, j - 1)]
+            right = st[(i, j)]
+            scalar = orc.numeric_flux_scalar_hll(2, orc.RECON_FIRST_ORDER, orc.LIMITER_NONE,
+                                                 np.concatenate([left, right]), dt, dx,
+                                                 direction)
+            got = flux[:, 0, j - flo[1], i - flo[0]]
+            assert np.array_equal(scalar, got), (i, j)
+
+
+# --- tests/test.PerfectGas.ExactRiemannProblem.cpp:55-135 + Toro Table 4.2/4.3 -
+def _prim_state(rho, u, p):
+    # the test's from_prim (energy = p/(gamma-1); momentum given directly)
+    return [rho, rho * u, p * (1.0 / (GAMMA - 1.0)), p, math.sqrt(GAMMA * p / rho)]
+
+
+def _toro_pstar(rhoL, uL, pL, rhoR, uR, pR):
+    """Independent textbook solver (Toro ch. 4): bisection on f(p) = 0."""
+    g = GAMMA
+    aL, aR = math.sqrt(g * pL / rhoL), math.sqrt(g * pR / rhoR)
+
+    def fk(p, rho, pk, ak):
+        if p > pk:
+            A, B = 2.0 / ((g + 1) * rho), (g - 1) / (g + 1) * pk
+            return (p - pk) * math.sqrt(A / (p + B))
+        return 2 * ak / (g - 1) * ((p / pk) ** ((g - 1) / (2 * g)) - 1.0)
+
+    def f(p):
+        return fk(p, rhoL, pL, aL) + fk(p, rhoR, pR, aR) + (uR - uL)
+
+    lo, hi = 1e-12, 10 * max(pL, pR) + 10
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if f(mid) > 0:
+            hi = mid
+        else:
+            lo = mid
+    p = 0.5 * (lo + hi)
+    u = 0.5 * (uL + uR) + 0.5 * (fk(p, rhoR, pR, aR) - fk(p, rhoL, pL, aL))
+    return p, u
+
+
+TORO = [
+    # (rhoL, uL, pL, rhoR, uR, pR, p*, u*) -- Toro Table 4.3 where available
+    (1.0, 0.0, 1.0, 0.125, 0.0, 0.1, 0.30313, 0.92745),
+    (1.0, -2.0, 0.4, 1.0, 2.0, 0.4, 0.00189, 0.0),
+    (1.0, 0.0, 1000.0, 1.0, 0.0, 0.01, 460.894, 19.5975),
+    (1.0, 0.0, 0.1, 1.0, 0.0, 100.0, None, None),  # reference uses pL=0.1 (:124)
+    (1.0, 0.0, 0.01, 1.0, 0.0, 100.0, 46.0950, -6.19633),  # Toro test 4 proper
+]
+
+
+@pytest.mark.parametrize("case", TORO)
+def test_exact_riemann_toro(oracle, case):
+    rhoL, uL, pL, rhoR, uR, pR, pstar, ustar = case
+    pu, sol = oracle.exact_riemann(1, _prim_state(rhoL, uL, pL), _prim_state(rhoR, uR, pR))
+    p_ref, u_ref = _toro_pstar(rhoL, uL, pL, rhoR, uR, pR)
+    # Newton tolerance in the reference is |f| < 1e-7
+    assert pu[0] == pytest.approx(p_ref, rel=1e-5, abs=1e-6)
+    assert pu[1] == pytest.approx(u_ref, rel=1e-5, abs=1e-6)
+    if pstar is not None:
+        assert pu[0] == pytest.approx(pstar, rel=2e-4, abs=2e-5)
+        assert pu[1] == pytest.approx(ustar, rel=2e-4, abs=2e-5)
+    assert np.all(np.isfinite(sol))
+    assert sol[0] > 0 and sol[3] > 0
+
+
+def test_exact_riemann_sod_sample(oracle):
+    # Sod: x/t = 0 lies inside the left rarefaction fan (sonic point not reached),
+    # textbook star-left state: rho*L = 0.42632, u* = 0.92745, p* = 0.30313
+    pu, sol = oracle.exact_riemann(1, _prim_state(1.0, 0.0, 1.0), _prim_state(0.125, 0.0, 0.1))
+    assert sol[0] == pytest.approx(0.42632, rel=2e-4)
+    assert sol[1] / sol[0] == pytest.approx(0.92745, rel=2e-4)
+    assert sol[3] == pytest.approx(0.30313, rel=2e-4)
+
+
+# --- tests/test.State.cpp:40-66: SoA layout rho, m[3], E, p, a ----------------
+def test_state_layout(oracle):
+    lvl = oracle.Level(3, [0, 0, 0], [7, 7, 7], [1, 1, 1], [([0, 0, 0], [7, 7, 7])],
+                       scratch_gcw=0, flux_gcw=0)
+    arr, lo, hi = lvl.scratch(0)
+    assert arr.shape == (7, 8, 8, 8)
+    assert arr.strides == (8 * 8 * 8 * 8, 8 * 8 * 8, 8 * 8, 8)  # x fastest, comp slowest
+
+
+# --- equation constants (PerfectGas.hpp:216-219) -----------------------------
+def test_gamma_minus_1_inv_is_not_2_5(oracle):
+    gm1inv = 1.0 / (1.4 - 1.0)
+    assert gm1inv != 2.5
+    q = oracle.complete_from_cons(1, [1.0, 0.0, 2.5])
+    assert q[3] == 2.5 / gm1inv
+    assert q[4] == math.sqrt(1.4 * q[3] / 1.0)
+
+
+def test_kinetic_energy_reduction_order(oracle):
+    # Eigen unrolled redux: m0^2 + (m1^2 + m2^2)
+    m = [0.1, 0.7, 1.3]
+    q = oracle.complete_from_cons(3, [1.7, *m, 9.0])
+    ke = 0.5 * (m[0] * m[0] + (m[1] * m[1] + m[2] * m[2])) / 1.7
+    assert q[5] == (9.0 - ke) / (1.0 / (1.4 - 1.0))
