@@ -1,0 +1,317 @@
+"""ctypes binding of libfvs_b200.so (include/fvs_b200.h).
+
+This is harness plumbing for tests/ and bench.py: every call goes straight
+through the C ABI, the same entry points the C++ policies in include/fub_b200/
+use.  There is no CPU fallback: loading fails loudly if the library has not
+been built, and creating a context fails without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvs_b200.so")
+
+BASE_HLLEM_LARROUTUROU, BASE_HLLEM, BASE_HLL_EINFELDT, BASE_GODUNOV_EXACT = 0, 1, 2, 3
+RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK = 0, 1
+LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
+BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
+SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
+OK, ERROR, TIME_STEP_TOO_LARGE = 0, -1, 1
+UNIQUE_ID_BYTES = 128
+
+# every symbol include/fvs_b200.h declares
+SYMBOLS = [
+    "fvs_last_error", "fvs_version", "fvs_device_count", "fvs_create", "fvs_destroy",
+    "fvs_set_method", "fvs_stencil_width", "fvs_level_define", "fvs_level_add_boundary",
+    "fvs_state_box", "fvs_flux_box", "fvs_upload_state", "fvs_download_state",
+    "fvs_upload_fluxes", "fvs_download_fluxes", "fvs_state_device_ptr",
+    "fvs_compute_stable_dt", "fvs_compute_numeric_fluxes", "fvs_update_conservatively",
+    "fvs_complete_from_cons", "fvs_sweep", "fvs_fill_ghost_layer",
+    "fvs_apply_boundary_condition", "fvs_compute_stable_dt_all", "fvs_advance_hierarchy",
+    "fvs_run", "fvs_set_regrid_frequency", "fvs_set_cycles", "fvs_cycles", "fvs_time_point",
+    "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
+    "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
+    "fvs_enable_timing", "fvs_sweep_time_ms",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("rank", C.c_int), ("gamma", C.c_double), ("base_method", C.c_int),
+                ("reconstruction", C.c_int), ("limiter", C.c_int), ("device", C.c_int),
+                ("comm_rank", C.c_int), ("comm_size", C.c_int)]
+
+
+class HaloCopy(C.Structure):
+    _fields_ = [("dst_box", C.c_int), ("src_box", C.c_int), ("dst_owner", C.c_int),
+                ("src_owner", C.c_int), ("lo", C.c_int * 3), ("hi", C.c_int * 3),
+                ("shift", C.c_int * 3)]
+
+
+_LIB = None
+
+
+def lib():
+    """Loads libfvs_b200.so; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m finitevolumesolver_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.fvs_last_error.restype = C.c_char_p
+        L.fvs_cycles.restype = C.c_long
+        L.fvs_time_point.restype = C.c_double
+        L.fvs_run.restype = C.c_long
+        L.fvs_halo_plan.restype = C.c_long
+        L.fvs_kernel_launches.restype = C.c_long
+        L.fvs_stream.restype = C.c_void_p
+        _LIB = L
+    return _LIB
+
+
+class FvsError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc < 0:
+        raise FvsError(lib().fvs_last_error().decode())
+    return rc
+
+
+def _i3(v, fill=0):
+    v = list(v) + [fill] * (3 - len(v))
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _d3(v, fill=1.0):
+    v = list(v) + [fill] * (3 - len(v))
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _boxes(boxes):
+    n = len(boxes)
+    lo = ((C.c_int * 3) * n)()
+    hi = ((C.c_int * 3) * n)()
+    for b, (l, h) in enumerate(boxes):
+        l = list(l) + [0] * (3 - len(l))
+        h = list(h) + [0] * (3 - len(h))
+        for d in range(3):
+            lo[b][d] = int(l[d])
+            hi[b][d] = int(h[d])
+    return lo, hi
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def device_count():
+    return lib().fvs_device_count()
+
+
+def halo_plan(rank, domain_lo, domain_hi, periodic, boxes, owner, scratch_gcw):
+    lo, hi = _boxes(boxes)
+    own = (C.c_int * len(boxes))(*[int(o) for o in owner])
+    n = _check(lib().fvs_halo_plan(rank, _i3(domain_lo), _i3(domain_hi), _i3(periodic),
+                                   len(boxes), lo, hi, own, scratch_gcw, None, 0))
+    buf = (HaloCopy * max(n, 1))()
+    _check(lib().fvs_halo_plan(rank, _i3(domain_lo), _i3(domain_hi), _i3(periodic),
+                               len(boxes), lo, hi, own, scratch_gcw, buf, n))
+    return [dict(dst_box=c.dst_box, src_box=c.src_box, dst_owner=c.dst_owner,
+                 src_owner=c.src_owner, lo=list(c.lo), hi=list(c.hi), shift=list(c.shift))
+            for c in buf[:n]]
+
+
+def stable_dt_face_mask(rank, box_lo, box_hi, scratch_gcw, stencil_width, direction):
+    n = _check(lib().fvs_stable_dt_face_mask(rank, _i3(box_lo), _i3(box_hi), scratch_gcw,
+                                             stencil_width, direction, None, 0))
+    buf = (C.c_ubyte * n)()
+    _check(lib().fvs_stable_dt_face_mask(rank, _i3(box_lo), _i3(box_hi), scratch_gcw,
+                                         stencil_width, direction, buf, n))
+    return np.frombuffer(buf, dtype=np.uint8).copy()
+
+
+def distribute_boxes(rank, boxes, nranks):
+    lo, hi = _boxes(boxes)
+    out = (C.c_int * len(boxes))()
+    _check(lib().fvs_distribute_boxes(rank, len(boxes), lo, hi, nranks, out))
+    return list(out)
+
+
+def comm_unique_id():
+    buf = (C.c_char * UNIQUE_ID_BYTES)()
+    _check(lib().fvs_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Context:
+    """One fvs_ctx with a single level (level 0)."""
+
+    def __init__(self, rank, domain_lo, domain_hi, dx, boxes, scratch_gcw=4, flux_gcw=2,
+                 periodic=(0, 0, 0), gamma=1.4, base=BASE_HLLEM_LARROUTUROU,
+                 recon=RECON_MUSCL_HANCOCK, limiter=LIMITER_VANLEER, device=-1,
+                 comm_rank=0, comm_size=1, owner=None):
+        self.rank = rank
+        self.ncomp = rank + 4
+        self.ncons = rank + 2
+        self.boxes = [(list(lo) + [0] * (3 - len(lo)), list(hi) + [0] * (3 - len(hi)))
+                      for lo, hi in boxes]
+        self.owner = list(owner) if owner is not None else [0] * len(boxes)
+        self.comm_rank = comm_rank
+        cfg = Config(rank, gamma, base, recon, limiter, device, comm_rank, comm_size)
+        self.h = C.c_void_p()
+        _check(lib().fvs_create(C.byref(cfg), C.byref(self.h)))
+        lo, hi = _boxes(self.boxes)
+        own = (C.c_int * len(boxes))(*self.owner)
+        _check(lib().fvs_level_define(self.h, 0, _i3(domain_lo), _i3(domain_hi), _d3(dx),
+                                      _i3(periodic), len(boxes), lo, hi, own, scratch_gcw,
+                                      flux_gcw))
+
+    def close(self):
+        if self.h:
+            lib().fvs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def owned_boxes(self):
+        return [b for b, o in enumerate(self.owner) if o == self.comm_rank]
+
+    def comm_init(self, unique_id):
+        _check(lib().fvs_comm_init(self.h, unique_id))
+
+    def set_method(self, base, recon, limiter):
+        _check(lib().fvs_set_method(self.h, base, recon, limiter))
+
+    def add_bc(self, direction, side, kind):
+        _check(lib().fvs_level_add_boundary(self.h, 0, direction, side, kind))
+
+    def set_regrid_frequency(self, f):
+        _check(lib().fvs_set_regrid_frequency(self.h, f))
+
+    def set_cycles(self, cycles, time_point=0.0):
+        _check(lib().fvs_set_cycles(self.h, C.c_long(cycles), C.c_double(time_point)))
+
+    @property
+    def cycles(self):
+        return lib().fvs_cycles(self.h)
+
+    @property
+    def time_point(self):
+        return lib().fvs_time_point(self.h)
+
+    def state_box(self, box):
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        _check(lib().fvs_state_box(self.h, 0, box, lo, hi, C.byref(nc)))
+        return list(lo), list(hi), nc.value
+
+    def flux_box(self, box, direction):
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        _check(lib().fvs_flux_box(self.h, 0, box, direction, lo, hi, C.byref(nc)))
+        return list(lo), list(hi), nc.value
+
+    @staticmethod
+    def _shape(lo, hi, nc):
+        return (nc, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+
+    def state_shape(self, box):
+        return self._shape(*self.state_box(box))
+
+    def upload_state(self, box, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == self.state_shape(box), (arr.shape, self.state_shape(box))
+        _check(lib().fvs_upload_state(self.h, 0, box, _dp(arr)))
+
+    def download_state(self, box, out=None):
+        if out is None:
+            out = np.empty(self.state_shape(box))
+        _check(lib().fvs_download_state(self.h, 0, box, _dp(out)))
+        return out
+
+    def download_fluxes(self, box, direction):
+        out = np.empty(self._shape(*self.flux_box(box, direction)))
+        _check(lib().fvs_download_fluxes(self.h, 0, box, direction, _dp(out)))
+        return out
+
+    def upload_fluxes(self, box, direction, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        assert arr.shape == self._shape(*self.flux_box(box, direction))
+        _check(lib().fvs_upload_fluxes(self.h, 0, box, direction, _dp(arr)))
+
+    def compute_stable_dt(self, direction):
+        out = C.c_double()
+        _check(lib().fvs_compute_stable_dt(self.h, 0, direction, C.byref(out)))
+        return out.value
+
+    def compute_stable_dt_all(self):
+        out = C.c_double()
+        _check(lib().fvs_compute_stable_dt_all(self.h, 0, C.byref(out)))
+        return out.value
+
+    def compute_numeric_fluxes(self, dt, direction):
+        _check(lib().fvs_compute_numeric_fluxes(self.h, 0, C.c_double(dt), direction))
+
+    def update_conservatively(self, dt, direction):
+        _check(lib().fvs_update_conservatively(self.h, 0, C.c_double(dt), direction))
+
+    def complete_from_cons(self):
+        _check(lib().fvs_complete_from_cons(self.h, 0))
+
+    def sweep(self, dt, direction):
+        """Fused sweep. Returns (status, level_dt)."""
+        out = C.c_double()
+        rc = _check(lib().fvs_sweep(self.h, 0, C.c_double(dt), direction, C.byref(out)))
+        return rc, out.value
+
+    def fill_ghost_layer(self):
+        _check(lib().fvs_fill_ghost_layer(self.h, 0))
+
+    def apply_boundary_condition(self, direction):
+        _check(lib().fvs_apply_boundary_condition(self.h, 0, direction))
+
+    def advance_hierarchy(self, dt, split):
+        """Returns (ok, failure_dt, sweep_dts)."""
+        too = C.c_double()
+        buf = (C.c_double * 16)()
+        n = C.c_int(16)
+        rc = _check(lib().fvs_advance_hierarchy(self.h, C.c_double(dt), split, C.byref(too),
+                                                buf, C.byref(n)))
+        return rc == 0, too.value, [buf[i] for i in range(min(n.value, 16))]
+
+    def run(self, cfl, final_time, max_cycles, split):
+        cap = max(int(max_cycles), 1) if max_cycles >= 0 else 100000
+        buf = np.zeros(cap)
+        retries = C.c_int()
+        n = lib().fvs_run(self.h, C.c_double(cfl), C.c_double(final_time), C.c_long(max_cycles),
+                          split, _dp(buf), C.c_long(cap), C.byref(retries))
+        _check(n)
+        return buf[:n].copy(), retries.value
+
+    def min_all(self, value):
+        v = C.c_double(value)
+        _check(lib().fvs_min_all(self.h, C.byref(v)))
+        return v.value
+
+    @property
+    def kernel_launches(self):
+        return lib().fvs_kernel_launches(self.h)
+
+    @property
+    def stream(self):
+        return lib().fvs_stream(self.h)
+
+    def enable_timing(self, on=True):
+        _check(lib().fvs_enable_timing(self.h, 1 if on else 0))
+
+    def sweep_time_ms(self):
+        ms, n = C.c_double(), C.c_long()
+        _check(lib().fvs_sweep_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,1357 @@
+// context.cu -- host side of libfvs_b200.so: the C ABI of include/fvs_b200.h.
+//
+// A context plays the role of the reference's fub::amrex::IntegratorContext
+// (src/AMReX/IntegratorContext.cpp) for the levels it is given: it owns the
+// scratch state of every box in HBM (patch-local SoA, FAB layout), derives
+// the iteration domains of the adapters (boxes.hpp), and sequences sweeps the
+// way DimensionalSplitLevelIntegrator / SubcycleFineFirstSolver /
+// RunSimulation do.  There is no CPU fallback: every numerical entry point
+// launches CUDA kernels and fails if no device is present.
+#include "../../include/fvs_b200.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "boxes.hpp"
+#include "launch.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define FVS_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      throw Error(std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+    }                                                                                         \
+  } while (0)
+
+template <typename F> int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return FVS_ERROR;
+  }
+}
+
+// ---- NCCL, loaded lazily (the library must load on a box without it) -------
+struct Nccl {
+  typedef struct ncclComm* comm_t;
+  struct unique_id {
+    char internal[128];
+  };
+  void* handle{nullptr};
+  int (*GetUniqueId)(unique_id*){nullptr};
+  int (*CommInitRank)(comm_t*, int, unique_id, int){nullptr};
+  int (*CommDestroy)(comm_t){nullptr};
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t){nullptr};
+  int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t){nullptr};
+  int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t){nullptr};
+  int (*GroupStart)(){nullptr};
+  int (*GroupEnd)(){nullptr};
+  const char* (*GetErrorString)(int){nullptr};
+  static constexpr int kDouble = 8; // ncclFloat64
+  static constexpr int kMax = 2;    // ncclMax
+  static constexpr int kMin = 3;    // ncclMin
+
+  static Nccl& get() {
+    static Nccl n;
+    if (!n.handle) {
+      n.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!n.handle) n.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+      if (!n.handle) throw Error(std::string("cannot load NCCL: ") + dlerror());
+      auto sym = [&](const char* name) {
+        void* p = dlsym(n.handle, name);
+        if (!p) throw Error(std::string("NCCL symbol missing: ") + name);
+        return p;
+      };
+      n.GetUniqueId = (decltype(n.GetUniqueId))sym("ncclGetUniqueId");
+      n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
+      n.CommDestroy = (decltype(n.CommDestroy))sym("ncclCommDestroy");
+      n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
+      n.Send = (decltype(n.Send))sym("ncclSend");
+      n.Recv = (decltype(n.Recv))sym("ncclRecv");
+      n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
+      n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
+      n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
+    }
+    return n;
+  }
+  void check(int rc, const char* what) {
+    if (rc != 0) throw Error(std::string(what) + ": " + GetErrorString(rc));
+  }
+};
+
+using fvs::Box;
+using fvs::BoxDesc;
+
+constexpr int kNumBuffers = 3;
+constexpr int kDtSlots = 64;
+
+struct Patch {
+  int global_index{0};
+  Box valid, sbox;
+  int n[3]{1, 1, 1};
+  long long cells{0};
+  double* buf[kNumBuffers]{nullptr, nullptr, nullptr};
+  double* flux[3]{nullptr, nullptr, nullptr};
+  Box fbox[3];
+  unsigned char* dtmask[2][3]{{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+};
+
+struct BoundaryCondition {
+  int dir, side, kind;
+};
+
+template <typename T> struct DeviceArray {
+  T* ptr{nullptr};
+  size_t count{0};
+  DeviceArray() = default;
+  DeviceArray(const DeviceArray&) = delete;
+  DeviceArray& operator=(const DeviceArray&) = delete;
+  ~DeviceArray() {
+    if (ptr) cudaFree(ptr);
+  }
+  void upload(const std::vector<T>& host) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = host.size();
+    if (count == 0) return;
+    FVS_CUDA(cudaMalloc(&ptr, count * sizeof(T)));
+    FVS_CUDA(cudaMemcpy(ptr, host.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+};
+
+struct PeerExchange {
+  int peer{0};
+  std::vector<fvs::HaloCopy> sends, recvs; // canonical (global plan) order
+  long long send_elems{0}, recv_elems{0};
+  double* sendbuf{nullptr};
+  double* recvbuf{nullptr};
+};
+
+struct Level {
+  bool defined{false};
+  int rank{1};
+  Box domain;
+  double dx[3]{1, 1, 1};
+  bool periodic[3]{false, false, false};
+  int scratch_gcw{0}, flux_gcw{0};
+  std::vector<Box> boxes; // all boxes of the level
+  std::vector<int> owner;
+  std::vector<int> local_of_global; // -1 if not owned
+  std::vector<Patch> patches;       // owned boxes only
+  std::vector<BoundaryCondition> bcs;
+  int cur{0};   // buffer holding the current state
+  int keep{-1}; // buffer that must not be overwritten (backup), -1 none
+  bool have_buf[kNumBuffers]{false, false, false};
+  int max_n[3]{1, 1, 1};
+  std::vector<fvs::HaloCopy> local_copies;
+  std::vector<PeerExchange> peers;
+  // descriptor caches, keyed by (kind, dir, src buffer, dst buffer, width)
+  std::map<std::tuple<int, int, int, int, int>, std::unique_ptr<DeviceArray<BoxDesc>>> box_cache;
+  std::map<int, std::unique_ptr<DeviceArray<fvs::CopyDesc>>> copy_cache;
+  std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::BcDesc>>> bc_cache;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceArray<fvs::PackDesc>>> pack_cache;
+  long long max_copy_cells{0};
+};
+
+} // namespace
+
+struct fvs_ctx {
+  fvs_config cfg{};
+  fvs::EqConst eq{};
+  fvs::MethodKey method{};
+  int device{0};
+  cudaStream_t stream{nullptr};
+  std::vector<Level> levels;
+  long launches{0};
+  long cycles{0};
+  double time_point{0.0};
+  int regrid_frequency{1};
+  // stable-dt accumulators
+  unsigned long long* d_slots{nullptr};
+  unsigned long long* h_slots{nullptr}; // pinned
+  int* d_fail{nullptr};
+  int* h_fail{nullptr}; // pinned
+  int next_slot{0};
+  // timing
+  bool timing{false};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> free_events;
+  double sweep_ms{0.0};
+  long sweep_count{0};
+  // comm
+  Nccl::comm_t comm{nullptr};
+
+  int stencil_width() const { return method.recon == fvs::kReconMusclHancock ? 2 : 1; }
+  int ncomp() const { return cfg.rank + 4; }
+  int ncons() const { return cfg.rank + 2; }
+
+  Level& level(int l) {
+    if (l < 0 || l >= (int)levels.size() || !levels[l].defined) {
+      throw Error("level " + std::to_string(l) + " is not defined");
+    }
+    return levels[l];
+  }
+  Patch& patch(Level& L, int box) {
+    if (box < 0 || box >= (int)L.boxes.size()) throw Error("box index out of range");
+    const int loc = L.local_of_global[box];
+    if (loc < 0) {
+      throw Error("box " + std::to_string(box) + " is owned by rank " +
+                  std::to_string(L.owner[box]) + ", not by this rank");
+    }
+    return L.patches[loc];
+  }
+  void use_device() { FVS_CUDA(cudaSetDevice(device)); }
+};
+
+namespace {
+
+void free_level(Level& L) {
+  for (Patch& p : L.patches) {
+    for (int b = 0; b < kNumBuffers; ++b)
+      if (p.buf[b]) cudaFree(p.buf[b]);
+    for (int d = 0; d < 3; ++d) {
+      if (p.flux[d]) cudaFree(p.flux[d]);
+      for (int w = 0; w < 2; ++w)
+        if (p.dtmask[w][d]) cudaFree(p.dtmask[w][d]);
+    }
+  }
+  for (PeerExchange& pe : L.peers) {
+    if (pe.sendbuf) cudaFree(pe.sendbuf);
+    if (pe.recvbuf) cudaFree(pe.recvbuf);
+  }
+  L = Level();
+}
+
+void ensure_buffer(fvs_ctx* ctx, Level& L, int b) {
+  if (L.have_buf[b]) return;
+  for (Patch& p : L.patches) {
+    const size_t bytes = (size_t)p.cells * ctx->ncomp() * sizeof(double);
+    FVS_CUDA(cudaMalloc(&p.buf[b], bytes));
+    FVS_CUDA(cudaMemsetAsync(p.buf[b], 0, bytes, ctx->stream));
+  }
+  L.have_buf[b] = true;
+  L.box_cache.clear();
+}
+
+void ensure_fluxes(fvs_ctx* ctx, Level& L, int dir) {
+  bool changed = false;
+  for (Patch& p : L.patches) {
+    if (!p.flux[dir]) {
+      const size_t bytes = (size_t)p.fbox[dir].size() * ctx->ncons() * sizeof(double);
+      FVS_CUDA(cudaMalloc(&p.flux[dir], bytes));
+      FVS_CUDA(cudaMemsetAsync(p.flux[dir], 0, bytes, ctx->stream));
+      changed = true;
+    }
+  }
+  if (changed) L.box_cache.clear();
+}
+
+// a buffer index different from `a` and `b` (and from the kept backup)
+int free_buffer(const Level& L, int a) {
+  for (int i = 0; i < kNumBuffers; ++i) {
+    if (i != a && i != L.keep) return i;
+  }
+  throw Error("no free state buffer");
+}
+
+enum DescKind { kDescSweep = 0 };
+
+const BoxDesc* box_descs(fvs_ctx* ctx, Level& L, int dir, int src, int dst, bool with_flux) {
+  const int w = ctx->stencil_width();
+  auto key = std::make_tuple(with_flux ? 1 : 0, dir, src, dst, w);
+  auto it = L.box_cache.find(key);
+  if (it != L.box_cache.end()) return it->second->ptr;
+  std::vector<BoxDesc> host;
+  for (Patch& p : L.patches) {
+    BoxDesc d{};
+    d.src = p.buf[src];
+    d.dst = p.buf[dst];
+    d.flux = with_flux ? p.flux[dir] : nullptr;
+    for (int e = 0; e < 3; ++e) {
+      d.n[e] = p.n[e];
+      d.fn[e] = p.fbox[dir].len(e);
+      d.foff[e] = p.fbox[dir].lo[e] - p.sbox.lo[e];
+    }
+    d.sc = p.cells;
+    d.fsc = p.fbox[dir].size();
+    int ulo, uhi, flo, fhi;
+    fvs::update_cell_range(p.valid, dir, L.flux_gcw, ulo, uhi);
+    fvs::flux_face_range(p.valid, dir, L.scratch_gcw, L.flux_gcw, w, flo, fhi);
+    d.ulo = ulo - p.sbox.lo[dir];
+    d.uhi = uhi - p.sbox.lo[dir];
+    d.flo = flo - p.sbox.lo[dir];
+    d.fhi = fhi - p.sbox.lo[dir];
+    d.dtmask = p.dtmask[w - 1][dir];
+    host.push_back(d);
+  }
+  auto arr = std::make_unique<DeviceArray<BoxDesc>>();
+  arr->upload(host);
+  const BoxDesc* ptr = arr->ptr;
+  L.box_cache[key] = std::move(arr);
+  return ptr;
+}
+
+int pick_seg_len(int rank, int dir, const int max_n[3], int nboxes) {
+  // enough independent pipelines to fill 148 SMs; segments overlap by the
+  // stencil, so keep them long when the box already provides the parallelism
+  const long long target = 148LL * 2048;
+  long long lanes;
+  int n = max_n[dir];
+  if (dir == 0) {
+    lanes = (long long)max_n[1] * max_n[2] * nboxes * 32; // one warp per row
+  } else {
+    lanes = (long long)max_n[0] * (dir == 1 ? max_n[2] : max_n[1]) * nboxes;
+  }
+  (void)rank;
+  int nseg = (int)std::min<long long>((target + lanes - 1) / lanes, std::max(n / 32, 1));
+  nseg = std::max(nseg, 1);
+  int seg = (n + nseg - 1) / nseg;
+  if (dir == 0) seg = ((seg + 31) / 32) * 32;
+  return std::max(seg, 1);
+}
+
+fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxDesc* boxes,
+                          int slot) {
+  fvs::SweepArgs A{};
+  A.eq = ctx->eq;
+  A.lambda = dt / L.dx[dir];
+  A.lambda_half = 0.5 * dt / L.dx[dir];
+  A.boxes = boxes;
+  A.nboxes = (int)L.patches.size();
+  for (int d = 0; d < 3; ++d) A.max_n[d] = L.max_n[d];
+  A.seg_len = pick_seg_len(ctx->cfg.rank, dir, L.max_n, A.nboxes);
+  A.max_signal = ctx->d_slots + slot;
+  A.fail_flag = ctx->d_fail;
+  return A;
+}
+
+int take_slot(fvs_ctx* ctx, int count = 1) {
+  if (ctx->next_slot + count > kDtSlots) ctx->next_slot = 0;
+  const int s = ctx->next_slot;
+  ctx->next_slot += count;
+  FVS_CUDA(cudaMemsetAsync(ctx->d_slots + s, 0, sizeof(unsigned long long) * count, ctx->stream));
+  return s;
+}
+
+void check_dir(const fvs_ctx* ctx, int dir) {
+  if (dir < 0 || dir >= ctx->cfg.rank) throw Error("direction out of range");
+}
+
+void check_launch(int rc) {
+  if (rc < 0) throw Error("method / dimension combination is not compiled in");
+  FVS_CUDA(cudaGetLastError());
+}
+
+// read `count` accumulators back (max over ranks), one synchronisation
+void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out) {
+  if (ctx->comm && ctx->cfg.comm_size > 1) {
+    Nccl& n = Nccl::get();
+    n.check(n.AllReduce(ctx->d_slots + slot, ctx->d_slots + slot, (size_t)count, Nccl::kDouble,
+                        Nccl::kMax, ctx->comm, ctx->stream),
+            "ncclAllReduce(max signal)");
+    n.check(n.AllReduce(ctx->d_fail, ctx->d_fail, 1, 2 /* ncclInt32 */, Nccl::kMax, ctx->comm,
+                        ctx->stream),
+            "ncclAllReduce(fail flag)");
+  }
+  FVS_CUDA(cudaMemcpyAsync(ctx->h_slots + slot, ctx->d_slots + slot,
+                           sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  FVS_CUDA(cudaMemcpyAsync(ctx->h_fail, ctx->d_fail, sizeof(int), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_fail) {
+    FVS_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), ctx->stream));
+    // include/fub/NewtonIteration.hpp:44-50
+    throw Error("Newton Iteration did not converge.");
+  }
+  for (int i = 0; i < count; ++i) {
+    double v;
+    std::memcpy(&v, ctx->h_slots + slot + i, sizeof(double));
+    out[i] = v;
+  }
+}
+
+// FluxMethodAdapter.hpp:78,96: min over faces of dx / max|s|, starting from DBL_MAX
+double dt_from_signal(double dx, double max_signal) {
+  double dt = std::numeric_limits<double>::max();
+  if (max_signal > 0.0) dt = std::min(dt, dx / max_signal);
+  return dt;
+}
+
+struct EventTimer {
+  fvs_ctx* ctx;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  explicit EventTimer(fvs_ctx* c) : ctx(c) {
+    if (!ctx->timing) return;
+    if (!ctx->free_events.empty()) {
+      ev = ctx->free_events.back();
+      ctx->free_events.pop_back();
+    } else {
+      FVS_CUDA(cudaEventCreate(&ev.first));
+      FVS_CUDA(cudaEventCreate(&ev.second));
+    }
+    FVS_CUDA(cudaEventRecord(ev.first, ctx->stream));
+  }
+  void stop() {
+    if (!ctx->timing) return;
+    FVS_CUDA(cudaEventRecord(ev.second, ctx->stream));
+    ctx->pending_events.push_back(ev);
+  }
+};
+
+void drain_events(fvs_ctx* ctx) {
+  for (auto& ev : ctx->pending_events) {
+    FVS_CUDA(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    FVS_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    ctx->sweep_ms += ms;
+    ctx->sweep_count += 1;
+    ctx->free_events.push_back(ev);
+  }
+  ctx->pending_events.clear();
+}
+
+// launches the fused sweep cur -> free buffer; does NOT flip
+int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out) {
+  const int src = L.cur;
+  const int dst = free_buffer(L, src);
+  ensure_buffer(ctx, L, dst);
+  const BoxDesc* boxes = box_descs(ctx, L, dir, src, dst, false);
+  const int slot = take_slot(ctx);
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot);
+  if (!L.patches.empty()) {
+    EventTimer t(ctx);
+    const int rc = fvs::launch_fused_sweep(ctx->method, dir, A, ctx->stream);
+    check_launch(rc);
+    ctx->launches += rc;
+    t.stop();
+  }
+  *dst_out = dst;
+  return slot;
+}
+
+// ---- ghost cells ------------------------------------------------------------
+const fvs::CopyDesc* copy_descs(fvs_ctx* ctx, Level& L, int buf, int* count) {
+  *count = (int)L.local_copies.size();
+  auto it = L.copy_cache.find(buf);
+  if (it != L.copy_cache.end()) return it->second->ptr;
+  std::vector<fvs::CopyDesc> host;
+  for (const fvs::HaloCopy& c : L.local_copies) {
+    Patch& dp = ctx->patch(L, c.dst_box);
+    Patch& sp = ctx->patch(L, c.src_box);
+    fvs::CopyDesc d{};
+    d.src = sp.buf[buf];
+    d.dst = dp.buf[buf];
+    for (int e = 0; e < 3; ++e) {
+      d.sn[e] = sp.n[e];
+      d.dn[e] = dp.n[e];
+      d.dlo[e] = c.region.lo[e] - dp.sbox.lo[e];
+      d.slo[e] = c.region.lo[e] - c.shift[e] - sp.sbox.lo[e];
+      d.len[e] = c.region.len(e);
+    }
+    d.ssc = sp.cells;
+    d.dsc = dp.cells;
+    host.push_back(d);
+  }
+  auto arr = std::make_unique<DeviceArray<fvs::CopyDesc>>();
+  arr->upload(host);
+  const fvs::CopyDesc* ptr = arr->ptr;
+  L.copy_cache[buf] = std::move(arr);
+  return ptr;
+}
+
+const fvs::PackDesc* pack_descs(fvs_ctx* ctx, Level& L, int peer_index, int buf, bool recv,
+                                int* count, long long* max_cells) {
+  PeerExchange& pe = L.peers[peer_index];
+  const std::vector<fvs::HaloCopy>& list = recv ? pe.recvs : pe.sends;
+  *count = (int)list.size();
+  *max_cells = 0;
+  for (const fvs::HaloCopy& c : list) *max_cells = std::max(*max_cells, c.region.size());
+  auto key = std::make_tuple(peer_index, buf, recv ? 1 : 0);
+  auto it = L.pack_cache.find(key);
+  if (it != L.pack_cache.end()) return it->second->ptr;
+  std::vector<fvs::PackDesc> host;
+  long long offset = 0;
+  for (const fvs::HaloCopy& c : list) {
+    Patch& p = ctx->patch(L, recv ? c.dst_box : c.src_box);
+    fvs::PackDesc d{};
+    d.array = p.buf[buf];
+    for (int e = 0; e < 3; ++e) {
+      d.n[e] = p.n[e];
+      d.lo[e] = c.region.lo[e] - (recv ? 0 : c.shift[e]) - p.sbox.lo[e];
+      d.len[e] = c.region.len(e);
+    }
+    d.sc = p.cells;
+    d.offset = offset;
+    offset += c.region.size() * ctx->ncomp();
+    host.push_back(d);
+  }
+  auto arr = std::make_unique<DeviceArray<fvs::PackDesc>>();
+  arr->upload(host);
+  const fvs::PackDesc* ptr = arr->ptr;
+  L.pack_cache[key] = std::move(arr);
+  return ptr;
+}
+
+void fill_boundary(fvs_ctx* ctx, Level& L) {
+  const int buf = L.cur;
+  // remote part first so that the transfers overlap the local copies
+  if (!L.peers.empty()) {
+    if (!ctx->comm) throw Error("level has boxes on other ranks but fvs_comm_init was not called");
+    Nccl& n = Nccl::get();
+    for (size_t i = 0; i < L.peers.size(); ++i) {
+      int count;
+      long long max_cells;
+      const fvs::PackDesc* descs = pack_descs(ctx, L, (int)i, buf, false, &count, &max_cells);
+      ctx->launches += fvs::launch_pack(descs, count, ctx->ncomp(), L.peers[i].sendbuf,
+                                        max_cells, 0, ctx->stream);
+    }
+    n.check(n.GroupStart(), "ncclGroupStart");
+    for (PeerExchange& pe : L.peers) {
+      if (pe.send_elems)
+        n.check(n.Send(pe.sendbuf, (size_t)pe.send_elems, Nccl::kDouble, pe.peer, ctx->comm,
+                       ctx->stream),
+                "ncclSend");
+      if (pe.recv_elems)
+        n.check(n.Recv(pe.recvbuf, (size_t)pe.recv_elems, Nccl::kDouble, pe.peer, ctx->comm,
+                       ctx->stream),
+                "ncclRecv");
+    }
+    n.check(n.GroupEnd(), "ncclGroupEnd");
+  }
+  int count;
+  const fvs::CopyDesc* descs = copy_descs(ctx, L, buf, &count);
+  ctx->launches +=
+      fvs::launch_copy_regions(descs, count, ctx->ncomp(), L.max_copy_cells, ctx->stream);
+  for (size_t i = 0; i < L.peers.size(); ++i) {
+    int n_regions;
+    long long max_cells;
+    const fvs::PackDesc* pd = pack_descs(ctx, L, (int)i, buf, true, &n_regions, &max_cells);
+    ctx->launches += fvs::launch_pack(pd, n_regions, ctx->ncomp(), L.peers[i].recvbuf, max_cells,
+                                      1, ctx->stream);
+  }
+  FVS_CUDA(cudaGetLastError());
+}
+
+void apply_bc(fvs_ctx* ctx, Level& L, int bc_index) {
+  const BoundaryCondition& bc = L.bcs[bc_index];
+  if (L.periodic[bc.dir]) return;
+  const int buf = L.cur;
+  auto key = std::make_tuple(bc_index, buf);
+  auto it = L.bc_cache.find(key);
+  if (it == L.bc_cache.end()) {
+    std::vector<fvs::BcDesc> host;
+    const Box slab = fvs::boundary_slab(ctx->cfg.rank, L.domain, L.periodic, L.scratch_gcw,
+                                        bc.dir, bc.side, bc.kind == FVS_BC_REFLECTIVE);
+    for (Patch& p : L.patches) {
+      const Box fill = fvs::intersect(p.sbox, slab);
+      if (!fill.ok()) continue;
+      fvs::BcDesc d{};
+      d.array = p.buf[buf];
+      for (int e = 0; e < 3; ++e) {
+        d.n[e] = p.n[e];
+        d.lo[e] = fill.lo[e] - p.sbox.lo[e];
+        d.len[e] = fill.len(e);
+      }
+      d.sc = p.cells;
+      const int boundary = bc.side == 0 ? L.domain.lo[bc.dir] : L.domain.hi[bc.dir];
+      d.src_plane = boundary - p.sbox.lo[bc.dir];
+      // reflective: src = 2*lo - 1 - idx (lower side), 2*hi + 1 - idx (upper side)
+      const int mirror = bc.side == 0 ? 2 * L.domain.lo[bc.dir] - 1 : 2 * L.domain.hi[bc.dir] + 1;
+      d.mirror_sum = mirror - 2 * p.sbox.lo[bc.dir];
+      if (d.src_plane < 0 || d.src_plane >= p.n[bc.dir]) continue;
+      host.push_back(d);
+    }
+    auto arr = std::make_unique<DeviceArray<fvs::BcDesc>>();
+    arr->upload(host);
+    it = L.bc_cache.emplace(key, std::move(arr)).first;
+  }
+  DeviceArray<fvs::BcDesc>& arr = *it->second;
+  if (arr.count == 0) return;
+  long long max_cells = 0;
+  for (Patch& p : L.patches) max_cells = std::max(max_cells, p.cells);
+  ctx->launches += fvs::launch_boundary(arr.ptr, (int)arr.count, ctx->ncomp(), bc.dir, bc.kind,
+                                        max_cells, ctx->stream);
+  FVS_CUDA(cudaGetLastError());
+}
+
+void apply_boundary_condition(fvs_ctx* ctx, Level& L, int dir) {
+  for (size_t i = 0; i < L.bcs.size(); ++i) {
+    if (L.bcs[i].dir == dir) apply_bc(ctx, L, (int)i);
+  }
+}
+
+void fill_ghost_layer(fvs_ctx* ctx, Level& L) {
+  fill_boundary(ctx, L);
+  for (size_t i = 0; i < L.bcs.size(); ++i) apply_bc(ctx, L, (int)i);
+}
+
+// sweeps of one split step: (slot of the direction list, fraction of dt)
+struct SweepPlanEntry {
+  int slot;
+  double dt;
+};
+void split2(int kind, double dt, int s1, int s2, std::vector<SweepPlanEntry>& out) {
+  // src/split_method/{Godunov,Strang,StrangLumped}Splitting.cpp:25-39
+  if (kind == FVS_SPLIT_GODUNOV) {
+    out.push_back({s1, dt});
+    out.push_back({s2, dt});
+  } else if (kind == FVS_SPLIT_STRANG) {
+    out.push_back({s1, 0.5 * dt});
+    out.push_back({s2, 0.5 * dt});
+    out.push_back({s2, 0.5 * dt});
+    out.push_back({s1, 0.5 * dt});
+  } else {
+    out.push_back({s1, 0.5 * dt});
+    out.push_back({s2, dt});
+    out.push_back({s1, 0.5 * dt});
+  }
+}
+std::vector<SweepPlanEntry> split_plan(int rank, int kind, double dt) {
+  std::vector<SweepPlanEntry> out;
+  if (rank == 1) {
+    out.push_back({0, dt});
+  } else if (rank == 2) {
+    split2(kind, dt, 0, 1, out);
+  } else if (kind == FVS_SPLIT_STRANG) {
+    // StrangSplitting.cpp:44-69
+    const double h = 0.5 * dt;
+    for (int s : {0, 1, 2, 2, 1, 0}) out.push_back({s, h});
+  } else {
+    // SplittingMethod.hpp:53-60: Advance(dt, a1, [a2, a3 recursively])
+    std::vector<SweepPlanEntry> outer;
+    split2(kind, dt, 0, -1, outer);
+    for (const SweepPlanEntry& e : outer) {
+      if (e.slot == 0) {
+        out.push_back(e);
+      } else {
+        split2(kind, e.dt, 1, 2, out);
+      }
+    }
+  }
+  return out;
+}
+
+} // namespace
+
+// =============================================================================
+extern "C" {
+
+const char* fvs_last_error(void) { return g_error.c_str(); }
+int fvs_version(void) { return FVS_VERSION; }
+
+int fvs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fvs_create(const fvs_config* config, fvs_ctx** out) {
+  return guarded([&] {
+    if (!config || !out) throw Error("null argument");
+    if (config->rank < 1 || config->rank > 3) throw Error("rank must be 1, 2 or 3");
+    if (!(config->gamma > 1.0)) throw Error("gamma must be > 1");
+    if (fvs_device_count() == 0) {
+      throw Error("no CUDA device: libfvs_b200 has no CPU fallback");
+    }
+    std::unique_ptr<fvs_ctx> ctx(new fvs_ctx);
+    ctx->cfg = *config;
+    if (ctx->cfg.comm_size < 1) ctx->cfg.comm_size = 1;
+    if (ctx->cfg.device < 0) {
+      FVS_CUDA(cudaGetDevice(&ctx->device));
+    } else {
+      ctx->device = ctx->cfg.device;
+    }
+    ctx->use_device();
+    ctx->eq.gamma = config->gamma;
+    ctx->eq.gamma_minus_1_inv = 1.0 / (config->gamma - 1.0);
+    ctx->eq.gamma_minus_1 = config->gamma - 1.0;
+    FVS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    FVS_CUDA(cudaMalloc(&ctx->d_slots, sizeof(unsigned long long) * kDtSlots));
+    FVS_CUDA(cudaMemset(ctx->d_slots, 0, sizeof(unsigned long long) * kDtSlots));
+    FVS_CUDA(cudaMallocHost(&ctx->h_slots, sizeof(unsigned long long) * kDtSlots));
+    FVS_CUDA(cudaMalloc(&ctx->d_fail, sizeof(int)));
+    FVS_CUDA(cudaMemset(ctx->d_fail, 0, sizeof(int)));
+    FVS_CUDA(cudaMallocHost(&ctx->h_fail, sizeof(int)));
+    *ctx->h_fail = 0;
+    fvs_ctx* raw = ctx.release();
+    *out = raw;
+    const int rc = fvs_set_method(raw, config->base_method, config->reconstruction, config->limiter);
+    if (rc != FVS_OK) {
+      fvs_destroy(raw);
+      *out = nullptr;
+      return rc;
+    }
+    return (int)FVS_OK;
+  });
+}
+
+void fvs_destroy(fvs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (Level& L : ctx->levels) free_level(L);
+  for (auto& ev : ctx->pending_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  for (auto& ev : ctx->free_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  if (ctx->comm) Nccl::get().CommDestroy(ctx->comm);
+  if (ctx->d_slots) cudaFree(ctx->d_slots);
+  if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+  if (ctx->d_fail) cudaFree(ctx->d_fail);
+  if (ctx->h_fail) cudaFreeHost(ctx->h_fail);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limiter) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (base_method < 0 || base_method > 3) throw Error("unknown base method");
+    if (reconstruction < 0 || reconstruction > 1) throw Error("unknown reconstruction");
+    if (limiter < 0 || limiter > 2) throw Error("unknown limiter");
+    const int w = reconstruction == FVS_RECON_MUSCL_HANCOCK ? 2 : 1;
+    for (Level& L : ctx->levels) {
+      if (L.defined && L.scratch_gcw < L.flux_gcw + w) {
+        throw Error("scratch_gcw must be >= flux_gcw + stencil width");
+      }
+    }
+    ctx->method = fvs::MethodKey{ctx->cfg.rank, base_method, reconstruction, limiter};
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_stencil_width(const fvs_ctx* ctx) { return ctx ? ctx->stencil_width() : FVS_ERROR; }
+
+int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int domain_hi[3],
+                     const double dx[3], const int periodic[3], int nboxes,
+                     const int (*box_lo)[3], const int (*box_hi)[3], const int* owner,
+                     int scratch_gcw, int flux_gcw) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (level < 0 || level > 64) throw Error("level out of range");
+    if (nboxes < 0) throw Error("negative box count");
+    if (scratch_gcw < 0 || flux_gcw < 0) throw Error("negative ghost width");
+    if (scratch_gcw < flux_gcw + ctx->stencil_width()) {
+      throw Error("scratch_gcw must be >= flux_gcw + stencil width");
+    }
+    ctx->use_device();
+    if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    free_level(ctx->levels[level]);
+    Level& L = ctx->levels[level];
+    const int rank = ctx->cfg.rank;
+    L.rank = rank;
+    L.domain = fvs::make_box(domain_lo, domain_hi);
+    for (int d = 0; d < 3; ++d) {
+      L.dx[d] = dx[d];
+      L.periodic[d] = periodic && periodic[d] != 0;
+      if (d >= rank && (L.domain.lo[d] != 0 || L.domain.hi[d] != 0)) {
+        throw Error("unused dimensions of the domain must be [0,0]");
+      }
+    }
+    L.scratch_gcw = scratch_gcw;
+    L.flux_gcw = flux_gcw;
+    L.boxes.resize(nboxes);
+    L.owner.assign(nboxes, 0);
+    L.local_of_global.assign(nboxes, -1);
+    for (int b = 0; b < nboxes; ++b) {
+      L.boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+      if (!L.boxes[b].ok()) throw Error("empty box");
+      for (int d = rank; d < 3; ++d) {
+        if (L.boxes[b].lo[d] != 0 || L.boxes[b].hi[d] != 0) {
+          throw Error("unused dimensions of a box must be [0,0]");
+        }
+      }
+      if (owner) L.owner[b] = owner[b];
+      if (L.owner[b] < 0 || L.owner[b] >= ctx->cfg.comm_size) throw Error("owner out of range");
+    }
+    for (int d = 0; d < 3; ++d) L.max_n[d] = 1;
+    for (int b = 0; b < nboxes; ++b) {
+      if (L.owner[b] != ctx->cfg.comm_rank) continue;
+      Patch p;
+      p.global_index = b;
+      p.valid = L.boxes[b];
+      p.sbox = fvs::state_box(p.valid, rank, scratch_gcw);
+      for (int d = 0; d < 3; ++d) {
+        p.n[d] = p.sbox.len(d);
+        L.max_n[d] = std::max(L.max_n[d], p.n[d]);
+      }
+      p.cells = p.sbox.size();
+      for (int d = 0; d < rank; ++d) {
+        p.fbox[d] = fvs::flux_box(p.valid, rank, d, scratch_gcw, flux_gcw);
+        for (int w = 1; w <= 2; ++w) {
+          const std::vector<unsigned char> mask =
+              fvs::stable_dt_face_mask(p.valid, scratch_gcw, w, d);
+          FVS_CUDA(cudaMalloc(&p.dtmask[w - 1][d], mask.size()));
+          FVS_CUDA(cudaMemcpy(p.dtmask[w - 1][d], mask.data(), mask.size(),
+                              cudaMemcpyHostToDevice));
+        }
+      }
+      L.local_of_global[b] = (int)L.patches.size();
+      L.patches.push_back(p);
+    }
+    L.defined = true;
+    L.cur = 0;
+    L.keep = -1;
+    ensure_buffer(ctx, L, 0);
+    // halo plan
+    const std::vector<fvs::HaloCopy> plan =
+        fvs::halo_plan(rank, L.domain, L.periodic, L.boxes, scratch_gcw);
+    const int me = ctx->cfg.comm_rank;
+    std::map<int, PeerExchange> peers;
+    for (const fvs::HaloCopy& c : plan) {
+      const int so = L.owner[c.src_box], dow = L.owner[c.dst_box];
+      if (so == me && dow == me) {
+        L.local_copies.push_back(c);
+        L.max_copy_cells = std::max(L.max_copy_cells, c.region.size());
+      } else if (so == me) {
+        PeerExchange& pe = peers[dow];
+        pe.peer = dow;
+        pe.sends.push_back(c);
+        pe.send_elems += c.region.size() * ctx->ncomp();
+      } else if (dow == me) {
+        PeerExchange& pe = peers[so];
+        pe.peer = so;
+        pe.recvs.push_back(c);
+        pe.recv_elems += c.region.size() * ctx->ncomp();
+      }
+    }
+    for (auto& kv : peers) {
+      PeerExchange& pe = kv.second;
+      if (pe.send_elems) FVS_CUDA(cudaMalloc(&pe.sendbuf, pe.send_elems * sizeof(double)));
+      if (pe.recv_elems) FVS_CUDA(cudaMalloc(&pe.recvbuf, pe.recv_elems * sizeof(double)));
+      L.peers.push_back(std::move(pe));
+    }
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_level_add_boundary(fvs_ctx* ctx, int level, int dir, int side, int kind) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    if (side < 0 || side > 1) throw Error("side must be 0 or 1");
+    if (kind != FVS_BC_TRANSMISSIVE && kind != FVS_BC_REFLECTIVE) throw Error("unknown boundary kind");
+    L.bcs.push_back({dir, side, kind});
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_state_box(const fvs_ctx* ctx, int level, int box, int lo[3], int hi[3], int* ncomp) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    const Level& L = const_cast<fvs_ctx*>(ctx)->level(level);
+    if (box < 0 || box >= (int)L.boxes.size()) throw Error("box index out of range");
+    const Box b = fvs::state_box(L.boxes[box], ctx->cfg.rank, L.scratch_gcw);
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = b.lo[d];
+      hi[d] = b.hi[d];
+    }
+    if (ncomp) *ncomp = ctx->ncomp();
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_flux_box(const fvs_ctx* ctx, int level, int box, int dir, int lo[3], int hi[3],
+                 int* ncomp) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    const Level& L = const_cast<fvs_ctx*>(ctx)->level(level);
+    if (box < 0 || box >= (int)L.boxes.size()) throw Error("box index out of range");
+    check_dir(ctx, dir);
+    const Box b = fvs::flux_box(L.boxes[box], ctx->cfg.rank, dir, L.scratch_gcw, L.flux_gcw);
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = b.lo[d];
+      hi[d] = b.hi[d];
+    }
+    if (ncomp) *ncomp = ctx->ncons();
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(p.buf[L.cur], host_fab, (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(host_fab, p.buf[L.cur], (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_upload_fluxes(fvs_ctx* ctx, int level, int box, int dir, const double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    ensure_fluxes(ctx, L, dir);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(p.flux[dir], host_fab,
+                             (size_t)p.fbox[dir].size() * ctx->ncons() * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_download_fluxes(fvs_ctx* ctx, int level, int box, int dir, double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    ensure_fluxes(ctx, L, dir);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(host_fab, p.flux[dir],
+                             (size_t)p.fbox[dir].size() * ctx->ncons() * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_state_device_ptr(fvs_ctx* ctx, int level, int box, double** dptr) {
+  return guarded([&] {
+    if (!ctx || !dptr) throw Error("null argument");
+    Level& L = ctx->level(level);
+    *dptr = ctx->patch(L, box).buf[L.cur];
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_compute_stable_dt(fvs_ctx* ctx, int level, int dir, double* dt_out) {
+  return guarded([&] {
+    if (!ctx || !dt_out) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, false);
+    const int slot = take_slot(ctx);
+    fvs::SweepArgs A = sweep_args(ctx, L, dir, 0.0, boxes, slot);
+    if (!L.patches.empty()) {
+      const int rc = fvs::launch_stable_dt(ctx->method, dir, A, ctx->stream);
+      check_launch(rc);
+      ctx->launches += rc;
+    }
+    double sig;
+    fetch_slots(ctx, slot, 1, &sig);
+    *dt_out = dt_from_signal(L.dx[dir], sig);
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_compute_numeric_fluxes(fvs_ctx* ctx, int level, double dt, int dir) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    ensure_fluxes(ctx, L, dir);
+    const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+    if (!L.patches.empty()) {
+      const int rc = fvs::launch_numeric_fluxes(ctx->method, dir, A, ctx->stream);
+      check_launch(rc);
+      ctx->launches += rc;
+    }
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_update_conservatively(fvs_ctx* ctx, int level, double dt, int dir) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    ensure_fluxes(ctx, L, dir);
+    const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+    if (!L.patches.empty()) {
+      const int rc = fvs::launch_update_conservatively(ctx->cfg.rank, dir, A, ctx->stream);
+      check_launch(rc);
+      ctx->launches += rc;
+    }
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_complete_from_cons(fvs_ctx* ctx, int level) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    const BoxDesc* boxes = box_descs(ctx, L, 0, L.cur, L.cur, false);
+    fvs::SweepArgs A = sweep_args(ctx, L, 0, 0.0, boxes, 0);
+    if (!L.patches.empty()) {
+      const int rc = fvs::launch_complete_from_cons(ctx->cfg.rank, A, ctx->stream);
+      check_launch(rc);
+      ctx->launches += rc;
+    }
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    check_dir(ctx, dir);
+    int dst;
+    const int slot = launch_sweep(ctx, L, dt, dir, &dst);
+    double sig;
+    fetch_slots(ctx, slot, 1, &sig);
+    const double level_dt = dt_from_signal(L.dx[dir], sig);
+    if (level_dt_out) *level_dt_out = level_dt;
+    // DimensionalSplitLevelIntegrator.hpp:243-245
+    if (level_dt < dt) return (int)FVS_TIME_STEP_TOO_LARGE;
+    L.cur = dst;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_fill_ghost_layer(fvs_ctx* ctx, int level) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    fill_ghost_layer(ctx, ctx->level(level));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_apply_boundary_condition(fvs_ctx* ctx, int level, int dir) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    check_dir(ctx, dir);
+    apply_boundary_condition(ctx, ctx->level(level), dir);
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
+  return guarded([&] {
+    if (!ctx || !dt_out) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    const int rank = ctx->cfg.rank;
+    fvs::DtAllArgs A{};
+    A.eq = ctx->eq;
+    for (int d = 0; d < 3; ++d) {
+      A.boxes[d] = box_descs(ctx, L, d < rank ? d : 0, L.cur, L.cur, false);
+      A.max_n[d] = L.max_n[d];
+    }
+    A.nboxes = (int)L.patches.size();
+    const int slot = take_slot(ctx, 3);
+    A.max_signal = ctx->d_slots + slot;
+    A.fail_flag = ctx->d_fail;
+    if (!L.patches.empty()) {
+      const int rc = fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
+      check_launch(rc);
+      ctx->launches += rc;
+    }
+    double sig[3];
+    fetch_slots(ctx, slot, 3, sig);
+    // DimensionalSplitLevelIntegrator.hpp:204-219
+    double min_dt = std::numeric_limits<double>::max();
+    for (int d = 0; d < rank; ++d) min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
+    *dt_out = min_dt;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind, double* failure_dt,
+                          double* sweep_dts, int* n_sweep_dts) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(0);
+    const int rank = ctx->cfg.rank;
+    if (split_kind < 0 || split_kind > 2) throw Error("unknown splitting method");
+    // MakeSplitDirections, include/fub/split_method/SplittingMethod.hpp:115-126
+    const bool is_odd = (ctx->cycles % 2) != 0;
+    int dirs[3];
+    for (int i = 0; i < rank; ++i) dirs[i] = is_odd ? (rank - 1 - i) : i;
+    const std::vector<SweepPlanEntry> plan = split_plan(rank, split_kind, dt);
+    if ((int)plan.size() > kDtSlots) throw Error("too many sweeps");
+    const int entry = L.cur;
+    const int old_keep = L.keep;
+    L.keep = entry; // the state at entry survives until the step is accepted
+    int counts[3] = {0, 0, 0};
+    std::vector<int> slots;
+    ctx->next_slot = 0;
+    try {
+      for (const SweepPlanEntry& e : plan) {
+        const int dir = dirs[e.slot];
+        if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir); // :228-234
+        counts[e.slot] += 1;
+        int dst;
+        slots.push_back(launch_sweep(ctx, L, e.dt, dir, &dst));
+        L.cur = dst;
+      }
+    } catch (...) {
+      L.cur = entry;
+      L.keep = old_keep;
+      throw;
+    }
+    // one synchronisation for all sweeps of the step
+    std::vector<double> sig(plan.size());
+    // slots are consecutive (next_slot was reset above)
+    try {
+      fetch_slots(ctx, slots.front(), (int)plan.size(), sig.data());
+    } catch (...) {
+      L.cur = entry;
+      L.keep = old_keep;
+      throw;
+    }
+    int n_out = 0;
+    const int cap = (sweep_dts && n_sweep_dts) ? *n_sweep_dts : 0;
+    int status = FVS_OK;
+    for (size_t i = 0; i < plan.size(); ++i) {
+      const double level_dt = dt_from_signal(L.dx[dirs[plan[i].slot]], sig[i]);
+      if (n_out < cap) sweep_dts[n_out] = level_dt;
+      ++n_out;
+      if (level_dt < plan[i].dt) { // :243-245
+        if (failure_dt) *failure_dt = level_dt;
+        status = FVS_TIME_STEP_TOO_LARGE;
+        break;
+      }
+    }
+    if (n_sweep_dts) *n_sweep_dts = n_out;
+    L.keep = old_keep;
+    if (status != FVS_OK) {
+      L.cur = entry; // roll back: the entry buffer was never written
+      return status;
+    }
+    // SubcycleFineFirstSolver.hpp:164-174,177-192
+    ctx->cycles += 1;
+    ctx->time_point = ctx->time_point + dt;
+    if (ctx->cycles % ctx->regrid_frequency == 0) fill_ghost_layer(ctx, L);
+    return (int)FVS_OK;
+  });
+}
+
+long fvs_run(fvs_ctx* ctx, double cfl, double final_time, long max_cycles, int split_kind,
+             double* dt_sequence, long dt_capacity, int* retries_out) {
+  long accepted = 0;
+  const int rc = guarded([&] {
+    if (!ctx) throw Error("null context");
+    const double eps = 1e-12; // RunOptions::smallest_time_step_size, RunSimulation.hpp:61-65
+    bool have_failure = false;
+    double failure_dt = 0.0;
+    int retries = 0;
+    while (ctx->time_point + eps < final_time && (max_cycles < 0 || ctx->cycles < max_cycles)) {
+      double stable_dt;
+      if (have_failure) {
+        stable_dt = failure_dt;
+      } else if (fvs_compute_stable_dt_all(ctx, 0, &stable_dt) != FVS_OK) {
+        throw Error(g_error);
+      }
+      const double limited_dt = std::min(final_time - ctx->time_point, cfl * stable_dt);
+      double fail = 0.0;
+      const int status = fvs_advance_hierarchy(ctx, limited_dt, split_kind, &fail, nullptr, nullptr);
+      if (status == FVS_ERROR) throw Error(g_error);
+      if (status == FVS_TIME_STEP_TOO_LARGE) {
+        have_failure = true;
+        failure_dt = fail;
+        if (++retries > 100) throw Error("too many CFL retries");
+      } else {
+        if (dt_sequence && accepted < dt_capacity) dt_sequence[accepted] = limited_dt;
+        ++accepted;
+        have_failure = false;
+      }
+    }
+    if (retries_out) *retries_out = retries;
+    return (int)FVS_OK;
+  });
+  return rc == FVS_OK ? accepted : (long)FVS_ERROR;
+}
+
+int fvs_set_regrid_frequency(fvs_ctx* ctx, int frequency) {
+  return guarded([&] {
+    if (!ctx || frequency < 1) throw Error("invalid regrid frequency");
+    ctx->regrid_frequency = frequency;
+    return (int)FVS_OK;
+  });
+}
+int fvs_set_cycles(fvs_ctx* ctx, long cycles, double time_point) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->cycles = cycles;
+    ctx->time_point = time_point;
+    return (int)FVS_OK;
+  });
+}
+long fvs_cycles(const fvs_ctx* ctx) { return ctx ? ctx->cycles : -1; }
+double fvs_time_point(const fvs_ctx* ctx) { return ctx ? ctx->time_point : 0.0; }
+
+int fvs_min_all(fvs_ctx* ctx, double* inout) {
+  return guarded([&] {
+    if (!ctx || !inout) throw Error("null argument");
+    if (!ctx->comm || ctx->cfg.comm_size <= 1) return (int)FVS_OK;
+    ctx->use_device();
+    Nccl& n = Nccl::get();
+    double* d = reinterpret_cast<double*>(ctx->d_slots + (kDtSlots - 1));
+    FVS_CUDA(cudaMemcpyAsync(d, inout, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    n.check(n.AllReduce(d, d, 1, Nccl::kDouble, Nccl::kMin, ctx->comm, ctx->stream),
+            "ncclAllReduce(min)");
+    FVS_CUDA(cudaMemcpyAsync(inout, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_comm_unique_id(void* out_id) {
+  return guarded([&] {
+    if (!out_id) throw Error("null argument");
+    Nccl& n = Nccl::get();
+    Nccl::unique_id id;
+    n.check(n.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(out_id, &id, sizeof(id));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_comm_init(fvs_ctx* ctx, const void* id_bytes) {
+  return guarded([&] {
+    if (!ctx || !id_bytes) throw Error("null argument");
+    ctx->use_device();
+    Nccl& n = Nccl::get();
+    Nccl::unique_id id;
+    std::memcpy(&id, id_bytes, sizeof(id));
+    n.check(n.CommInitRank(&ctx->comm, ctx->cfg.comm_size, id, ctx->cfg.comm_rank),
+            "ncclCommInitRank");
+    return (int)FVS_OK;
+  });
+}
+
+long fvs_halo_plan(int rank, const int domain_lo[3], const int domain_hi[3],
+                   const int periodic[3], int nboxes, const int (*box_lo)[3],
+                   const int (*box_hi)[3], const int* owner, int scratch_gcw,
+                   fvs_halo_copy* out, long capacity) {
+  long count = 0;
+  const int rc = guarded([&] {
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    bool per[3];
+    for (int d = 0; d < 3; ++d) per[d] = periodic && periodic[d] != 0;
+    const auto plan =
+        fvs::halo_plan(rank, fvs::make_box(domain_lo, domain_hi), per, boxes, scratch_gcw);
+    for (const fvs::HaloCopy& c : plan) {
+      if (out && count < capacity) {
+        fvs_halo_copy& o = out[count];
+        o.dst_box = c.dst_box;
+        o.src_box = c.src_box;
+        o.dst_owner = owner ? owner[c.dst_box] : 0;
+        o.src_owner = owner ? owner[c.src_box] : 0;
+        for (int d = 0; d < 3; ++d) {
+          o.lo[d] = c.region.lo[d];
+          o.hi[d] = c.region.hi[d];
+          o.shift[d] = c.shift[d];
+        }
+      }
+      ++count;
+    }
+    return (int)FVS_OK;
+  });
+  return rc == FVS_OK ? count : (long)FVS_ERROR;
+}
+
+int fvs_stable_dt_face_mask(int rank, const int box_lo[3], const int box_hi[3], int scratch_gcw,
+                            int stencil_width, int dir, unsigned char* mask, int capacity) {
+  return guarded([&] {
+    if (dir < 0 || dir >= rank) throw Error("direction out of range");
+    const auto m = fvs::stable_dt_face_mask(fvs::make_box(box_lo, box_hi), scratch_gcw,
+                                            stencil_width, dir);
+    if (mask) {
+      for (int i = 0; i < (int)m.size() && i < capacity; ++i) mask[i] = m[i];
+    }
+    return (int)m.size();
+  });
+}
+
+int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3], const int (*box_hi)[3],
+                         int nranks, int* owner_out) {
+  return guarded([&] {
+    (void)rank;
+    if (nranks < 1 || !owner_out) throw Error("invalid argument");
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    const std::vector<int> owner = fvs::distribute_boxes(boxes, nranks);
+    for (int b = 0; b < nboxes; ++b) owner_out[b] = owner[b];
+    return (int)FVS_OK;
+  });
+}
+
+long fvs_kernel_launches(const fvs_ctx* ctx) { return ctx ? ctx->launches : -1; }
+void* fvs_stream(fvs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int fvs_enable_timing(fvs_ctx* ctx, int on) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->timing = on != 0;
+    ctx->sweep_ms = 0.0;
+    ctx->sweep_count = 0;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_sweep_time_ms(fvs_ctx* ctx, double* total_ms, long* n_sweeps) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    drain_events(ctx);
+    if (total_ms) *total_ms = ctx->sweep_ms;
+    if (n_sweeps) *n_sweeps = ctx->sweep_count;
+    return (int)FVS_OK;
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,101 @@
+// launch.h -- plain-old-data descriptors shared by the host context and the
+// kernel translation units, and the launcher entry points each instantiation
+// unit (sweep_inst.cu compiled once per space dimension and base method)
+// exports.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "numerics.cuh"
+
+namespace fvs {
+
+// One box (patch) of a level as the sweep kernels see it.  All indices are
+// relative to the lower corner of the state array (which includes ghosts).
+struct BoxDesc {
+  const double* src; // state read by the kernel, ncomp components
+  double* dst;       // state written by the kernel (fused sweep), or == src
+  double* flux;      // flux array of the sweep direction (unfused kernels)
+  int n[3];          // extents of the state array
+  int fn[3];         // extents of the flux array
+  int foff[3];       // flux index = cell index - foff (per dimension)
+  long long sc;      // component stride of the state array
+  long long fsc;     // component stride of the flux array
+  int ulo, uhi;      // cells updated along the sweep direction (inclusive)
+  int flo, fhi;      // faces computed along the sweep direction (face f lies between cells f-1 and f)
+  const unsigned char* dtmask; // n[dir] bytes: dtmask[i] != 0 iff face (i | i+1) enters the stable dt
+};
+
+struct SweepArgs {
+  EqConst eq;
+  double lambda;      // dt / dx
+  double lambda_half; // (0.5 * dt) / dx
+  const BoxDesc* boxes; // device array
+  int nboxes;
+  int max_n[3];       // max extents over the boxes (grid sizing)
+  int seg_len;        // output cells per segment along the sweep direction
+  unsigned long long* max_signal; // device: bit pattern of the max signal speed (non-negative double)
+  int* fail_flag;     // device: set to 1 if a Newton iteration failed
+};
+
+struct MethodKey {
+  int rank, base, recon, limiter;
+};
+
+// Each returns the number of kernels launched, or -1 if the combination is
+// not compiled into this unit.
+using SweepLauncher = int (*)(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+
+// fused: stable dt + numeric flux + conservative update + complete, src -> dst
+int launch_fused_sweep(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+// unfused policies (operate on src in place, fluxes through BoxDesc::flux)
+int launch_stable_dt(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+int launch_numeric_fluxes(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+int launch_update_conservatively(int rank, int dir, const SweepArgs&, cudaStream_t);
+int launch_complete_from_cons(int rank, const SweepArgs&, cudaStream_t);
+// stable dt of all directions in one pass (masks: one per direction)
+struct DtAllArgs {
+  EqConst eq;
+  const BoxDesc* boxes[3]; // per direction (dtmask differs)
+  int nboxes;
+  int max_n[3];
+  unsigned long long* max_signal; // [3] one accumulator per direction
+  int* fail_flag;
+};
+int launch_stable_dt_all(const MethodKey&, const DtAllArgs&, cudaStream_t);
+
+// ---- ghost cells -----------------------------------------------------------
+struct CopyDesc {
+  const double* src;
+  double* dst;
+  int sn[3];
+  int dn[3]; // extents of source / destination arrays
+  long long ssc, dsc;
+  int slo[3]; // first source cell (array-relative)
+  int dlo[3]; // first destination cell (array-relative)
+  int len[3]; // region extents
+};
+int launch_copy_regions(const CopyDesc* regions, int nregions, int ncomp, long long max_cells,
+                        cudaStream_t);
+// pack / unpack of regions to / from a contiguous buffer (multi-GPU halo)
+struct PackDesc {
+  double* array; // state array
+  int n[3];
+  long long sc;
+  int lo[3], len[3];
+  long long offset; // first element in the packed buffer
+};
+int launch_pack(const PackDesc* regions, int nregions, int ncomp, double* buffer,
+                long long max_cells, int unpack, cudaStream_t);
+
+struct BcDesc {
+  double* array;
+  int n[3];
+  long long sc;
+  int lo[3], len[3]; // fill region (array-relative)
+  int src_plane;     // transmissive: array-relative index of the boundary cell along dir
+  int mirror_sum;    // reflective: src = mirror_sum - idx along dir
+};
+int launch_boundary(const BcDesc* regions, int nregions, int ncomp, int dir, int kind,
+                    long long max_cells, cudaStream_t);
+
+} // namespace fvs

@@ -1,0 +1,672 @@
+// numerics.cuh -- per-cell / per-face fp64 numerics of the PerfectGas split
+// sweep, one value per thread.  Compiled for sm_100a with -fmad=false: every
+// + - * / sqrt below is a single IEEE-754 round-to-nearest operation in the
+// order the reference's array (Eigen) code path evaluates it, so results are
+// bit-identical to the reference's CPU path (DESIGN.md "Bitwise strategy").
+//
+// Space dimension D and sweep direction DIR are template parameters so that
+// every momentum index is a compile-time constant and states stay in
+// registers.
+//
+// Reference (paths relative to maikel/FiniteVolumeSolver):
+//   src/equations/PerfectGas.cpp:31-144              KineticEnergy, Flux, CompleteFromCons
+//   include/fub/flux_method/MusclHancockMethod.hpp:31-187,419-485  limiters, MUSCL-Hancock
+//   src/equations/perfect_gas/HllemMethod.hpp:711-1072,1152-1216   HLLEM flux, stable dt
+//   src/equations/perfect_gas/EinfeldtSignalVelocities.hpp:64-97   Einfeldt signals
+//   include/fub/flux_method/HllMethod.hpp:260-293,337-347          HLL flux, stable dt
+//   src/equations/perfect_gas/ExactRiemannSolver.hpp:34-353        exact solver
+//   include/fub/flux_method/GodunovMethod.hpp:129-199              Godunov
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace fvs {
+
+enum : int { kBaseHllemLarrouturou = 0, kBaseHllem = 1, kBaseHllEinfeldt = 2, kBaseGodunovExact = 3 };
+enum : int { kReconFirstOrder = 0, kReconMusclHancock = 1 };
+enum : int { kLimiterNone = 0, kLimiterMinMod = 1, kLimiterVanLeer = 2 };
+
+// PerfectGas equation constants (include/fub/equations/PerfectGas.hpp:216-219):
+// gamma_minus_1_inv = 1.0 / (gamma - 1.0) evaluated in fp64 on the host.
+struct EqConst {
+  double gamma;
+  double gamma_minus_1_inv;
+  double gamma_minus_1; // gamma - 1.0
+};
+
+template <int D> struct Cons {
+  double rho;
+  double mom[D];
+  double E;
+};
+template <int D> struct Complete {
+  double rho;
+  double mom[D];
+  double E;
+  double p;
+  double a;
+};
+
+#define FVS_DEV __device__ __forceinline__
+
+// Eigen-style min/max (array8 semantics of the oracle): a < b ? a : b
+FVS_DEV double vmin(double a, double b) { return a < b ? a : b; }
+FVS_DEV double vmax(double a, double b) { return a > b ? a : b; }
+
+// Unrolled reduction order of Eigen's squaredNorm on a fixed-size column:
+// D=1: x0; D=2: x0+x1; D=3: x0+(x1+x2).
+template <int D> FVS_DEV double squared_norm(const double (&m)[D]) {
+  if constexpr (D == 1) {
+    return m[0] * m[0];
+  } else if constexpr (D == 2) {
+    return m[0] * m[0] + m[1] * m[1];
+  } else {
+    return m[0] * m[0] + (m[1] * m[1] + m[2] * m[2]);
+  }
+}
+
+// src/equations/PerfectGas.cpp:31-37
+template <int D> FVS_DEV double kinetic_energy(double rho, const double (&mom)[D]) {
+  return 0.5 * squared_norm<D>(mom) / rho;
+}
+
+// src/equations/PerfectGas.cpp:66-77
+template <int D, int DIR, typename State>
+FVS_DEV void euler_flux(Cons<D>& f, const State& s) {
+  const double velocity = s.mom[DIR] / s.rho;
+  f.rho = s.mom[DIR];
+#pragma unroll
+  for (int d = 0; d < D; ++d) f.mom[d] = velocity * s.mom[d];
+  f.mom[DIR] = f.mom[DIR] + s.p;
+  f.E = velocity * (s.E + s.p);
+}
+
+// src/equations/PerfectGas.cpp:112-124: fills p and a of `q` from its
+// conservative part.
+template <int D> FVS_DEV void complete_from_cons(const EqConst& eq, Complete<D>& q) {
+  const double e_kin = kinetic_energy<D>(q.rho, q.mom);
+  const double e_int = q.E - e_kin;
+  q.p = e_int / eq.gamma_minus_1_inv;
+  q.a = sqrt(eq.gamma * q.p / q.rho);
+}
+
+// ---------------------------------------------------------------------------
+// Limiters, include/fub/flux_method/MusclHancockMethod.hpp:31-187 (array path)
+template <int LIM> FVS_DEV double limited_slope(double qL, double qM, double qR) {
+  const double sL = qM - qL;
+  const double sR = qR - qM;
+  if constexpr (LIM == kLimiterNone) {
+    return 0.5 * (sL + sR); // :49-51
+  } else if constexpr (LIM == kLimiterMinMod) {
+    // :117 (sR > 0).select(zero.max(sL.min(sR)), zero.min(sL.max(sR)))
+    return sR > 0.0 ? vmax(0.0, vmin(sL, sR)) : vmin(0.0, vmax(sL, sR));
+  } else {
+    const double r = 2.0 * sL * sR; // :144-147
+    return r > 0.0 ? r / (sL + sR) : 0.0;
+  }
+}
+
+// MUSCL-Hancock predictor of ONE cell (MusclHancockMethod.hpp:428-451 and its
+// mirror :456-479).  The reference evaluates this once for each of the two
+// faces of the cell; all operations that lead to the two edge states are
+// identical, so both are produced here in one go:
+//   recL: predicted state at the cell's lower face  (q_L + lambda/2 (f(q_L) - f(q_R)))
+//   recR: predicted state at the cell's upper face  (q_R + lambda/2 (f(q_L) - f(q_R)))
+template <int D, int DIR, int LIM, typename S0, typename S1, typename S2>
+FVS_DEV void muscl_predict(const EqConst& eq, const S0& qm, const S1& q0, const S2& qp,
+                           double lambda_half, Complete<D>& recL, Complete<D>& recR) {
+  Complete<D> qL, qR;
+  {
+    const double s = limited_slope<LIM>(qm.rho, q0.rho, qp.rho);
+    qL.rho = q0.rho - 0.5 * s;
+    qR.rho = q0.rho + 0.5 * s;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double s = limited_slope<LIM>(qm.mom[d], q0.mom[d], qp.mom[d]);
+    qL.mom[d] = q0.mom[d] - 0.5 * s;
+    qR.mom[d] = q0.mom[d] + 0.5 * s;
+  }
+  {
+    const double s = limited_slope<LIM>(qm.E, q0.E, qp.E);
+    qL.E = q0.E - 0.5 * s;
+    qR.E = q0.E + 0.5 * s;
+  }
+  complete_from_cons<D>(eq, qL);
+  complete_from_cons<D>(eq, qR);
+  Cons<D> fL, fR;
+  euler_flux<D, DIR>(fL, qL);
+  euler_flux<D, DIR>(fR, qR);
+  {
+    const double c = lambda_half * (fL.rho - fR.rho);
+    recL.rho = qL.rho + c;
+    recR.rho = qR.rho + c;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double c = lambda_half * (fL.mom[d] - fR.mom[d]);
+    recL.mom[d] = qL.mom[d] + c;
+    recR.mom[d] = qR.mom[d] + c;
+  }
+  {
+    const double c = lambda_half * (fL.E - fR.E);
+    recL.E = qL.E + c;
+    recR.E = qR.E + c;
+  }
+  complete_from_cons<D>(eq, recL);
+  complete_from_cons<D>(eq, recR);
+}
+
+// ---------------------------------------------------------------------------
+// HLLEM, array code path.  src/equations/perfect_gas/HllemMethod.hpp:711-1072.
+// Msq = Minv = 1 for PerfectGas (include/fub/equations/EulerEquation.hpp:53-62).
+// Returns the numeric flux between `left` and `right`.
+template <int D, int DIR, bool LARROUTUROU>
+FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
+                        Complete<D> right) {
+  const double rhoL = left.rho;
+  const double rhoR = right.rho;
+  double vL_[D], vR_[D];
+  double eKinRL = 0.0, eKinRR = 0.0;
+  if constexpr (LARROUTUROU) {
+    // :729-745 -- tangential momenta are multiplied by 0.0 (keeps their sign
+    // bit) and their kinetic energy is taken out of E.
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      vL_[i] = left.mom[i] / rhoL;
+      vR_[i] = right.mom[i] / rhoR;
+      if (i != DIR) {
+        eKinRL += vL_[i] * vL_[i];
+        eKinRR += vR_[i] * vR_[i];
+        left.mom[i] *= 0.0;
+        right.mom[i] *= 0.0;
+      }
+    }
+    eKinRL *= 0.5;
+    eKinRR *= 0.5;
+    left.E -= rhoL * eKinRL;
+    right.E -= rhoR * eKinRR;
+  }
+  Cons<D> fluxL, fluxR;
+  euler_flux<D, DIR>(fluxL, left);
+  euler_flux<D, DIR>(fluxR, right);
+
+  // :752-797 Einfeldt signal velocities with the full Roe velocity
+  const double aL = left.a;
+  const double aR = right.a;
+  const double rhoEL = left.E;
+  const double rhoER = right.E;
+  const double pL = left.p;
+  const double pR = right.p;
+  const double hL = (rhoEL + pL) / rhoL;
+  const double hR = (rhoER + pR) / rhoR;
+  const double sqRhoL = sqrt(rhoL);
+  const double sqRhoR = sqrt(rhoR);
+  const double sqRhoSum = sqRhoL + sqRhoR;
+  const double sqRhoL_over_Sum = sqRhoL / sqRhoSum;
+  const double sqRhoR_over_Sum = sqRhoR / sqRhoSum;
+  double uL[D], uR[D], roeU[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    uL[i] = left.mom[i] / rhoL;
+    uR[i] = right.mom[i] / rhoR;
+    roeU[i] = sqRhoL_over_Sum * uL[i] + sqRhoR_over_Sum * uR[i];
+  }
+  const double roeH = sqRhoL_over_Sum * hL + sqRhoR_over_Sum * hR;
+  double squaredNormRoeU = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) squaredNormRoeU += roeU[i] * roeU[i];
+  const double squaredNormRoeU_half = 0.5 * squaredNormRoeU;
+  const double roeGamma = (sqRhoL * eq.gamma + sqRhoR * eq.gamma) / sqRhoSum;
+  const double gm1 = roeGamma - 1.0;
+  const double roeA2 = gm1 * (roeH - squaredNormRoeU_half);
+  const double roeA = sqrt(roeA2);
+  const double maxA = vmax(aL, aR);
+  const double sL1 = uL[DIR] - maxA;
+  const double sL2 = roeU[DIR] - roeA;
+  const double sR1 = roeU[DIR] + roeA;
+  const double sR2 = uR[DIR] + maxA;
+  const double sL = vmin(sL1, sL2);
+  const double sR = vmax(sR1, sR2);
+
+  // :799-811 HLLE flux
+  const double bL = vmin(sL, 0.0);
+  const double bR = vmax(sR, 0.0);
+  const double bLbR = bL * bR;
+  const double db = bR - bL;
+  const double db_positive = db > 0.0 ? db : 1.0;
+  Cons<D> hlle;
+  hlle.rho = (bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho)) / db_positive;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    hlle.mom[d] =
+        (bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d])) /
+        db_positive;
+  }
+  hlle.E = (bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E)) / db_positive;
+
+  // :813-823
+  const double u_bar = 0.5 * (sR + sL);
+  const double u_bar_abs = fabs(u_bar);
+  const double delta = roeA / (roeA + u_bar_abs);
+  const double b = bLbR / db_positive;
+  const double deltaRho = rhoR - rhoL;
+  double deltaRhoU[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) deltaRhoU[i] = right.mom[i] - left.mom[i];
+  const double deltaRhoE = rhoER - rhoEL;
+  const double gm1_over_roeA2 = gm1 / roeA2;
+  const double l21 = gm1_over_roeA2 * (roeH - squaredNormRoeU);
+
+  if constexpr (D == 1) {
+    // :825-835
+    const double l22 = gm1_over_roeA2 * roeU[0];
+    const double l23 = gm1_over_roeA2 * (-1.0);
+    const double alpha_2 = l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoE;
+    const double b_delta_alpha_2 = b * delta * alpha_2;
+    flux.rho = hlle.rho - b_delta_alpha_2;
+    flux.mom[0] = hlle.mom[0] - b_delta_alpha_2 * roeU[0];
+    flux.E = hlle.E - b_delta_alpha_2 * squaredNormRoeU_half;
+  } else if constexpr (D == 2) {
+    // :892-923
+    constexpr int ix = DIR;
+    constexpr int iy = (ix == 0) ? 1 : 0;
+    const double l22 = gm1_over_roeA2 * roeU[0];
+    const double l23 = gm1_over_roeA2 * roeU[1];
+    const double l24 = -gm1_over_roeA2;
+    const double alpha_2 =
+        l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] + l24 * deltaRhoE;
+    const double b_delta = b * delta;
+    const double b_delta_alpha_2 = b_delta * alpha_2;
+    flux.rho = hlle.rho - b_delta_alpha_2;
+    flux.mom[ix] = hlle.mom[ix] - b_delta_alpha_2 * roeU[ix];
+    if constexpr (LARROUTUROU) {
+      const bool upwind = flux.rho > 0.0;
+      flux.mom[iy] = flux.rho * (upwind ? vL_[iy] : vR_[iy]);
+      const double f_rhoE = flux.rho * (upwind ? eKinRL : eKinRR);
+      flux.E = hlle.E - b_delta_alpha_2 * squaredNormRoeU_half + f_rhoE;
+    } else {
+      const double l31 = -roeU[iy];
+      const double alpha_3 = l31 * deltaRho + deltaRhoU[iy];
+      const double b_delta_alpha_3 = b_delta * alpha_3;
+      flux.mom[iy] = hlle.mom[iy] - b_delta_alpha_2 * roeU[iy] - b_delta_alpha_3;
+      flux.E = hlle.E - b_delta_alpha_2 * squaredNormRoeU_half - b_delta_alpha_3 * roeU[iy];
+    }
+  } else {
+    // :974-1019
+    constexpr int ix = DIR;
+    constexpr int iy = (ix + 1) % 3;
+    constexpr int iz = (iy + 1) % 3;
+    const double l22 = gm1_over_roeA2 * roeU[0];
+    const double l23 = gm1_over_roeA2 * roeU[1];
+    const double l24 = gm1_over_roeA2 * roeU[2];
+    const double l25 = -gm1_over_roeA2;
+    const double alpha_2 = l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] +
+                           l24 * deltaRhoU[2] + l25 * deltaRhoE;
+    const double b_delta = b * delta;
+    const double b_delta_alpha_2 = b_delta * alpha_2;
+    flux.rho = hlle.rho - b_delta_alpha_2;
+    // :991-992 uses roeU.row(iy), not row(ix): reference behaviour, reproduced
+    flux.mom[ix] = hlle.mom[ix] - b_delta_alpha_2 * roeU[iy];
+    if constexpr (LARROUTUROU) {
+      const bool upwind = flux.rho > 0.0;
+      flux.mom[iy] = flux.rho * (upwind ? vL_[iy] : vR_[iy]);
+      flux.mom[iz] = flux.rho * (upwind ? vL_[iz] : vR_[iz]);
+      const double f_rhoE = flux.rho * (upwind ? eKinRL : eKinRR);
+      flux.E = hlle.E - b_delta_alpha_2 * squaredNormRoeU_half + f_rhoE;
+    } else {
+      const double l31 = -roeU[iy];
+      const double l41 = -roeU[iz];
+      const double alpha_3 = l31 * deltaRho + deltaRhoU[iy];
+      const double alpha_4 = l41 * deltaRho + deltaRhoU[iz];
+      const double b_delta_alpha_3 = b_delta * alpha_3;
+      const double b_delta_alpha_4 = b_delta * alpha_4;
+      flux.mom[iy] = hlle.mom[iy] - b_delta_alpha_2 * roeU[iy] - b_delta_alpha_3;
+      flux.mom[iz] = hlle.mom[iz] - b_delta_alpha_2 * roeU[iz] - b_delta_alpha_4;
+      flux.E = hlle.E - b_delta_alpha_2 * squaredNormRoeU_half -
+               b_delta_alpha_3 * roeU[iy] - b_delta_alpha_4 * roeU[iz];
+    }
+  }
+}
+
+// Per-cell part of the HLLEM stable-dt signal evaluation
+// (HllemMethod.hpp:1152-1216): quantities that depend on one state only.  A
+// cell takes part in two faces; they are computed once per cell.
+template <int D> struct DtCell {
+  double u[D];
+  double h;
+  double sq_rho;
+  double a;
+};
+template <int D, typename State> FVS_DEV void dt_cell(DtCell<D>& c, const State& q) {
+  c.h = (q.E + q.p) / q.rho;
+  c.sq_rho = sqrt(q.rho);
+#pragma unroll
+  for (int i = 0; i < D; ++i) c.u[i] = q.mom[i] / q.rho;
+  c.a = q.a;
+}
+
+// max(|sL|, |sR|) of HllemMethod.hpp:1152-1216; the stable dt of the face is
+// dx / (this value).
+template <int D, int DIR>
+FVS_DEV double hllem_max_signal(const EqConst& eq, const DtCell<D>& L, const DtCell<D>& R) {
+  const double sqRhoSum = L.sq_rho + R.sq_rho;
+  const double wL = L.sq_rho / sqRhoSum;
+  const double wR = R.sq_rho / sqRhoSum;
+  double roeU[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) roeU[i] = wL * L.u[i] + wR * R.u[i];
+  const double roeH = wL * L.h + wR * R.h;
+  double sq = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) sq += roeU[i] * roeU[i];
+  const double sq_half = 0.5 * sq;
+  const double roeA2 = eq.gamma_minus_1 * (roeH - sq_half);
+  const double roeA = sqrt(roeA2);
+  const double maxA = vmax(L.a, R.a);
+  const double sL = vmin(L.u[DIR] - maxA, roeU[DIR] - roeA);
+  const double sR = vmax(roeU[DIR] + roeA, R.u[DIR] + maxA);
+  return vmax(fabs(sL), fabs(sR));
+}
+
+// ---------------------------------------------------------------------------
+// Einfeldt signal velocities (normal Roe velocity only),
+// src/equations/perfect_gas/EinfeldtSignalVelocities.hpp:64-97
+template <int D, int DIR, typename SL, typename SR>
+FVS_DEV void einfeldt_signals(const EqConst& eq, const SL& left, const SR& right,
+                              double& s0, double& s1) {
+  const double rhoL = left.rho;
+  const double rhoR = right.rho;
+  const double sqRhoL = sqrt(rhoL);
+  const double sqRhoR = sqrt(rhoR);
+  const double uL = left.mom[DIR] / rhoL;
+  const double uR = right.mom[DIR] / rhoR;
+  const double oosqRhoSum = 1.0 / (sqRhoL + sqRhoR);
+  const double roeU = (uL * sqRhoL + uR * sqRhoR) * oosqRhoSum;
+  const double hL = (left.E + left.p) / rhoL;
+  const double hR = (right.E + right.p) / rhoR;
+  const double roeH = (hL * sqRhoL + hR * sqRhoR) * oosqRhoSum;
+  const double roeA2 = (eq.gamma - 1.0) * (roeH - 0.5 * roeU * roeU);
+  const double roeA = sqrt(roeA2);
+  s0 = vmin(uL - left.a, roeU - roeA);
+  s1 = vmax(roeU + roeA, uR + right.a);
+}
+
+// include/fub/flux_method/HllMethod.hpp:260-293
+template <int D, int DIR>
+FVS_DEV void hll_einfeldt_flux(const EqConst& eq, Cons<D>& nf, const Complete<D>& left,
+                               const Complete<D>& right) {
+  double s0, s1;
+  einfeldt_signals<D, DIR>(eq, left, right, s0, s1);
+  Cons<D> fL, fR;
+  euler_flux<D, DIR>(fL, left);
+  euler_flux<D, DIR>(fR, right);
+  const double sL = vmin(s0, 0.0);
+  const double sR = vmax(s1, 0.0);
+  const double sLsR = sL * sR;
+  double ds = sR - sL;
+  ds = ds > 0.0 ? ds : 1.0;
+  nf.rho = (sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho)) / ds;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    nf.mom[d] = (sR * fL.mom[d] - sL * fR.mom[d] + sLsR * (right.mom[d] - left.mom[d])) / ds;
+  }
+  nf.E = (sR * fL.E - sL * fR.E + sLsR * (right.E - left.E)) / ds;
+}
+
+// include/fub/flux_method/HllMethod.hpp:337-347: max(0, |s0|, |s1|)
+template <int D, int DIR, typename SL, typename SR>
+FVS_DEV double hll_einfeldt_max_signal(const EqConst& eq, const SL& left, const SR& right) {
+  double s0, s1;
+  einfeldt_signals<D, DIR>(eq, left, right, s0, s1);
+  double m = 0.0;
+  m = vmax(m, fabs(s0));
+  m = vmax(m, fabs(s1));
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// Exact Riemann solver, src/equations/perfect_gas/ExactRiemannSolver.hpp.
+// Uses pow(); libm and CUDA pow differ in the last ulp, so every method built
+// on it is compared with a tolerance, not bitwise.
+struct NewtonStatus {
+  int failed;
+};
+
+template <int D, int DIR> struct ExactRiemann {
+  const EqConst& eq;
+  FVS_DEV explicit ExactRiemann(const EqConst& e) : eq(e) {}
+
+  struct Side {
+    double rho, p, a, A, B;
+  };
+  FVS_DEV double f_side(const Side& s, double p, double gm1, double exponent) const {
+    if (p > s.p) {
+      return (p - s.p) * sqrt(s.A / (p + s.B));
+    }
+    return 2.0 * s.a / gm1 * (pow(p / s.p, exponent) - 1.0);
+  }
+  FVS_DEV double df_side(const Side& s, double p, double d_exponent) const {
+    if (p > s.p) {
+      return sqrt(s.A / (s.B + p)) * (1.0 - 0.5 * (p - s.p) / (s.B + p));
+    }
+    return pow(p / s.p, d_exponent) / (s.rho * s.a);
+  }
+
+  // :34-97 + include/fub/NewtonIteration.hpp:28-52
+  template <typename SL, typename SR>
+  FVS_DEV void middle_state(const SL& left, const SR& right, double& pM, double& uM,
+                            int& failed) const {
+    const double g = eq.gamma;
+    const double gp1 = g + 1.0;
+    const double gm1 = g - 1.0;
+    Side L{left.rho, left.p, left.a, 2.0 / (gp1 * left.rho), gm1 / gp1 * left.p};
+    Side R{right.rho, right.p, right.a, 2.0 / (gp1 * right.rho), gm1 / gp1 * right.p};
+    const double exponent = 0.5 * gm1 / g;
+    const double d_exponent = -0.5 * gp1 / g;
+    const double uL = left.mom[DIR] / left.rho;
+    const double uR = right.mom[DIR] / right.rho;
+    const double du = uR - uL;
+    double x = 0.5 * (L.p + R.p);
+    double fx = f_side(R, x, gm1, exponent) + f_side(L, x, gm1, exponent) + du;
+    int counter = 0;
+    double err = fabs(fx);
+    while (err > 1e-7 && counter < 5000) {
+      const double dfx = df_side(R, x, d_exponent) + df_side(L, x, d_exponent);
+      const double offset = fx / dfx;
+      const double next = x - offset;
+      x = ((next - next) != (next - next) || next < 0.0) ? 0.5 * x : next;
+      fx = f_side(R, x, gm1, exponent) + f_side(L, x, gm1, exponent) + du;
+      err = fabs(fx);
+      counter += 1;
+    }
+    if (counter == 5000 && fx > 1e-7) failed = 1;
+    pM = x;
+    const double fL = f_side(L, pM, gm1, exponent);
+    const double fR = f_side(R, pM, gm1, exponent);
+    uM = 0.5 * (uL + uR) + 0.5 * (fR - fL);
+  }
+
+  // :105-148
+  template <typename SL, typename SR>
+  FVS_DEV void signals(const SL& left, const SR& right, double& s0, double& s1,
+                       int& failed) const {
+    double pM, uM;
+    middle_state(left, right, pM, uM, failed);
+    const double g = eq.gamma;
+    const double gp1 = g + 1.0;
+    const double gm1 = g - 1.0;
+    const double uL = left.mom[DIR] / left.rho;
+    const double pL_ratio = pM / left.p;
+    if (pM > left.p) {
+      s0 = uL - left.a * sqrt((gp1 * pL_ratio + gm1) / (2.0 * g));
+    } else {
+      s0 = uL - left.a;
+    }
+    const double uR = right.mom[DIR] / right.rho;
+    const double pR_ratio = pM / right.p;
+    if (pM > right.p) {
+      s1 = uR + right.a * sqrt((gp1 * pR_ratio + gm1) / (2.0 * g));
+    } else {
+      s1 = uR + right.a;
+    }
+  }
+
+  FVS_DEV void set_momentum(Complete<D>& s, double momentum, const Complete<D>& side) const {
+    if constexpr (D > 1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) s.mom[d] = s.rho * (side.mom[d] / side.rho);
+    }
+    s.mom[DIR] = momentum;
+  }
+  FVS_DEV void from_prim(Complete<D>& s) const {
+    const double rhoE_kin = 0.5 * squared_norm<D>(s.mom) / s.rho;
+    const double rhoE_internal = s.p * eq.gamma_minus_1_inv;
+    s.E = rhoE_internal + rhoE_kin;
+    s.a = sqrt(eq.gamma * s.p / s.rho);
+  }
+
+  // :204-353, sampled at x/t = 0.  `state` must be zero-initialised by the
+  // caller (GodunovMethod.hpp:129-145 keeps a zeroed member).
+  FVS_DEV void solve(Complete<D>& state, const Complete<D>& left, const Complete<D>& right,
+                     int& failed) const {
+    if (!(0.0 < left.rho && 0.0 < right.rho)) return;
+    double pM, uM;
+    middle_state(left, right, pM, uM, failed);
+    const double g = eq.gamma;
+    const double gp1 = g + 1.0;
+    const double gm1 = g - 1.0;
+    const double g_ratio = gm1 / gp1;
+    if (0.0 <= uM) {
+      const double uL = left.mom[DIR] / left.rho;
+      const double aL = left.a;
+      const double pL = left.p;
+      const double p_ratio = pM / pL;
+      if (pM > pL) {
+        const double shock_speed = uL - aL * sqrt((gp1 * p_ratio + gm1) / (2.0 * g));
+        if (shock_speed < 0.0) {
+          state.rho = left.rho * (p_ratio + g_ratio) / (g_ratio * p_ratio + 1.0);
+          set_momentum(state, state.rho * uM, left);
+          state.p = pM;
+          from_prim(state);
+        } else {
+          state = left;
+        }
+      } else {
+        const double aM = aL * pow(p_ratio, gm1 / (2.0 * g));
+        const double speed_TL = uM - aM;
+        const double speed_HL = uL - aL;
+        if (0.0 < speed_HL) {
+          state = left;
+        } else if (speed_TL < 0.0) {
+          state.rho = left.rho * pow(p_ratio, 1 / g);
+          set_momentum(state, state.rho * uM, left);
+          state.p = pM;
+          from_prim(state);
+        } else {
+          state.rho = left.rho * pow(2.0 / gp1 + g_ratio * uL / aL, 2.0 / gm1);
+          const double u = 2.0 / gp1 * (aL + 0.5 * gm1 * uL);
+          set_momentum(state, state.rho * u, left);
+          state.p = pL * pow(2.0 / gp1 + g_ratio * uL / aL, 2.0 * g / gm1);
+          from_prim(state);
+        }
+      }
+    } else {
+      const double uR = right.mom[DIR] / right.rho;
+      const double aR = right.a;
+      const double pR = right.p;
+      const double p_ratio = pM / pR;
+      if (pM > pR) {
+        const double shock_speed = uR + aR * sqrt((gp1 * p_ratio + gm1) / (2.0 * g));
+        if (0.0 < shock_speed) {
+          state.rho = right.rho * (p_ratio + g_ratio) / (g_ratio * p_ratio + 1.0);
+          set_momentum(state, state.rho * uM, right);
+          state.p = pM;
+          from_prim(state);
+        } else {
+          state = right;
+        }
+      } else {
+        const double aM = aR * pow(p_ratio, gm1 / (2.0 * g));
+        const double speed_TR = uM + aM;
+        const double speed_HR = uR + aR;
+        if (speed_HR <= 0.0) {
+          state = right;
+        } else if (speed_TR >= 0.0) {
+          state.rho = right.rho * pow(p_ratio, 1 / g);
+          set_momentum(state, state.rho * uM, right);
+          state.p = pM;
+          from_prim(state);
+        } else {
+          state.rho = right.rho * pow(2.0 / gp1 - g_ratio * uR / aR, 2.0 / gm1);
+          const double u = 2.0 / gp1 * (-aR + 0.5 * gm1 * uR);
+          set_momentum(state, state.rho * u, right);
+          state.p = pR * pow(2.0 / gp1 - g_ratio * uR / aR, 2.0 * g / gm1);
+          from_prim(state);
+        }
+      }
+    }
+  }
+};
+
+// include/fub/flux_method/GodunovMethod.hpp:129-145 over the exact solver
+template <int D, int DIR>
+FVS_DEV void godunov_exact_flux(const EqConst& eq, Cons<D>& nf, const Complete<D>& left,
+                                const Complete<D>& right, int& failed) {
+  Complete<D> sol;
+  sol.rho = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) sol.mom[d] = 0.0;
+  sol.E = 0.0;
+  sol.p = 0.0;
+  sol.a = 0.0;
+  ExactRiemann<D, DIR>(eq).solve(sol, left, right, failed);
+  euler_flux<D, DIR>(nf, sol);
+}
+
+template <int D, int DIR, typename SL, typename SR>
+FVS_DEV double godunov_exact_max_signal(const EqConst& eq, const SL& left, const SR& right,
+                                        int& failed) {
+  double s0, s1;
+  ExactRiemann<D, DIR>(eq).signals(left, right, s0, s1, failed);
+  double m = 0.0;
+  m = fmax(m, fabs(s0));
+  m = fmax(m, fabs(s1));
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// Dispatch on the base method.
+template <int D, int DIR, int BASE>
+FVS_DEV void base_flux(const EqConst& eq, Cons<D>& f, const Complete<D>& left,
+                       const Complete<D>& right, int& failed) {
+  if constexpr (BASE == kBaseHllemLarrouturou) {
+    hllem_flux<D, DIR, true>(eq, f, left, right);
+  } else if constexpr (BASE == kBaseHllem) {
+    hllem_flux<D, DIR, false>(eq, f, left, right);
+  } else if constexpr (BASE == kBaseHllEinfeldt) {
+    hll_einfeldt_flux<D, DIR>(eq, f, left, right);
+  } else {
+    godunov_exact_flux<D, DIR>(eq, f, left, right, failed);
+  }
+}
+
+// max signal speed of the face between two STORED states (the stable dt of a
+// face is dx / value; min over faces == dx / max over faces because IEEE
+// division is monotone in its divisor).
+template <int D, int DIR, int BASE, typename SL, typename SR>
+FVS_DEV double base_max_signal(const EqConst& eq, const SL& left, const SR& right,
+                               int& failed) {
+  if constexpr (BASE == kBaseHllemLarrouturou || BASE == kBaseHllem) {
+    DtCell<D> L, R;
+    dt_cell<D>(L, left);
+    dt_cell<D>(R, right);
+    return hllem_max_signal<D, DIR>(eq, L, R);
+  } else if constexpr (BASE == kBaseHllEinfeldt) {
+    return hll_einfeldt_max_signal<D, DIR>(eq, left, right);
+  } else {
+    return godunov_exact_max_signal<D, DIR>(eq, left, right, failed);
+  }
+}
+
+} // namespace fvs

@@ -1,0 +1,130 @@
+// sweep_inst.cu -- instantiates the method-dependent kernels for ONE space
+// dimension (FVS_INST_D) and ONE base method (FVS_INST_BASE); compiled twelve
+// times by the build (3 dimensions x 4 base methods) so the translation
+// units build in parallel.
+#include "sweep_kernels.cuh"
+
+#ifndef FVS_INST_D
+#error "define FVS_INST_D"
+#endif
+#ifndef FVS_INST_BASE
+#error "define FVS_INST_BASE"
+#endif
+
+#define FVS_CAT3(a, b, c) a##b##_##c
+#define FVS_CAT(a, b, c) FVS_CAT3(a, b, c)
+#define FVS_FN(name) FVS_CAT(name##_D, FVS_INST_D, FVS_INST_BASE)
+
+namespace fvs {
+namespace {
+
+constexpr int D = FVS_INST_D;
+constexpr int BASE = FVS_INST_BASE;
+
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+template <int DIR, int RECON, int LIM>
+int fused(const SweepArgs& A, cudaStream_t s) {
+  if constexpr (DIR == 0) {
+    const long long rows = (long long)A.max_n[1] * A.max_n[2];
+    const int nseg = (A.max_n[0] + A.seg_len - 1) / A.seg_len;
+    dim3 grid(cdiv(rows * nseg, kSweepThreads / 32), A.nboxes, 1);
+    fused_sweep_x_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+  } else {
+    const long long lines = (long long)A.max_n[0] * (DIR == 1 ? A.max_n[2] : A.max_n[1]);
+    const int nseg = (A.max_n[DIR] + A.seg_len - 1) / A.seg_len;
+    dim3 grid(cdiv(lines, kSweepThreads), A.nboxes, nseg);
+    fused_sweep_yz_kernel<D, DIR, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+  }
+  return 1;
+}
+
+template <int DIR, int RECON, int LIM>
+int fluxes(const SweepArgs& A, cudaStream_t s) {
+  long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+  // along DIR there is at most one more face than cells
+  total += total / A.max_n[DIR];
+  dim3 grid(cdiv(total, 128), A.nboxes, 1);
+  numeric_flux_kernel<D, DIR, BASE, RECON, LIM><<<grid, 128, 0, s>>>(A);
+  return 1;
+}
+
+template <int DIR>
+int stable_dt(const SweepArgs& A, cudaStream_t s) {
+  const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+  dim3 grid(cdiv(total, 256), A.nboxes, 1);
+  stable_dt_kernel<D, DIR, BASE><<<grid, 256, 0, s>>>(A);
+  return 1;
+}
+
+template <int DIR, typename F0, typename F1, typename F2, typename F3>
+int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer) {
+  if (k.recon == kReconFirstOrder) return fo();
+  switch (k.limiter) {
+  case kLimiterNone: return none();
+  case kLimiterMinMod: return minmod();
+  case kLimiterVanLeer: return vanleer();
+  }
+  return -1;
+}
+
+template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+  return by_recon<DIR>(
+      k, [&] { return fused<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
+      [&] { return fused<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
+      [&] { return fused<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
+      [&] { return fused<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+}
+template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+  return by_recon<DIR>(
+      k, [&] { return fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
+      [&] { return fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
+      [&] { return fluxes<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
+      [&] { return fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+}
+
+} // namespace
+
+int FVS_FN(launch_fused_sweep)(const MethodKey& k, int dir, const SweepArgs& A,
+                               cudaStream_t s) {
+  if (dir == 0) return fused_dir<0>(k, A, s);
+  if constexpr (D >= 2) {
+    if (dir == 1) return fused_dir<1>(k, A, s);
+  }
+  if constexpr (D >= 3) {
+    if (dir == 2) return fused_dir<2>(k, A, s);
+  }
+  return -1;
+}
+
+int FVS_FN(launch_numeric_fluxes)(const MethodKey& k, int dir, const SweepArgs& A,
+                                  cudaStream_t s) {
+  if (dir == 0) return fluxes_dir<0>(k, A, s);
+  if constexpr (D >= 2) {
+    if (dir == 1) return fluxes_dir<1>(k, A, s);
+  }
+  if constexpr (D >= 3) {
+    if (dir == 2) return fluxes_dir<2>(k, A, s);
+  }
+  return -1;
+}
+
+int FVS_FN(launch_stable_dt)(const MethodKey&, int dir, const SweepArgs& A, cudaStream_t s) {
+  if (dir == 0) return stable_dt<0>(A, s);
+  if constexpr (D >= 2) {
+    if (dir == 1) return stable_dt<1>(A, s);
+  }
+  if constexpr (D >= 3) {
+    if (dir == 2) return stable_dt<2>(A, s);
+  }
+  return -1;
+}
+
+int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStream_t s) {
+  const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+  dim3 grid(cdiv(total, 256), A.nboxes, 1);
+  stable_dt_all_kernel<D, BASE><<<grid, 256, 0, s>>>(A);
+  return 1;
+}
+
+} // namespace fvs

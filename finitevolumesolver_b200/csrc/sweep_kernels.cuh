@@ -1,0 +1,443 @@
+// sweep_kernels.cuh -- the split-sweep kernels.
+//
+// Fused sweep (the hot path): ONE pass over the state does what the reference
+// does in four (DimensionalSplitLevelIntegrator.hpp:235-256):
+//   K1 ComputeStableDt      (FluxMethod.hpp:341-382 over the stored states)
+//   K2 ComputeNumericFluxes (FluxMethod.hpp:246-293)
+//   K3 UpdateConservatively (src/HyperbolicPatchIntegrator.cpp:35-85)
+//   K4 CompleteFromCons     (CompleteFromCons.hpp:141-204)
+// reading every Complete state once and writing it once (112 B per 3-D
+// cell-update).  The state is read from `src` and written to `dst` (the
+// context ping-pongs buffers), so any decomposition of the box is race free.
+//
+// Work decomposition: a software pipeline that marches along the sweep
+// direction and evaluates every MUSCL-Hancock cell predictor exactly once and
+// every face flux exactly once:
+//   stage A (cell  j-1): slopes + half-step predictor -> edge states recL, recR
+//   stage B (face  j-1): base flux(recR(j-2), recL(j-1))
+//   stage C (cell  j-2): u += dt/dx (F(j-2) - F(j-1)); p, a from cons; store
+//   stage D (face j-1|j): signal speeds of the STORED states -> stable dt
+// * y / z sweeps: one thread per grid line; threads of a warp are adjacent in
+//   x, so every load and store is a coalesced 256-byte row segment; the
+//   pipeline state lives in registers.
+// * x sweeps: one warp per grid row; lane l holds cell c0+l; neighbours come
+//   from warp shuffles and the two-cell carry between 32-cell chunks goes
+//   through shared memory.
+#pragma once
+#include "launch.h"
+
+namespace fvs {
+
+template <int D> FVS_DEV void load_complete(Complete<D>& q, const double* p, long long sc) {
+  q.rho = __ldg(p);
+#pragma unroll
+  for (int d = 0; d < D; ++d) q.mom[d] = __ldg(p + sc * (1 + d));
+  q.E = __ldg(p + sc * (1 + D));
+  q.p = __ldg(p + sc * (2 + D));
+  q.a = __ldg(p + sc * (3 + D));
+}
+template <int D> FVS_DEV void store_complete(double* p, long long sc, const Complete<D>& q) {
+  p[0] = q.rho;
+#pragma unroll
+  for (int d = 0; d < D; ++d) p[sc * (1 + d)] = q.mom[d];
+  p[sc * (1 + D)] = q.E;
+  p[sc * (2 + D)] = q.p;
+  p[sc * (3 + D)] = q.a;
+}
+template <int D> FVS_DEV void copy_cons(Cons<D>& c, const Complete<D>& q) {
+  c.rho = q.rho;
+#pragma unroll
+  for (int d = 0; d < D; ++d) c.mom[d] = q.mom[d];
+  c.E = q.E;
+}
+
+FVS_DEV double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
+template <int D> FVS_DEV Complete<D> shfl_up_complete(const Complete<D>& q, int delta) {
+  Complete<D> r;
+  r.rho = shfl_up_d(q.rho, delta);
+#pragma unroll
+  for (int d = 0; d < D; ++d) r.mom[d] = shfl_up_d(q.mom[d], delta);
+  r.E = shfl_up_d(q.E, delta);
+  r.p = shfl_up_d(q.p, delta);
+  r.a = shfl_up_d(q.a, delta);
+  return r;
+}
+template <int D> FVS_DEV Cons<D> shfl_up_cons(const Cons<D>& q, int delta) {
+  Cons<D> r;
+  r.rho = shfl_up_d(q.rho, delta);
+#pragma unroll
+  for (int d = 0; d < D; ++d) r.mom[d] = shfl_up_d(q.mom[d], delta);
+  r.E = shfl_up_d(q.E, delta);
+  return r;
+}
+
+// Block-wide max of a non-negative double, then one atomic per block.  The
+// bit pattern of a non-negative IEEE double is monotone as an unsigned
+// integer, so atomicMax on the bits is an exact max.
+FVS_DEV void reduce_max_signal(double v, unsigned long long* target) {
+  // NaN never enters: callers pass `v` built with `x > v ? x : v`.
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  __shared__ double warp_max[32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) warp_max[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? warp_max[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = w > v ? w : v;
+    }
+    if (lane == 0 && v > 0.0) {
+      atomicMax(target, (unsigned long long)__double_as_longlong(v));
+    }
+  }
+}
+
+// cons_new = cons + lambda * (F_left - F_right), then p and a
+// (src/HyperbolicPatchIntegrator.cpp:35-61, PerfectGas.cpp:112-124)
+template <int D>
+FVS_DEV void update_and_complete(const EqConst& eq, Complete<D>& out, const Cons<D>& q,
+                                 const Cons<D>& Fl, const Cons<D>& Fr, double lambda,
+                                 bool update) {
+  if (update) {
+    out.rho = q.rho + lambda * (Fl.rho - Fr.rho);
+#pragma unroll
+    for (int d = 0; d < D; ++d) out.mom[d] = q.mom[d] + lambda * (Fl.mom[d] - Fr.mom[d]);
+    out.E = q.E + lambda * (Fl.E - Fr.E);
+  } else {
+    out.rho = q.rho;
+#pragma unroll
+    for (int d = 0; d < D; ++d) out.mom[d] = q.mom[d];
+    out.E = q.E;
+  }
+  complete_from_cons<D>(eq, out);
+}
+
+constexpr int kSweepThreads = 128;
+
+// ---------------------------------------------------------------------------
+// Fused sweep along y or z: thread per line, register pipeline.
+template <int D, int DIR, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(kSweepThreads)
+fused_sweep_yz_kernel(const SweepArgs A) {
+  static_assert(DIR >= 1 && DIR < D, "y/z sweep");
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  const int n0 = B.n[0];
+  const int nother = (DIR == 1) ? B.n[2] : B.n[1];
+  const long long nlines = (long long)n0 * nother;
+  const long long line = (long long)blockIdx.x * kSweepThreads + threadIdx.x;
+  const int nd = B.n[DIR];
+  const int o_first = blockIdx.z * A.seg_len;
+  double maxsig = 0.0;
+  int failed = 0;
+  if (line < nlines && o_first < nd) {
+    const int o_last = min(nd, o_first + A.seg_len) - 1;
+    const long long stride = (DIR == 1) ? (long long)n0 : (long long)n0 * B.n[1];
+    long long base;
+    if (DIR == 1) {
+      const int x = (int)(line % n0);
+      const int z = (int)(line / n0);
+      base = x + (long long)n0 * B.n[1] * z;
+    } else {
+      base = line;
+    }
+    const double* src = B.src + base;
+    double* dst = B.dst + base;
+    const long long sc = B.sc;
+    const int ulo = B.ulo, uhi = B.uhi;
+    const unsigned char* dtmask = B.dtmask;
+
+    Complete<D> q0, q1;  // cells j, j-1
+    Cons<D> q2;          // cell j-2
+    Complete<D> recR_prev; // upper edge state of cell j-2
+    Cons<D> F_prev;        // flux through face j-2
+    const int jstart = max(o_first - 2, 0);
+    load_complete<D>(q0, src + stride * jstart, sc);
+    q1 = q0;
+    copy_cons<D>(q2, q0);
+    recR_prev = q0;
+    copy_cons<D>(F_prev, q0);
+    for (int j = jstart; j <= o_last + 2; ++j) {
+      if (j > jstart && j < nd) load_complete<D>(q0, src + stride * j, sc);
+      // stage A: cell j-1
+      Complete<D> recL, recR;
+      if constexpr (RECON == kReconMusclHancock) {
+        if (j >= jstart + 2 && j - 1 >= ulo - 1 && j - 1 <= uhi + 1) {
+          muscl_predict<D, DIR, LIM>(A.eq, q2, q1, q0, A.lambda_half, recL, recR);
+        } else {
+          recL = q1;
+          recR = q1;
+        }
+      } else {
+        recL = q1;
+        recR = q1;
+      }
+      // stage B: face j-1
+      Cons<D> F;
+      if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo && j - 1 <= uhi + 1) {
+        base_flux<D, DIR, BASE>(A.eq, F, recR_prev, recL, failed);
+      } else {
+        F = F_prev;
+      }
+      // stage C: cell j-2
+      if (j - 2 >= o_first) {
+        Complete<D> out;
+        update_and_complete<D>(A.eq, out, q2, F_prev, F, A.lambda,
+                               j - 2 >= ulo && j - 2 <= uhi);
+        store_complete<D>(dst + stride * (j - 2), sc, out);
+      }
+      // stage D: face (j-1 | j) of the stored states
+      if (j > jstart && j < nd && dtmask[j - 1]) {
+        const double s = base_max_signal<D, DIR, BASE>(A.eq, q1, q0, failed);
+        maxsig = s > maxsig ? s : maxsig;
+      }
+      copy_cons<D>(q2, q1);
+      q1 = q0;
+      recR_prev = recR;
+      F_prev = F;
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
+  if (failed) *A.fail_flag = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Fused sweep along x: warp per row, shuffle pipeline.
+template <int D, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(kSweepThreads)
+fused_sweep_x_kernel(const SweepArgs A) {
+  constexpr int DIR = 0;
+  constexpr int kWarps = kSweepThreads / 32;
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  const int n0 = B.n[0];
+  const long long nrows = (long long)B.n[1] * B.n[2];
+  const int nseg = (n0 + A.seg_len - 1) / A.seg_len;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * kWarps + warp;
+  // carry between consecutive 32-cell chunks of a row (per warp)
+  __shared__ Complete<D> carry_q[kWarps][2]; // cells of lanes 30, 31
+  __shared__ Complete<D> carry_rec[kWarps];  // recR of lane 31
+  __shared__ Cons<D> carry_F[kWarps];        // F of lane 31
+  double maxsig = 0.0;
+  int failed = 0;
+  if (w < nrows * nseg) {
+    const long long row = w / nseg;
+    const int seg = (int)(w % nseg);
+    const int o_first = seg * A.seg_len;
+    const int o_last = min(n0, o_first + A.seg_len) - 1;
+    const double* src = B.src + row * n0;
+    double* dst = B.dst + row * n0;
+    const long long sc = B.sc;
+    const int ulo = B.ulo, uhi = B.uhi;
+    const unsigned char* dtmask = B.dtmask;
+    bool first = true;
+    for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
+      const int c = c0 + lane;
+      const int cl = min(max(c, 0), n0 - 1);
+      Complete<D> q0;
+      load_complete<D>(q0, src + cl, sc);
+      Complete<D> q1 = shfl_up_complete<D>(q0, 1);
+      Complete<D> q2c = shfl_up_complete<D>(q0, 2);
+      if (first) {
+        // no carry yet: lanes 0..3 produce no output in the first chunk; give
+        // their missing neighbours real data to keep the arithmetic benign
+        if (lane < 1) q1 = q0;
+        if (lane < 2) q2c = q0;
+      } else {
+        if (lane == 0) {
+          q1 = carry_q[warp][1];
+          q2c = carry_q[warp][0];
+        } else if (lane == 1) {
+          q2c = carry_q[warp][1];
+        }
+      }
+      // stage A: cell c-1
+      Complete<D> recL, recR;
+      if constexpr (RECON == kReconMusclHancock) {
+        muscl_predict<D, DIR, LIM>(A.eq, q2c, q1, q0, A.lambda_half, recL, recR);
+      } else {
+        recL = q1;
+        recR = q1;
+      }
+      // stage B: face c-1 = (c-2 | c-1)
+      Complete<D> recR_prev = shfl_up_complete<D>(recR, 1);
+      if (lane == 0) {
+        if (first) {
+          recR_prev = recR;
+        } else {
+          recR_prev = carry_rec[warp];
+        }
+      }
+      Cons<D> F;
+      base_flux<D, DIR, BASE>(A.eq, F, recR_prev, recL, failed);
+      // stage C: cell c-2
+      Cons<D> F_prev = shfl_up_cons<D>(F, 1);
+      if (lane == 0) {
+        if (first) {
+          F_prev = F;
+        } else {
+          F_prev = carry_F[warp];
+        }
+      }
+      __syncwarp();
+      if (lane >= 30) carry_q[warp][lane - 30] = q0;
+      if (lane == 31) {
+        carry_rec[warp] = recR;
+        carry_F[warp] = F;
+      }
+      __syncwarp();
+      const int o = c - 2;
+      if ((!first || lane >= 4) && o >= o_first && o <= o_last) {
+        Cons<D> q2;
+        copy_cons<D>(q2, q2c);
+        Complete<D> out;
+        update_and_complete<D>(A.eq, out, q2, F_prev, F, A.lambda, o >= ulo && o <= uhi);
+        store_complete<D>(dst + o, sc, out);
+      }
+      // stage D: face (c-1 | c) of the stored states
+      if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+        const double s = base_max_signal<D, DIR, BASE>(A.eq, q1, q0, failed);
+        maxsig = s > maxsig ? s : maxsig;
+      }
+      first = false;
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
+  if (failed) *A.fail_flag = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Unfused policies (thread per face / cell): the per-policy drop-in behind
+// fub::HyperbolicMethod's three members.
+
+// K2  FluxMethod<Base>::ComputeNumericFluxes, FluxMethod.hpp:246-293
+template <int D, int DIR, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(128) numeric_flux_kernel(const SweepArgs A) {
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  // faces: along DIR flo..fhi, other dims the whole state array
+  int len[3] = {B.n[0], B.n[1], B.n[2]};
+  len[DIR] = B.fhi - B.flo + 1;
+  const long long total = (long long)len[0] * len[1] * len[2];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int failed = 0;
+  if (len[DIR] > 0 && t < total) {
+    int idx[3];
+    idx[0] = (int)(t % len[0]);
+    idx[1] = (int)((t / len[0]) % len[1]);
+    idx[2] = (int)(t / ((long long)len[0] * len[1]));
+    idx[DIR] += B.flo;
+    const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
+    const long long cell = idx[0] + (long long)B.n[0] * (idx[1] + (long long)B.n[1] * idx[2]);
+    const double* p = B.src + cell; // cell idx = right neighbour of the face
+    Cons<D> F;
+    if constexpr (RECON == kReconMusclHancock) {
+      Complete<D> s0, s1, s2, s3;
+      load_complete<D>(s0, p - 2 * stride, B.sc);
+      load_complete<D>(s1, p - stride, B.sc);
+      load_complete<D>(s2, p, B.sc);
+      load_complete<D>(s3, p + stride, B.sc);
+      Complete<D> recL_unused, recR_left, recL_right, recR_unused;
+      muscl_predict<D, DIR, LIM>(A.eq, s0, s1, s2, A.lambda_half, recL_unused, recR_left);
+      muscl_predict<D, DIR, LIM>(A.eq, s1, s2, s3, A.lambda_half, recL_right, recR_unused);
+      base_flux<D, DIR, BASE>(A.eq, F, recR_left, recL_right, failed);
+    } else {
+      Complete<D> s0, s1;
+      load_complete<D>(s0, p - stride, B.sc);
+      load_complete<D>(s1, p, B.sc);
+      base_flux<D, DIR, BASE>(A.eq, F, s0, s1, failed);
+    }
+    const long long fcell = (idx[0] - B.foff[0]) +
+                            (long long)B.fn[0] * ((idx[1] - B.foff[1]) +
+                                                  (long long)B.fn[1] * (idx[2] - B.foff[2]));
+    double* f = B.flux + fcell;
+    f[0] = F.rho;
+#pragma unroll
+    for (int d = 0; d < D; ++d) f[B.fsc * (1 + d)] = F.mom[d];
+    f[B.fsc * (1 + D)] = F.E;
+  }
+  if (failed) *A.fail_flag = 1;
+}
+
+// K1  FluxMethodAdapter::ComputeStableDt, FluxMethodAdapter.hpp:69-114
+template <int D, int DIR, int BASE>
+__global__ void __launch_bounds__(256) stable_dt_kernel(const SweepArgs A) {
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  const long long total = (long long)B.n[0] * B.n[1] * B.n[2];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double maxsig = 0.0;
+  int failed = 0;
+  if (t < total) {
+    int idx[3];
+    idx[0] = (int)(t % B.n[0]);
+    idx[1] = (int)((t / B.n[0]) % B.n[1]);
+    idx[2] = (int)(t / ((long long)B.n[0] * B.n[1]));
+    if (idx[DIR] + 1 < B.n[DIR] && B.dtmask[idx[DIR]]) {
+      const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
+      Complete<D> l, r;
+      load_complete<D>(l, B.src + t, B.sc);
+      load_complete<D>(r, B.src + t + stride, B.sc);
+      maxsig = base_max_signal<D, DIR, BASE>(A.eq, l, r, failed);
+      maxsig = maxsig > 0.0 ? maxsig : 0.0; // drops NaN
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
+  if (failed) *A.fail_flag = 1;
+}
+
+// stable dt in all directions, one pass (DimensionalSplitLevelIntegrator.hpp:204-219)
+template <int D, int BASE>
+__global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
+  const BoxDesc& B = A.boxes[0][blockIdx.y];
+  const long long total = (long long)B.n[0] * B.n[1] * B.n[2];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double maxsig[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) maxsig[d] = 0.0;
+  int failed = 0;
+  if (t < total) {
+    int idx[3];
+    idx[0] = (int)(t % B.n[0]);
+    idx[1] = (int)((t / B.n[0]) % B.n[1]);
+    idx[2] = (int)(t / ((long long)B.n[0] * B.n[1]));
+    Complete<D> l;
+    load_complete<D>(l, B.src + t, B.sc);
+    if (idx[0] + 1 < B.n[0] && A.boxes[0][blockIdx.y].dtmask[idx[0]]) {
+      Complete<D> r;
+      load_complete<D>(r, B.src + t + 1, B.sc);
+      const double s = base_max_signal<D, 0, BASE>(A.eq, l, r, failed);
+      maxsig[0] = s > 0.0 ? s : 0.0;
+    }
+    if constexpr (D >= 2) {
+      if (idx[1] + 1 < B.n[1] && A.boxes[1][blockIdx.y].dtmask[idx[1]]) {
+        Complete<D> r;
+        load_complete<D>(r, B.src + t + B.n[0], B.sc);
+        const double s = base_max_signal<D, 1, BASE>(A.eq, l, r, failed);
+        maxsig[1] = s > 0.0 ? s : 0.0;
+      }
+    }
+    if constexpr (D >= 3) {
+      if (idx[2] + 1 < B.n[2] && A.boxes[2][blockIdx.y].dtmask[idx[2]]) {
+        Complete<D> r;
+        load_complete<D>(r, B.src + t + (long long)B.n[0] * B.n[1], B.sc);
+        const double s = base_max_signal<D, 2, BASE>(A.eq, l, r, failed);
+        maxsig[2] = s > 0.0 ? s : 0.0;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    reduce_max_signal(maxsig[d], A.max_signal + d);
+    __syncthreads();
+  }
+  if (failed) *A.fail_flag = 1;
+}
+
+} // namespace fvs

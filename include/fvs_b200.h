@@ -1,0 +1,235 @@
+/* fvs_b200.h -- C ABI of libfvs_b200.so, the B200 (sm_100a) split-sweep
+ * finite-volume patch integrator.
+ *
+ * This is the drop-in boundary: plain C, plain pointers
+ * and sizes, no C++/torch types.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repository
+ * maikel/FiniteVolumeSolver).  All functions return 0 on success and a
+ * negative value on error (text via fvs_last_error()); nothing throws across
+ * the boundary.  A context is driven by one host thread, like the reference's
+ * IntegratorContext (one driver thread per MPI rank).  Device work is
+ * stream-ordered on the context's stream; a call synchronises only where it
+ * returns a host value (dt) or fills a host buffer.
+ *
+ * Array layout ("FAB layout", include/fub/core/mdspan.hpp:731-732,
+ * include/fub/AMReX/ViewFArrayBox.hpp:74-92): Fortran order, x fastest, then
+ * y, z, component slowest; the box of a state array includes its ghost cells.
+ * State components (include/fub/equations/PerfectGas.hpp:40-45,132-137):
+ *   rho, momentum[rank], energy, pressure, speed_of_sound   (rank + 4)
+ * Flux components: rho, momentum[rank], energy               (rank + 2)
+ * Index triples are always int[3]; unused dimensions hold lo = hi = 0.
+ */
+#ifndef FVS_B200_H
+#define FVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVS_VERSION 1
+
+/* Base (Riemann) method.  src/equations/perfect_gas/HllemMethod.hpp,
+ * include/fub/flux_method/HllMethod.hpp + EinfeldtSignalVelocities.hpp,
+ * include/fub/flux_method/GodunovMethod.hpp + ExactRiemannSolver.hpp */
+enum {
+  FVS_BASE_HLLEM_LARROUTUROU = 0,
+  FVS_BASE_HLLEM = 1,
+  FVS_BASE_HLL_EINFELDT = 2,
+  FVS_BASE_GODUNOV_EXACT = 3
+};
+/* include/fub/flux_method/MusclHancockMethod.hpp:189-571 */
+enum { FVS_RECON_FIRST_ORDER = 0, FVS_RECON_MUSCL_HANCOCK = 1 };
+/* include/fub/flux_method/MusclHancockMethod.hpp:31-187 */
+enum { FVS_LIMITER_NONE = 0, FVS_LIMITER_MINMOD = 1, FVS_LIMITER_VANLEER = 2 };
+/* src/AMReX/boundary_condition/TransmissiveBoundary.cpp,
+ * include/fub/AMReX/boundary_condition/ReflectiveBoundary.hpp */
+enum { FVS_BC_TRANSMISSIVE = 0, FVS_BC_REFLECTIVE = 1 };
+/* src/split_method/{Godunov,Strang,StrangLumped}Splitting.cpp */
+enum { FVS_SPLIT_GODUNOV = 0, FVS_SPLIT_STRANG = 1, FVS_SPLIT_STRANG_LUMPED = 2 };
+
+/* status codes */
+enum {
+  FVS_OK = 0,
+  FVS_ERROR = -1,           /* see fvs_last_error() */
+  FVS_TIME_STEP_TOO_LARGE = 1 /* fub::TimeStepTooLarge, include/fub/TimeStepError.hpp:71-78 */
+};
+
+typedef struct fvs_ctx fvs_ctx;
+
+typedef struct fvs_config {
+  int rank;           /* space dimension 1, 2 or 3 (PerfectGas<rank>) */
+  double gamma;       /* PerfectGas::gamma, include/fub/equations/PerfectGas.hpp:216-219 */
+  int base_method;    /* FVS_BASE_* */
+  int reconstruction; /* FVS_RECON_* */
+  int limiter;        /* FVS_LIMITER_* (ignored for first order) */
+  int device;         /* CUDA device ordinal, -1 = current device */
+  int comm_rank;      /* this process' index among the ranks sharing the level (0 if single) */
+  int comm_size;      /* number of ranks (1 if single) */
+} fvs_config;
+
+const char* fvs_last_error(void);
+int fvs_version(void);
+
+/* Number of CUDA devices visible (0 if none); never fails. */
+int fvs_device_count(void);
+
+/* replaces: construction of fub::amrex::IntegratorContext + HyperbolicMethod
+ * (src/AMReX/IntegratorContext.cpp:60-120, include/fub/HyperbolicMethod.hpp:155-159) */
+int fvs_create(const fvs_config* config, fvs_ctx** out);
+void fvs_destroy(fvs_ctx* ctx);
+
+/* Change the numerical method of an existing context (HyperbolicMethod is a
+ * value that can be swapped, include/fub/HyperbolicMethod.hpp:155-159). */
+int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limiter);
+/* FluxMethod::GetStencilWidth(), README.md:882-892 */
+int fvs_stencil_width(const fvs_ctx* ctx);
+
+/* replaces: IntegratorContext::ResetHierarchyConfiguration (allocation of the
+ * scratch and flux MultiFabs, src/AMReX/IntegratorContext.cpp:292-345).
+ * `owner[b]` is the comm rank that holds box b (NULL: all on rank 0); only
+ * owned boxes get device storage.  Requires scratch_gcw >= flux_gcw + stencil
+ * width of the widest method that will be used (2). */
+int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3],
+                     const int domain_hi[3], const double dx[3],
+                     const int periodic[3], int nboxes, const int (*box_lo)[3],
+                     const int (*box_hi)[3], const int* owner, int scratch_gcw,
+                     int flux_gcw);
+
+/* replaces: BoundarySet of the GriddingAlgorithm
+ * (include/fub/AMReX/boundary_condition/BoundarySet.hpp, src/.../BoundarySet.cpp:26-41).
+ * Conditions are applied in the order they were added. */
+int fvs_level_add_boundary(fvs_ctx* ctx, int level, int dir, int side, int kind);
+
+/* Geometry of the scratch array of one box (cells incl. ghosts). */
+int fvs_state_box(const fvs_ctx* ctx, int level, int box, int lo[3], int hi[3],
+                  int* ncomp);
+/* Geometry of the flux array of one box in direction dir (face centred in dir). */
+int fvs_flux_box(const fvs_ctx* ctx, int level, int box, int dir, int lo[3],
+                 int hi[3], int* ncomp);
+
+/* replaces: host<->MultiFab views, IntegratorContext::GetScratch(level)
+ * (src/AMReX/IntegratorContext.cpp:229-231) + MakeView (ViewFArrayBox.hpp:182-228).
+ * host_fab holds (rank+4) components over fvs_state_box in FAB layout. */
+int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab);
+int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab);
+/* IntegratorContext::GetFluxes(level, dir), src/AMReX/IntegratorContext.cpp:233-236 */
+int fvs_upload_fluxes(fvs_ctx* ctx, int level, int box, int dir, const double* host_fab);
+int fvs_download_fluxes(fvs_ctx* ctx, int level, int box, int dir, double* host_fab);
+/* Device pointer of the current state array of a box (for zero-copy callers). */
+int fvs_state_device_ptr(fvs_ctx* ctx, int level, int box, double** dptr);
+
+/* ---- the three policies of fub::HyperbolicMethod, unfused --------------- */
+/* FluxMethodAdapter::ComputeStableDt (include/fub/AMReX/FluxMethodAdapter.hpp:69-114)
+ * followed by MinAll over the ranks (src/ext/Mpi.cpp:54-59). */
+int fvs_compute_stable_dt(fvs_ctx* ctx, int level, int dir, double* dt_out);
+/* FluxMethodAdapter::ComputeNumericFluxes (FluxMethodAdapter.hpp:120-150) */
+int fvs_compute_numeric_fluxes(fvs_ctx* ctx, int level, double dt, int dir);
+/* ForwardIntegrator::UpdateConservatively (src/AMReX/TimeIntegrator.cpp:29-67) */
+int fvs_update_conservatively(fvs_ctx* ctx, int level, double dt, int dir);
+/* Reconstruction::CompleteFromCons (include/fub/AMReX/Reconstruction.hpp:44-60) */
+int fvs_complete_from_cons(fvs_ctx* ctx, int level);
+
+/* ---- fused fast path ---------------------------------------------------- */
+/* One directional sweep of DimensionalSplitLevelIntegrator
+ * (include/fub/solver/DimensionalSplitLevelIntegrator.hpp:235-256):
+ * ComputeStableDt + MinAll + ComputeNumericFluxes + UpdateConservatively +
+ * CompleteFromCons in ONE kernel pass.  *level_dt_out receives the stable dt
+ * of the state BEFORE the sweep; returns FVS_TIME_STEP_TOO_LARGE (and leaves
+ * the state untouched) if it is smaller than dt. */
+int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out);
+
+/* IntegratorContext::FillGhostLayerSingleLevel (src/AMReX/IntegratorContext.cpp:422-449):
+ * intra-level ghost copy (FillBoundary, incl. periodic images and boxes owned
+ * by other ranks) followed by every physical boundary condition. */
+int fvs_fill_ghost_layer(fvs_ctx* ctx, int level);
+/* IntegratorContext::ApplyBoundaryCondition(level, dir) (IntegratorContext.cpp:347-359) */
+int fvs_apply_boundary_condition(fvs_ctx* ctx, int level, int dir);
+
+/* DimensionalSplitLevelIntegrator::ComputeStableDt(level): min over all
+ * directions (DimensionalSplitLevelIntegrator.hpp:204-219), one fused pass. */
+int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out);
+
+/* DimensionalSplitLevelIntegrator::AdvanceLevelNonRecursively
+ * (DimensionalSplitLevelIntegrator.hpp:221-276) for one level followed by the
+ * single-level part of SubcycleFineFirstSolver::AdvanceHierarchy
+ * (SubcycleFineFirstSolver.hpp:177-193: cycles += 1, time += dt, ghost refill
+ * every regrid_frequency cycles).  Sweeps run speculatively without host
+ * synchronisation; on a CFL violation the level is rolled back to its state at
+ * entry, *failure_dt receives the offending level dt and the call returns
+ * FVS_TIME_STEP_TOO_LARGE.  sweep_dts (may be NULL) receives the per-sweep
+ * stable dts; *n_sweep_dts is its capacity on entry, the count on exit. */
+int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind,
+                          double* failure_dt, double* sweep_dts, int* n_sweep_dts);
+
+/* fub::RunSimulation without output (include/fub/RunSimulation.hpp:83-191):
+ * stable dt -> min(final_time - t, cfl * dt) -> advance -> retry on
+ * TimeStepTooLarge.  dt_sequence (capacity dt_capacity) receives the accepted
+ * step sizes; returns the number of accepted steps (>= 0) or FVS_ERROR. */
+long fvs_run(fvs_ctx* ctx, double cfl, double final_time, long max_cycles,
+             int split_kind, double* dt_sequence, long dt_capacity, int* retries);
+
+int fvs_set_regrid_frequency(fvs_ctx* ctx, int frequency);
+int fvs_set_cycles(fvs_ctx* ctx, long cycles, double time_point);
+long fvs_cycles(const fvs_ctx* ctx);
+double fvs_time_point(const fvs_ctx* ctx);
+
+/* fub::MinAll (src/ext/Mpi.cpp:54-59): min over the ranks of the context. */
+int fvs_min_all(fvs_ctx* ctx, double* inout);
+
+/* ---- multi-GPU plumbing (one process per GPU) --------------------------- */
+/* NCCL bootstrap: rank 0 calls fvs_comm_unique_id, the host distributes the
+ * 128 bytes (e.g. torch.distributed broadcast), every rank calls
+ * fvs_comm_init.  Replaces ParallelContext::CommunicatorAll
+ * (src/AMReX/IntegratorContext.cpp:208-210). */
+#define FVS_UNIQUE_ID_BYTES 128
+int fvs_comm_unique_id(void* out_id);
+int fvs_comm_init(fvs_ctx* ctx, const void* id);
+
+/* Host-only description of the halo exchange (no CUDA needed; used by the
+ * gloo tests).  A "copy" moves region [lo,hi] of the cell index space, read
+ * from box src_box at index - shift, to the ghost cells of box dst_box.
+ * Returns the number of copies; fills at most `capacity` records. */
+typedef struct fvs_halo_copy {
+  int dst_box, src_box;
+  int dst_owner, src_owner;
+  int lo[3], hi[3];
+  int shift[3];
+} fvs_halo_copy;
+long fvs_halo_plan(int rank, const int domain_lo[3], const int domain_hi[3],
+                   const int periodic[3], int nboxes, const int (*box_lo)[3],
+                   const int (*box_hi)[3], const int* owner, int scratch_gcw,
+                   fvs_halo_copy* out, long capacity);
+
+/* Host-only: the faces that FluxMethodAdapter::ComputeStableDt evaluates in
+ * direction dir for one box (tile size 1024000 x 8 x 8, growntilebox, stencil
+ * 2*width; FluxMethodAdapter.hpp:82-98 + FluxMethod.hpp:347-353).  mask has
+ * one byte per cell index of the grown box along dir: mask[i] != 0 iff the
+ * face between cells i and i+1 takes part. Returns the mask length. */
+int fvs_stable_dt_face_mask(int rank, const int box_lo[3], const int box_hi[3],
+                            int scratch_gcw, int stencil_width, int dir,
+                            unsigned char* mask, int capacity);
+
+/* Host-only: split boxes of a level over `nranks` ranks (space-filling
+ * order, equal cell counts); replaces amrex::DistributionMapping for the
+ * uniform case. */
+int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3],
+                         const int (*box_hi)[3], int nranks, int* owner_out);
+
+/* ---- statistics ---------------------------------------------------------- */
+/* Number of kernels this context has launched so far. */
+long fvs_kernel_launches(const fvs_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all work of the context is ordered on. */
+void* fvs_stream(fvs_ctx* ctx);
+/* Elapsed device time (ms) of the most recent fvs_sweep / sweep inside
+ * fvs_advance_hierarchy, measured with CUDA events on the context's stream
+ * when timing was enabled with fvs_enable_timing(ctx, 1). */
+int fvs_enable_timing(fvs_ctx* ctx, int on);
+int fvs_sweep_time_ms(fvs_ctx* ctx, double* total_ms, long* n_sweeps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVS_B200_H */

@@ -1,0 +1,124 @@
+"""Shared set-up for the parity tests: builds the same level on the CPU oracle
+and on the CUDA path and fills both with identical data."""
+import numpy as np
+
+GAMMA = 1.4
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bitwise_equal(got, ref, what=""):
+    """Bit-for-bit equality (signed zeros included)."""
+    got = np.ascontiguousarray(got)
+    ref = np.ascontiguousarray(ref)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    neq = bits(got) != bits(ref)
+    if neq.any():
+        idx = np.argwhere(neq)[0]
+        t = tuple(idx)
+        rel = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+        raise AssertionError(
+            f"{what}: {int(neq.sum())} of {neq.size} values differ, first at {t}: "
+            f"got {got[t]!r} ref {ref[t]!r}; max rel diff {rel:.3e}")
+
+
+def rel_linf(got, ref):
+    scale = np.max(np.abs(ref))
+    return float(np.max(np.abs(got - ref)) / max(scale, 1e-300))
+
+
+def complete_from_prim(rank, rho, vel, p):
+    """[rank+4, ...] Complete state arrays from primitive fields (same fp64
+    operation order as the reference's CompleteFromPrim, PerfectGas.cpp:146-158)."""
+    mom = [rho * v for v in vel]
+    if rank == 1:
+        sq = mom[0] * mom[0]
+    elif rank == 2:
+        sq = mom[0] * mom[0] + mom[1] * mom[1]
+    else:
+        sq = mom[0] * mom[0] + (mom[1] * mom[1] + mom[2] * mom[2])
+    e_kin = 0.5 * sq / rho
+    gm1_inv = 1.0 / (GAMMA - 1.0)
+    E = e_kin + p * gm1_inv
+    a = np.sqrt(GAMMA * p / rho)
+    return np.stack([rho, *mom, E, p, a])
+
+
+def cell_centers(lo, hi, dx, origin):
+    """z, y, x coordinate arrays broadcastable to [z, y, x]."""
+    xs = [origin[d] + (np.arange(lo[d], hi[d] + 1) + 0.5) * dx[d] for d in range(3)]
+    return (xs[2][:, None, None], xs[1][None, :, None], xs[0][None, None, :])
+
+
+def smooth_state(rank, lo, hi, dx, seed=0):
+    """A smooth, strictly subsonic-ish field with all velocity components
+    non-zero; deterministic in the GLOBAL cell index (so neighbouring boxes
+    agree in their overlap)."""
+    z, y, x = cell_centers(lo, hi, dx, (0.0, 0.0, 0.0))
+    shape = (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+    ph = 0.37 * seed
+    rho = 1.0 + 0.2 * np.sin(2 * np.pi * x + ph) * np.cos(2 * np.pi * y) * np.cos(3 * z) + np.zeros(shape)
+    u = 0.3 * np.sin(2 * np.pi * (x + y) + ph) + 0.1 * z + np.zeros(shape)
+    v = -0.2 * np.cos(2 * np.pi * (x - z)) + 0.15 * y + np.zeros(shape)
+    w = 0.25 * np.sin(4 * np.pi * y + ph) * np.cos(2 * np.pi * x) + np.zeros(shape)
+    p = 1.0 + 0.3 * np.cos(2 * np.pi * (x + 0.5 * y) + ph) * np.sin(2 * z + 1.0) + np.zeros(shape)
+    return complete_from_prim(rank, rho, [u, v, w][:rank], p)
+
+
+def riemann_state(rank, lo, hi, dx, origin, radius=0.4, inner=(1.0, 1.0), outer=(0.125, 0.1)):
+    """Spherical (circular / 1-D) Riemann problem at rest: SURVEY 8d W1/W2."""
+    z, y, x = cell_centers(lo, hi, dx, origin)
+    shape = (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+    r2 = x * x + np.zeros(shape)
+    if rank >= 2:
+        r2 = r2 + y * y
+    if rank >= 3:
+        r2 = r2 + z * z
+    inside = r2 < radius * radius
+    rho = np.where(inside, inner[0], outer[0])
+    p = np.where(inside, inner[1], outer[1])
+    zero = np.zeros(shape)
+    return complete_from_prim(rank, rho, [zero] * rank, p)
+
+
+class Pair:
+    """The same single-level problem on the oracle and on the GPU."""
+
+    def __init__(self, orc, fvs, rank, domain_lo, domain_hi, dx, boxes, scratch_gcw, flux_gcw,
+                 periodic=(0, 0, 0), base=0, recon=1, limiter=2, bcs=(), gamma=GAMMA):
+        self.rank = rank
+        self.nboxes = len(boxes)
+        self.cpu = orc.Level(rank, domain_lo, domain_hi, dx, boxes, scratch_gcw=scratch_gcw,
+                             flux_gcw=flux_gcw, periodic=periodic, gamma=gamma)
+        self.cpu.set_method(base, recon, limiter)
+        self.gpu = fvs.Context(rank, domain_lo, domain_hi, dx, boxes, scratch_gcw=scratch_gcw,
+                               flux_gcw=flux_gcw, periodic=periodic, gamma=gamma, base=base,
+                               recon=recon, limiter=limiter)
+        for (d, s, k) in bcs:
+            self.cpu.add_bc(d, s, k)
+            self.gpu.add_bc(d, s, k)
+
+    def fill(self, fn):
+        """fn(lo, hi) -> [ncomp, z, y, x] state for the fab box [lo, hi]."""
+        for b in range(self.nboxes):
+            arr, lo, hi = self.cpu.scratch(b)
+            data = fn(lo, hi)
+            arr[...] = data
+            self.gpu.upload_state(b, data)
+
+    def compare_states(self, what="state", tol=None):
+        worst = 0.0
+        for b in range(self.nboxes):
+            ref, _, _ = self.cpu.scratch(b)
+            got = self.gpu.download_state(b)
+            if tol is None:
+                assert_bitwise_equal(got, ref, f"{what} box {b}")
+            else:
+                worst = max(worst, rel_linf(got, ref))
+                assert worst <= tol, f"{what} box {b}: rel Linf {worst:.3e} > {tol:.1e}"
+        return worst
+
+    def close(self):
+        self.gpu.close()

@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact for every method built on + - * / sqrt (HLLEM, HLL-Einfeldt, all
+limiters); 1e-12 relative L-inf for the exact Riemann solver, which calls
+pow() (libm and CUDA pow differ in the last ulp) -- the tolerance north_star
+states for conserved variables per step.
+"""
+import numpy as np
+import pytest
+
+from helpers import GAMMA, Pair, assert_bitwise_equal, rel_linf, riemann_state, smooth_state
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12   # north_star: conserved variables per step
+TOL_100 = 1e-10    # north_star: after 100 steps
+
+
+@pytest.fixture(scope="module")
+def fvs():
+    from finitevolumesolver_b200 import capi
+    assert capi.device_count() > 0, "no CUDA device"
+    return capi
+
+
+BITWISE_METHODS = [
+    # (base, recon, limiter)
+    (0, 1, 2),  # MUSCL-Hancock<HLLEM Larrouturou, VanLeer>  (headline)
+    (0, 1, 1), (0, 1, 0), (0, 0, 0),
+    (1, 1, 2), (1, 0, 0),
+    (2, 1, 1), (2, 1, 2), (2, 0, 0),
+]
+
+
+def geometry(rank, n, gs):
+    lo = [0] * 3
+    hi = [n[d] - 1 if d < rank else 0 for d in range(3)]
+    dx = [1.0 / n[d] if d < rank else 1.0 for d in range(3)]
+    return lo, hi, dx
+
+
+SIZES = {1: (70,), 2: (37, 21), 3: (35, 12, 19)}
+
+
+@pytest.mark.parametrize("rank", [1, 2, 3])
+@pytest.mark.parametrize("method", BITWISE_METHODS)
+def test_unfused_policies_bitwise(oracle, fvs, rank, method):
+    base, recon, limiter = method
+    n = SIZES[rank]
+    lo, hi, dx = geometry(rank, n, 4)
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx[:rank], [(lo[:rank], hi[:rank])],
+                4, 2, base=base, recon=recon, limiter=limiter)
+    pair.fill(lambda l, h: smooth_state(rank, l, h, dx, seed=rank))
+    for d in range(rank):
+        dt_ref = pair.cpu.compute_stable_dt(d)
+        dt_gpu = pair.gpu.compute_stable_dt(d)
+        assert dt_gpu == dt_ref, (d, dt_gpu, dt_ref)
+        dt = 0.4 * dt_ref
+        pair.cpu.compute_numeric_fluxes(dt, d)
+        pair.gpu.compute_numeric_fluxes(dt, d)
+        fref, _, _ = pair.cpu.fluxes(0, d)
+        assert_bitwise_equal(pair.gpu.download_fluxes(0, d), fref, f"fluxes dir {d}")
+        pair.cpu.update_conservatively(dt, d)
+        pair.gpu.update_conservatively(dt, d)
+        pair.compare_states(f"after update dir {d}")
+        pair.cpu.complete_from_cons()
+        pair.gpu.complete_from_cons()
+        pair.compare_states(f"after complete dir {d}")
+    pair.close()
+
+
+@pytest.mark.parametrize("rank", [1, 2, 3])
+@pytest.mark.parametrize("method", BITWISE_METHODS)
+def test_fused_sweep_bitwise(oracle, fvs, rank, method):
+    base, recon, limiter = method
+    n = SIZES[rank]
+    lo, hi, dx = geometry(rank, n, 4)
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx[:rank], [(lo[:rank], hi[:rank])],
+                4, 2, base=base, recon=recon, limiter=limiter)
+    pair.fill(lambda l, h: smooth_state(rank, l, h, dx, seed=2 + rank))
+    for sweep in range(2 * rank):
+        d = sweep % rank
+        dt_ref = pair.cpu.compute_stable_dt(d)
+        dt = 0.45 * dt_ref
+        pair.cpu.sweep(dt, d)
+        rc, level_dt = pair.gpu.sweep(dt, d)
+        assert rc == fvs.OK
+        assert level_dt == dt_ref, (d, level_dt, dt_ref)
+        pair.compare_states(f"fused sweep {sweep} dir {d}")
+    pair.close()
+
+
+def test_fused_sweep_rejects_too_large_dt(oracle, fvs):
+    rank, n = 2, (24, 16)
+    lo, hi, dx = geometry(rank, n, 4)
+    pair = Pair(oracle, fvs, rank, lo[:2], hi[:2], dx[:2], [(lo[:2], hi[:2])], 4, 2)
+    pair.fill(lambda l, h: smooth_state(rank, l, h, dx))
+    before = pair.gpu.download_state(0)
+    dt_ref = pair.cpu.compute_stable_dt(0)
+    rc, level_dt = pair.gpu.sweep(2.0 * dt_ref, 0)
+    assert rc == fvs.TIME_STEP_TOO_LARGE
+    assert level_dt == dt_ref
+    assert_bitwise_equal(pair.gpu.download_state(0), before, "state after rejected sweep")
+    pair.close()
+
+
+@pytest.mark.parametrize("rank,gs,gf", [(1, 2, 0), (2, 8, 6), (3, 8, 6), (3, 4, 2), (2, 2, 0)])
+def test_ghost_widths_and_segments(oracle, fvs, rank, gs, gf):
+    """Reference ghost-width conventions: PerfectGas1d (2/0), SodShockTube2d (8/6)."""
+    n = {1: (200,), 2: (48, 40), 3: (24, 20, 18)}[rank]
+    lo, hi, dx = geometry(rank, n, gs)
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx[:rank], [(lo[:rank], hi[:rank])],
+                gs, gf)
+    pair.fill(lambda l, h: smooth_state(rank, l, h, dx, seed=7))
+    for d in range(rank):
+        dt_ref = pair.cpu.compute_stable_dt(d)
+        pair.cpu.sweep(0.5 * dt_ref, d)
+        rc, level_dt = pair.gpu.sweep(0.5 * dt_ref, d)
+        assert rc == fvs.OK and level_dt == dt_ref
+        pair.compare_states(f"dir {d}")
+    pair.close()
+
+
+def multi_boxes(rank, n, parts):
+    """Regular decomposition of [0, n) into parts[d] boxes per dimension."""
+    edges = [np.linspace(0, n[d], parts[d] + 1).astype(int) if d < rank else np.array([0, 1])
+             for d in range(3)]
+    boxes = []
+    for k in range(len(edges[2]) - 1):
+        for j in range(len(edges[1]) - 1):
+            for i in range(len(edges[0]) - 1):
+                lo = [edges[0][i], edges[1][j], edges[2][k]]
+                hi = [edges[0][i + 1] - 1, edges[1][j + 1] - 1, edges[2][k + 1] - 1]
+                boxes.append((lo[:rank], hi[:rank]))
+    return boxes
+
+
+@pytest.mark.parametrize("rank,periodic,bckind", [
+    (2, (0, 0, 0), 0), (2, (0, 0, 0), 1), (2, (1, 0, 0), 1), (2, (1, 1, 0), 0),
+    (3, (0, 0, 0), 0), (3, (0, 1, 0), 1), (1, (0, 0, 0), 1), (1, (1, 0, 0), 0),
+])
+def test_ghost_fill_and_boundaries_bitwise(oracle, fvs, rank, periodic, bckind):
+    n = {1: (64,), 2: (32, 24), 3: (16, 16, 12)}[rank]
+    parts = {1: (4,), 2: (2, 3), 3: (2, 2, 2)}[rank]
+    lo, hi, dx = geometry(rank, n, 4)
+    boxes = multi_boxes(rank, n, parts)
+    bcs = [(d, s, bckind) for d in range(rank) for s in (0, 1)]
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx[:rank], boxes, 4, 2,
+                periodic=periodic, bcs=bcs)
+    rng = np.random.default_rng(5)
+
+    def fill(l, h):
+        s = smooth_state(rank, l, h, dx, seed=3)
+        # scramble the ghost values so that only a correct fill makes them agree
+        return s * (1.0 + 0.0 * s) + 0.0
+
+    pair.fill(fill)
+    # poison ghosts identically on both sides
+    for b in range(pair.nboxes):
+        arr, l, h = pair.cpu.scratch(b)
+        noise = 1.0 + rng.random(arr.shape)
+        valid = np.zeros(arr.shape[1:], dtype=bool)
+        (blo, bhi) = boxes[b]
+        sl = [slice(None)] * 3
+        for d in range(rank):
+            sl[2 - d] = slice(blo[d] - l[d], bhi[d] - l[d] + 1)
+        valid[tuple(sl)] = True
+        data = np.where(valid[None], arr, arr * noise)
+        arr[...] = data
+        pair.gpu.upload_state(b, data)
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+    pair.compare_states("after FillGhostLayerSingleLevel")
+    for d in range(rank):
+        pair.cpu.apply_boundary_condition(d)
+        pair.gpu.apply_boundary_condition(d)
+    pair.compare_states("after ApplyBoundaryCondition")
+    pair.close()
+
+
+@pytest.mark.parametrize("split", [0, 1, 2])
+@pytest.mark.parametrize("rank", [2, 3])
+def test_advance_hierarchy_multibox_bitwise(oracle, fvs, rank, split):
+    n = {2: (40, 32), 3: (20, 16, 16)}[rank]
+    parts = {2: (2, 2), 3: (2, 1, 2)}[rank]
+    lo, hi, _ = geometry(rank, n, 8)
+    dx = [2.0 / n[d] for d in range(rank)]
+    origin = [-1.0] * 3
+    boxes = multi_boxes(rank, n, parts)
+    bcs = [(d, s, 0) for d in range(rank) for s in (0, 1)]
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx, boxes, 8, 6, bcs=bcs)
+    dx3 = dx + [1.0] * (3 - rank)
+    pair.fill(lambda l, h: riemann_state(rank, l, h, dx3, origin))
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+    for step in range(4):
+        dt_ref = 0.5 * min(pair.cpu.compute_stable_dt(d) for d in range(rank))
+        dt_gpu = 0.5 * pair.gpu.compute_stable_dt_all()
+        assert dt_gpu == dt_ref
+        ok_c, _, dts_c = pair.cpu.advance_hierarchy(dt_ref, split)
+        ok_g, _, dts_g = pair.gpu.advance_hierarchy(dt_ref, split)
+        assert ok_c and ok_g
+        assert dts_g == dts_c, (step, dts_g, dts_c)
+        pair.compare_states(f"step {step}")
+    assert pair.gpu.cycles == pair.cpu.cycles == 4
+    pair.close()
+
+
+def test_advance_hierarchy_rolls_back_on_cfl_violation(oracle, fvs):
+    rank, n = 2, (32, 32)
+    lo, hi, _ = geometry(rank, n, 8)
+    dx = [2.0 / 32] * 2
+    bcs = [(d, s, 0) for d in range(2) for s in (0, 1)]
+    pair = Pair(oracle, fvs, rank, lo[:2], hi[:2], dx, [(lo[:2], hi[:2])], 8, 6, bcs=bcs)
+    pair.fill(lambda l, h: riemann_state(rank, l, h, dx + [1.0], [-1.0] * 3))
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+    before = pair.gpu.download_state(0)
+    stable = pair.gpu.compute_stable_dt_all()
+    ok_c, fail_c, _ = pair.cpu.advance_hierarchy(3.0 * stable, 1)
+    ok_g, fail_g, _ = pair.gpu.advance_hierarchy(3.0 * stable, 1)
+    assert not ok_c and not ok_g
+    assert fail_g == fail_c
+    assert pair.gpu.cycles == 0
+    assert_bitwise_equal(pair.gpu.download_state(0), before, "rolled back state")
+    pair.close()
+
+
+def test_sod_1d_run_identical_dt_sequence(oracle, fvs):
+    """BASELINE config 1: examples/AMReX/PerfectGas1d.cpp -- 200 cells on
+    [-1, 1], reflective walls, gcw 2/0, Godunov splitting, CFL 0.5, t = 0.25,
+    with the headline MUSCL-Hancock<HLLEM, VanLeer>."""
+    n = 200
+    dx = [2.0 / n]
+    bcs = [(0, 0, 1), (0, 1, 1)]
+    pair = Pair(oracle, fvs, 1, [0], [n - 1], dx, [([0], [n - 1])], 2, 0, bcs=bcs)
+
+    def sod(l, h):
+        x = -1.0 + (np.arange(l[0], h[0] + 1) + 0.5) * dx[0]
+        rho = np.where(x < 0.0, 1.0, 0.125)[None, None, :]
+        p = np.where(x < 0.0, 1.0, 0.1)[None, None, :]
+        from helpers import complete_from_prim
+        return complete_from_prim(1, rho, [np.zeros_like(rho)], p)
+
+    pair.fill(sod)
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+    dts_c, retries_c = pair.cpu.run(0.5, 0.25, -1, 0)
+    dts_g, retries_g = pair.gpu.run(0.5, 0.25, -1, 0)
+    assert retries_c == retries_g
+    assert len(dts_c) == len(dts_g) and len(dts_c) > 50
+    assert_bitwise_equal(dts_g, dts_c, "dt sequence")
+    pair.compare_states("Sod t=0.25")
+    assert pair.gpu.time_point == pair.cpu.time_point
+    pair.close()
+
+
+def test_spherical_riemann_3d_100_steps(oracle, fvs):
+    """BASELINE config 2 at oracle-sized resolution: 32^3, Strang, gcw 8/6,
+    transmissive, CFL 0.5, 100 steps.  Bit-exact, which is stronger than the
+    1e-10 north_star asks for after 100 steps."""
+    rank, n = 3, (32, 32, 32)
+    lo, hi, _ = geometry(rank, n, 8)
+    dx = [2.0 / 32] * 3
+    bcs = [(d, s, 0) for d in range(3) for s in (0, 1)]
+    pair = Pair(oracle, fvs, rank, lo, hi, dx, multi_boxes(3, n, (2, 2, 2)), 8, 6, bcs=bcs)
+    pair.fill(lambda l, h: riemann_state(rank, l, h, dx, [-1.0] * 3))
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+    dts_c, _ = pair.cpu.run(0.5, 1e9, 100, 1)
+    dts_g, _ = pair.gpu.run(0.5, 1e9, 100, 1)
+    assert len(dts_g) == len(dts_c) == 100
+    assert_bitwise_equal(dts_g, dts_c, "dt sequence")
+    worst = pair.compare_states("after 100 steps", tol=TOL_100)
+    pair.compare_states("after 100 steps (bitwise)")
+    assert worst == 0.0
+    pair.close()
+
+
+@pytest.mark.parametrize("rank", [1, 2, 3])
+@pytest.mark.parametrize("recon,limiter", [(0, 0), (1, 1)])
+def test_godunov_exact_riemann_within_tolerance(oracle, fvs, rank, recon, limiter):
+    """Default MusclHancockMethod{eq} = Godunov + exact Riemann + MinMod
+    (MusclHancockMethod.hpp:189-192).  pow() => tolerance, not bitwise."""
+    n = {1: (64,), 2: (24, 20), 3: (14, 12, 10)}[rank]
+    lo, hi, dx = geometry(rank, n, 4)
+    pair = Pair(oracle, fvs, rank, lo[:rank], hi[:rank], dx[:rank], [(lo[:rank], hi[:rank])],
+                4, 2, base=3, recon=recon, limiter=limiter)
+    pair.fill(lambda l, h: smooth_state(rank, l, h, dx, seed=11))
+    for d in range(rank):
+        dt_ref = pair.cpu.compute_stable_dt(d)
+        dt_gpu = pair.gpu.compute_stable_dt(d)
+        assert abs(dt_gpu - dt_ref) <= 1e-12 * dt_ref
+        dt = 0.4 * dt_ref
+        pair.cpu.sweep(dt, d)
+        rc, level_dt = pair.gpu.sweep(dt, d)
+        assert rc == fvs.OK
+        assert abs(level_dt - dt_ref) <= 1e-12 * dt_ref
+        pair.compare_states(f"exact dir {d}", tol=TOL_STEP)
+    pair.close()
+
+
+def test_no_cpu_fallback_symbols(fvs):
+    """The product library must not link the oracle."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", fvs.LIB_PATH], capture_output=True, text=True).stdout
+    assert "fvso_" not in out
