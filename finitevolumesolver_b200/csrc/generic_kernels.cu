@@ -88,7 +88,10 @@ template <int D> __global__ void __launch_bounds__(256) complete_kernel(const Sw
 #pragma unroll
   for (int d = 0; d < D; ++d) q.mom[d] = u[B.sc * (1 + d)];
   q.E = u[B.sc * (1 + D)];
-  complete_from_cons<D>(A.eq, q);
+  const Eqs eq(A.eq);
+  with_fallback([&](auto M, Flag& fl) {
+    complete_from_cons<decltype(M), D>(eq.m, q, decltype(M)::rcp(q.rho), fl);
+  });
   u[B.sc * (2 + D)] = q.p;
   u[B.sc * (3 + D)] = q.a;
 }

@@ -48,6 +48,19 @@ template <int D> struct Complete {
 };
 
 #define FVS_DEV __device__ __forceinline__
+} // namespace fvs
+#include "fastmath.cuh"
+namespace fvs {
+
+// Equation constants plus the prepared reciprocal of gamma_minus_1_inv (the
+// reference divides by it, PerfectGas.cpp:121).
+struct EqM {
+  double gamma;
+  double gamma_minus_1;
+  Rcp gm1_inv;
+  FVS_DEV explicit EqM(const EqConst& e)
+      : gamma(e.gamma), gamma_minus_1(e.gamma_minus_1), gm1_inv(FastMath::rcp(e.gamma_minus_1_inv)) {}
+};
 
 // Eigen-style min/max (array8 semantics of the oracle): a < b ? a : b
 FVS_DEV double vmin(double a, double b) { return a < b ? a : b; }
@@ -65,15 +78,9 @@ template <int D> FVS_DEV double squared_norm(const double (&m)[D]) {
   }
 }
 
-// src/equations/PerfectGas.cpp:31-37
-template <int D> FVS_DEV double kinetic_energy(double rho, const double (&mom)[D]) {
-  return 0.5 * squared_norm<D>(mom) / rho;
-}
-
-// src/equations/PerfectGas.cpp:66-77
+// src/equations/PerfectGas.cpp:66-77; `velocity` = s.mom[DIR] / s.rho
 template <int D, int DIR, typename State>
-FVS_DEV void euler_flux(Cons<D>& f, const State& s) {
-  const double velocity = s.mom[DIR] / s.rho;
+FVS_DEV void euler_flux_v(Cons<D>& f, const State& s, double velocity) {
   f.rho = s.mom[DIR];
 #pragma unroll
   for (int d = 0; d < D; ++d) f.mom[d] = velocity * s.mom[d];
@@ -81,18 +88,20 @@ FVS_DEV void euler_flux(Cons<D>& f, const State& s) {
   f.E = velocity * (s.E + s.p);
 }
 
-// src/equations/PerfectGas.cpp:112-124: fills p and a of `q` from its
-// conservative part.
-template <int D> FVS_DEV void complete_from_cons(const EqConst& eq, Complete<D>& q) {
-  const double e_kin = kinetic_energy<D>(q.rho, q.mom);
+// src/equations/PerfectGas.cpp:31-37,112-124: fills p and a of `q` from its
+// conservative part; rc = rcp(q.rho).
+template <class M, int D>
+FVS_DEV void complete_from_cons(const EqM& eq, Complete<D>& q, const Rcp& rc, Flag& fl) {
+  const double e_kin = M::div(0.5 * squared_norm<D>(q.mom), rc, fl);
   const double e_int = q.E - e_kin;
-  q.p = e_int / eq.gamma_minus_1_inv;
-  q.a = sqrt(eq.gamma * q.p / q.rho);
+  q.p = M::div(e_int, eq.gm1_inv, fl);
+  q.a = M::sqrt(M::div(eq.gamma * q.p, rc, fl), fl);
 }
 
 // ---------------------------------------------------------------------------
 // Limiters, include/fub/flux_method/MusclHancockMethod.hpp:31-187 (array path)
-template <int LIM> FVS_DEV double limited_slope(double qL, double qM, double qR) {
+template <class M, int LIM>
+FVS_DEV double limited_slope(double qL, double qM, double qR, Flag& fl) {
   const double sL = qM - qL;
   const double sR = qR - qM;
   if constexpr (LIM == kLimiterNone) {
@@ -102,9 +111,18 @@ template <int LIM> FVS_DEV double limited_slope(double qL, double qM, double qR)
     return sR > 0.0 ? vmax(0.0, vmin(sL, sR)) : vmin(0.0, vmax(sL, sR));
   } else {
     const double r = 2.0 * sL * sR; // :144-147
-    return r > 0.0 ? r / (sL + sR) : 0.0;
+    const bool pos = r > 0.0;
+    const double q = M::div(r, sL + sR, fl, pos);
+    return pos ? q : 0.0;
   }
 }
+
+// A predicted edge state together with the reciprocal of its density (the
+// base flux divides several numerators by it).
+template <int D> struct Edge {
+  Complete<D> q;
+  Rcp rc;
+};
 
 // MUSCL-Hancock predictor of ONE cell (MusclHancockMethod.hpp:428-451 and its
 // mirror :456-479).  The reference evaluates this once for each of the two
@@ -112,74 +130,90 @@ template <int LIM> FVS_DEV double limited_slope(double qL, double qM, double qR)
 // identical, so both are produced here in one go:
 //   recL: predicted state at the cell's lower face  (q_L + lambda/2 (f(q_L) - f(q_R)))
 //   recR: predicted state at the cell's upper face  (q_R + lambda/2 (f(q_L) - f(q_R)))
-template <int D, int DIR, int LIM, typename S0, typename S1, typename S2>
-FVS_DEV void muscl_predict(const EqConst& eq, const S0& qm, const S1& q0, const S2& qp,
-                           double lambda_half, Complete<D>& recL, Complete<D>& recR) {
+template <class M, int D, int DIR, int LIM, typename S0, typename S1, typename S2>
+FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp,
+                           double lambda_half, Edge<D>& recL, Edge<D>& recR, Flag& fl) {
   Complete<D> qL, qR;
   {
-    const double s = limited_slope<LIM>(qm.rho, q0.rho, qp.rho);
+    const double s = limited_slope<M, LIM>(qm.rho, q0.rho, qp.rho, fl);
     qL.rho = q0.rho - 0.5 * s;
     qR.rho = q0.rho + 0.5 * s;
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    const double s = limited_slope<LIM>(qm.mom[d], q0.mom[d], qp.mom[d]);
+    const double s = limited_slope<M, LIM>(qm.mom[d], q0.mom[d], qp.mom[d], fl);
     qL.mom[d] = q0.mom[d] - 0.5 * s;
     qR.mom[d] = q0.mom[d] + 0.5 * s;
   }
   {
-    const double s = limited_slope<LIM>(qm.E, q0.E, qp.E);
+    const double s = limited_slope<M, LIM>(qm.E, q0.E, qp.E, fl);
     qL.E = q0.E - 0.5 * s;
     qR.E = q0.E + 0.5 * s;
   }
-  complete_from_cons<D>(eq, qL);
-  complete_from_cons<D>(eq, qR);
+  const Rcp rcL = M::rcp(qL.rho);
+  const Rcp rcR = M::rcp(qR.rho);
+  complete_from_cons<M, D>(eq, qL, rcL, fl);
+  complete_from_cons<M, D>(eq, qR, rcR, fl);
   Cons<D> fL, fR;
-  euler_flux<D, DIR>(fL, qL);
-  euler_flux<D, DIR>(fR, qR);
+  euler_flux_v<D, DIR>(fL, qL, M::div(qL.mom[DIR], rcL, fl));
+  euler_flux_v<D, DIR>(fR, qR, M::div(qR.mom[DIR], rcR, fl));
   {
     const double c = lambda_half * (fL.rho - fR.rho);
-    recL.rho = qL.rho + c;
-    recR.rho = qR.rho + c;
+    recL.q.rho = qL.rho + c;
+    recR.q.rho = qR.rho + c;
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const double c = lambda_half * (fL.mom[d] - fR.mom[d]);
-    recL.mom[d] = qL.mom[d] + c;
-    recR.mom[d] = qR.mom[d] + c;
+    recL.q.mom[d] = qL.mom[d] + c;
+    recR.q.mom[d] = qR.mom[d] + c;
   }
   {
     const double c = lambda_half * (fL.E - fR.E);
-    recL.E = qL.E + c;
-    recR.E = qR.E + c;
+    recL.q.E = qL.E + c;
+    recR.q.E = qR.E + c;
   }
-  complete_from_cons<D>(eq, recL);
-  complete_from_cons<D>(eq, recR);
+  recL.rc = M::rcp(recL.q.rho);
+  recR.rc = M::rcp(recR.q.rho);
+  complete_from_cons<M, D>(eq, recL.q, recL.rc, fl);
+  complete_from_cons<M, D>(eq, recR.q, recR.rc, fl);
 }
 
 // ---------------------------------------------------------------------------
 // HLLEM, array code path.  src/equations/perfect_gas/HllemMethod.hpp:711-1072.
 // Msq = Minv = 1 for PerfectGas (include/fub/equations/EulerEquation.hpp:53-62).
-// Returns the numeric flux between `left` and `right`.
-template <int D, int DIR, bool LARROUTUROU>
-FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
-                        Complete<D> right) {
+// Returns the numeric flux between the edge states `eL` and `eR`.
+template <class M, int D, int DIR, bool LARROUTUROU>
+FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const Edge<D>& eR,
+                        Flag& fl) {
+  Complete<D> left = eL.q;
+  Complete<D> right = eR.q;
+  const Rcp& rcL = eL.rc;
+  const Rcp& rcR = eR.rc;
   const double rhoL = left.rho;
   const double rhoR = right.rho;
-  double vL_[D], vR_[D];
+  double vL_[D], vR_[D]; // velocities of the unmodified states
+  double uL[D], uR[D];   // velocities after the Larrouturou modification
   double eKinRL = 0.0, eKinRR = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    vL_[i] = M::div(left.mom[i], rcL, fl);
+    vR_[i] = M::div(right.mom[i], rcR, fl);
+    uL[i] = vL_[i];
+    uR[i] = vR_[i];
+  }
   if constexpr (LARROUTUROU) {
     // :729-745 -- tangential momenta are multiplied by 0.0 (keeps their sign
     // bit) and their kinetic energy is taken out of E.
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      vL_[i] = left.mom[i] / rhoL;
-      vR_[i] = right.mom[i] / rhoR;
       if (i != DIR) {
         eKinRL += vL_[i] * vL_[i];
         eKinRR += vR_[i] * vR_[i];
         left.mom[i] *= 0.0;
         right.mom[i] *= 0.0;
+        uL[i] = M::div_zero(left.mom[i], rcL); // (+-0) / rho, :774-775
+        uR[i] = M::div_zero(right.mom[i], rcR);
       }
     }
     eKinRL *= 0.5;
@@ -188,8 +222,8 @@ FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
     right.E -= rhoR * eKinRR;
   }
   Cons<D> fluxL, fluxR;
-  euler_flux<D, DIR>(fluxL, left);
-  euler_flux<D, DIR>(fluxR, right);
+  euler_flux_v<D, DIR>(fluxL, left, uL[DIR]);
+  euler_flux_v<D, DIR>(fluxR, right, uR[DIR]);
 
   // :752-797 Einfeldt signal velocities with the full Roe velocity
   const double aL = left.a;
@@ -198,29 +232,26 @@ FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
   const double rhoER = right.E;
   const double pL = left.p;
   const double pR = right.p;
-  const double hL = (rhoEL + pL) / rhoL;
-  const double hR = (rhoER + pR) / rhoR;
-  const double sqRhoL = sqrt(rhoL);
-  const double sqRhoR = sqrt(rhoR);
+  const double hL = M::div(rhoEL + pL, rcL, fl);
+  const double hR = M::div(rhoER + pR, rcR, fl);
+  const double sqRhoL = M::sqrt(rhoL, fl);
+  const double sqRhoR = M::sqrt(rhoR, fl);
   const double sqRhoSum = sqRhoL + sqRhoR;
-  const double sqRhoL_over_Sum = sqRhoL / sqRhoSum;
-  const double sqRhoR_over_Sum = sqRhoR / sqRhoSum;
-  double uL[D], uR[D], roeU[D];
+  const Rcp rcSum = M::rcp(sqRhoSum);
+  const double sqRhoL_over_Sum = M::div(sqRhoL, rcSum, fl);
+  const double sqRhoR_over_Sum = M::div(sqRhoR, rcSum, fl);
+  double roeU[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    uL[i] = left.mom[i] / rhoL;
-    uR[i] = right.mom[i] / rhoR;
-    roeU[i] = sqRhoL_over_Sum * uL[i] + sqRhoR_over_Sum * uR[i];
-  }
+  for (int i = 0; i < D; ++i) roeU[i] = sqRhoL_over_Sum * uL[i] + sqRhoR_over_Sum * uR[i];
   const double roeH = sqRhoL_over_Sum * hL + sqRhoR_over_Sum * hR;
   double squaredNormRoeU = 0.0;
 #pragma unroll
   for (int i = 0; i < D; ++i) squaredNormRoeU += roeU[i] * roeU[i];
   const double squaredNormRoeU_half = 0.5 * squaredNormRoeU;
-  const double roeGamma = (sqRhoL * eq.gamma + sqRhoR * eq.gamma) / sqRhoSum;
+  const double roeGamma = M::div(sqRhoL * eq.gamma + sqRhoR * eq.gamma, rcSum, fl);
   const double gm1 = roeGamma - 1.0;
   const double roeA2 = gm1 * (roeH - squaredNormRoeU_half);
-  const double roeA = sqrt(roeA2);
+  const double roeA = M::sqrt(roeA2, fl);
   const double maxA = vmax(aL, aR);
   const double sL1 = uL[DIR] - maxA;
   const double sL2 = roeU[DIR] - roeA;
@@ -235,27 +266,28 @@ FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
   const double bLbR = bL * bR;
   const double db = bR - bL;
   const double db_positive = db > 0.0 ? db : 1.0;
+  const Rcp rcDb = M::rcp(db_positive);
   Cons<D> hlle;
-  hlle.rho = (bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho)) / db_positive;
+  hlle.rho =
+      M::div(bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho), rcDb, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    hlle.mom[d] =
-        (bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d])) /
-        db_positive;
+    hlle.mom[d] = M::div(
+        bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]), rcDb, fl);
   }
-  hlle.E = (bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E)) / db_positive;
+  hlle.E = M::div(bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E), rcDb, fl);
 
   // :813-823
   const double u_bar = 0.5 * (sR + sL);
   const double u_bar_abs = fabs(u_bar);
-  const double delta = roeA / (roeA + u_bar_abs);
-  const double b = bLbR / db_positive;
+  const double delta = M::div(roeA, roeA + u_bar_abs, fl);
+  const double b = M::div(bLbR, rcDb, fl);
   const double deltaRho = rhoR - rhoL;
   double deltaRhoU[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) deltaRhoU[i] = right.mom[i] - left.mom[i];
   const double deltaRhoE = rhoER - rhoEL;
-  const double gm1_over_roeA2 = gm1 / roeA2;
+  const double gm1_over_roeA2 = M::div(gm1, roeA2, fl);
   const double l21 = gm1_over_roeA2 * (roeH - squaredNormRoeU);
 
   if constexpr (D == 1) {
@@ -329,30 +361,35 @@ FVS_DEV void hllem_flux(const EqConst& eq, Cons<D>& flux, Complete<D> left,
   }
 }
 
-// Per-cell part of the HLLEM stable-dt signal evaluation
-// (HllemMethod.hpp:1152-1216): quantities that depend on one state only.  A
-// cell takes part in two faces; they are computed once per cell.
+// Per-cell part of the stable-dt signal evaluation: quantities that depend on
+// one stored state only (HllemMethod.hpp:1152-1216 /
+// EinfeldtSignalVelocities.hpp:64-97).  A cell takes part in two faces; they
+// are computed once per cell and carried along the sweep.
 template <int D> struct DtCell {
   double u[D];
   double h;
   double sq_rho;
   double a;
 };
-template <int D, typename State> FVS_DEV void dt_cell(DtCell<D>& c, const State& q) {
-  c.h = (q.E + q.p) / q.rho;
-  c.sq_rho = sqrt(q.rho);
+template <class M, int D, typename State>
+FVS_DEV void dt_cell(DtCell<D>& c, const State& q, Flag& fl) {
+  const Rcp rc = M::rcp(q.rho);
+  c.h = M::div(q.E + q.p, rc, fl);
+  c.sq_rho = M::sqrt(q.rho, fl);
 #pragma unroll
-  for (int i = 0; i < D; ++i) c.u[i] = q.mom[i] / q.rho;
+  for (int i = 0; i < D; ++i) c.u[i] = M::div(q.mom[i], rc, fl);
   c.a = q.a;
 }
 
 // max(|sL|, |sR|) of HllemMethod.hpp:1152-1216; the stable dt of the face is
 // dx / (this value).
-template <int D, int DIR>
-FVS_DEV double hllem_max_signal(const EqConst& eq, const DtCell<D>& L, const DtCell<D>& R) {
+template <class M, int D, int DIR>
+FVS_DEV double hllem_max_signal(const EqM& eq, const DtCell<D>& L, const DtCell<D>& R,
+                                Flag& fl) {
   const double sqRhoSum = L.sq_rho + R.sq_rho;
-  const double wL = L.sq_rho / sqRhoSum;
-  const double wR = R.sq_rho / sqRhoSum;
+  const Rcp rcSum = M::rcp(sqRhoSum);
+  const double wL = M::div(L.sq_rho, rcSum, fl);
+  const double wR = M::div(R.sq_rho, rcSum, fl);
   double roeU[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) roeU[i] = wL * L.u[i] + wR * R.u[i];
@@ -362,7 +399,7 @@ FVS_DEV double hllem_max_signal(const EqConst& eq, const DtCell<D>& L, const DtC
   for (int i = 0; i < D; ++i) sq += roeU[i] * roeU[i];
   const double sq_half = 0.5 * sq;
   const double roeA2 = eq.gamma_minus_1 * (roeH - sq_half);
-  const double roeA = sqrt(roeA2);
+  const double roeA = M::sqrt(roeA2, fl);
   const double maxA = vmax(L.a, R.a);
   const double sL = vmin(L.u[DIR] - maxA, roeU[DIR] - roeA);
   const double sR = vmax(roeU[DIR] + roeA, R.u[DIR] + maxA);
@@ -371,54 +408,59 @@ FVS_DEV double hllem_max_signal(const EqConst& eq, const DtCell<D>& L, const DtC
 
 // ---------------------------------------------------------------------------
 // Einfeldt signal velocities (normal Roe velocity only),
-// src/equations/perfect_gas/EinfeldtSignalVelocities.hpp:64-97
-template <int D, int DIR, typename SL, typename SR>
-FVS_DEV void einfeldt_signals(const EqConst& eq, const SL& left, const SR& right,
-                              double& s0, double& s1) {
-  const double rhoL = left.rho;
-  const double rhoR = right.rho;
-  const double sqRhoL = sqrt(rhoL);
-  const double sqRhoR = sqrt(rhoR);
-  const double uL = left.mom[DIR] / rhoL;
-  const double uR = right.mom[DIR] / rhoR;
-  const double oosqRhoSum = 1.0 / (sqRhoL + sqRhoR);
+// src/equations/perfect_gas/EinfeldtSignalVelocities.hpp:64-97, from the
+// per-cell quantities uL = m_d / rho, hL = (E + p) / rho, sqrt(rho), a.
+template <class M>
+FVS_DEV void einfeldt_signals(const EqM& eq, double uL, double hL, double sqRhoL, double aL,
+                              double uR, double hR, double sqRhoR, double aR, double& s0,
+                              double& s1, Flag& fl) {
+  const double oosqRhoSum = M::div(1.0, sqRhoL + sqRhoR, fl);
   const double roeU = (uL * sqRhoL + uR * sqRhoR) * oosqRhoSum;
-  const double hL = (left.E + left.p) / rhoL;
-  const double hR = (right.E + right.p) / rhoR;
   const double roeH = (hL * sqRhoL + hR * sqRhoR) * oosqRhoSum;
   const double roeA2 = (eq.gamma - 1.0) * (roeH - 0.5 * roeU * roeU);
-  const double roeA = sqrt(roeA2);
-  s0 = vmin(uL - left.a, roeU - roeA);
-  s1 = vmax(roeU + roeA, uR + right.a);
+  const double roeA = M::sqrt(roeA2, fl);
+  s0 = vmin(uL - aL, roeU - roeA);
+  s1 = vmax(roeU + roeA, uR + aR);
 }
 
 // include/fub/flux_method/HllMethod.hpp:260-293
-template <int D, int DIR>
-FVS_DEV void hll_einfeldt_flux(const EqConst& eq, Cons<D>& nf, const Complete<D>& left,
-                               const Complete<D>& right) {
+template <class M, int D, int DIR>
+FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
+                               const Edge<D>& eR, Flag& fl) {
+  const Complete<D>& left = eL.q;
+  const Complete<D>& right = eR.q;
+  const double uL = M::div(left.mom[DIR], eL.rc, fl);
+  const double uR = M::div(right.mom[DIR], eR.rc, fl);
+  const double hL = M::div(left.E + left.p, eL.rc, fl);
+  const double hR = M::div(right.E + right.p, eR.rc, fl);
   double s0, s1;
-  einfeldt_signals<D, DIR>(eq, left, right, s0, s1);
+  einfeldt_signals<M>(eq, uL, hL, M::sqrt(left.rho, fl), left.a, uR, hR,
+                      M::sqrt(right.rho, fl), right.a, s0, s1, fl);
   Cons<D> fL, fR;
-  euler_flux<D, DIR>(fL, left);
-  euler_flux<D, DIR>(fR, right);
+  euler_flux_v<D, DIR>(fL, left, uL);
+  euler_flux_v<D, DIR>(fR, right, uR);
   const double sL = vmin(s0, 0.0);
   const double sR = vmax(s1, 0.0);
   const double sLsR = sL * sR;
   double ds = sR - sL;
   ds = ds > 0.0 ? ds : 1.0;
-  nf.rho = (sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho)) / ds;
+  const Rcp rcDs = M::rcp(ds);
+  nf.rho = M::div(sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho), rcDs, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    nf.mom[d] = (sR * fL.mom[d] - sL * fR.mom[d] + sLsR * (right.mom[d] - left.mom[d])) / ds;
+    nf.mom[d] =
+        M::div(sR * fL.mom[d] - sL * fR.mom[d] + sLsR * (right.mom[d] - left.mom[d]), rcDs, fl);
   }
-  nf.E = (sR * fL.E - sL * fR.E + sLsR * (right.E - left.E)) / ds;
+  nf.E = M::div(sR * fL.E - sL * fR.E + sLsR * (right.E - left.E), rcDs, fl);
 }
 
 // include/fub/flux_method/HllMethod.hpp:337-347: max(0, |s0|, |s1|)
-template <int D, int DIR, typename SL, typename SR>
-FVS_DEV double hll_einfeldt_max_signal(const EqConst& eq, const SL& left, const SR& right) {
+template <class M, int D, int DIR>
+FVS_DEV double hll_einfeldt_max_signal(const EqM& eq, const DtCell<D>& L, const DtCell<D>& R,
+                                       Flag& fl) {
   double s0, s1;
-  einfeldt_signals<D, DIR>(eq, left, right, s0, s1);
+  einfeldt_signals<M>(eq, L.u[DIR], L.h, L.sq_rho, L.a, R.u[DIR], R.h, R.sq_rho, R.a, s0, s1,
+                      fl);
   double m = 0.0;
   m = vmax(m, fabs(s0));
   m = vmax(m, fabs(s1));
@@ -621,7 +663,7 @@ FVS_DEV void godunov_exact_flux(const EqConst& eq, Cons<D>& nf, const Complete<D
   sol.p = 0.0;
   sol.a = 0.0;
   ExactRiemann<D, DIR>(eq).solve(sol, left, right, failed);
-  euler_flux<D, DIR>(nf, sol);
+  euler_flux_v<D, DIR>(nf, sol, sol.mom[DIR] / sol.rho);
 }
 
 template <int D, int DIR, typename SL, typename SR>
@@ -637,36 +679,76 @@ FVS_DEV double godunov_exact_max_signal(const EqConst& eq, const SL& left, const
 
 // ---------------------------------------------------------------------------
 // Dispatch on the base method.
-template <int D, int DIR, int BASE>
-FVS_DEV void base_flux(const EqConst& eq, Cons<D>& f, const Complete<D>& left,
-                       const Complete<D>& right, int& failed) {
+struct Eqs {
+  EqConst c;
+  EqM m;
+  FVS_DEV explicit Eqs(const EqConst& e) : c(e), m(e) {}
+};
+
+template <class M, int D, int DIR, int BASE>
+FVS_DEV void base_flux(const Eqs& eq, Cons<D>& f, const Edge<D>& left, const Edge<D>& right,
+                       Flag& fl, int& failed) {
   if constexpr (BASE == kBaseHllemLarrouturou) {
-    hllem_flux<D, DIR, true>(eq, f, left, right);
+    hllem_flux<M, D, DIR, true>(eq.m, f, left, right, fl);
   } else if constexpr (BASE == kBaseHllem) {
-    hllem_flux<D, DIR, false>(eq, f, left, right);
+    hllem_flux<M, D, DIR, false>(eq.m, f, left, right, fl);
   } else if constexpr (BASE == kBaseHllEinfeldt) {
-    hll_einfeldt_flux<D, DIR>(eq, f, left, right);
+    hll_einfeldt_flux<M, D, DIR>(eq.m, f, left, right, fl);
   } else {
-    godunov_exact_flux<D, DIR>(eq, f, left, right, failed);
+    godunov_exact_flux<D, DIR>(eq.c, f, left.q, right.q, failed);
   }
 }
 
-// max signal speed of the face between two STORED states (the stable dt of a
+// Per-cell data of the stable-dt evaluation for a base method: the signal
+// speeds of a face need these from its two STORED neighbour states.
+template <int D, int BASE> struct DtData {
+  DtCell<D> c;
+};
+template <int D> struct DtData<D, kBaseGodunovExact> {
+  Complete<D> c; // the exact solver needs the whole state
+};
+
+template <class M, int D, int BASE>
+FVS_DEV void dt_prepare(DtData<D, BASE>& out, const Complete<D>& q, Flag& fl) {
+  if constexpr (BASE == kBaseGodunovExact) {
+    out.c = q;
+  } else {
+    dt_cell<M, D>(out.c, q, fl);
+  }
+}
+
+// max signal speed of the face between two stored states (the stable dt of a
 // face is dx / value; min over faces == dx / max over faces because IEEE
 // division is monotone in its divisor).
-template <int D, int DIR, int BASE, typename SL, typename SR>
-FVS_DEV double base_max_signal(const EqConst& eq, const SL& left, const SR& right,
-                               int& failed) {
+template <class M, int D, int DIR, int BASE>
+FVS_DEV double base_max_signal(const Eqs& eq, const DtData<D, BASE>& left,
+                               const DtData<D, BASE>& right, Flag& fl, int& failed) {
   if constexpr (BASE == kBaseHllemLarrouturou || BASE == kBaseHllem) {
-    DtCell<D> L, R;
-    dt_cell<D>(L, left);
-    dt_cell<D>(R, right);
-    return hllem_max_signal<D, DIR>(eq, L, R);
+    return hllem_max_signal<M, D, DIR>(eq.m, left.c, right.c, fl);
   } else if constexpr (BASE == kBaseHllEinfeldt) {
-    return hll_einfeldt_max_signal<D, DIR>(eq, left, right);
+    return hll_einfeldt_max_signal<M, D, DIR>(eq.m, left.c, right.c, fl);
   } else {
-    return godunov_exact_max_signal<D, DIR>(eq, left, right, failed);
+    return godunov_exact_max_signal<D, DIR>(eq.c, left.c, right.c, failed);
   }
+}
+
+// Runs `f(policy, flag)` with the branch-free arithmetic and, if any
+// operation left the fast-path domain, again with the plain operators.
+#ifndef FVS_FASTMATH
+#define FVS_FASTMATH 1
+#endif
+template <typename F> FVS_DEV void with_fallback(F&& f) {
+#if FVS_FASTMATH
+  Flag fl;
+  f(FastMath{}, fl);
+  if (fl.any()) {
+    Flag unused;
+    f(SafeMath{}, unused);
+  }
+#else
+  Flag unused;
+  f(SafeMath{}, unused);
+#endif
 }
 
 } // namespace fvs

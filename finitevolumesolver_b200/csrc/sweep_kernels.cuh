@@ -52,7 +52,7 @@ template <int D> FVS_DEV void copy_cons(Cons<D>& c, const Complete<D>& q) {
 }
 
 FVS_DEV double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
-template <int D> FVS_DEV Complete<D> shfl_up_complete(const Complete<D>& q, int delta) {
+template <int D> FVS_DEV Complete<D> shfl_up(const Complete<D>& q, int delta) {
   Complete<D> r;
   r.rho = shfl_up_d(q.rho, delta);
 #pragma unroll
@@ -62,12 +62,33 @@ template <int D> FVS_DEV Complete<D> shfl_up_complete(const Complete<D>& q, int 
   r.a = shfl_up_d(q.a, delta);
   return r;
 }
-template <int D> FVS_DEV Cons<D> shfl_up_cons(const Cons<D>& q, int delta) {
+template <int D> FVS_DEV Cons<D> shfl_up(const Cons<D>& q, int delta) {
   Cons<D> r;
   r.rho = shfl_up_d(q.rho, delta);
 #pragma unroll
   for (int d = 0; d < D; ++d) r.mom[d] = shfl_up_d(q.mom[d], delta);
   r.E = shfl_up_d(q.E, delta);
+  return r;
+}
+template <int D> FVS_DEV Edge<D> shfl_up(const Edge<D>& e, int delta) {
+  Edge<D> r;
+  r.q = shfl_up<D>(e.q, delta);
+  r.rc.b = r.q.rho;
+  r.rc.r = shfl_up_d(e.rc.r, delta);
+  return r;
+}
+template <int D> FVS_DEV DtCell<D> shfl_up(const DtCell<D>& c, int delta) {
+  DtCell<D> r;
+#pragma unroll
+  for (int d = 0; d < D; ++d) r.u[d] = shfl_up_d(c.u[d], delta);
+  r.h = shfl_up_d(c.h, delta);
+  r.sq_rho = shfl_up_d(c.sq_rho, delta);
+  r.a = shfl_up_d(c.a, delta);
+  return r;
+}
+template <int D, int BASE> FVS_DEV DtData<D, BASE> shfl_up(const DtData<D, BASE>& c, int delta) {
+  DtData<D, BASE> r;
+  r.c = shfl_up<D>(c.c, delta);
   return r;
 }
 
@@ -100,12 +121,34 @@ FVS_DEV void reduce_max_signal(double v, unsigned long long* target) {
   }
 }
 
-// cons_new = cons + lambda * (F_left - F_right), then p and a
+// Pipeline stages -----------------------------------------------------------
+// stage A: the two predicted edge states of the cell with neighbours qm, qp
+template <int D, int DIR, int RECON, int LIM, typename S0, typename S2>
+FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const Complete<D>& q0, const S2& qp,
+                           double lambda_half, Edge<D>& recL, Edge<D>& recR) {
+  if constexpr (RECON == kReconMusclHancock) {
+    with_fallback([&](auto M, Flag& fl) {
+      muscl_predict<decltype(M), D, DIR, LIM>(eq.m, qm, q0, qp, lambda_half, recL, recR, fl);
+    });
+  } else {
+    recL.q = q0;
+    recL.rc = FastMath::rcp(q0.rho);
+    recR = recL;
+  }
+}
+// stage B: base flux through the face between two edge states
+template <int D, int DIR, int BASE>
+FVS_DEV void stage_flux(const Eqs& eq, Cons<D>& F, const Edge<D>& left, const Edge<D>& right,
+                        int& failed) {
+  with_fallback([&](auto M, Flag& fl) {
+    base_flux<decltype(M), D, DIR, BASE>(eq, F, left, right, fl, failed);
+  });
+}
+// stage C: cons_new = cons + lambda * (F_left - F_right), then p and a
 // (src/HyperbolicPatchIntegrator.cpp:35-61, PerfectGas.cpp:112-124)
-template <int D>
-FVS_DEV void update_and_complete(const EqConst& eq, Complete<D>& out, const Cons<D>& q,
-                                 const Cons<D>& Fl, const Cons<D>& Fr, double lambda,
-                                 bool update) {
+template <int D, typename S>
+FVS_DEV void stage_update(const Eqs& eq, Complete<D>& out, const S& q, const Cons<D>& Fl,
+                          const Cons<D>& Fr, double lambda, bool update) {
   if (update) {
     out.rho = q.rho + lambda * (Fl.rho - Fr.rho);
 #pragma unroll
@@ -117,7 +160,23 @@ FVS_DEV void update_and_complete(const EqConst& eq, Complete<D>& out, const Cons
     for (int d = 0; d < D; ++d) out.mom[d] = q.mom[d];
     out.E = q.E;
   }
-  complete_from_cons<D>(eq, out);
+  with_fallback([&](auto M, Flag& fl) {
+    complete_from_cons<decltype(M), D>(eq.m, out, decltype(M)::rcp(out.rho), fl);
+  });
+}
+// stage D: per-cell stable-dt data and the signal speed of a face
+template <int D, int BASE>
+FVS_DEV void stage_dt_cell(DtData<D, BASE>& out, const Complete<D>& q) {
+  with_fallback([&](auto M, Flag& fl) { dt_prepare<decltype(M), D, BASE>(out, q, fl); });
+}
+template <int D, int DIR, int BASE>
+FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtData<D, BASE>& r,
+                             int& failed) {
+  double s = 0.0;
+  with_fallback([&](auto M, Flag& fl) {
+    s = base_max_signal<decltype(M), D, DIR, BASE>(eq, l, r, fl, failed);
+  });
+  return s;
 }
 
 constexpr int kSweepThreads = 128;
@@ -138,6 +197,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
   double maxsig = 0.0;
   int failed = 0;
   if (line < nlines && o_first < nd) {
+    const Eqs eq(A.eq);
     const int o_last = min(nd, o_first + A.seg_len) - 1;
     const long long stride = (DIR == 1) ? (long long)n0 : (long long)n0 * B.n[1];
     long long base;
@@ -156,52 +216,56 @@ fused_sweep_yz_kernel(const SweepArgs A) {
 
     Complete<D> q0, q1;  // cells j, j-1
     Cons<D> q2;          // cell j-2
-    Complete<D> recR_prev; // upper edge state of cell j-2
-    Cons<D> F_prev;        // flux through face j-2
+    Edge<D> recR_prev;   // upper edge state of cell j-2
+    Cons<D> F_prev;      // flux through face j-2
+    DtData<D, BASE> dt_prev, dt_cur;
     const int jstart = max(o_first - 2, 0);
     load_complete<D>(q0, src + stride * jstart, sc);
     q1 = q0;
     copy_cons<D>(q2, q0);
-    recR_prev = q0;
+    recR_prev.q = q0;
+    recR_prev.rc = FastMath::rcp(q0.rho);
     copy_cons<D>(F_prev, q0);
+    stage_dt_cell<D, BASE>(dt_cur, q0);
+    dt_prev = dt_cur;
     for (int j = jstart; j <= o_last + 2; ++j) {
-      if (j > jstart && j < nd) load_complete<D>(q0, src + stride * j, sc);
+      if (j > jstart && j < nd) {
+        load_complete<D>(q0, src + stride * j, sc);
+        stage_dt_cell<D, BASE>(dt_cur, q0);
+      }
       // stage A: cell j-1
-      Complete<D> recL, recR;
-      if constexpr (RECON == kReconMusclHancock) {
-        if (j >= jstart + 2 && j - 1 >= ulo - 1 && j - 1 <= uhi + 1) {
-          muscl_predict<D, DIR, LIM>(A.eq, q2, q1, q0, A.lambda_half, recL, recR);
-        } else {
-          recL = q1;
-          recR = q1;
-        }
+      Edge<D> recL, recR;
+      if (j >= jstart + (RECON == kReconMusclHancock ? 2 : 1) && j - 1 >= ulo - 1 &&
+          j - 1 <= uhi + 1) {
+        stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
       } else {
-        recL = q1;
-        recR = q1;
+        recL = recR_prev;
+        recR = recR_prev;
       }
       // stage B: face j-1
       Cons<D> F;
-      if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo && j - 1 <= uhi + 1) {
-        base_flux<D, DIR, BASE>(A.eq, F, recR_prev, recL, failed);
+      if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo &&
+          j - 1 <= uhi + 1) {
+        stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
       } else {
         F = F_prev;
       }
       // stage C: cell j-2
       if (j - 2 >= o_first) {
         Complete<D> out;
-        update_and_complete<D>(A.eq, out, q2, F_prev, F, A.lambda,
-                               j - 2 >= ulo && j - 2 <= uhi);
+        stage_update<D>(eq, out, q2, F_prev, F, A.lambda, j - 2 >= ulo && j - 2 <= uhi);
         store_complete<D>(dst + stride * (j - 2), sc, out);
       }
       // stage D: face (j-1 | j) of the stored states
       if (j > jstart && j < nd && dtmask[j - 1]) {
-        const double s = base_max_signal<D, DIR, BASE>(A.eq, q1, q0, failed);
+        const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
         maxsig = s > maxsig ? s : maxsig;
       }
       copy_cons<D>(q2, q1);
       q1 = q0;
       recR_prev = recR;
       F_prev = F;
+      dt_prev = dt_cur;
     }
   }
   reduce_max_signal(maxsig, A.max_signal);
@@ -223,12 +287,14 @@ fused_sweep_x_kernel(const SweepArgs A) {
   const int warp = threadIdx.x >> 5;
   const long long w = (long long)blockIdx.x * kWarps + warp;
   // carry between consecutive 32-cell chunks of a row (per warp)
-  __shared__ Complete<D> carry_q[kWarps][2]; // cells of lanes 30, 31
-  __shared__ Complete<D> carry_rec[kWarps];  // recR of lane 31
-  __shared__ Cons<D> carry_F[kWarps];        // F of lane 31
+  __shared__ Complete<D> carry_q[kWarps][2];        // cells of lanes 30, 31
+  __shared__ Edge<D> carry_rec[kWarps];             // recR of lane 31
+  __shared__ Cons<D> carry_F[kWarps];               // F of lane 31
+  __shared__ DtData<D, BASE> carry_dt[kWarps];      // dt data of lane 31
   double maxsig = 0.0;
   int failed = 0;
   if (w < nrows * nseg) {
+    const Eqs eq(A.eq);
     const long long row = w / nseg;
     const int seg = (int)(w % nseg);
     const int o_first = seg * A.seg_len;
@@ -244,31 +310,33 @@ fused_sweep_x_kernel(const SweepArgs A) {
       const int cl = min(max(c, 0), n0 - 1);
       Complete<D> q0;
       load_complete<D>(q0, src + cl, sc);
-      Complete<D> q1 = shfl_up_complete<D>(q0, 1);
-      Complete<D> q2c = shfl_up_complete<D>(q0, 2);
+      DtData<D, BASE> dt_cur;
+      stage_dt_cell<D, BASE>(dt_cur, q0);
+      Complete<D> q1 = shfl_up<D>(q0, 1);
+      Complete<D> q2 = shfl_up<D>(q0, 2);
+      DtData<D, BASE> dt_prev = shfl_up<D, BASE>(dt_cur, 1);
       if (first) {
         // no carry yet: lanes 0..3 produce no output in the first chunk; give
         // their missing neighbours real data to keep the arithmetic benign
-        if (lane < 1) q1 = q0;
-        if (lane < 2) q2c = q0;
+        if (lane < 1) {
+          q1 = q0;
+          dt_prev = dt_cur;
+        }
+        if (lane < 2) q2 = q0;
       } else {
         if (lane == 0) {
           q1 = carry_q[warp][1];
-          q2c = carry_q[warp][0];
+          q2 = carry_q[warp][0];
+          dt_prev = carry_dt[warp];
         } else if (lane == 1) {
-          q2c = carry_q[warp][1];
+          q2 = carry_q[warp][1];
         }
       }
       // stage A: cell c-1
-      Complete<D> recL, recR;
-      if constexpr (RECON == kReconMusclHancock) {
-        muscl_predict<D, DIR, LIM>(A.eq, q2c, q1, q0, A.lambda_half, recL, recR);
-      } else {
-        recL = q1;
-        recR = q1;
-      }
+      Edge<D> recL, recR;
+      stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
       // stage B: face c-1 = (c-2 | c-1)
-      Complete<D> recR_prev = shfl_up_complete<D>(recR, 1);
+      Edge<D> recR_prev = shfl_up<D>(recR, 1);
       if (lane == 0) {
         if (first) {
           recR_prev = recR;
@@ -277,9 +345,9 @@ fused_sweep_x_kernel(const SweepArgs A) {
         }
       }
       Cons<D> F;
-      base_flux<D, DIR, BASE>(A.eq, F, recR_prev, recL, failed);
+      stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
       // stage C: cell c-2
-      Cons<D> F_prev = shfl_up_cons<D>(F, 1);
+      Cons<D> F_prev = shfl_up<D>(F, 1);
       if (lane == 0) {
         if (first) {
           F_prev = F;
@@ -292,19 +360,18 @@ fused_sweep_x_kernel(const SweepArgs A) {
       if (lane == 31) {
         carry_rec[warp] = recR;
         carry_F[warp] = F;
+        carry_dt[warp] = dt_cur;
       }
       __syncwarp();
       const int o = c - 2;
       if ((!first || lane >= 4) && o >= o_first && o <= o_last) {
-        Cons<D> q2;
-        copy_cons<D>(q2, q2c);
         Complete<D> out;
-        update_and_complete<D>(A.eq, out, q2, F_prev, F, A.lambda, o >= ulo && o <= uhi);
+        stage_update<D>(eq, out, q2, F_prev, F, A.lambda, o >= ulo && o <= uhi);
         store_complete<D>(dst + o, sc, out);
       }
       // stage D: face (c-1 | c) of the stored states
       if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
-        const double s = base_max_signal<D, DIR, BASE>(A.eq, q1, q0, failed);
+        const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
         maxsig = s > maxsig ? s : maxsig;
       }
       first = false;
@@ -337,23 +404,25 @@ __global__ void __launch_bounds__(128) numeric_flux_kernel(const SweepArgs A) {
     const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
     const long long cell = idx[0] + (long long)B.n[0] * (idx[1] + (long long)B.n[1] * idx[2]);
     const double* p = B.src + cell; // cell idx = right neighbour of the face
+    const Eqs eq(A.eq);
     Cons<D> F;
+    Edge<D> unused, left, right;
     if constexpr (RECON == kReconMusclHancock) {
       Complete<D> s0, s1, s2, s3;
       load_complete<D>(s0, p - 2 * stride, B.sc);
       load_complete<D>(s1, p - stride, B.sc);
       load_complete<D>(s2, p, B.sc);
       load_complete<D>(s3, p + stride, B.sc);
-      Complete<D> recL_unused, recR_left, recL_right, recR_unused;
-      muscl_predict<D, DIR, LIM>(A.eq, s0, s1, s2, A.lambda_half, recL_unused, recR_left);
-      muscl_predict<D, DIR, LIM>(A.eq, s1, s2, s3, A.lambda_half, recL_right, recR_unused);
-      base_flux<D, DIR, BASE>(A.eq, F, recR_left, recL_right, failed);
+      stage_predict<D, DIR, RECON, LIM>(eq, s0, s1, s2, A.lambda_half, unused, left);
+      stage_predict<D, DIR, RECON, LIM>(eq, s1, s2, s3, A.lambda_half, right, unused);
     } else {
       Complete<D> s0, s1;
       load_complete<D>(s0, p - stride, B.sc);
       load_complete<D>(s1, p, B.sc);
-      base_flux<D, DIR, BASE>(A.eq, F, s0, s1, failed);
+      stage_predict<D, DIR, RECON, LIM>(eq, s0, s0, s0, A.lambda_half, unused, left);
+      stage_predict<D, DIR, RECON, LIM>(eq, s1, s1, s1, A.lambda_half, right, unused);
     }
+    stage_flux<D, DIR, BASE>(eq, F, left, right, failed);
     const long long fcell = (idx[0] - B.foff[0]) +
                             (long long)B.fn[0] * ((idx[1] - B.foff[1]) +
                                                   (long long)B.fn[1] * (idx[2] - B.foff[2]));
@@ -381,10 +450,14 @@ __global__ void __launch_bounds__(256) stable_dt_kernel(const SweepArgs A) {
     idx[2] = (int)(t / ((long long)B.n[0] * B.n[1]));
     if (idx[DIR] + 1 < B.n[DIR] && B.dtmask[idx[DIR]]) {
       const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
+      const Eqs eq(A.eq);
       Complete<D> l, r;
       load_complete<D>(l, B.src + t, B.sc);
       load_complete<D>(r, B.src + t + stride, B.sc);
-      maxsig = base_max_signal<D, DIR, BASE>(A.eq, l, r, failed);
+      DtData<D, BASE> dl, dr;
+      stage_dt_cell<D, BASE>(dl, l);
+      stage_dt_cell<D, BASE>(dr, r);
+      maxsig = stage_dt_face<D, DIR, BASE>(eq, dl, dr, failed);
       maxsig = maxsig > 0.0 ? maxsig : 0.0; // drops NaN
     }
   }
@@ -407,19 +480,24 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
     idx[0] = (int)(t % B.n[0]);
     idx[1] = (int)((t / B.n[0]) % B.n[1]);
     idx[2] = (int)(t / ((long long)B.n[0] * B.n[1]));
+    const Eqs eq(A.eq);
     Complete<D> l;
     load_complete<D>(l, B.src + t, B.sc);
+    DtData<D, BASE> dl, dr;
+    stage_dt_cell<D, BASE>(dl, l);
     if (idx[0] + 1 < B.n[0] && A.boxes[0][blockIdx.y].dtmask[idx[0]]) {
       Complete<D> r;
       load_complete<D>(r, B.src + t + 1, B.sc);
-      const double s = base_max_signal<D, 0, BASE>(A.eq, l, r, failed);
+      stage_dt_cell<D, BASE>(dr, r);
+      const double s = stage_dt_face<D, 0, BASE>(eq, dl, dr, failed);
       maxsig[0] = s > 0.0 ? s : 0.0;
     }
     if constexpr (D >= 2) {
       if (idx[1] + 1 < B.n[1] && A.boxes[1][blockIdx.y].dtmask[idx[1]]) {
         Complete<D> r;
         load_complete<D>(r, B.src + t + B.n[0], B.sc);
-        const double s = base_max_signal<D, 1, BASE>(A.eq, l, r, failed);
+        stage_dt_cell<D, BASE>(dr, r);
+        const double s = stage_dt_face<D, 1, BASE>(eq, dl, dr, failed);
         maxsig[1] = s > 0.0 ? s : 0.0;
       }
     }
@@ -427,7 +505,8 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
       if (idx[2] + 1 < B.n[2] && A.boxes[2][blockIdx.y].dtmask[idx[2]]) {
         Complete<D> r;
         load_complete<D>(r, B.src + t + (long long)B.n[0] * B.n[1], B.sc);
-        const double s = base_max_signal<D, 2, BASE>(A.eq, l, r, failed);
+        stage_dt_cell<D, BASE>(dr, r);
+        const double s = stage_dt_face<D, 2, BASE>(eq, dl, dr, failed);
         maxsig[2] = s > 0.0 ? s : 0.0;
       }
     }
