@@ -68,6 +68,7 @@ def _compile(unit, force, verbose, extra):
 
 def build(force=False, verbose=False, extra=()):
     os.makedirs(OBJ, exist_ok=True)
+    extra = list(extra) + os.environ.get("FVS_NVCC_EXTRA", "").split()
     units = _units()
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
         results = list(ex.map(lambda u: _compile(u, force, verbose, list(extra)), units))

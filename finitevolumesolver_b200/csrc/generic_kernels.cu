@@ -90,7 +90,9 @@ template <int D> __global__ void __launch_bounds__(256) complete_kernel(const Sw
   q.E = u[B.sc * (1 + D)];
   const Eqs eq(A.eq);
   with_fallback([&](auto M, Flag& fl) {
-    complete_from_cons<decltype(M), D>(eq.m, q, decltype(M)::rcp(q.rho), fl);
+    const Rcp rc = decltype(M)::rcp(q.rho);
+    decltype(M)::check(rc, fl);
+    complete_from_cons<decltype(M), D>(eq.m, q, rc, fl);
   });
   u[B.sc * (2 + D)] = q.p;
   u[B.sc * (3 + D)] = q.a;

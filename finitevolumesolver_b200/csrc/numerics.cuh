@@ -152,6 +152,8 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   }
   const Rcp rcL = M::rcp(qL.rho);
   const Rcp rcR = M::rcp(qR.rho);
+  M::check(rcL, fl);
+  M::check(rcR, fl);
   complete_from_cons<M, D>(eq, qL, rcL, fl);
   complete_from_cons<M, D>(eq, qR, rcR, fl);
   Cons<D> fL, fR;
@@ -175,6 +177,8 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   }
   recL.rc = M::rcp(recL.q.rho);
   recR.rc = M::rcp(recR.q.rho);
+  M::check(recL.rc, fl);
+  M::check(recR.rc, fl);
   complete_from_cons<M, D>(eq, recL.q, recL.rc, fl);
   complete_from_cons<M, D>(eq, recR.q, recR.rc, fl);
 }
@@ -190,6 +194,8 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   Complete<D> right = eR.q;
   const Rcp& rcL = eL.rc;
   const Rcp& rcR = eR.rc;
+  M::check(rcL, fl);
+  M::check(rcR, fl);
   const double rhoL = left.rho;
   const double rhoR = right.rho;
   double vL_[D], vR_[D]; // velocities of the unmodified states
@@ -238,6 +244,7 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   const double sqRhoR = M::sqrt(rhoR, fl);
   const double sqRhoSum = sqRhoL + sqRhoR;
   const Rcp rcSum = M::rcp(sqRhoSum);
+  M::check(rcSum, fl);
   const double sqRhoL_over_Sum = M::div(sqRhoL, rcSum, fl);
   const double sqRhoR_over_Sum = M::div(sqRhoR, rcSum, fl);
   double roeU[D];
@@ -267,6 +274,7 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   const double db = bR - bL;
   const double db_positive = db > 0.0 ? db : 1.0;
   const Rcp rcDb = M::rcp(db_positive);
+  M::check(rcDb, fl);
   Cons<D> hlle;
   hlle.rho =
       M::div(bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho), rcDb, fl);
@@ -374,6 +382,7 @@ template <int D> struct DtCell {
 template <class M, int D, typename State>
 FVS_DEV void dt_cell(DtCell<D>& c, const State& q, Flag& fl) {
   const Rcp rc = M::rcp(q.rho);
+  M::check(rc, fl);
   c.h = M::div(q.E + q.p, rc, fl);
   c.sq_rho = M::sqrt(q.rho, fl);
 #pragma unroll
@@ -388,6 +397,7 @@ FVS_DEV double hllem_max_signal(const EqM& eq, const DtCell<D>& L, const DtCell<
                                 Flag& fl) {
   const double sqRhoSum = L.sq_rho + R.sq_rho;
   const Rcp rcSum = M::rcp(sqRhoSum);
+  M::check(rcSum, fl);
   const double wL = M::div(L.sq_rho, rcSum, fl);
   const double wR = M::div(R.sq_rho, rcSum, fl);
   double roeU[D];
@@ -429,6 +439,8 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
                                const Edge<D>& eR, Flag& fl) {
   const Complete<D>& left = eL.q;
   const Complete<D>& right = eR.q;
+  M::check(eL.rc, fl);
+  M::check(eR.rc, fl);
   const double uL = M::div(left.mom[DIR], eL.rc, fl);
   const double uR = M::div(right.mom[DIR], eR.rc, fl);
   const double hL = M::div(left.E + left.p, eL.rc, fl);
@@ -445,6 +457,7 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
   double ds = sR - sL;
   ds = ds > 0.0 ? ds : 1.0;
   const Rcp rcDs = M::rcp(ds);
+  M::check(rcDs, fl);
   nf.rho = M::div(sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho), rcDs, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {

@@ -24,6 +24,8 @@
 //   from warp shuffles and the two-cell carry between 32-cell chunks goes
 //   through shared memory.
 #pragma once
+#include <type_traits>
+
 #include "launch.h"
 
 namespace fvs {
@@ -161,7 +163,9 @@ FVS_DEV void stage_update(const Eqs& eq, Complete<D>& out, const S& q, const Con
     out.E = q.E;
   }
   with_fallback([&](auto M, Flag& fl) {
-    complete_from_cons<decltype(M), D>(eq.m, out, decltype(M)::rcp(out.rho), fl);
+    const Rcp rc = decltype(M)::rcp(out.rho);
+    decltype(M)::check(rc, fl);
+    complete_from_cons<decltype(M), D>(eq.m, out, rc, fl);
   });
 }
 // stage D: per-cell stable-dt data and the signal speed of a face
@@ -179,12 +183,18 @@ FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtDa
   return s;
 }
 
-constexpr int kSweepThreads = 128;
+#ifndef FVS_SWEEP_THREADS
+#define FVS_SWEEP_THREADS 128
+#endif
+#ifndef FVS_SWEEP_MIN_BLOCKS
+#define FVS_SWEEP_MIN_BLOCKS 2
+#endif
+constexpr int kSweepThreads = FVS_SWEEP_THREADS;
 
 // ---------------------------------------------------------------------------
 // Fused sweep along y or z: thread per line, register pipeline.
 template <int D, int DIR, int BASE, int RECON, int LIM>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
 fused_sweep_yz_kernel(const SweepArgs A) {
   static_assert(DIR >= 1 && DIR < D, "y/z sweep");
   const BoxDesc& B = A.boxes[blockIdx.y];
@@ -214,13 +224,15 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
 
-    Complete<D> q0, q1;  // cells j, j-1
-    Cons<D> q2;          // cell j-2
-    Edge<D> recR_prev;   // upper edge state of cell j-2
-    Cons<D> F_prev;      // flux through face j-2
+    Complete<D> q0, q1, qn; // cells j, j-1 and the prefetched cell j+1
+    Cons<D> q2;             // cell j-2
+    Edge<D> recR_prev;      // upper edge state of cell j-2
+    Cons<D> F_prev;         // flux through face j-2
     DtData<D, BASE> dt_prev, dt_cur;
     const int jstart = max(o_first - 2, 0);
     load_complete<D>(q0, src + stride * jstart, sc);
+    qn = q0;
+    if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
     q1 = q0;
     copy_cons<D>(q2, q0);
     recR_prev.q = q0;
@@ -228,33 +240,68 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     copy_cons<D>(F_prev, q0);
     stage_dt_cell<D, BASE>(dt_cur, q0);
     dt_prev = dt_cur;
-    for (int j = jstart; j <= o_last + 2; ++j) {
-      if (j > jstart && j < nd) {
-        load_complete<D>(q0, src + stride * j, sc);
-        stage_dt_cell<D, BASE>(dt_cur, q0);
+
+    // One pipeline step.  STEADY: every stage is active (interior of the
+    // update range), so A, B and C share one fast-path validity test and the
+    // step has no range tests.
+    const int jend = o_last + 2;
+    // steady range: all of A (cell j-1), B (face j-1), C (cell j-2) active
+    const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
+    const int je = min(min(uhi + 2, nd - 1), jend); // inclusive
+#pragma unroll 2
+    for (int j = jstart; j <= jend; ++j) {
+      if (j > jstart) {
+        q0 = qn;
+        if (j < nd) stage_dt_cell<D, BASE>(dt_cur, q0);
       }
-      // stage A: cell j-1
+      if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
       Edge<D> recL, recR;
-      if (j >= jstart + (RECON == kReconMusclHancock ? 2 : 1) && j - 1 >= ulo - 1 &&
-          j - 1 <= uhi + 1) {
-        stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
-      } else {
-        recL = recR_prev;
-        recR = recR_prev;
-      }
-      // stage B: face j-1
       Cons<D> F;
-      if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo &&
-          j - 1 <= uhi + 1) {
-        stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
-      } else {
-        F = F_prev;
-      }
-      // stage C: cell j-2
-      if (j - 2 >= o_first) {
+      if (j >= js && j <= je) {
         Complete<D> out;
-        stage_update<D>(eq, out, q2, F_prev, F, A.lambda, j - 2 >= ulo && j - 2 <= uhi);
+        with_fallback([&](auto M, Flag& fl) {
+          using MM = decltype(M);
+          if constexpr (RECON == kReconMusclHancock) {
+            muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, A.lambda_half, recL, recR, fl);
+          } else {
+            recL.q = q1;
+            recL.rc = MM::rcp(q1.rho);
+            recR = recL;
+          }
+          base_flux<MM, D, DIR, BASE>(eq, F, recR_prev, recL, fl, failed);
+          out.rho = q2.rho + A.lambda * (F_prev.rho - F.rho);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            out.mom[d] = q2.mom[d] + A.lambda * (F_prev.mom[d] - F.mom[d]);
+          }
+          out.E = q2.E + A.lambda * (F_prev.E - F.E);
+          const Rcp rc = MM::rcp(out.rho);
+          MM::check(rc, fl);
+          complete_from_cons<MM, D>(eq.m, out, rc, fl);
+        });
         store_complete<D>(dst + stride * (j - 2), sc, out);
+      } else {
+        // stage A: cell j-1
+        if (j >= jstart + (RECON == kReconMusclHancock ? 2 : 1) && j - 1 >= ulo - 1 &&
+            j - 1 <= uhi + 1) {
+          stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
+        } else {
+          recL = recR_prev;
+          recR = recR_prev;
+        }
+        // stage B: face j-1
+        if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo &&
+            j - 1 <= uhi + 1) {
+          stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
+        } else {
+          F = F_prev;
+        }
+        // stage C: cell j-2
+        if (j - 2 >= o_first) {
+          Complete<D> out;
+          stage_update<D>(eq, out, q2, F_prev, F, A.lambda, j - 2 >= ulo && j - 2 <= uhi);
+          store_complete<D>(dst + stride * (j - 2), sc, out);
+        }
       }
       // stage D: face (j-1 | j) of the stored states
       if (j > jstart && j < nd && dtmask[j - 1]) {
@@ -275,7 +322,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
 // ---------------------------------------------------------------------------
 // Fused sweep along x: warp per row, shuffle pipeline.
 template <int D, int BASE, int RECON, int LIM>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
 fused_sweep_x_kernel(const SweepArgs A) {
   constexpr int DIR = 0;
   constexpr int kWarps = kSweepThreads / 32;

@@ -40,8 +40,10 @@ __global__ void check(unsigned long long seed, int iters, unsigned long long* ou
     double a2 = draw(s, mode);
     Flag f;
     const Rcp rc = FastMath::rcp(b);
+    FastMath::check(rc, f);
     const double q1 = FastMath::div(a, rc, f);
     Flag f2;
+    FastMath::check(rc, f2);
     const double q2 = FastMath::div(a2, rc, f2);
     const double r1 = a / b, r2 = a2 / b;
     if (!f.bad) {
