@@ -37,6 +37,7 @@ def _units():
             units.append(("sweep_inst.cu", f"sweep_D{d}_B{b}.o",
                           [f"-DFVS_INST_D={d}", f"-DFVS_INST_BASE={b}"]))
     units.append(("generic_kernels.cu", "generic_kernels.o", []))
+    units.append(("cutcell.cu", "cutcell.o", []))
     units.append(("context.cu", "context.o", []))
     return units
 

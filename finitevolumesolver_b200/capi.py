@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvs_b200.so")
+# FVS_B200_LIB: tuning builds (tools/build_variant.py) only; the product library is libfvs_b200.so
+LIB_PATH = os.environ.get("FVS_B200_LIB") or os.path.join(_HERE, "libfvs_b200.so")
 
 BASE_HLLEM_LARROUTUROU, BASE_HLLEM, BASE_HLL_EINFELDT, BASE_GODUNOV_EXACT = 0, 1, 2, 3
 RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK = 0, 1
@@ -19,6 +20,10 @@ LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
 BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
 SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
 OK, ERROR, TIME_STEP_TOO_LARGE = 0, -1, 1
+FAB_COVERED, FAB_REGULAR, FAB_SINGLEVALUED = -1, 0, 1
+RIEMANN_HLL_EINFELDT, RIEMANN_EXACT = 0, 1
+(EB_ALPHA, EB_BETA, EB_BCENT, EB_BNORM, EB_US, EB_SL, EB_SR, EB_DS, EB_REFERENCE,
+ EB_BOUNDARY_FLUX, EB_STABILIZED, EB_SHIELDED_LEFT, EB_SHIELDED_RIGHT) = range(13)
 UNIQUE_ID_BYTES = 128
 
 # every symbol include/fvs_b200.h declares
@@ -34,6 +39,9 @@ SYMBOLS = [
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
     "fvs_enable_timing", "fvs_sweep_time_ms",
+    "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
+    "fvs_eb_array_box", "fvs_download_eb_array", "fvs_cut_cell_flags",
+    "fvs_tag_gradient", "fvs_tag_cutcells", "fvs_tag_buffer",
 ]
 
 
@@ -67,6 +75,7 @@ def lib():
         L.fvs_run.restype = C.c_long
         L.fvs_halo_plan.restype = C.c_long
         L.fvs_kernel_launches.restype = C.c_long
+        L.fvs_cut_cell_flags.restype = C.c_long
         L.fvs_stream.restype = C.c_void_p
         _LIB = L
     return _LIB
@@ -196,6 +205,60 @@ class Context:
 
     def set_regrid_frequency(self, f):
         _check(lib().fvs_set_regrid_frequency(self.h, f))
+
+    # ---- cut cells / tagging ------------------------------------------------
+    def enable_eb(self, kbn_riemann=RIEMANN_HLL_EINFELDT):
+        _check(lib().fvs_set_cutcell_riemann_solver(self.h, kbn_riemann))
+
+    def set_eb(self, box, geom, fab_type):
+        alpha = np.ascontiguousarray(geom["alpha"], dtype=np.float64)
+        betas = [np.ascontiguousarray(b, dtype=np.float64) for b in geom["beta"]]
+        bcent = np.ascontiguousarray(geom["bcent"], dtype=np.float64)
+        bnorm = np.ascontiguousarray(geom["bnorm"], dtype=np.float64)
+        ptrs = (C.POINTER(C.c_double) * 3)(*[_dp(b) for b in betas])
+        _check(lib().fvs_level_set_eb(self.h, 0, box, _dp(alpha), ptrs, _dp(bcent), _dp(bnorm),
+                                      fab_type))
+
+    def pre_advance_hierarchy(self):
+        _check(lib().fvs_pre_advance_hierarchy(self.h))
+
+    def eb_array(self, box, kind, direction=0):
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        _check(lib().fvs_eb_array_box(self.h, 0, box, kind, direction, lo, hi, C.byref(nc)))
+        out = np.empty(self._shape(list(lo), list(hi), nc.value))
+        _check(lib().fvs_download_eb_array(self.h, 0, box, kind, direction, _dp(out)))
+        return out
+
+    def is_cut_cell(self, box):
+        out = np.zeros(self.state_shape(box)[1:], dtype=np.uint8)
+        n = lib().fvs_cut_cell_flags(self.h, 0, box, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        if n < 0:
+            raise FvsError(lib().fvs_last_error().decode())
+        return out, n
+
+    def _tag_shape(self, box):
+        lo, hi = self.boxes[box]
+        return (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+
+    def tag_gradient(self, box, conditions, use_alpha=False, tags=None):
+        if tags is None:
+            tags = np.zeros(self._tag_shape(box), dtype=np.int8)
+        comps = (C.c_int * len(conditions))(*[c for c, _ in conditions])
+        tols = (C.c_double * len(conditions))(*[t for _, t in conditions])
+        _check(lib().fvs_tag_gradient(self.h, 0, box, len(conditions), comps, tols,
+                                      1 if use_alpha else 0, tags.ctypes.data_as(C.c_char_p)))
+        return tags
+
+    def tag_cutcells(self, box, tags=None):
+        if tags is None:
+            tags = np.zeros(self._tag_shape(box), dtype=np.int8)
+        _check(lib().fvs_tag_cutcells(self.h, 0, box, tags.ctypes.data_as(C.c_char_p)))
+        return tags
+
+    def tag_buffer(self, tags, rank, width):
+        n = (C.c_int * 3)(*(list(tags.shape[::-1]) + [1, 1])[:3])
+        _check(lib().fvs_tag_buffer(self.h, rank, tags.ctypes.data_as(C.c_char_p), n, width))
+        return tags
 
     def set_cycles(self, cycles, time_point=0.0):
         _check(lib().fvs_set_cycles(self.h, C.c_long(cycles), C.c_double(time_point)))

@@ -104,6 +104,30 @@ using fvs::BoxDesc;
 constexpr int kNumBuffers = 3;
 constexpr int kDtSlots = 64;
 
+// Embedded-boundary data of one box (fvs_level_set_eb); CutCellData of
+// include/fub/CutCellData.hpp:48-75 plus the cut-cell arrays of
+// cutcell::IntegratorContext (src/AMReX/cutcell/IntegratorContext.cpp:470-533).
+struct EbPatch {
+  int fab_type{FVS_FAB_REGULAR};
+  double* alpha{nullptr};
+  double* beta[3]{nullptr, nullptr, nullptr};
+  double* bcent{nullptr};
+  double* bnorm{nullptr};
+  double* us[3]{nullptr, nullptr, nullptr};
+  double* sl[3]{nullptr, nullptr, nullptr};
+  double* sr[3]{nullptr, nullptr, nullptr};
+  double* ds[3]{nullptr, nullptr, nullptr};
+  double* reference{nullptr};
+  double* boundary_flux{nullptr};
+  double* stab[3]{nullptr, nullptr, nullptr};
+  double* shl[3]{nullptr, nullptr, nullptr};
+  double* shr[3]{nullptr, nullptr, nullptr};
+  long long* cut_cells{nullptr};
+  int n_cut{0};
+  unsigned char* complete_mode{nullptr};
+  unsigned char* flags{nullptr}; // IsCutCell map
+};
+
 struct Patch {
   int global_index{0};
   Box valid, sbox;
@@ -113,6 +137,7 @@ struct Patch {
   double* flux[3]{nullptr, nullptr, nullptr};
   Box fbox[3];
   unsigned char* dtmask[2][3]{{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  EbPatch eb;
 };
 
 struct BoundaryCondition {
@@ -170,6 +195,9 @@ struct Level {
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::BcDesc>>> bc_cache;
   std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceArray<fvs::PackDesc>>> pack_cache;
   long long max_copy_cells{0};
+  // embedded boundary
+  bool has_eb{false};
+  std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::EbDesc>>> eb_cache;
 };
 
 } // namespace
@@ -185,6 +213,7 @@ struct fvs_ctx {
   long cycles{0};
   double time_point{0.0};
   int regrid_frequency{1};
+  int cutcell_riemann{FVS_RIEMANN_HLL_EINFELDT};
   // stable-dt accumulators
   unsigned long long* d_slots{nullptr};
   unsigned long long* h_slots{nullptr}; // pinned
@@ -232,6 +261,17 @@ void free_level(Level& L) {
       if (p.flux[d]) cudaFree(p.flux[d]);
       for (int w = 0; w < 2; ++w)
         if (p.dtmask[w][d]) cudaFree(p.dtmask[w][d]);
+    }
+    EbPatch& e = p.eb;
+    void* single[] = {e.alpha, e.bcent, e.bnorm, e.reference, e.boundary_flux, e.cut_cells,
+                      e.complete_mode, e.flags};
+    for (void* q : single)
+      if (q) cudaFree(q);
+    for (int d = 0; d < 3; ++d) {
+      void* per_dir[] = {e.beta[d], e.us[d], e.sl[d], e.sr[d], e.ds[d], e.stab[d], e.shl[d],
+                         e.shr[d]};
+      for (void* q : per_dir)
+        if (q) cudaFree(q);
     }
   }
   for (PeerExchange& pe : L.peers) {
@@ -301,6 +341,9 @@ const BoxDesc* box_descs(fvs_ctx* ctx, Level& L, int dir, int src, int dst, bool
     d.flo = flo - p.sbox.lo[dir];
     d.fhi = fhi - p.sbox.lo[dir];
     d.dtmask = p.dtmask[w - 1][dir];
+    d.alpha = p.eb.alpha;
+    d.beta = p.eb.beta[dir];
+    d.fab_type = p.eb.fab_type;
     host.push_back(d);
   }
   auto arr = std::make_unique<DeviceArray<BoxDesc>>();
@@ -651,6 +694,255 @@ std::vector<SweepPlanEntry> split_plan(int rank, int kind, double dt) {
   return out;
 }
 
+
+// ---- embedded boundary -------------------------------------------------------
+Box beta_box(const Patch& p, int d) {
+  Box b = p.sbox;
+  b.hi[d] += 1;
+  return b;
+}
+
+template <typename T> T* device_alloc_zero(fvs_ctx* ctx, size_t count) {
+  T* ptr = nullptr;
+  if (count == 0) return ptr;
+  FVS_CUDA(cudaMalloc(&ptr, count * sizeof(T)));
+  FVS_CUDA(cudaMemsetAsync(ptr, 0, count * sizeof(T), ctx->stream));
+  return ptr;
+}
+
+// allocates the cut-cell arrays of every owned box; geometry defaults to "all
+// regular" (alpha = beta = 1)
+void enable_eb(fvs_ctx* ctx, Level& L) {
+  if (L.has_eb) return;
+  const int rank = ctx->cfg.rank;
+  if (rank < 2) throw Error("cut cells need rank 2 or 3");
+  if (L.scratch_gcw != L.flux_gcw + ctx->stencil_width()) {
+    throw Error("EB levels need scratch_gcw == flux_gcw + stencil width");
+  }
+  for (int d = 0; d < rank; ++d) ensure_fluxes(ctx, L, d);
+  for (Patch& p : L.patches) {
+    EbPatch& e = p.eb;
+    const size_t cells = (size_t)p.cells;
+    e.alpha = device_alloc_zero<double>(ctx, cells);
+    e.bcent = device_alloc_zero<double>(ctx, cells * rank);
+    e.bnorm = device_alloc_zero<double>(ctx, cells * rank);
+    e.reference = device_alloc_zero<double>(ctx, cells * ctx->ncomp());
+    e.boundary_flux = device_alloc_zero<double>(ctx, cells * ctx->ncons());
+    e.complete_mode = device_alloc_zero<unsigned char>(ctx, cells);
+    e.flags = device_alloc_zero<unsigned char>(ctx, cells);
+    std::vector<double> ones(cells, 1.0);
+    FVS_CUDA(cudaMemcpyAsync(e.alpha, ones.data(), cells * sizeof(double), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    std::vector<unsigned char> mode(cells, 1);
+    FVS_CUDA(cudaMemcpyAsync(e.complete_mode, mode.data(), cells, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    for (int d = 0; d < rank; ++d) {
+      const size_t faces = (size_t)beta_box(p, d).size();
+      e.beta[d] = device_alloc_zero<double>(ctx, faces);
+      std::vector<double> fones(faces, 1.0);
+      FVS_CUDA(cudaMemcpyAsync(e.beta[d], fones.data(), faces * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+      e.us[d] = device_alloc_zero<double>(ctx, 2 * faces);
+      e.sl[d] = device_alloc_zero<double>(ctx, 2 * faces);
+      e.sr[d] = device_alloc_zero<double>(ctx, 2 * faces);
+      e.ds[d] = device_alloc_zero<double>(ctx, 2 * faces);
+      const size_t fl = (size_t)p.fbox[d].size() * ctx->ncons();
+      e.stab[d] = device_alloc_zero<double>(ctx, fl);
+      e.shl[d] = device_alloc_zero<double>(ctx, fl);
+      e.shr[d] = device_alloc_zero<double>(ctx, fl);
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  L.has_eb = true;
+  L.box_cache.clear();
+  L.eb_cache.clear();
+}
+
+// host twin of fub::IsCutCell (src/CutCellData.cpp:225-256), array-relative
+bool host_is_cut_cell(int rank, const Patch& p, const double* alpha, const double* const beta[3],
+                      int i, int j, int k) {
+  const double a = alpha[i + (long long)p.n[0] * (j + (long long)p.n[1] * k)];
+  if (a <= 0.0) return false;
+  if (a < 1.0) return true;
+  for (int d = 0; d < rank; ++d) {
+    const long long bn0 = p.n[0] + (d == 0 ? 1 : 0);
+    const long long bn1 = p.n[1] + (d == 1 ? 1 : 0);
+    const long long left = i + bn0 * (j + bn1 * k);
+    const long long step = d == 0 ? 1 : (d == 1 ? bn0 : bn0 * bn1);
+    if (beta[d][left] < 1.0 || beta[d][left + step] < 1.0) return true;
+  }
+  return false;
+}
+
+// cutcell::Reconstruction (include/fub/AMReX/cutcell/Reconstruction.hpp:169-193)
+// takes the EBCellFlagFab type of every GROWN TILE BOX (tiles 1024000 x 16 x 32,
+// ForEachFab.hpp:48-57): all cells regular -> plain CompleteFromCons, all
+// covered -> nothing, otherwise masked by alpha > 0.
+std::vector<unsigned char> complete_modes(int rank, const Level& L, const Patch& p,
+                                          const double* alpha, const double* const beta[3]) {
+  std::vector<unsigned char> mode((size_t)p.cells, 1);
+  const int tile[3] = {1024000, 16, 32};
+  std::vector<std::array<int, 2>> ranges[3];
+  for (int d = 0; d < 3; ++d) {
+    if (d < rank) {
+      ranges[d] = fvs::tile_ranges(p.valid.lo[d], p.valid.hi[d], tile[d]);
+      for (auto& r : ranges[d]) {
+        if (r[0] == p.valid.lo[d]) r[0] -= L.scratch_gcw;
+        if (r[1] == p.valid.hi[d]) r[1] += L.scratch_gcw;
+      }
+    } else {
+      ranges[d].push_back({p.valid.lo[d], p.valid.hi[d]});
+    }
+  }
+  for (const auto& rz : ranges[2])
+    for (const auto& ry : ranges[1])
+      for (const auto& rx : ranges[0]) {
+        long long n = 0, ncov = 0, nreg = 0;
+        for (int k = rz[0]; k <= rz[1]; ++k)
+          for (int j = ry[0]; j <= ry[1]; ++j)
+            for (int i = rx[0]; i <= rx[1]; ++i) {
+              const int ai = i - p.sbox.lo[0], aj = j - p.sbox.lo[1], ak = k - p.sbox.lo[2];
+              ++n;
+              if (alpha[ai + (long long)p.n[0] * (aj + (long long)p.n[1] * ak)] <= 0.0) {
+                ++ncov;
+              } else if (!host_is_cut_cell(rank, p, alpha, beta, ai, aj, ak)) {
+                ++nreg;
+              }
+            }
+        const unsigned char m = nreg == n ? 1 : (ncov == n ? 0 : 2);
+        for (int k = rz[0]; k <= rz[1]; ++k)
+          for (int j = ry[0]; j <= ry[1]; ++j)
+            for (int i = rx[0]; i <= rx[1]; ++i) {
+              const int ai = i - p.sbox.lo[0], aj = j - p.sbox.lo[1], ak = k - p.sbox.lo[2];
+              mode[(size_t)(ai + (long long)p.n[0] * (aj + (long long)p.n[1] * ak))] = m;
+            }
+      }
+  return mode;
+}
+
+const fvs::EbDesc* eb_descs(fvs_ctx* ctx, Level& L, int dir, int buf) {
+  auto key = std::make_tuple(dir, buf);
+  auto it = L.eb_cache.find(key);
+  if (it != L.eb_cache.end()) return it->second->ptr;
+  const int w = ctx->stencil_width();
+  std::vector<fvs::EbDesc> host;
+  for (Patch& p : L.patches) {
+    fvs::EbDesc d{};
+    const EbPatch& e = p.eb;
+    d.fab_type = e.fab_type;
+    const Box bb = beta_box(p, dir);
+    for (int k = 0; k < 3; ++k) {
+      d.n[k] = p.n[k];
+      d.fn[k] = p.fbox[dir].len(k);
+      d.foff[k] = p.fbox[dir].lo[k] - p.sbox.lo[k];
+      d.bn[k] = bb.len(k);
+    }
+    d.sc = p.cells;
+    d.fsc = p.fbox[dir].size();
+    d.bsc = bb.size();
+    int ulo, uhi, flo, fhi;
+    fvs::update_cell_range(p.valid, dir, L.flux_gcw, ulo, uhi);
+    fvs::flux_face_range(p.valid, dir, L.scratch_gcw, L.flux_gcw, w, flo, fhi);
+    d.ulo = ulo - p.sbox.lo[dir];
+    d.uhi = uhi - p.sbox.lo[dir];
+    d.flo = flo - p.sbox.lo[dir];
+    d.fhi = fhi - p.sbox.lo[dir];
+    d.state = p.buf[buf];
+    d.alpha = e.alpha;
+    d.beta = e.beta[dir];
+    d.bcent = e.bcent;
+    d.bnorm = e.bnorm;
+    d.us = e.us[dir];
+    d.sl = e.sl[dir];
+    d.sr = e.sr[dir];
+    d.reference = e.reference;
+    d.boundary_flux = e.boundary_flux;
+    d.flux = p.flux[dir];
+    d.stab = e.stab[dir];
+    d.shl = e.shl[dir];
+    d.shr = e.shr[dir];
+    d.cut_cells = e.cut_cells;
+    d.n_cut = e.n_cut;
+    d.complete_mode = e.complete_mode;
+    host.push_back(d);
+  }
+  auto arr = std::make_unique<DeviceArray<fvs::EbDesc>>();
+  arr->upload(host);
+  const fvs::EbDesc* ptr = arr->ptr;
+  L.eb_cache[key] = std::move(arr);
+  return ptr;
+}
+
+fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt) {
+  fvs::EbArgs A{};
+  A.eq = ctx->eq;
+  A.boxes = eb_descs(ctx, L, dir, L.cur);
+  A.nboxes = (int)L.patches.size();
+  A.rank = ctx->cfg.rank;
+  A.dir = dir;
+  A.riemann = ctx->cutcell_riemann;
+  A.lambda = dt / L.dx[dir];
+  A.max_cells = 0;
+  A.max_cut = 0;
+  for (const Patch& p : L.patches) {
+    // one more plane along dir for the face-centred kernels
+    A.max_cells = std::max(A.max_cells, p.cells + p.cells / p.n[dir]);
+    A.max_cut = std::max(A.max_cut, p.eb.n_cut);
+  }
+  A.fail_flag = ctx->d_fail;
+  return A;
+}
+
+// cutcell::FluxMethod::ComputeStableDt into accumulator `slot`
+void cc_stable_dt(fvs_ctx* ctx, Level& L, int dir, int slot) {
+  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, 0.0, boxes, slot);
+  if (L.patches.empty()) return;
+  const int rc = fvs::launch_cc_stable_dt(ctx->method, dir, A, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+// cutcell::FluxMethod::ComputeNumericFluxes: boundary fluxes, (masked) regular
+// fluxes, stabilised fluxes
+void cc_numeric_fluxes(fvs_ctx* ctx, Level& L, double dt, int dir) {
+  if (L.patches.empty()) return;
+  for (Patch& p : L.patches) { // boundary_fluxes.setVal(0.0), FluxMethod.hpp:173
+    FVS_CUDA(cudaMemsetAsync(p.eb.boundary_flux, 0,
+                             (size_t)p.cells * ctx->ncons() * sizeof(double), ctx->stream));
+  }
+  const fvs::EbArgs E = eb_args(ctx, L, dir, dt);
+  int rc = fvs::launch_cc_boundary_fluxes(E, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+  rc = fvs::launch_cc_numeric_fluxes(ctx->method, dir, A, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+  rc = fvs::launch_cc_stabilised_fluxes(E, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+void cc_update(fvs_ctx* ctx, Level& L, double dt, int dir) {
+  if (L.patches.empty()) return;
+  const int rc = fvs::launch_cc_update(eb_args(ctx, L, dir, dt), ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+void cc_complete(fvs_ctx* ctx, Level& L) {
+  if (L.patches.empty()) return;
+  const int rc = fvs::launch_cc_complete(eb_args(ctx, L, 0, 0.0), ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+void cc_pre_advance(fvs_ctx* ctx, Level& L) {
+  if (!L.has_eb || L.patches.empty()) return;
+  const int rc = fvs::launch_cc_reference_states(eb_args(ctx, L, 0, 0.0), ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+
 } // namespace
 
 // =============================================================================
@@ -971,6 +1263,14 @@ int fvs_compute_stable_dt(fvs_ctx* ctx, int level, int dir, double* dt_out) {
     ctx->use_device();
     Level& L = ctx->level(level);
     check_dir(ctx, dir);
+    if (L.has_eb) {
+      const int slot = take_slot(ctx);
+      cc_stable_dt(ctx, L, dir, slot);
+      double sig;
+      fetch_slots(ctx, slot, 1, &sig);
+      *dt_out = dt_from_signal(L.dx[dir], sig);
+      return (int)FVS_OK;
+    }
     const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, false);
     const int slot = take_slot(ctx);
     fvs::SweepArgs A = sweep_args(ctx, L, dir, 0.0, boxes, slot);
@@ -992,6 +1292,10 @@ int fvs_compute_numeric_fluxes(fvs_ctx* ctx, int level, double dt, int dir) {
     ctx->use_device();
     Level& L = ctx->level(level);
     check_dir(ctx, dir);
+    if (L.has_eb) {
+      cc_numeric_fluxes(ctx, L, dt, dir);
+      return (int)FVS_OK;
+    }
     ensure_fluxes(ctx, L, dir);
     const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
     fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
@@ -1010,6 +1314,10 @@ int fvs_update_conservatively(fvs_ctx* ctx, int level, double dt, int dir) {
     ctx->use_device();
     Level& L = ctx->level(level);
     check_dir(ctx, dir);
+    if (L.has_eb) {
+      cc_update(ctx, L, dt, dir);
+      return (int)FVS_OK;
+    }
     ensure_fluxes(ctx, L, dir);
     const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
     fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
@@ -1027,6 +1335,10 @@ int fvs_complete_from_cons(fvs_ctx* ctx, int level) {
     if (!ctx) throw Error("null context");
     ctx->use_device();
     Level& L = ctx->level(level);
+    if (L.has_eb) {
+      cc_complete(ctx, L);
+      return (int)FVS_OK;
+    }
     const BoxDesc* boxes = box_descs(ctx, L, 0, L.cur, L.cur, false);
     fvs::SweepArgs A = sweep_args(ctx, L, 0, 0.0, boxes, 0);
     if (!L.patches.empty()) {
@@ -1044,6 +1356,21 @@ int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out)
     ctx->use_device();
     Level& L = ctx->level(level);
     check_dir(ctx, dir);
+    if (L.has_eb) {
+      // cut-cell levels: the unfused sequence, in place; the dt check comes
+      // first so that a rejected sweep leaves the state untouched
+      const int slot = take_slot(ctx);
+      cc_stable_dt(ctx, L, dir, slot);
+      double sig;
+      fetch_slots(ctx, slot, 1, &sig);
+      const double level_dt = dt_from_signal(L.dx[dir], sig);
+      if (level_dt_out) *level_dt_out = level_dt;
+      if (level_dt < dt) return (int)FVS_TIME_STEP_TOO_LARGE;
+      cc_numeric_fluxes(ctx, L, dt, dir);
+      cc_update(ctx, L, dt, dir);
+      cc_complete(ctx, L);
+      return (int)FVS_OK;
+    }
     int dst;
     const int slot = launch_sweep(ctx, L, dt, dir, &dst);
     double sig;
@@ -1082,6 +1409,16 @@ int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
     ctx->use_device();
     Level& L = ctx->level(level);
     const int rank = ctx->cfg.rank;
+    if (L.has_eb) {
+      const int slot = take_slot(ctx, 3);
+      for (int d = 0; d < rank; ++d) cc_stable_dt(ctx, L, d, slot + d);
+      double sig[3];
+      fetch_slots(ctx, slot, 3, sig);
+      double min_dt = std::numeric_limits<double>::max();
+      for (int d = 0; d < rank; ++d) min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
+      *dt_out = min_dt;
+      return (int)FVS_OK;
+    }
     fvs::DtAllArgs A{};
     A.eq = ctx->eq;
     for (int d = 0; d < 3; ++d) {
@@ -1128,10 +1465,31 @@ int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind, double* failu
     std::vector<int> slots;
     ctx->next_slot = 0;
     try {
+      if (L.has_eb) {
+        // cut-cell levels work in place on a copy of the entry state
+        const int work = free_buffer(L, entry);
+        ensure_buffer(ctx, L, work);
+        for (Patch& p : L.patches) {
+          FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[entry],
+                                   (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        L.cur = work;
+        cc_pre_advance(ctx, L); // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
+      }
       for (const SweepPlanEntry& e : plan) {
         const int dir = dirs[e.slot];
         if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir); // :228-234
         counts[e.slot] += 1;
+        if (L.has_eb) {
+          const int slot = take_slot(ctx);
+          cc_stable_dt(ctx, L, dir, slot);
+          cc_numeric_fluxes(ctx, L, e.dt, dir);
+          cc_update(ctx, L, e.dt, dir);
+          cc_complete(ctx, L);
+          slots.push_back(slot);
+          continue;
+        }
         int dst;
         slots.push_back(launch_sweep(ctx, L, e.dt, dir, &dst));
         L.cur = dst;
@@ -1326,6 +1684,253 @@ int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3], const int
     for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
     const std::vector<int> owner = fvs::distribute_boxes(boxes, nranks);
     for (int b = 0; b < nboxes; ++b) owner_out[b] = owner[b];
+    return (int)FVS_OK;
+  });
+}
+
+// ---- embedded boundary ---------------------------------------------------------
+int fvs_level_set_eb(fvs_ctx* ctx, int level, int box, const double* alpha,
+                     const double* const beta[3], const double* bcent, const double* bnorm,
+                     int fab_type) {
+  return guarded([&] {
+    if (!ctx || !alpha || !beta || !bcent || !bnorm) throw Error("null argument");
+    if (fab_type < FVS_FAB_COVERED || fab_type > FVS_FAB_SINGLEVALUED) throw Error("unknown fab type");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    const int rank = ctx->cfg.rank;
+    enable_eb(ctx, L);
+    Patch& p = ctx->patch(L, box);
+    EbPatch& e = p.eb;
+    e.fab_type = fab_type;
+    const size_t cells = (size_t)p.cells;
+    FVS_CUDA(cudaMemcpyAsync(e.alpha, alpha, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FVS_CUDA(cudaMemcpyAsync(e.bcent, bcent, cells * rank * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FVS_CUDA(cudaMemcpyAsync(e.bnorm, bnorm, cells * rank * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    for (int d = 0; d < rank; ++d) {
+      if (!beta[d]) throw Error("null face-fraction array");
+      const Box bb = beta_box(p, d);
+      FVS_CUDA(cudaMemcpyAsync(e.beta[d], beta[d], (size_t)bb.size() * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+      const int bn[3] = {bb.len(0), bb.len(1), bb.len(2)};
+      FVS_CUDA(cudaMemsetAsync(e.us[d], 0, 2 * (size_t)bb.size() * sizeof(double), ctx->stream));
+      FVS_CUDA(cudaMemsetAsync(e.sl[d], 0, 2 * (size_t)bb.size() * sizeof(double), ctx->stream));
+      FVS_CUDA(cudaMemsetAsync(e.sr[d], 0, 2 * (size_t)bb.size() * sizeof(double), ctx->stream));
+      FVS_CUDA(cudaMemsetAsync(e.ds[d], 0, 2 * (size_t)bb.size() * sizeof(double), ctx->stream));
+      ctx->launches += fvs::launch_fill_cutcell_data(e.beta[d], e.us[d], e.sl[d], e.sr[d], e.ds[d],
+                                                     bn, d, ctx->stream);
+    }
+    // IsCutCell map on the device, compacted into the cut-cell list
+    ctx->launches += fvs::launch_cut_cell_flags(e.alpha, e.beta, p.n, rank, e.flags, ctx->stream);
+    std::vector<unsigned char> flags(cells);
+    FVS_CUDA(cudaMemcpyAsync(flags.data(), e.flags, cells, cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    FVS_CUDA(cudaGetLastError());
+    std::vector<long long> list;
+    for (size_t c = 0; c < cells; ++c)
+      if (flags[c]) list.push_back((long long)c);
+    if (e.cut_cells) cudaFree(e.cut_cells);
+    e.cut_cells = nullptr;
+    e.n_cut = (int)list.size();
+    if (!list.empty()) {
+      FVS_CUDA(cudaMalloc(&e.cut_cells, list.size() * sizeof(long long)));
+      FVS_CUDA(cudaMemcpy(e.cut_cells, list.data(), list.size() * sizeof(long long),
+                          cudaMemcpyHostToDevice));
+    }
+    const std::vector<unsigned char> mode = complete_modes(rank, L, p, alpha, beta);
+    FVS_CUDA(cudaMemcpy(e.complete_mode, mode.data(), cells, cudaMemcpyHostToDevice));
+    L.box_cache.clear();
+    L.eb_cache.clear();
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_set_cutcell_riemann_solver(fvs_ctx* ctx, int kind) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (kind != FVS_RIEMANN_HLL_EINFELDT && kind != FVS_RIEMANN_EXACT) {
+      throw Error("unknown Riemann solver");
+    }
+    ctx->cutcell_riemann = kind;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_pre_advance_hierarchy(fvs_ctx* ctx) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    for (Level& L : ctx->levels) {
+      if (L.defined) cc_pre_advance(ctx, L);
+    }
+    FVS_CUDA(cudaGetLastError());
+    return (int)FVS_OK;
+  });
+}
+
+namespace {
+// device pointer, box and component count of an EB array
+double* eb_array(fvs_ctx* ctx, Level& L, Patch& p, int kind, int dir, Box* box, int* ncomp) {
+  if (!L.has_eb) throw Error("level has no embedded boundary (fvs_level_set_eb)");
+  const int rank = ctx->cfg.rank;
+  const bool per_dir = kind == FVS_EB_BETA || (kind >= FVS_EB_UNSHIELDED && kind <= FVS_EB_DOUBLY_SHIELDED) ||
+                       kind >= FVS_EB_STABILIZED_FLUXES;
+  if (per_dir) check_dir(ctx, dir);
+  EbPatch& e = p.eb;
+  switch (kind) {
+  case FVS_EB_ALPHA: *box = p.sbox; *ncomp = 1; return e.alpha;
+  case FVS_EB_BETA: *box = beta_box(p, dir); *ncomp = 1; return e.beta[dir];
+  case FVS_EB_BCENT: *box = p.sbox; *ncomp = rank; return e.bcent;
+  case FVS_EB_BNORM: *box = p.sbox; *ncomp = rank; return e.bnorm;
+  case FVS_EB_UNSHIELDED: *box = beta_box(p, dir); *ncomp = 2; return e.us[dir];
+  case FVS_EB_SHIELDED_LEFT: *box = beta_box(p, dir); *ncomp = 2; return e.sl[dir];
+  case FVS_EB_SHIELDED_RIGHT: *box = beta_box(p, dir); *ncomp = 2; return e.sr[dir];
+  case FVS_EB_DOUBLY_SHIELDED: *box = beta_box(p, dir); *ncomp = 2; return e.ds[dir];
+  case FVS_EB_REFERENCE_STATES: *box = p.sbox; *ncomp = ctx->ncomp(); return e.reference;
+  case FVS_EB_BOUNDARY_FLUXES: *box = p.sbox; *ncomp = ctx->ncons(); return e.boundary_flux;
+  case FVS_EB_STABILIZED_FLUXES: *box = p.fbox[dir]; *ncomp = ctx->ncons(); return e.stab[dir];
+  case FVS_EB_SHIELDED_LEFT_FLUXES: *box = p.fbox[dir]; *ncomp = ctx->ncons(); return e.shl[dir];
+  case FVS_EB_SHIELDED_RIGHT_FLUXES: *box = p.fbox[dir]; *ncomp = ctx->ncons(); return e.shr[dir];
+  }
+  throw Error("unknown EB array kind");
+}
+} // namespace
+
+int fvs_eb_array_box(const fvs_ctx* cctx, int level, int box, int kind, int dir, int lo[3],
+                     int hi[3], int* ncomp) {
+  return guarded([&] {
+    fvs_ctx* ctx = const_cast<fvs_ctx*>(cctx);
+    if (!ctx || !lo || !hi) throw Error("null argument");
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    Box b;
+    int nc = 0;
+    eb_array(ctx, L, p, kind, dir, &b, &nc);
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = b.lo[d];
+      hi[d] = b.hi[d];
+    }
+    if (ncomp) *ncomp = nc;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_download_eb_array(fvs_ctx* ctx, int level, int box, int kind, int dir, double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    Box b;
+    int nc = 0;
+    const double* src = eb_array(ctx, L, p, kind, dir, &b, &nc);
+    FVS_CUDA(cudaMemcpyAsync(host_fab, src, (size_t)b.size() * nc * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+long fvs_cut_cell_flags(fvs_ctx* ctx, int level, int box, unsigned char* flags) {
+  long count = 0;
+  const int rc = guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    if (!L.has_eb) throw Error("level has no embedded boundary (fvs_level_set_eb)");
+    Patch& p = ctx->patch(L, box);
+    if (flags) {
+      FVS_CUDA(cudaMemcpyAsync(flags, p.eb.flags, (size_t)p.cells, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    count = p.eb.n_cut;
+    return (int)FVS_OK;
+  });
+  return rc == FVS_OK ? count : (long)FVS_ERROR;
+}
+
+// ---- tagging ---------------------------------------------------------------------
+namespace {
+struct DeviceTags {
+  char* ptr{nullptr};
+  size_t bytes;
+  explicit DeviceTags(size_t n) : bytes(n) { FVS_CUDA(cudaMalloc(&ptr, std::max<size_t>(n, 1))); }
+  ~DeviceTags() {
+    if (ptr) cudaFree(ptr);
+  }
+};
+} // namespace
+
+int fvs_tag_gradient(fvs_ctx* ctx, int level, int box, int ncond, const int* comps,
+                     const double* tols, int use_alpha, char* tags) {
+  return guarded([&] {
+    if (!ctx || !tags || (ncond > 0 && (!comps || !tols))) throw Error("null argument");
+    if (ncond < 0 || ncond > 8) throw Error("at most 8 tagging conditions");
+    for (int c = 0; c < ncond; ++c)
+      if (comps[c] < 0 || comps[c] >= ctx->ncomp()) throw Error("component out of range");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    if (L.scratch_gcw < 1) throw Error("gradient tagging needs one ghost cell");
+    if (use_alpha && !L.has_eb) throw Error("level has no embedded boundary (fvs_level_set_eb)");
+    Patch& p = ctx->patch(L, box);
+    int lo[3], len[3];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = p.valid.lo[d] - p.sbox.lo[d];
+      len[d] = p.valid.len(d);
+    }
+    const size_t n = (size_t)p.valid.size();
+    DeviceTags dt(n);
+    FVS_CUDA(cudaMemcpyAsync(dt.ptr, tags, n, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = fvs::launch_tag_gradient(p.buf[L.cur], p.cells, p.n, use_alpha ? p.eb.alpha : nullptr,
+                                            ctx->cfg.rank, lo, len, ncond, comps, tols, dt.ptr,
+                                            ctx->stream);
+    check_launch(rc);
+    ctx->launches += rc;
+    FVS_CUDA(cudaMemcpyAsync(tags, dt.ptr, n, cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_tag_cutcells(fvs_ctx* ctx, int level, int box, char* tags) {
+  return guarded([&] {
+    if (!ctx || !tags) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    if (!L.has_eb) throw Error("level has no embedded boundary (fvs_level_set_eb)");
+    Patch& p = ctx->patch(L, box);
+    int lo[3], len[3];
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = p.valid.lo[d] - p.sbox.lo[d];
+      len[d] = p.valid.len(d);
+    }
+    const size_t n = (size_t)p.valid.size();
+    DeviceTags dt(n);
+    FVS_CUDA(cudaMemcpyAsync(dt.ptr, tags, n, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = fvs::launch_tag_cutcells(p.eb.alpha, p.n, lo, len, dt.ptr, ctx->stream);
+    check_launch(rc);
+    ctx->launches += rc;
+    FVS_CUDA(cudaMemcpyAsync(tags, dt.ptr, n, cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width) {
+  return guarded([&] {
+    if (!ctx || !tags || !n) throw Error("null argument");
+    if (rank < 1 || rank > 3 || width < 0) throw Error("invalid argument");
+    ctx->use_device();
+    int nn[3] = {n[0], rank >= 2 ? n[1] : 1, rank >= 3 ? n[2] : 1};
+    const size_t total = (size_t)nn[0] * nn[1] * nn[2];
+    if (total == 0) return (int)FVS_OK;
+    DeviceTags dt(total), scratch(total);
+    FVS_CUDA(cudaMemcpyAsync(dt.ptr, tags, total, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = fvs::launch_tag_buffer(dt.ptr, scratch.ptr, rank, nn, width, ctx->stream);
+    check_launch(rc);
+    ctx->launches += rc;
+    FVS_CUDA(cudaMemcpyAsync(tags, dt.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
     return (int)FVS_OK;
   });
 }

@@ -15,6 +15,17 @@ namespace fvs {
 FVS_DECL_D(1)
 FVS_DECL_D(2)
 FVS_DECL_D(3)
+#define FVS_DECL_CC(D, B)                                                                     \
+  int launch_cc_numeric_fluxes_D##D##_##B(const MethodKey&, int, const SweepArgs&,           \
+                                          cudaStream_t);                                     \
+  int launch_cc_stable_dt_D##D##_##B(const MethodKey&, int, const SweepArgs&, cudaStream_t);
+#define FVS_DECL_CC_D(D) FVS_DECL_CC(D, 0) FVS_DECL_CC(D, 1) FVS_DECL_CC(D, 2) FVS_DECL_CC(D, 3)
+FVS_DECL_CC_D(2)
+FVS_DECL_CC_D(3)
+#define FVS_ALL_CC(fn, ...)                                                                   \
+  FVS_CASE(2, 0, fn, __VA_ARGS__) FVS_CASE(2, 1, fn, __VA_ARGS__) FVS_CASE(2, 2, fn, __VA_ARGS__) \
+  FVS_CASE(2, 3, fn, __VA_ARGS__) FVS_CASE(3, 0, fn, __VA_ARGS__) FVS_CASE(3, 1, fn, __VA_ARGS__) \
+  FVS_CASE(3, 2, fn, __VA_ARGS__) FVS_CASE(3, 3, fn, __VA_ARGS__)
 
 #define FVS_CASE(D, B, fn, ...)                                                               \
   if (k.rank == D && k.base == B) return fn##_D##D##_##B(__VA_ARGS__);
@@ -34,6 +45,14 @@ int launch_numeric_fluxes(const MethodKey& k, int dir, const SweepArgs& A, cudaS
 }
 int launch_stable_dt(const MethodKey& k, int dir, const SweepArgs& A, cudaStream_t s) {
   FVS_ALL(launch_stable_dt, k, dir, A, s)
+  return -1;
+}
+int launch_cc_numeric_fluxes(const MethodKey& k, int dir, const SweepArgs& A, cudaStream_t s) {
+  FVS_ALL_CC(launch_cc_numeric_fluxes, k, dir, A, s)
+  return -1;
+}
+int launch_cc_stable_dt(const MethodKey& k, int dir, const SweepArgs& A, cudaStream_t s) {
+  FVS_ALL_CC(launch_cc_stable_dt, k, dir, A, s)
   return -1;
 }
 int launch_stable_dt_all(const MethodKey& k, const DtAllArgs& A, cudaStream_t s) {

@@ -23,6 +23,10 @@ struct BoxDesc {
   int ulo, uhi;      // cells updated along the sweep direction (inclusive)
   int flo, fhi;      // faces computed along the sweep direction (face f lies between cells f-1 and f)
   const unsigned char* dtmask; // n[dir] bytes: dtmask[i] != 0 iff face (i | i+1) enters the stable dt
+  // embedded boundary (levels with fvs_level_set_eb only; null / 0 otherwise)
+  const double* alpha; // volume fractions, extents n[]
+  const double* beta;  // face fractions of the sweep direction, extents n[] + 1 along dir
+  int fab_type;        // -1 covered, 0 regular, 1 single valued
 };
 
 struct SweepArgs {
@@ -62,6 +66,70 @@ struct DtAllArgs {
   int* fail_flag;
 };
 int launch_stable_dt_all(const MethodKey&, const DtAllArgs&, cudaStream_t);
+
+// ---- cut cells (embedded boundary) ------------------------------------------
+// masked regular fluxes (KbnCutCellMethod::ComputeRegularFluxes) and the
+// cut-cell adapter's stable dt, per method instantiation unit
+int launch_cc_numeric_fluxes(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+int launch_cc_stable_dt(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+
+// One box of an EB level as the method-independent cut-cell kernels see it.
+struct EbDesc {
+  int fab_type;
+  int n[3];      // state array extents
+  long long sc;  // state component stride
+  int fn[3], foff[3];
+  long long fsc; // flux arrays of the sweep direction
+  int bn[3];
+  long long bsc; // face-fraction arrays of the sweep direction (extents n + e_dir)
+  int ulo, uhi, flo, fhi;
+  double* state;
+  const double* alpha;
+  const double* beta;
+  const double* bcent; // D components, stride sc
+  const double* bnorm; // D components, stride sc
+  const double* us;    // 2 components (absolute, relative), stride bsc
+  const double* sl;
+  const double* sr;
+  double* reference;     // Complete components, stride sc
+  double* boundary_flux; // Conservative components, stride sc
+  double* flux;          // regular ("unshielded") fluxes, stride fsc
+  double* stab;
+  double* shl;
+  double* shr;
+  const long long* cut_cells; // compacted list: state-array offsets of the cut cells
+  int n_cut;
+  const unsigned char* complete_mode; // per cell: 0 skip, 1 plain, 2 masked by alpha
+};
+struct EbArgs {
+  EqConst eq;
+  const EbDesc* boxes;
+  int nboxes;
+  int rank, dir;
+  int riemann; // 0 HLL + Einfeldt, 1 exact
+  double lambda;
+  long long max_cells; // grid sizing
+  int max_cut;
+  int* fail_flag;
+};
+int launch_cc_reference_states(const EbArgs&, cudaStream_t);
+int launch_cc_boundary_fluxes(const EbArgs&, cudaStream_t);
+int launch_cc_stabilised_fluxes(const EbArgs&, cudaStream_t);
+int launch_cc_update(const EbArgs&, cudaStream_t);
+int launch_cc_complete(const EbArgs&, cudaStream_t);
+// FillCutCellData for one direction of one box
+int launch_fill_cutcell_data(const double* beta, double* us, double* sl, double* sr, double* ds,
+                             const int bn[3], int dir, cudaStream_t);
+int launch_cut_cell_flags(const double* alpha, const double* const beta[3], const int n[3],
+                          int rank, unsigned char* flags, cudaStream_t);
+// tagging
+int launch_tag_gradient(const double* state, long long sc, const int n[3], const double* alpha,
+                        int rank, const int lo[3], const int len[3], int ncond, const int* comps,
+                        const double* tols, char* tags, cudaStream_t);
+int launch_tag_cutcells(const double* alpha, const int n[3], const int lo[3], const int len[3],
+                        char* tags, cudaStream_t);
+int launch_tag_buffer(char* tags, char* scratch, int rank, const int n[3], int width,
+                      cudaStream_t);
 
 // ---- ghost cells -----------------------------------------------------------
 struct CopyDesc {

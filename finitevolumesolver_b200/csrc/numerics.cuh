@@ -130,32 +130,56 @@ template <int D> struct Edge {
 // identical, so both are produced here in one go:
 //   recL: predicted state at the cell's lower face  (q_L + lambda/2 (f(q_L) - f(q_R)))
 //   recR: predicted state at the cell's upper face  (q_R + lambda/2 (f(q_L) - f(q_R)))
-template <class M, int D, int DIR, int LIM, typename S0, typename S1, typename S2>
+// Masked CompleteFromCons of the cut-cell path (PerfectGas.cpp:126-144 on a
+// valid face): a state whose density is not positive becomes all zeros, and
+// the masked Flux (PerfectGas.cpp:79-93) then divides by 1 instead.
+template <class M, int D, bool MASKED>
+FVS_DEV void complete_edge(const EqM& eq, Complete<D>& q, Rcp& rc, Flag& fl) {
+  if constexpr (MASKED) {
+    if (!(q.rho > 0.0)) {
+      q.rho = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) q.mom[d] = 0.0;
+      q.E = 0.0;
+      q.p = 0.0;
+      q.a = 0.0;
+      rc = M::rcp(1.0);
+      return;
+    }
+  }
+  M::check(rc, fl);
+  complete_from_cons<M, D>(eq, q, rc, fl);
+}
+
+template <class M, int D, int DIR, int LIM, bool MASKED = false, typename S0, typename S1,
+          typename S2>
 FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp,
-                           double lambda_half, Edge<D>& recL, Edge<D>& recR, Flag& fl) {
+                           double lambda_half, Edge<D>& recL, Edge<D>& recR, Flag& fl,
+                           bool slope_ok = true) {
   Complete<D> qL, qR;
   {
-    const double s = limited_slope<M, LIM>(qm.rho, q0.rho, qp.rho, fl);
+    double s = limited_slope<M, LIM>(qm.rho, q0.rho, qp.rho, fl);
+    if constexpr (MASKED) s = slope_ok ? s : 0.0; // MusclHancockMethod.hpp:499-503
     qL.rho = q0.rho - 0.5 * s;
     qR.rho = q0.rho + 0.5 * s;
   }
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    const double s = limited_slope<M, LIM>(qm.mom[d], q0.mom[d], qp.mom[d], fl);
+    double s = limited_slope<M, LIM>(qm.mom[d], q0.mom[d], qp.mom[d], fl);
+    if constexpr (MASKED) s = slope_ok ? s : 0.0;
     qL.mom[d] = q0.mom[d] - 0.5 * s;
     qR.mom[d] = q0.mom[d] + 0.5 * s;
   }
   {
-    const double s = limited_slope<M, LIM>(qm.E, q0.E, qp.E, fl);
+    double s = limited_slope<M, LIM>(qm.E, q0.E, qp.E, fl);
+    if constexpr (MASKED) s = slope_ok ? s : 0.0;
     qL.E = q0.E - 0.5 * s;
     qR.E = q0.E + 0.5 * s;
   }
-  const Rcp rcL = M::rcp(qL.rho);
-  const Rcp rcR = M::rcp(qR.rho);
-  M::check(rcL, fl);
-  M::check(rcR, fl);
-  complete_from_cons<M, D>(eq, qL, rcL, fl);
-  complete_from_cons<M, D>(eq, qR, rcR, fl);
+  Rcp rcL = M::rcp(qL.rho);
+  Rcp rcR = M::rcp(qR.rho);
+  complete_edge<M, D, MASKED>(eq, qL, rcL, fl);
+  complete_edge<M, D, MASKED>(eq, qR, rcR, fl);
   Cons<D> fL, fR;
   euler_flux_v<D, DIR>(fL, qL, M::div(qL.mom[DIR], rcL, fl));
   euler_flux_v<D, DIR>(fR, qR, M::div(qR.mom[DIR], rcR, fl));
@@ -177,10 +201,8 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   }
   recL.rc = M::rcp(recL.q.rho);
   recR.rc = M::rcp(recR.q.rho);
-  M::check(recL.rc, fl);
-  M::check(recR.rc, fl);
-  complete_from_cons<M, D>(eq, recL.q, recL.rc, fl);
-  complete_from_cons<M, D>(eq, recR.q, recR.rc, fl);
+  complete_edge<M, D, MASKED>(eq, recL.q, recL.rc, fl);
+  complete_edge<M, D, MASKED>(eq, recR.q, recR.rc, fl);
 }
 
 // ---------------------------------------------------------------------------
@@ -433,8 +455,27 @@ FVS_DEV void einfeldt_signals(const EqM& eq, double uL, double hL, double sqRhoL
   s1 = vmax(roeU + roeA, uR + aR);
 }
 
-// include/fub/flux_method/HllMethod.hpp:260-293
-template <class M, int D, int DIR>
+// Masked variant, EinfeldtSignalVelocities.hpp:99-142: the Roe weights are
+// sqrt(rho_K) / (sqrt(rho_L) + sqrt(rho_R)) (two divisions) instead of a
+// multiplication with the reciprocal of the sum.
+template <class M>
+FVS_DEV void einfeldt_signals_masked(const EqM& eq, double uL, double hL, double sqRhoL,
+                                     double aL, double uR, double hR, double sqRhoR, double aR,
+                                     double& s0, double& s1, Flag& fl) {
+  const double sqRho = sqRhoL + sqRhoR;
+  const double wL = M::div(sqRhoL, sqRho, fl);
+  const double wR = M::div(sqRhoR, sqRho, fl);
+  const double roeU = uL * wL + uR * wR;
+  const double roeH = hL * wL + hR * wR;
+  const double roeA2 = (eq.gamma - 1.0) * (roeH - 0.5 * roeU * roeU);
+  const double roeA = M::sqrt(roeA2, fl);
+  s0 = vmin(uL - aL, roeU - roeA);
+  s1 = vmax(roeU + roeA, uR + aR);
+}
+
+// include/fub/flux_method/HllMethod.hpp:260-293 (MASKED: :295-335 on a face
+// with positive face fraction)
+template <class M, int D, int DIR, bool MASKED = false>
 FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
                                const Edge<D>& eR, Flag& fl) {
   const Complete<D>& left = eL.q;
@@ -446,8 +487,13 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
   const double hL = M::div(left.E + left.p, eL.rc, fl);
   const double hR = M::div(right.E + right.p, eR.rc, fl);
   double s0, s1;
-  einfeldt_signals<M>(eq, uL, hL, M::sqrt(left.rho, fl), left.a, uR, hR,
-                      M::sqrt(right.rho, fl), right.a, s0, s1, fl);
+  if constexpr (MASKED) {
+    einfeldt_signals_masked<M>(eq, uL, hL, M::sqrt(left.rho, fl), left.a, uR, hR,
+                               M::sqrt(right.rho, fl), right.a, s0, s1, fl);
+  } else {
+    einfeldt_signals<M>(eq, uL, hL, M::sqrt(left.rho, fl), left.a, uR, hR,
+                        M::sqrt(right.rho, fl), right.a, s0, s1, fl);
+  }
   Cons<D> fL, fR;
   euler_flux_v<D, DIR>(fL, left, uL);
   euler_flux_v<D, DIR>(fR, right, uR);
@@ -455,7 +501,7 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
   const double sR = vmax(s1, 0.0);
   const double sLsR = sL * sR;
   double ds = sR - sL;
-  ds = ds > 0.0 ? ds : 1.0;
+  if constexpr (!MASKED) ds = ds > 0.0 ? ds : 1.0;
   const Rcp rcDs = M::rcp(ds);
   M::check(rcDs, fl);
   nf.rho = M::div(sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho), rcDs, fl);
@@ -468,12 +514,17 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
 }
 
 // include/fub/flux_method/HllMethod.hpp:337-347: max(0, |s0|, |s1|)
-template <class M, int D, int DIR>
+template <class M, int D, int DIR, bool MASKED = false>
 FVS_DEV double hll_einfeldt_max_signal(const EqM& eq, const DtCell<D>& L, const DtCell<D>& R,
                                        Flag& fl) {
   double s0, s1;
-  einfeldt_signals<M>(eq, L.u[DIR], L.h, L.sq_rho, L.a, R.u[DIR], R.h, R.sq_rho, R.a, s0, s1,
-                      fl);
+  if constexpr (MASKED) {
+    einfeldt_signals_masked<M>(eq, L.u[DIR], L.h, L.sq_rho, L.a, R.u[DIR], R.h, R.sq_rho, R.a,
+                               s0, s1, fl);
+  } else {
+    einfeldt_signals<M>(eq, L.u[DIR], L.h, L.sq_rho, L.a, R.u[DIR], R.h, R.sq_rho, R.a, s0, s1,
+                        fl);
+  }
   double m = 0.0;
   m = vmax(m, fabs(s0));
   m = vmax(m, fabs(s1));
@@ -698,7 +749,7 @@ struct Eqs {
   FVS_DEV explicit Eqs(const EqConst& e) : c(e), m(e) {}
 };
 
-template <class M, int D, int DIR, int BASE>
+template <class M, int D, int DIR, int BASE, bool MASKED = false>
 FVS_DEV void base_flux(const Eqs& eq, Cons<D>& f, const Edge<D>& left, const Edge<D>& right,
                        Flag& fl, int& failed) {
   if constexpr (BASE == kBaseHllemLarrouturou) {
@@ -706,7 +757,7 @@ FVS_DEV void base_flux(const Eqs& eq, Cons<D>& f, const Edge<D>& left, const Edg
   } else if constexpr (BASE == kBaseHllem) {
     hllem_flux<M, D, DIR, false>(eq.m, f, left, right, fl);
   } else if constexpr (BASE == kBaseHllEinfeldt) {
-    hll_einfeldt_flux<M, D, DIR>(eq.m, f, left, right, fl);
+    hll_einfeldt_flux<M, D, DIR, MASKED>(eq.m, f, left, right, fl);
   } else {
     godunov_exact_flux<D, DIR>(eq.c, f, left.q, right.q, failed);
   }
@@ -733,13 +784,13 @@ FVS_DEV void dt_prepare(DtData<D, BASE>& out, const Complete<D>& q, Flag& fl) {
 // max signal speed of the face between two stored states (the stable dt of a
 // face is dx / value; min over faces == dx / max over faces because IEEE
 // division is monotone in its divisor).
-template <class M, int D, int DIR, int BASE>
+template <class M, int D, int DIR, int BASE, bool MASKED = false>
 FVS_DEV double base_max_signal(const Eqs& eq, const DtData<D, BASE>& left,
                                const DtData<D, BASE>& right, Flag& fl, int& failed) {
   if constexpr (BASE == kBaseHllemLarrouturou || BASE == kBaseHllem) {
     return hllem_max_signal<M, D, DIR>(eq.m, left.c, right.c, fl);
   } else if constexpr (BASE == kBaseHllEinfeldt) {
-    return hll_einfeldt_max_signal<M, D, DIR>(eq.m, left.c, right.c, fl);
+    return hll_einfeldt_max_signal<M, D, DIR, MASKED>(eq.m, left.c, right.c, fl);
   } else {
     return godunov_exact_max_signal<D, DIR>(eq.c, left.c, right.c, failed);
   }

@@ -57,6 +57,24 @@ int stable_dt(const SweepArgs& A, cudaStream_t s) {
   return 1;
 }
 
+template <int DIR, int RECON, int LIM>
+int cc_fluxes(const SweepArgs& A, cudaStream_t s) {
+  long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+  total += total / A.max_n[DIR];
+  dim3 grid(cdiv(total, 128), A.nboxes, 1);
+  cc_numeric_flux_kernel<D, DIR, BASE, RECON, LIM><<<grid, 128, 0, s>>>(A);
+  return 1;
+}
+
+template <int DIR>
+int cc_stable_dt(const SweepArgs& A, cudaStream_t s) {
+  long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+  total += total / A.max_n[DIR];
+  dim3 grid(cdiv(total, 256), A.nboxes, 1);
+  cc_stable_dt_kernel<D, DIR, BASE><<<grid, 256, 0, s>>>(A);
+  return 1;
+}
+
 template <int DIR, typename F0, typename F1, typename F2, typename F3>
 int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer) {
   if (k.recon == kReconFirstOrder) return fo();
@@ -83,7 +101,35 @@ template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaSt
       [&] { return fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
 }
 
+template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+  return by_recon<DIR>(
+      k, [&] { return cc_fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
+      [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
+      [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
+      [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+}
+
 } // namespace
+
+#if FVS_INST_D >= 2
+int FVS_FN(launch_cc_numeric_fluxes)(const MethodKey& k, int dir, const SweepArgs& A,
+                                     cudaStream_t s) {
+  if (dir == 0) return cc_fluxes_dir<0>(k, A, s);
+  if (dir == 1) return cc_fluxes_dir<1>(k, A, s);
+  if constexpr (D >= 3) {
+    if (dir == 2) return cc_fluxes_dir<2>(k, A, s);
+  }
+  return -1;
+}
+int FVS_FN(launch_cc_stable_dt)(const MethodKey&, int dir, const SweepArgs& A, cudaStream_t s) {
+  if (dir == 0) return cc_stable_dt<0>(A, s);
+  if (dir == 1) return cc_stable_dt<1>(A, s);
+  if constexpr (D >= 3) {
+    if (dir == 2) return cc_stable_dt<2>(A, s);
+  }
+  return -1;
+}
+#endif
 
 int FVS_FN(launch_fused_sweep)(const MethodKey& k, int dir, const SweepArgs& A,
                                cudaStream_t s) {

@@ -189,7 +189,11 @@ FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtDa
 #ifndef FVS_SWEEP_MIN_BLOCKS
 #define FVS_SWEEP_MIN_BLOCKS 2
 #endif
+#ifndef FVS_SWEEP_UNROLL
+#define FVS_SWEEP_UNROLL 2
+#endif
 constexpr int kSweepThreads = FVS_SWEEP_THREADS;
+constexpr int kSweepUnroll = FVS_SWEEP_UNROLL;
 
 // ---------------------------------------------------------------------------
 // Fused sweep along y or z: thread per line, register pipeline.
@@ -248,7 +252,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     // steady range: all of A (cell j-1), B (face j-1), C (cell j-2) active
     const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
     const int je = min(min(uhi + 2, nd - 1), jend); // inclusive
-#pragma unroll 2
+#pragma unroll kSweepUnroll
     for (int j = jstart; j <= jend; ++j) {
       if (j > jstart) {
         q0 = qn;
@@ -563,6 +567,141 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
     reduce_max_signal(maxsig[d], A.max_signal + d);
     __syncthreads();
   }
+  if (failed) *A.fail_flag = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Cut-cell (embedded boundary) levels.  Thread per face, plain operators: the
+// cut-cell fabs are the small, branchy part of an EB run (regular fabs of an
+// EB level use the same kernels with fab_type == 0).
+
+// KbnCutCellMethod::ComputeRegularFluxes, KbnStabilisation.hpp:347-429 ->
+// masked MusclHancock (MusclHancockMethod.hpp:487-571) -> masked base method
+// (HllemMethod.hpp:1074-1093, HllMethod.hpp:295-335, GodunovMethod.hpp:147-160);
+// regular fabs: FluxMethod::ComputeNumericFluxes as in numeric_flux_kernel.
+template <int D, int DIR, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(128) cc_numeric_flux_kernel(const SweepArgs A) {
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  if (B.fab_type < 0) return; // covered fab: nothing is computed
+  int len[3] = {B.n[0], B.n[1], B.n[2]};
+  len[DIR] = B.fhi - B.flo + 1;
+  const long long total = (long long)len[0] * len[1] * len[2];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int failed = 0;
+  if (len[DIR] > 0 && t < total) {
+    int idx[3];
+    idx[0] = (int)(t % len[0]);
+    idx[1] = (int)((t / len[0]) % len[1]);
+    idx[2] = (int)(t / ((long long)len[0] * len[1]));
+    idx[DIR] += B.flo;
+    const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
+    const long long cell = idx[0] + (long long)B.n[0] * (idx[1] + (long long)B.n[1] * idx[2]);
+    const double* p = B.src + cell; // right neighbour of the face
+    const Eqs eq(A.eq);
+    Cons<D> F;
+    const bool single = B.fab_type == 1;
+    bool valid = true;
+    if (single) {
+      const int bn0 = B.n[0] + (DIR == 0 ? 1 : 0);
+      const int bn1 = B.n[1] + (DIR == 1 ? 1 : 0);
+      const double beta = B.beta[idx[0] + (long long)bn0 * (idx[1] + (long long)bn1 * idx[2])];
+      valid = beta > 0.0;
+    }
+    if (!valid) {
+      F.rho = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) F.mom[d] = 0.0;
+      F.E = 0.0;
+    } else {
+      Flag fl;
+      Edge<D> unused, left, right;
+      if constexpr (RECON == kReconMusclHancock) {
+        Complete<D> s0, s1, s2, s3;
+        load_complete<D>(s0, p - 2 * stride, B.sc);
+        load_complete<D>(s1, p - stride, B.sc);
+        load_complete<D>(s2, p, B.sc);
+        load_complete<D>(s3, p + stride, B.sc);
+        if (single) {
+          const double* al = B.alpha + cell;
+          const bool a0 = al[-2 * stride] > 0.0, a1 = al[-stride] > 0.0, a2 = al[0] > 0.0,
+                     a3 = al[stride] > 0.0;
+          muscl_predict<SafeMath, D, DIR, LIM, true>(eq.m, s0, s1, s2, A.lambda_half, unused, left,
+                                                     fl, a0 && a1 && a2);
+          muscl_predict<SafeMath, D, DIR, LIM, true>(eq.m, s1, s2, s3, A.lambda_half, right,
+                                                     unused, fl, a1 && a2 && a3);
+        } else {
+          muscl_predict<SafeMath, D, DIR, LIM>(eq.m, s0, s1, s2, A.lambda_half, unused, left, fl);
+          muscl_predict<SafeMath, D, DIR, LIM>(eq.m, s1, s2, s3, A.lambda_half, right, unused, fl);
+        }
+      } else {
+        load_complete<D>(left.q, p - stride, B.sc);
+        load_complete<D>(right.q, p, B.sc);
+        left.rc = SafeMath::rcp(left.q.rho);
+        right.rc = SafeMath::rcp(right.q.rho);
+      }
+      if (single) {
+        base_flux<SafeMath, D, DIR, BASE, true>(eq, F, left, right, fl, failed);
+      } else {
+        base_flux<SafeMath, D, DIR, BASE, false>(eq, F, left, right, fl, failed);
+      }
+    }
+    const long long fcell = (idx[0] - B.foff[0]) +
+                            (long long)B.fn[0] * ((idx[1] - B.foff[1]) +
+                                                  (long long)B.fn[1] * (idx[2] - B.foff[2]));
+    double* f = B.flux + fcell;
+    f[0] = F.rho;
+#pragma unroll
+    for (int d = 0; d < D; ++d) f[B.fsc * (1 + d)] = F.mom[d];
+    f[B.fsc * (1 + D)] = F.E;
+  }
+  if (failed) *A.fail_flag = 1;
+}
+
+// cutcell::FluxMethod::ComputeStableDt (include/fub/AMReX/cutcell/FluxMethod.hpp:258-289):
+// the faces are those of the flux box whose stencil fits (flo..fhi), not the
+// grown-tile set of the regular adapter; single-valued fabs take the masked
+// signal formulas on faces with a positive face fraction
+// (KbnStabilisation.hpp:277-345).
+template <int D, int DIR, int BASE>
+__global__ void __launch_bounds__(256) cc_stable_dt_kernel(const SweepArgs A) {
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  int len[3] = {B.n[0], B.n[1], B.n[2]};
+  len[DIR] = B.fhi - B.flo + 1;
+  const long long total = (long long)len[0] * len[1] * len[2];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double maxsig = 0.0;
+  int failed = 0;
+  if (B.fab_type >= 0 && len[DIR] > 0 && t < total) {
+    int idx[3];
+    idx[0] = (int)(t % len[0]);
+    idx[1] = (int)((t / len[0]) % len[1]);
+    idx[2] = (int)(t / ((long long)len[0] * len[1]));
+    idx[DIR] += B.flo;
+    const long long stride = DIR == 0 ? 1 : (DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1]);
+    const long long cell = idx[0] + (long long)B.n[0] * (idx[1] + (long long)B.n[1] * idx[2]);
+    const bool single = B.fab_type == 1;
+    bool valid = true;
+    if (single) {
+      const int bn0 = B.n[0] + (DIR == 0 ? 1 : 0);
+      const int bn1 = B.n[1] + (DIR == 1 ? 1 : 0);
+      valid = B.beta[idx[0] + (long long)bn0 * (idx[1] + (long long)bn1 * idx[2])] > 0.0;
+    }
+    if (valid) {
+      const Eqs eq(A.eq);
+      Complete<D> l, r;
+      load_complete<D>(l, B.src + cell - stride, B.sc);
+      load_complete<D>(r, B.src + cell, B.sc);
+      DtData<D, BASE> dl, dr;
+      Flag fl;
+      dt_prepare<SafeMath, D, BASE>(dl, l, fl);
+      dt_prepare<SafeMath, D, BASE>(dr, r, fl);
+      const double s = single
+                           ? base_max_signal<SafeMath, D, DIR, BASE, true>(eq, dl, dr, fl, failed)
+                           : base_max_signal<SafeMath, D, DIR, BASE, false>(eq, dl, dr, fl, failed);
+      maxsig = s > 0.0 ? s : 0.0; // drops NaN
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
   if (failed) *A.fail_flag = 1;
 }
 

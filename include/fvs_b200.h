@@ -50,6 +50,27 @@ enum { FVS_BC_TRANSMISSIVE = 0, FVS_BC_REFLECTIVE = 1 };
 /* src/split_method/{Godunov,Strang,StrangLumped}Splitting.cpp */
 enum { FVS_SPLIT_GODUNOV = 0, FVS_SPLIT_STRANG = 1, FVS_SPLIT_STRANG_LUMPED = 2 };
 
+/* amrex::FabType of a box (include/fub/AMReX/cutcell/FluxMethod.hpp:180,205) */
+enum { FVS_FAB_COVERED = -1, FVS_FAB_REGULAR = 0, FVS_FAB_SINGLEVALUED = 1 };
+/* RiemannSolver of KbnCutCellMethod (include/fub/cutcell_method/KbnStabilisation.hpp:90-100) */
+enum { FVS_RIEMANN_HLL_EINFELDT = 0, FVS_RIEMANN_EXACT = 1 };
+/* arrays of an EB level readable with fvs_download_eb_array */
+enum {
+  FVS_EB_ALPHA = 0,          /* volume fractions                (1 comp, cells)  */
+  FVS_EB_BETA = 1,           /* face fractions of dir           (1 comp, faces)  */
+  FVS_EB_BCENT = 2,          /* boundary centroids              (rank, cells)    */
+  FVS_EB_BNORM = 3,          /* boundary normals (AMReX sign)   (rank, cells)    */
+  FVS_EB_UNSHIELDED = 4,     /* abs + rel fractions of dir      (2 comps, faces) */
+  FVS_EB_SHIELDED_LEFT = 5,
+  FVS_EB_SHIELDED_RIGHT = 6,
+  FVS_EB_DOUBLY_SHIELDED = 7,
+  FVS_EB_REFERENCE_STATES = 8, /* rank + 4 comps, cells */
+  FVS_EB_BOUNDARY_FLUXES = 9,  /* rank + 2 comps, cells */
+  FVS_EB_STABILIZED_FLUXES = 10, /* rank + 2 comps, flux box of dir */
+  FVS_EB_SHIELDED_LEFT_FLUXES = 11,
+  FVS_EB_SHIELDED_RIGHT_FLUXES = 12
+};
+
 /* status codes */
 enum {
   FVS_OK = 0,
@@ -217,6 +238,56 @@ int fvs_stable_dt_face_mask(int rank, const int box_lo[3], const int box_hi[3],
  * uniform case. */
 int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3],
                          const int (*box_hi)[3], int nranks, int* owner_out);
+
+/* ---- embedded boundary: Klein-2009 KbnCutCellMethod ------------------------ */
+/* Hands the EB geometry of one box to the library and turns the level into a
+ * cut-cell level: replaces cutcell::PatchHierarchy::GetCutCellData
+ * (src/AMReX/cutcell/PatchHierarchy.cpp:507-547, the arrays come from
+ * amrex::EBFArrayBoxFactory: getVolFrac, getAreaFrac, getBndryCent,
+ * getBndryNormal) and runs FillCutCellData
+ * (src/AMReX/cutcell/FillCutCellData.cpp:28-118) plus IsCutCell
+ * (src/CutCellData.cpp:225-256) on the device.  alpha / bcent / bnorm live on
+ * fvs_state_box (1 / rank / rank components), beta[d] on that box with one more
+ * face along d; FAB layout.  Boxes that were not given keep fab_type regular.
+ * Requires rank >= 2 and scratch_gcw == flux_gcw + stencil width (the cut-cell
+ * context sizes its flux arrays that way, cutcell/IntegratorContext.cpp:523-525).
+ * From then on fvs_compute_stable_dt / fvs_compute_numeric_fluxes /
+ * fvs_update_conservatively / fvs_complete_from_cons / fvs_sweep /
+ * fvs_advance_hierarchy follow the cut-cell adapters
+ * (include/fub/AMReX/cutcell/FluxMethod.hpp:153-289,
+ * src/AMReX/cutcell/TimeIntegrator.cpp:317-411,
+ * include/fub/AMReX/cutcell/Reconstruction.hpp:169-193). */
+int fvs_level_set_eb(fvs_ctx* ctx, int level, int box, const double* alpha,
+                     const double* const beta[3], const double* bcent, const double* bnorm,
+                     int fab_type);
+int fvs_set_cutcell_riemann_solver(fvs_ctx* ctx, int kind);
+/* cutcell::FluxMethod::PreAdvanceHierarchy (include/fub/AMReX/cutcell/FluxMethod.hpp:108-133):
+ * reference states of all cut cells of all levels.  fvs_advance_hierarchy calls
+ * it itself (cutcell::IntegratorContext::PreAdvanceLevel, IntegratorContext.cpp:802-806). */
+int fvs_pre_advance_hierarchy(fvs_ctx* ctx);
+/* Box / component count of an EB array (FVS_EB_*), and its contents. */
+int fvs_eb_array_box(const fvs_ctx* ctx, int level, int box, int kind, int dir, int lo[3],
+                     int hi[3], int* ncomp);
+int fvs_download_eb_array(fvs_ctx* ctx, int level, int box, int kind, int dir, double* host_fab);
+/* fub::IsCutCell for every cell of fvs_state_box (1 byte per cell); returns
+ * the number of cut cells (the length of the compacted list) or FVS_ERROR. */
+long fvs_cut_cell_flags(fvs_ctx* ctx, int level, int box, unsigned char* flags);
+
+/* ---- tagging (patch level) ------------------------------------------------ */
+/* ScalarGradientDetector_::TagCellsForRefinement
+ * (include/fub/tagging_method/GradientDetector.hpp:156-232) on the valid cells
+ * of a box, reading the device-resident state and its first ghost layer;
+ * condition c tags where the relative jump of state component comps[c]
+ * exceeds tols[c] (at most 8 conditions); use_alpha != 0 selects the EB
+ * variant (all three volume fractions > 0).  tags (1 byte per valid cell,
+ * x fastest) is OR-ed into. */
+int fvs_tag_gradient(fvs_ctx* ctx, int level, int box, int ncond, const int* comps,
+                     const double* tols, int use_alpha, char* tags);
+/* fub::TagCutCells (src/tagging_method/TagCutCells.cpp:27-35) */
+int fvs_tag_cutcells(fvs_ctx* ctx, int level, int box, char* tags);
+/* fub::TagBuffer (src/tagging_method/TagBuffer.cpp:27-86) on a dense view of
+ * extents n[] (x fastest), in place. */
+int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width);
 
 /* ---- statistics ---------------------------------------------------------- */
 /* Number of kernels this context has launched so far. */

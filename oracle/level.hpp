@@ -9,6 +9,7 @@
 // Citations are relative to /root/reference.
 #pragma once
 #include "patch.hpp"
+#include "cutcell.hpp"
 
 #include <cfloat>
 #include <functional>
@@ -84,6 +85,12 @@ struct Level {
   MethodSpec method;
   long cycles{0};
   double time_point{0.0};
+  // embedded boundary (src/AMReX/cutcell/IntegratorContext.cpp:470-533)
+  bool has_eb{false};
+  int kbn_riemann{kRiemannHllEinfeldt};
+  std::vector<CutCellData> eb;
+  std::vector<Fab> references, boundary_fluxes;
+  std::vector<Fab> stabilized[3], shielded_left[3], shielded_right[3];
 
   int ncomp() const { return rank + 4; }
   int ncons() const { return rank + 2; }
@@ -101,6 +108,152 @@ struct Level {
           fb = grow(fb, e, e == d ? flux_gcw : scratch_gcw);
         }
         fluxes[d][b].define(fb, ncons());
+      }
+    }
+  }
+
+  // cut-cell arrays of the context; geometry is filled in by the caller
+  void allocate_eb() {
+    if (scratch_gcw != flux_gcw + method.stencil_width()) {
+      // the cut-cell context allocates fluxes with flux_gcw + stencil width
+      // ghost faces across the sweep direction (IntegratorContext.cpp:523-525)
+      throw std::runtime_error("EB levels need scratch_gcw == flux_gcw + stencil width");
+    }
+    has_eb = true;
+    eb.resize(boxes.size());
+    references.resize(boxes.size());
+    boundary_fluxes.resize(boxes.size());
+    for (int d = 0; d < rank; ++d) {
+      stabilized[d].resize(boxes.size());
+      shielded_left[d].resize(boxes.size());
+      shielded_right[d].resize(boxes.size());
+    }
+    for (size_t b = 0; b < boxes.size(); ++b) {
+      eb[b].define(scratch[b].box, rank);
+      references[b].define(scratch[b].box, ncomp());
+      boundary_fluxes[b].define(scratch[b].box, ncons());
+      for (int d = 0; d < rank; ++d) {
+        stabilized[d][b].define(fluxes[d][b].box, ncons());
+        shielded_left[d][b].define(fluxes[d][b].box, ncons());
+        shielded_right[d][b].define(fluxes[d][b].box, ncons());
+      }
+    }
+  }
+
+  // include/fub/AMReX/cutcell/FluxMethod.hpp:108-133
+  void PreAdvanceHierarchy() {
+    if (!has_eb) return;
+    for (size_t b = 0; b < boxes.size(); ++b) {
+      if (eb[b].fab_type != kFabSingleValued) continue;
+      switch (rank) {
+      case 2: Kbn<2>(eq, kbn_riemann).PreAdvanceHierarchy(references[b], scratch[b], eb[b], scratch[b].box); break;
+      case 3: Kbn<3>(eq, kbn_riemann).PreAdvanceHierarchy(references[b], scratch[b], eb[b], scratch[b].box); break;
+      default: throw std::runtime_error("cut cells need rank 2 or 3");
+      }
+    }
+  }
+
+  // include/fub/AMReX/cutcell/FluxMethod.hpp:258-289
+  template <int D> double ComputeStableDtEbD(int dir) const {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, dir);
+    const double dxd = dx[dir];
+    const int w = method.stencil_width();
+    double min_dt = std::numeric_limits<double>::infinity();
+    if constexpr (D >= 2) {
+      const Kbn<D> kbn(eq, kbn_riemann);
+      with_method<D>(method, eq, [&](const auto& m) {
+        for (size_t t = 0; t < tiles.size(); ++t) {
+          const size_t b = tiles[t].fab;
+          Box cells, faces;
+          GetCellsAndFacesInStencilRange(cells, faces, scratch[b].box, tiles[t].tile.grown, w, dir);
+          if (eb[b].fab_type == kFabSingleValued) {
+            min_dt = std::min(min_dt, kbn.ComputeStableDt(m, scratch[b], eb[b], cells, dxd, dir));
+          } else if (eb[b].fab_type == kFabRegular) {
+            min_dt = std::min(min_dt, fvso::ComputeStableDt(m, scratch[b], cells, dxd, dir));
+          }
+        }
+      });
+    }
+    return min_dt;
+  }
+
+  // include/fub/AMReX/cutcell/FluxMethod.hpp:153-256
+  template <int D> void ComputeNumericFluxesEbD(double dt, int dir) {
+    if constexpr (D >= 2) {
+      const Kbn<D> kbn(eq, kbn_riemann);
+      for (size_t b = 0; b < boxes.size(); ++b) {
+        std::fill(boundary_fluxes[b].data.begin(), boundary_fluxes[b].data.end(), 0.0);
+        if (eb[b].fab_type == kFabSingleValued) {
+          kbn.ComputeBoundaryFluxes(boundary_fluxes[b], scratch[b], references[b], eb[b],
+                                    scratch[b].box, dir);
+        }
+      }
+      const int tile_size[3] = {1024000, 16, 32};
+      const std::vector<TileRef> tiles = Tiles(tile_size, dir);
+      const double dxd = dx[dir];
+      const int w = method.stencil_width();
+      with_method<D>(method, eq, [&](const auto& m) {
+        for (size_t t = 0; t < tiles.size(); ++t) {
+          const size_t b = tiles[t].fab;
+          Box cells, faces;
+          GetCellsAndFacesInStencilRange(cells, faces, scratch[b].box, tiles[t].tile.grown, w, dir);
+          if (eb[b].fab_type == kFabSingleValued) {
+            kbn.ComputeRegularFluxes(m, fluxes[dir][b], faces, scratch[b], eb[b], dt, dxd, dir);
+            kbn.ComputeCutCellFluxes(stabilized[dir][b], shielded_left[dir][b],
+                                     shielded_right[dir][b], boundary_fluxes[b], fluxes[dir][b],
+                                     faces, eb[b], dir);
+          } else if (eb[b].fab_type == kFabRegular) {
+            fvso::ComputeNumericFluxes(m, fluxes[dir][b], faces, scratch[b], dt, dxd, dir);
+          }
+        }
+      });
+    }
+  }
+
+  // src/AMReX/cutcell/TimeIntegrator.cpp:317-411
+  void UpdateConservativelyEb(double dt, int dir) {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, -1);
+    const double dt_over_dx = dt / dx[dir];
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      const size_t b = tiles[t].fab;
+      const Box all_faces = surrounding_nodes(tiles[t].tile.grown, dir);
+      const Box flux_box = intersect(all_faces, fluxes[dir][b].box);
+      const Box cell_box = enclosed_cells(flux_box, dir);
+      if (eb[b].fab_type == kFabSingleValued) {
+        CutCellUpdateConservatively(scratch[b], fluxes[dir][b], stabilized[dir][b],
+                                    shielded_left[dir][b], shielded_right[dir][b],
+                                    boundary_fluxes[b], eb[b], cell_box, ncons(), dt_over_dx, dir);
+      } else if (eb[b].fab_type == kFabRegular) {
+        fvso::UpdateConservatively(scratch[b], scratch[b], fluxes[dir][b], cell_box, ncons(), dt,
+                                   dx[dir], dir);
+      }
+    }
+  }
+
+  // include/fub/AMReX/cutcell/Reconstruction.hpp:169-193: the flag type is
+  // taken per grown tile box
+  int CompleteTileType(size_t b, const Box& grown) const {
+    return CellFlagType(eb[b], rank, grown);
+  }
+  void CompleteFromConsEb() {
+    const int tile_size[3] = {1024000, 16, 32};
+    const std::vector<TileRef> tiles = Tiles(tile_size, -1);
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      const size_t b = tiles[t].fab;
+      const Box& box = tiles[t].tile.grown;
+      const int type = CompleteTileType(b, box);
+      if (type == kFabRegular) {
+        switch (rank) {
+        case 2: CompleteFromConsBox<2>(eq, scratch[b], box); break;
+        default: CompleteFromConsBox<3>(eq, scratch[b], box); break;
+        }
+      } else if (type == kFabSingleValued) {
+        switch (rank) {
+        case 2: CompleteFromConsBoxMasked<2>(eq, scratch[b], eb[b].alpha, box); break;
+        default: CompleteFromConsBoxMasked<3>(eq, scratch[b], eb[b].alpha, box); break;
+        }
       }
     }
   }
@@ -282,6 +435,9 @@ struct Level {
     return min_dt;
   }
   double ComputeStableDt(int dir) const {
+    if (has_eb) {
+      return rank == 2 ? ComputeStableDtEbD<2>(dir) : ComputeStableDtEbD<3>(dir);
+    }
     switch (rank) {
     case 1: return ComputeStableDtD<1>(dir);
     case 2: return ComputeStableDtD<2>(dir);
@@ -309,6 +465,14 @@ struct Level {
     });
   }
   void ComputeNumericFluxes_(double dt, int dir) {
+    if (has_eb) {
+      if (rank == 2) {
+        ComputeNumericFluxesEbD<2>(dt, dir);
+      } else {
+        ComputeNumericFluxesEbD<3>(dt, dir);
+      }
+      return;
+    }
     switch (rank) {
     case 1: ComputeNumericFluxesD<1>(dt, dir); break;
     case 2: ComputeNumericFluxesD<2>(dt, dir); break;
@@ -318,6 +482,7 @@ struct Level {
 
   // src/AMReX/TimeIntegrator.cpp:29-67
   void UpdateConservatively_(double dt, int dir) {
+    if (has_eb) return UpdateConservativelyEb(dt, dir);
     const int tile_size[3] = {1024000, 16, 32};
     const std::vector<TileRef> tiles = Tiles(tile_size, -1);
 #pragma omp parallel for schedule(dynamic)
@@ -333,6 +498,7 @@ struct Level {
 
   // include/fub/AMReX/Reconstruction.hpp:44-60
   void CompleteFromCons_() {
+    if (has_eb) return CompleteFromConsEb();
     const int tile_size[3] = {1024000, 16, 32};
     const std::vector<TileRef> tiles = Tiles(tile_size, -1);
 #pragma omp parallel for schedule(dynamic)
@@ -437,6 +603,7 @@ struct Level {
   std::optional<TimeStepTooLarge>
   AdvanceHierarchy(double dt, int split_kind,
                    std::vector<double>* sweep_dts = nullptr) {
+    PreAdvanceHierarchy(); // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
     if (auto r = AdvanceLevelNonRecursively(dt, split_kind, sweep_dts)) {
       return r;
     }

@@ -19,6 +19,10 @@ RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK = 0, 1
 LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
 BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
 SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
+FAB_COVERED, FAB_REGULAR, FAB_SINGLEVALUED = -1, 0, 1
+RIEMANN_HLL_EINFELDT, RIEMANN_EXACT = 0, 1
+(EB_ALPHA, EB_BETA, EB_BCENT, EB_BNORM, EB_US, EB_SL, EB_SR, EB_DS, EB_REFERENCE,
+ EB_BOUNDARY_FLUX, EB_STABILIZED, EB_SHIELDED_LEFT, EB_SHIELDED_RIGHT) = range(13)
 
 
 def build():
@@ -36,6 +40,7 @@ def lib():
         L.fvso_level_create.restype = C.c_void_p
         L.fvso_level_scratch.restype = C.POINTER(C.c_double)
         L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
+        L.fvso_level_eb_array.restype = C.POINTER(C.c_double)
         L.fvso_level_cycles.restype = C.c_long
         L.fvso_level_time.restype = C.c_double
         _LIB = L
@@ -159,6 +164,55 @@ class Level:
                                                  C.byref(too), buf, C.byref(n)))
         return rc == 0, too.value, [buf[i] for i in range(min(n.value, 16))]
 
+    # ---- cut cells / tagging ------------------------------------------------
+    def enable_eb(self, kbn_riemann=RIEMANN_HLL_EINFELDT):
+        _check(lib().fvso_level_enable_eb(self.h, kbn_riemann))
+
+    def eb_array(self, box, kind, direction=0):
+        lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
+        p = lib().fvso_level_eb_array(self.h, box, kind, direction, lo, hi, C.byref(nc))
+        if not p:
+            raise RuntimeError("no such EB array")
+        return self._view(p, lo, hi, nc.value)
+
+    def set_eb(self, box, geom, fab_type):
+        """geom: dict alpha [1,z,y,x], beta list of [1,z,y,x(+1 in d)], bcent, bnorm [rank,z,y,x]."""
+        self.eb_array(box, EB_ALPHA)[0][...] = geom["alpha"]
+        for d in range(self.rank):
+            self.eb_array(box, EB_BETA, d)[0][...] = geom["beta"][d]
+        self.eb_array(box, EB_BCENT)[0][...] = geom["bcent"]
+        self.eb_array(box, EB_BNORM)[0][...] = geom["bnorm"]
+        _check(lib().fvso_level_eb_finalize(self.h, box, fab_type))
+
+    def is_cut_cell(self, box):
+        arr, lo, hi = self.eb_array(box, EB_ALPHA)
+        out = np.zeros(arr.shape[1:], dtype=np.uint8)
+        _check(lib().fvso_level_is_cut_cell(self.h, box, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return out
+
+    def pre_advance_hierarchy(self):
+        _check(lib().fvso_level_pre_advance(self.h))
+
+    def _tag_shape(self, box):
+        lo, hi = self.boxes[box]
+        return (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+
+    def tag_gradient(self, box, conditions, use_alpha=False, tags=None):
+        """conditions: [(component, tolerance)]; tags |= over the valid box."""
+        if tags is None:
+            tags = np.zeros(self._tag_shape(box), dtype=np.int8)
+        comps = _ia([c for c, _ in conditions])
+        tols = _da([t for _, t in conditions])
+        _check(lib().fvso_tag_gradient(self.h, box, len(conditions), comps, tols,
+                                       1 if use_alpha else 0, tags.ctypes.data_as(C.c_char_p)))
+        return tags
+
+    def tag_cutcells(self, box, tags=None):
+        if tags is None:
+            tags = np.zeros(self._tag_shape(box), dtype=np.int8)
+        _check(lib().fvso_tag_cutcells(self.h, box, tags.ctypes.data_as(C.c_char_p)))
+        return tags
+
     def run(self, cfl, final_time, max_cycles, split):
         cap = max(int(max_cycles), 1) if max_cycles >= 0 else 100000
         buf = np.zeros(cap)
@@ -167,6 +221,13 @@ class Level:
                                   C.c_long(max_cycles), split, _dp(buf), cap,
                                   C.byref(retries)))
         return buf[:n].copy(), retries.value
+
+
+def tag_buffer(tags, rank, width):
+    """fub::TagBuffer on a dense [z, y, x] int8 view, in place."""
+    n = _ia(list(tags.shape[::-1]))
+    _check(lib().fvso_tag_buffer(tags.ctypes.data_as(C.c_char_p), rank, n, width))
+    return tags
 
 
 def update_conservatively(prev, flux, dt, dx):

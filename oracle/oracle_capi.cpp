@@ -187,6 +187,86 @@ int fvso_run(void* h, double cfl, double final_time, long max_cycles,
   return rc < 0 ? rc : n;
 }
 
+// ------------------------------------------------------------ cut cells
+int fvso_level_enable_eb(void* h, int kbn_riemann) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(h);
+    L->kbn_riemann = kbn_riemann;
+    L->allocate_eb();
+  });
+}
+// kind: 0 alpha, 1 beta, 2 bcent, 3 bnorm, 4 us, 5 sl, 6 sr, 7 ds,
+//       8 reference states, 9 boundary fluxes, 10 stabilised, 11 shielded
+//       left, 12 shielded right fluxes
+double* fvso_level_eb_array(void* h, int box, int kind, int dir, int* lo, int* hi, int* ncomp) {
+  Level* L = static_cast<Level*>(h);
+  if (!L->has_eb) return nullptr;
+  const size_t b = size_t(box);
+  Fab* f = nullptr;
+  switch (kind) {
+  case 0: f = &L->eb[b].alpha; break;
+  case 1: f = &L->eb[b].beta[dir]; break;
+  case 2: f = &L->eb[b].bcent; break;
+  case 3: f = &L->eb[b].bnorm; break;
+  case 4: f = &L->eb[b].us[dir]; break;
+  case 5: f = &L->eb[b].sl[dir]; break;
+  case 6: f = &L->eb[b].sr[dir]; break;
+  case 7: f = &L->eb[b].ds[dir]; break;
+  case 8: f = &L->references[b]; break;
+  case 9: f = &L->boundary_fluxes[b]; break;
+  case 10: f = &L->stabilized[dir][b]; break;
+  case 11: f = &L->shielded_left[dir][b]; break;
+  case 12: f = &L->shielded_right[dir][b]; break;
+  default: return nullptr;
+  }
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = f->box.lo[d];
+    hi[d] = f->box.hi[d];
+  }
+  *ncomp = f->ncomp;
+  return f->data.data();
+}
+int fvso_level_eb_finalize(void* h, int box, int fab_type) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(h);
+    L->eb[size_t(box)].fab_type = fab_type;
+    FillCutCellData(L->eb[size_t(box)], L->rank);
+  });
+}
+int fvso_level_is_cut_cell(void* h, int box, unsigned char* out) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(h);
+    const CutCellData& g = L->eb[size_t(box)];
+    const Box& bx = g.alpha.box;
+    size_t n = 0;
+    for (int k = bx.lo[2]; k <= bx.hi[2]; ++k)
+      for (int j = bx.lo[1]; j <= bx.hi[1]; ++j)
+        for (int i = bx.lo[0]; i <= bx.hi[0]; ++i) out[n++] = IsCutCell(g, L->rank, i, j, k) ? 1 : 0;
+  });
+}
+int fvso_level_pre_advance(void* h) {
+  return guarded([&] { static_cast<Level*>(h)->PreAdvanceHierarchy(); });
+}
+// ------------------------------------------------------------ tagging
+int fvso_tag_gradient(void* h, int box, int ncond, const int* comps, const double* tols,
+                      int use_alpha, char* tags) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(h);
+    const size_t b = size_t(box);
+    TagGradient(tags, L->boxes[b], L->scratch[b], use_alpha ? &L->eb[b].alpha : nullptr, L->rank,
+                ncond, comps, tols);
+  });
+}
+int fvso_tag_cutcells(void* h, int box, char* tags) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(h);
+    TagCutCells(tags, L->boxes[size_t(box)], L->eb[size_t(box)].alpha);
+  });
+}
+int fvso_tag_buffer(char* tags, int rank, const int* n, int width) {
+  return guarded([&] { TagBuffer(tags, rank, n, width); });
+}
+
 // ----------------------------------------------------- unit-level helpers
 // UpdateConservatively on a bare array pair: `cells` x-cells, 1 component,
 // direction X (tests/test.HyperbolicSplitPatchIntegrator.cpp).

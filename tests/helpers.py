@@ -83,6 +83,75 @@ def riemann_state(rank, lo, hi, dx, origin, radius=0.4, inner=(1.0, 1.0), outer=
     return complete_from_prim(rank, rho, [zero] * rank, p)
 
 
+def eb_geometry(rank, lo, hi, dx, origin, phi, nsub=8):
+    """Embedded-boundary arrays for the fab box [lo, hi] from a level-set
+    function phi(x, y, z) (> 0 in the fluid), by deterministic sub-sampling:
+    alpha = fluid fraction of nsub^rank samples per cell, beta[d] the same on
+    the faces, boundary centroid = closest interface point to the cell centre
+    (units of dx, clipped to [-1/2, 1/2]), bnorm = normal pointing into the
+    body (AMReX convention; the reference negates it).  This stands in for
+    AMReX EB2 (absent here): oracle and GPU get the SAME arrays."""
+    off = (np.arange(nsub) + 0.5) / nsub
+    n = [hi[d] - lo[d] + 1 for d in range(3)]
+
+    def coords(d, nodal, sub):
+        base = origin[d] + (np.arange(lo[d], hi[d] + 1 + (1 if nodal else 0))) * dx[d]
+        if d >= rank:
+            return base[:, None] * 0.0 + 0.0 * off[None, :1]
+        if nodal:
+            return base[:, None] + 0.0 * off[None, :1]
+        return base[:, None] + (off[None, :] if sub else np.array([[0.5]])) * dx[d]
+
+    def fraction(nodal_dir):
+        cs = [coords(d, d == nodal_dir, True) for d in range(3)]  # [n_d, s_d]
+        X = cs[0][None, None, :, None, None, :]
+        Y = cs[1][None, :, None, None, :, None]
+        Z = cs[2][:, None, None, :, None, None]
+        val = phi(X, Y, Z) > 0.0
+        val = np.broadcast_to(val, (cs[2].shape[0], cs[1].shape[0], cs[0].shape[0],
+                                    cs[2].shape[1], cs[1].shape[1], cs[0].shape[1]))
+        return val.reshape(val.shape[:3] + (-1,)).mean(axis=3)[None]
+
+    alpha = fraction(-1)
+    beta = [fraction(d) for d in range(rank)]
+    # a face is open only if both of its cells hold fluid (EB2 consistency)
+    for d in range(rank):
+        ax = 3 - d  # axis of direction d in [1, z, y, x]
+        covered = (alpha == 0.0)
+        sl_lo = [slice(None)] * 4
+        sl_hi = [slice(None)] * 4
+        sl_lo[ax] = slice(1, None)   # faces 1..n  have a left cell  0..n-1
+        sl_hi[ax] = slice(0, -1)     # faces 0..n-1 have a right cell 0..n-1
+        beta[d][tuple(sl_lo)] = np.where(covered, 0.0, beta[d][tuple(sl_lo)])
+        beta[d][tuple(sl_hi)] = np.where(covered, 0.0, beta[d][tuple(sl_hi)])
+    cc = [coords(d, False, False)[:, 0] for d in range(3)]
+    X, Y, Z = cc[0][None, None, :], cc[1][None, :, None], cc[2][:, None, None]
+    p0 = phi(X, Y, Z) + np.zeros((n[2], n[1], n[0]))
+    h = 1e-4 * dx[0]
+    grads = []
+    for d in range(rank):
+        e = [0.0, 0.0, 0.0]
+        e[d] = h
+        grads.append((phi(X + e[0], Y + e[1], Z + e[2]) - phi(X - e[0], Y - e[1], Z - e[2])) / (2 * h)
+                     + np.zeros_like(p0))
+    norm = np.sqrt(sum(g * g for g in grads))
+    norm = np.where(norm > 0, norm, 1.0)
+    cut = (alpha[0] > 0) & (alpha[0] < 1)
+    bnorm = np.stack([np.where(cut, -g / norm, 0.0) for g in grads])
+    bcent = np.stack([np.where(cut, np.clip(-p0 * (grads[d] / norm) / norm / dx[d], -0.5, 0.5), 0.0)
+                      for d in range(rank)])
+    return {"alpha": alpha, "beta": beta, "bcent": bcent, "bnorm": bnorm}
+
+
+def eb_fab_type(geom):
+    a = geom["alpha"]
+    if np.all(a == 0.0):
+        return -1
+    if np.all(a == 1.0) and all(np.all(b == 1.0) for b in geom["beta"]):
+        return 0
+    return 1
+
+
 class Pair:
     """The same single-level problem on the oracle and on the GPU."""
 
@@ -122,3 +191,36 @@ class Pair:
 
     def close(self):
         self.gpu.close()
+
+
+def polygon_phi(points):
+    """Level set (> 0 outside) of a convex polygon: max over its edges of the
+    signed distance to the edge line."""
+    pts = [tuple(map(float, p)) for p in points]
+    cx = sum(p[0] for p in pts) / len(pts)
+    cy = sum(p[1] for p in pts) / len(pts)
+    edges = []
+    for i in range(len(pts)):
+        x0, y0 = pts[i]
+        x1, y1 = pts[(i + 1) % len(pts)]
+        nx, ny = (y1 - y0), -(x1 - x0)
+        ln = float(np.hypot(nx, ny))
+        nx, ny = nx / ln, ny / ln
+        if (cx - x0) * nx + (cy - y0) * ny > 0:  # make the normal point outwards
+            nx, ny = -nx, -ny
+        edges.append((x0, y0, nx, ny))
+
+    def phi(x, y, z):
+        v = None
+        for (x0, y0, nx, ny) in edges:
+            t = (x - x0) * nx + (y - y0) * ny
+            v = t if v is None else np.maximum(v, t)
+        return v + 0 * z
+    return phi
+
+
+def sphere_phi(center, radius, inside_fluid=False):
+    def phi(x, y, z):
+        r = np.sqrt((x - center[0]) ** 2 + (y - center[1]) ** 2 + (z - center[2]) ** 2)
+        return (radius - r) if inside_fluid else (r - radius)
+    return phi

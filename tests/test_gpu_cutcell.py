@@ -1,0 +1,232 @@
+"""Parity of the CUDA cut-cell (Klein-2009 KbnCutCellMethod) and tagging path
+against the CPU oracle, through the C ABI.  Same geometry arrays on both
+sides (tests/helpers.py:eb_geometry stands in for AMReX EB2).  Bit-exact for
+everything built on + - * / sqrt, bit-exact cut-cell indexing and tags; 1e-12
+when the exact Riemann solver (pow) is the Kbn wall solver."""
+import numpy as np
+import pytest
+
+from helpers import (Pair, assert_bitwise_equal, complete_from_prim, eb_fab_type, eb_geometry,
+                     polygon_phi, rel_linf, sphere_phi)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fvs():
+    from finitevolumesolver_b200 import capi
+    assert capi.device_count() > 0, "no CUDA device"
+    return capi
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as orc
+    orc.build()
+    return orc
+
+
+WEDGE = [(0.02, 0.05), (0.05, 0.0655), (0.05, 0.0345)]
+
+
+def make_pair(orc, fvs, rank, n, boxes, gcw, method, phi, extent, riemann=0, nsub=8):
+    dx = [extent[d] / n[d] for d in range(rank)] + [1.0] * (3 - rank)
+    hi = [n[d] - 1 if d < rank else 0 for d in range(3)]
+    bcs = [(d, s, 0) for d in range(rank) for s in (0, 1)]
+    pair = Pair(orc, fvs, rank, [0] * 3, hi, dx, boxes, gcw[0], gcw[1], base=method[0],
+                recon=method[1], limiter=method[2], bcs=bcs)
+    pair.cpu.enable_eb(riemann)
+    pair.gpu.enable_eb(riemann)
+    geoms = []
+    for b in range(pair.nboxes):
+        _, lo, hi_b = pair.cpu.scratch(b)
+        g = eb_geometry(rank, lo, hi_b, dx, [0.0] * 3, phi, nsub=nsub)
+        t = eb_fab_type(g)
+        pair.cpu.set_eb(b, g, t)
+        pair.gpu.set_eb(b, g, t)
+        geoms.append(g)
+    return pair, dx, geoms
+
+
+def shock_fill(pair, rank, dx, geoms, x_shock, p_ratio, rho0=1.0):
+    for b in range(pair.nboxes):
+        arr, lo, hi = pair.cpu.scratch(b)
+        shape = arr.shape[1:]
+        x = (np.arange(lo[0], hi[0] + 1) + 0.5) * dx[0]
+        y = (np.arange(lo[1], hi[1] + 1) + 0.5) * dx[1]
+        rho = rho0 + 0.05 * np.sin(40 * x)[None, None, :] * np.cos(30 * y)[None, :, None] + np.zeros(shape)
+        p = np.where(x < x_shock, p_ratio * 101325.0, 101325.0)[None, None, :] + np.zeros(shape)
+        vel = [5.0 * np.cos(25 * y)[None, :, None] + np.zeros(shape),
+               -3.0 * np.sin(35 * x)[None, None, :] + np.zeros(shape),
+               2.0 + np.zeros(shape)][:rank]
+        st = complete_from_prim(rank, rho, vel, p) * (geoms[b]["alpha"][0] > 0)
+        arr[...] = st
+        pair.gpu.upload_state(b, st)
+    pair.cpu.fill_ghost_layer()
+    pair.gpu.fill_ghost_layer()
+
+
+def wedge_pair(orc, fvs, method=(0, 1, 2), gcw=(4, 2), n=(40, 28), boxes=None, riemann=0):
+    boxes = boxes or [([0, 0, 0], [n[0] - 1, n[1] - 1, 0])]
+    pair, dx, geoms = make_pair(orc, fvs, 2, n, boxes, gcw, method, polygon_phi(WEDGE),
+                                (0.15, 0.10), riemann)
+    shock_fill(pair, 2, dx, geoms, 0.015, 5.0)
+    return pair, dx, geoms
+
+
+EB_KINDS_DIR = ["EB_US", "EB_SL", "EB_SR", "EB_DS"]
+
+
+def test_fill_cutcell_data_and_flags_bitwise(oracle, fvs):
+    pair, dx, geoms = wedge_pair(oracle, fvs)
+    for d in range(2):
+        for name in EB_KINDS_DIR:
+            ref = pair.cpu.eb_array(0, getattr(oracle, name), d)[0]
+            got = pair.gpu.eb_array(0, getattr(fvs, name), d)
+            assert_bitwise_equal(got, ref, f"{name} dir {d}")
+    flags, count = pair.gpu.is_cut_cell(0)
+    ref = pair.cpu.is_cut_cell(0)
+    assert np.array_equal(flags, ref)
+    assert count == int(ref.sum()) and count > 10
+    pair.close()
+
+
+METHODS = [(0, 1, 2), (0, 0, 0), (1, 1, 1), (2, 1, 1), (2, 0, 0), (2, 1, 2)]
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_cutcell_policies_bitwise(oracle, fvs, method):
+    """PreAdvanceHierarchy, ComputeStableDt, ComputeNumericFluxes (boundary,
+    regular, stabilised, shielded), UpdateConservatively, CompleteFromCons."""
+    gcw = (4, 2) if method[1] == 1 else (3, 2)
+    pair, dx, geoms = wedge_pair(oracle, fvs, method=method, gcw=gcw)
+    pair.cpu.pre_advance_hierarchy()
+    pair.gpu.pre_advance_hierarchy()
+    assert_bitwise_equal(pair.gpu.eb_array(0, fvs.EB_REFERENCE),
+                         pair.cpu.eb_array(0, oracle.EB_REFERENCE)[0], "reference states")
+    for d in range(2):
+        dt_c = pair.cpu.compute_stable_dt(d)
+        dt_g = pair.gpu.compute_stable_dt(d)
+        assert dt_c == dt_g, (d, dt_c, dt_g)
+    dt = 0.3 * min(pair.cpu.compute_stable_dt(d) for d in range(2))
+    for d in (0, 1):
+        pair.cpu.compute_numeric_fluxes(dt, d)
+        pair.gpu.compute_numeric_fluxes(dt, d)
+        assert_bitwise_equal(pair.gpu.eb_array(0, fvs.EB_BOUNDARY_FLUX),
+                             pair.cpu.eb_array(0, oracle.EB_BOUNDARY_FLUX)[0], f"boundary flux {d}")
+        assert_bitwise_equal(pair.gpu.download_fluxes(0, d), pair.cpu.fluxes(0, d)[0],
+                             f"regular flux {d}")
+        for name in ("EB_STABILIZED", "EB_SHIELDED_LEFT", "EB_SHIELDED_RIGHT"):
+            assert_bitwise_equal(pair.gpu.eb_array(0, getattr(fvs, name), d),
+                                 pair.cpu.eb_array(0, getattr(oracle, name), d)[0], f"{name} {d}")
+        pair.cpu.update_conservatively(dt, d)
+        pair.gpu.update_conservatively(dt, d)
+        pair.compare_states(f"update dir {d}")
+        pair.cpu.complete_from_cons()
+        pair.gpu.complete_from_cons()
+        pair.compare_states(f"complete dir {d}")
+    pair.close()
+
+
+@pytest.mark.parametrize("split", [0, 1])
+def test_wedge_run_bitwise_identical_dt_sequence(oracle, fvs, split):
+    pair, dx, geoms = wedge_pair(oracle, fvs, gcw=(8, 6), n=(48, 32))
+    for step in range(15):
+        dt_c = min(pair.cpu.compute_stable_dt(d) for d in range(2))
+        dt_g = pair.gpu.compute_stable_dt_all()
+        assert dt_c == dt_g, (step, dt_c, dt_g)
+        ok_c, _, dts_c = pair.cpu.advance_hierarchy(0.4 * dt_c, split)
+        ok_g, _, dts_g = pair.gpu.advance_hierarchy(0.4 * dt_g, split)
+        assert ok_c and ok_g and dts_c == dts_g, (step, dts_c, dts_g)
+    pair.compare_states("wedge, 15 steps")
+    pair.close()
+
+
+def test_multibox_regular_cut_and_covered_fabs(oracle, fvs):
+    """Four boxes: the wedge cuts some, one is fully regular; plus a box inside
+    a big body (covered)."""
+    n = (48, 32)
+    boxes = [([0, 0, 0], [23, 15, 0]), ([24, 0, 0], [47, 15, 0]), ([0, 16, 0], [23, 31, 0]),
+             ([24, 16, 0], [47, 31, 0])]
+    body = polygon_phi([(0.08, 0.0), (0.16, 0.0), (0.16, 0.05), (0.08, 0.05)])
+    pair, dx, geoms = make_pair(oracle, fvs, 2, n, boxes, (4, 2), (0, 1, 2), body, (0.15, 0.10))
+    types = [eb_fab_type(g) for g in geoms]
+    assert 0 in types and 1 in types
+    shock_fill(pair, 2, dx, geoms, 0.015, 3.0)
+    for step in range(6):
+        dt_c = min(pair.cpu.compute_stable_dt(d) for d in range(2))
+        assert dt_c == pair.gpu.compute_stable_dt_all()
+        ok_c, _, dts_c = pair.cpu.advance_hierarchy(0.4 * dt_c, 1)
+        ok_g, _, dts_g = pair.gpu.advance_hierarchy(0.4 * dt_c, 1)
+        assert ok_c and ok_g and dts_c == dts_g
+    pair.compare_states("multibox EB, 6 steps")
+    pair.close()
+
+
+def test_cfl_violation_rolls_back_cutcell_level(oracle, fvs):
+    pair, dx, geoms = wedge_pair(oracle, fvs)
+    before = pair.gpu.download_state(0)
+    dt = 5.0 * pair.gpu.compute_stable_dt_all()
+    ok_c, fail_c, _ = pair.cpu.advance_hierarchy(dt, 1)
+    ok_g, fail_g, _ = pair.gpu.advance_hierarchy(dt, 1)
+    assert not ok_c and not ok_g and fail_c == fail_g
+    assert_bitwise_equal(pair.gpu.download_state(0), before, "rolled back state")
+    pair.close()
+
+
+def test_sphere_3d_divider_method_bitwise(oracle, fvs):
+    """3-D, MusclHancock<HLL Einfeldt, MinMod> + Kbn(HLL) and Godunov
+    splitting: the method combination of examples/AMReX/EB/3D/Divider.cpp."""
+    n = (20, 16, 12)
+    boxes = [([0, 0, 0], [9, 15, 11]), ([10, 0, 0], [19, 15, 11])]
+    pair, dx, geoms = make_pair(oracle, fvs, 3, n, boxes, (4, 2), (2, 1, 1),
+                                sphere_phi((0.5, 0.4, 0.3), 0.21), (1.0, 0.8, 0.6), nsub=4)
+    shock_fill(pair, 3, dx, geoms, 0.2, 8.0, rho0=1.22)
+    for step in range(4):
+        dt_c = min(pair.cpu.compute_stable_dt(d) for d in range(3))
+        assert dt_c == pair.gpu.compute_stable_dt_all()
+        ok_c, _, dts_c = pair.cpu.advance_hierarchy(0.5 * dt_c, 0)
+        ok_g, _, dts_g = pair.gpu.advance_hierarchy(0.5 * dt_c, 0)
+        assert ok_c and ok_g and dts_c == dts_g
+    pair.compare_states("3-D sphere, 4 steps")
+    flags, count = pair.gpu.is_cut_cell(0)
+    assert np.array_equal(flags, pair.cpu.is_cut_cell(0)) and count > 20
+    pair.close()
+
+
+def test_exact_riemann_wall_solver_within_tolerance(oracle, fvs):
+    pair, dx, geoms = wedge_pair(oracle, fvs, riemann=1)
+    for step in range(5):
+        dt = 0.4 * min(pair.cpu.compute_stable_dt(d) for d in range(2))
+        ok_c, _, _ = pair.cpu.advance_hierarchy(dt, 1)
+        ok_g, _, _ = pair.gpu.advance_hierarchy(dt, 1)
+        assert ok_c and ok_g
+        pair.compare_states(f"exact wall solver step {step}", tol=1e-12 * (step + 1))
+    pair.close()
+
+
+def test_tagging_bitwise(oracle, fvs):
+    pair, dx, geoms = wedge_pair(oracle, fvs)
+    for _ in range(5):
+        dt = 0.4 * pair.gpu.compute_stable_dt_all()
+        pair.cpu.advance_hierarchy(dt, 1)
+        pair.gpu.advance_hierarchy(dt, 1)
+    conds = [(0, 1e-2), (4, 0.05)]
+    for use_alpha in (False, True):
+        ref = pair.cpu.tag_gradient(0, conds, use_alpha)
+        got = pair.gpu.tag_gradient(0, conds, use_alpha)
+        assert np.array_equal(got, ref) and ref.sum() > 0
+    ref = pair.cpu.tag_cutcells(0, pair.cpu.tag_gradient(0, conds, True))
+    got = pair.gpu.tag_cutcells(0, pair.gpu.tag_gradient(0, conds, True))
+    assert np.array_equal(got, ref)
+    ref2 = oracle.tag_buffer(ref.copy(), 2, 4)
+    got2 = pair.gpu.tag_buffer(got.copy(), 2, 4)
+    assert np.array_equal(got2, ref2) and (ref2 == 3).sum() > 0
+    rng = np.random.default_rng(7)
+    t3 = (rng.random((9, 11, 13)) < 0.05).astype(np.int8)
+    assert np.array_equal(pair.gpu.tag_buffer(t3.copy(), 3, 2), oracle.tag_buffer(t3.copy(), 3, 2))
+    t1 = (rng.random((1, 1, 64)) < 0.1).astype(np.int8)
+    assert np.array_equal(pair.gpu.tag_buffer(t1.copy(), 1, 3), oracle.tag_buffer(t1.copy(), 1, 3))
+    t2 = rng.integers(0, 4, size=(1, 23, 17)).astype(np.int8)
+    assert np.array_equal(pair.gpu.tag_buffer(t2.copy(), 2, 3), oracle.tag_buffer(t2.copy(), 2, 3))
+    pair.close()

@@ -1,0 +1,37 @@
+"""Tuning helper: builds libfvs_b200_<tag>.so with extra -D flags for the
+3-D HLLEM-Larrouturou unit only (the bench configuration); the other objects
+are reused from the normal build.  Select with FVS_B200_LIB=<path>.
+
+    python tools/build_variant.py <tag> [-DNAME=VALUE ...]
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from finitevolumesolver_b200 import build as b  # noqa: E402
+
+
+def main():
+    tag, flags = sys.argv[1], sys.argv[2:]
+    b.build()
+    obj = os.path.join(b.OBJ, f"variant_{tag}.o")
+    cmd = [b.NVCC] + b.NVCC_FLAGS + flags + ["-DFVS_INST_D=3", "-DFVS_INST_BASE=0", "-Xptxas", "-v",
+           "-I", b.INCLUDE, "-c", os.path.join(b.CSRC, "sweep_inst.cu"), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        raise SystemExit(r.stderr)
+    lines = r.stderr.splitlines()
+    for i, l in enumerate(lines):
+        if "fused_sweep" in l and "ELi1ELi2E" in l and "Compiling" in l:
+            print(l.split("'")[1][:60], "|", lines[i + 2].strip() if i + 2 < len(lines) else "",
+                  "|", lines[i + 1].strip())
+    objs = [os.path.join(b.OBJ, u[1]) for u in b._units() if u[1] != "sweep_D3_B0.o"] + [obj]
+    lib = os.path.join(b.HERE, f"libfvs_b200_{tag}.so")
+    subprocess.check_call([b.NVCC, "-shared", "-o", lib, "-ccbin", "/usr/bin/g++"] + objs + ["-ldl"])
+    print(lib)
+
+
+if __name__ == "__main__":
+    main()
