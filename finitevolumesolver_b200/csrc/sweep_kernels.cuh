@@ -125,8 +125,8 @@ FVS_DEV void reduce_max_signal(double v, unsigned long long* target) {
 
 // Pipeline stages -----------------------------------------------------------
 // stage A: the two predicted edge states of the cell with neighbours qm, qp
-template <int D, int DIR, int RECON, int LIM, typename S0, typename S2>
-FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const Complete<D>& q0, const S2& qp,
+template <int D, int DIR, int RECON, int LIM, typename S0, typename S1, typename S2>
+FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const S1& q0, const S2& qp,
                            double lambda_half, Edge<D>& recL, Edge<D>& recR) {
   if constexpr (RECON == kReconMusclHancock) {
     with_fallback([&](auto M, Flag& fl) {
@@ -324,9 +324,225 @@ fused_sweep_yz_kernel(const SweepArgs A) {
 }
 
 // ---------------------------------------------------------------------------
-// Fused sweep along x: warp per row, shuffle pipeline.
-template <int D, int BASE, int RECON, int LIM>
+// Fused sweep along y or z, shared-memory pipeline: the same march as above,
+// but the loop-carried pipeline state (the conservative parts of cells j-1 and
+// j-2, the upper edge state of cell j-2, the flux through face j-2 and the dt
+// data of cell j-1) lives in thread-private shared-memory slots instead of
+// registers, and the stages are separated by compiler barriers.  The register
+// budget is then the largest single stage, not the whole pipeline, which
+// doubles the resident warps per SM; the kernel is latency bound on dependent
+// fp64 chains (profiles/), so occupancy is what buys throughput.  Slots are
+// padded to an odd number of doubles: a warp's 64-bit accesses are then
+// bank-conflict free.
+template <typename T, bool kOdd = (sizeof(T) / 8) % 2 == 1> struct Slot {
+  T v;
+};
+template <typename T> struct Slot<T, false> {
+  T v;
+  double pad;
+};
+#define FVS_STAGE_BARRIER() asm volatile("" ::: "memory")
+
+#ifndef FVS_SWEEP_PREFETCH
+#define FVS_SWEEP_PREFETCH 1
+#endif
+
+template <int D, int DIR, int BASE, int RECON, int LIM>
 __global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
+fused_sweep_yz_smem_kernel(const SweepArgs A) {
+  static_assert(DIR >= 0 && DIR < D, "sweep direction");
+  // first order needs the stored p and a of the neighbour, MUSCL only its
+  // conservative part
+  using QT = std::conditional_t<RECON == kReconMusclHancock, Cons<D>, Complete<D>>;
+  __shared__ Slot<QT> s_q[3][kSweepThreads];        // ring: slot j % 3 holds cell j
+  __shared__ Slot<Edge<D>> s_rec[2][kSweepThreads]; // ring: slot j & 1 holds recR of cell j-1
+  __shared__ Slot<Cons<D>> s_F[kSweepThreads];      // flux through face j-2
+  __shared__ Slot<DtData<D, BASE>> s_dt[kSweepThreads]; // dt data of cell j-1
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  const int n0 = B.n[0];
+  // DIR == 0: one thread per grid ROW (lanes of a warp are adjacent in y);
+  // every 8-byte load then touches its own 32-byte sector, which L1 serves
+  // again for the next three cells of the row
+  const long long nlines = DIR == 0 ? (long long)B.n[1] * B.n[2]
+                                    : (long long)n0 * ((DIR == 1) ? B.n[2] : B.n[1]);
+  const long long line = (long long)blockIdx.x * kSweepThreads + threadIdx.x;
+  const int nd = B.n[DIR];
+  const int o_first = blockIdx.z * A.seg_len;
+  const int tid = threadIdx.x;
+  double maxsig = 0.0;
+  int failed = 0;
+  if (line < nlines && o_first < nd) {
+    const Eqs eq(A.eq);
+    const int o_last = min(nd, o_first + A.seg_len) - 1;
+    const long long stride =
+        DIR == 0 ? 1 : ((DIR == 1) ? (long long)n0 : (long long)n0 * B.n[1]);
+    long long base;
+    if (DIR == 0) {
+      base = line * n0;
+    } else if (DIR == 1) {
+      const int x = (int)(line % n0);
+      const int z = (int)(line / n0);
+      base = x + (long long)n0 * B.n[1] * z;
+    } else {
+      base = line;
+    }
+    const double* src = B.src + base;
+    double* dst = B.dst + base;
+    const long long sc = B.sc;
+    const int ulo = B.ulo, uhi = B.uhi;
+    const unsigned char* dtmask = B.dtmask;
+
+    Complete<D> q0; // cell j
+#if FVS_SWEEP_PREFETCH
+    Complete<D> qn; // prefetched cell j+1
+#endif
+    DtData<D, BASE> dt_cur;
+    const int jstart = max(o_first - 2, 0);
+    load_complete<D>(q0, src + stride * jstart, sc);
+#if FVS_SWEEP_PREFETCH
+    qn = q0;
+    if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
+#endif
+    {
+      Cons<D> c0;
+      copy_cons<D>(c0, q0);
+      QT r0;
+      if constexpr (RECON == kReconMusclHancock) {
+        r0 = c0;
+      } else {
+        r0 = q0;
+      }
+      s_q[0][tid].v = r0;
+      s_q[1][tid].v = r0;
+      s_q[2][tid].v = r0;
+      Edge<D> e0;
+      e0.q = q0;
+      e0.rc = FastMath::rcp(q0.rho);
+      s_rec[0][tid].v = e0;
+      s_rec[1][tid].v = e0;
+      s_F[tid].v = c0;
+      stage_dt_cell<D, BASE>(dt_cur, q0);
+      s_dt[tid].v = dt_cur;
+    }
+    const int jend = o_last + 2;
+    const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
+    const int je = min(min(uhi + 2, nd - 1), jend); // inclusive
+    int m3 = jstart % 3; // j % 3
+#pragma unroll 1
+    for (int j = jstart; j <= jend; ++j) {
+      if (j > jstart) {
+#if FVS_SWEEP_PREFETCH
+        q0 = qn;
+#else
+        if (j < nd) load_complete<D>(q0, src + stride * j, sc);
+#endif
+        if (j < nd) stage_dt_cell<D, BASE>(dt_cur, q0);
+      }
+#if FVS_SWEEP_PREFETCH
+      if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
+#endif
+      const int i1 = m3 == 0 ? 2 : m3 - 1;  // (j - 1) % 3
+      const int i2 = i1 == 0 ? 2 : i1 - 1;  // (j - 2) % 3
+      const int cr = j & 1;
+      QT& q1 = s_q[i1][tid].v;
+      QT& q2 = s_q[i2][tid].v;
+      Edge<D>& recR_prev = s_rec[cr ^ 1][tid].v;
+      Edge<D>& recR_out = s_rec[cr][tid].v;
+      Cons<D>& F_prev = s_F[tid].v;
+      Edge<D> recL;
+      Cons<D> F;
+      if (j >= js && j <= je) {
+        // steady state: stages A, B, C share one fast-path validity flag
+        Complete<D> out;
+        with_fallback([&](auto M, Flag& fl) {
+          using MM = decltype(M);
+          {
+            Edge<D> recR;
+            if constexpr (RECON == kReconMusclHancock) {
+              muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, A.lambda_half, recL, recR, fl);
+            } else {
+              recL.q = q1;
+              recL.rc = MM::rcp(q1.rho);
+              recR = recL;
+            }
+            recR_out = recR;
+          }
+          FVS_STAGE_BARRIER();
+          base_flux<MM, D, DIR, BASE>(eq, F, recR_prev, recL, fl, failed);
+          FVS_STAGE_BARRIER();
+          out.rho = q2.rho + A.lambda * (F_prev.rho - F.rho);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            out.mom[d] = q2.mom[d] + A.lambda * (F_prev.mom[d] - F.mom[d]);
+          }
+          out.E = q2.E + A.lambda * (F_prev.E - F.E);
+          const Rcp rc = MM::rcp(out.rho);
+          MM::check(rc, fl);
+          complete_from_cons<MM, D>(eq.m, out, rc, fl);
+        });
+        store_complete<D>(dst + stride * (j - 2), sc, out);
+      } else {
+        // stage A: cell j-1
+        if (j >= jstart + (RECON == kReconMusclHancock ? 2 : 1) && j - 1 >= ulo - 1 &&
+            j - 1 <= uhi + 1) {
+          Edge<D> recR;
+          if constexpr (RECON == kReconMusclHancock) {
+            stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
+          } else {
+            recL.q = q1;
+            recL.rc = FastMath::rcp(q1.rho);
+            recR = recL;
+          }
+          recR_out = recR;
+        } else {
+          recL = recR_prev;
+          recR_out = recR_prev;
+        }
+        FVS_STAGE_BARRIER();
+        // stage B: face j-1
+        if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo &&
+            j - 1 <= uhi + 1) {
+          stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
+        } else {
+          F = F_prev;
+        }
+        FVS_STAGE_BARRIER();
+        // stage C: cell j-2
+        if (j - 2 >= o_first) {
+          Complete<D> out;
+          stage_update<D>(eq, out, q2, F_prev, F, A.lambda, j - 2 >= ulo && j - 2 <= uhi);
+          store_complete<D>(dst + stride * (j - 2), sc, out);
+        }
+      }
+      FVS_STAGE_BARRIER();
+      // stage D: face (j-1 | j) of the stored states
+      if (j > jstart && j < nd && dtmask[j - 1]) {
+        const double s = stage_dt_face<D, DIR, BASE>(eq, s_dt[tid].v, dt_cur, failed);
+        maxsig = s > maxsig ? s : maxsig;
+      }
+      // rotate: slot j % 3 <- cell j, flux and dt slots
+      if constexpr (RECON == kReconMusclHancock) {
+        copy_cons<D>(s_q[m3][tid].v, q0);
+      } else {
+        s_q[m3][tid].v = q0;
+      }
+      F_prev = F;
+      s_dt[tid].v = dt_cur;
+      FVS_STAGE_BARRIER();
+      m3 = m3 == 2 ? 0 : m3 + 1;
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
+  if (failed) *A.fail_flag = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Fused sweep along x: warp per row, shuffle pipeline.
+#ifndef FVS_SWEEP_X_MIN_BLOCKS
+#define FVS_SWEEP_X_MIN_BLOCKS 2
+#endif
+template <int D, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_X_MIN_BLOCKS)
 fused_sweep_x_kernel(const SweepArgs A) {
   constexpr int DIR = 0;
   constexpr int kWarps = kSweepThreads / 32;

@@ -143,15 +143,15 @@ def test_wedge_run_bitwise_identical_dt_sequence(oracle, fvs, split):
 
 
 def test_multibox_regular_cut_and_covered_fabs(oracle, fvs):
-    """Four boxes: the wedge cuts some, one is fully regular; plus a box inside
-    a big body (covered)."""
-    n = (48, 32)
-    boxes = [([0, 0, 0], [23, 15, 0]), ([24, 0, 0], [47, 15, 0]), ([0, 16, 0], [23, 31, 0]),
-             ([24, 16, 0], [47, 31, 0])]
-    body = polygon_phi([(0.08, 0.0), (0.16, 0.0), (0.16, 0.05), (0.08, 0.05)])
+    """Three boxes along x: one regular, one cut by the body's face, one fully
+    covered (ghost cells included) -- all three amrex::FabType branches."""
+    n = (72, 16)
+    boxes = [([0, 0, 0], [23, 15, 0]), ([24, 0, 0], [47, 15, 0]), ([48, 0, 0], [71, 15, 0])]
+    dxx = 0.15 / 72
+    body = polygon_phi([(40.3 * dxx, -1.0), (2.0, -1.0), (2.0, 1.0), (38.6 * dxx, 1.0)])
     pair, dx, geoms = make_pair(oracle, fvs, 2, n, boxes, (4, 2), (0, 1, 2), body, (0.15, 0.10))
     types = [eb_fab_type(g) for g in geoms]
-    assert 0 in types and 1 in types
+    assert types == [0, 1, -1], types
     shock_fill(pair, 2, dx, geoms, 0.015, 3.0)
     for step in range(6):
         dt_c = min(pair.cpu.compute_stable_dt(d) for d in range(2))

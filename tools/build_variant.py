@@ -21,12 +21,11 @@ def main():
            "-I", b.INCLUDE, "-c", os.path.join(b.CSRC, "sweep_inst.cu"), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
-        raise SystemExit(r.stderr)
+        raise SystemExit("\n".join(x for x in r.stderr.splitlines() if "error" in x.lower()))
     lines = r.stderr.splitlines()
     for i, l in enumerate(lines):
-        if "fused_sweep" in l and "ELi1ELi2E" in l and "Compiling" in l:
-            print(l.split("'")[1][:60], "|", lines[i + 2].strip() if i + 2 < len(lines) else "",
-                  "|", lines[i + 1].strip())
+        if "fused_sweep" in l and "ELi1ELi2E" in l and "Function properties" in l:
+            print(tag, l.split()[-1][:48], "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
     objs = [os.path.join(b.OBJ, u[1]) for u in b._units() if u[1] != "sweep_D3_B0.o"] + [obj]
     lib = os.path.join(b.HERE, f"libfvs_b200_{tag}.so")
     subprocess.check_call([b.NVCC, "-shared", "-o", lib, "-ccbin", "/usr/bin/g++"] + objs + ["-ldl"])
