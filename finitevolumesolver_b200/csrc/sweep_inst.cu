@@ -5,7 +5,7 @@
 #include "sweep_kernels.cuh"
 
 #ifndef FVS_SWEEP_SMEM
-#define FVS_SWEEP_SMEM 0
+#define FVS_SWEEP_SMEM 1
 #endif
 #ifndef FVS_SWEEP_X_LINES
 #define FVS_SWEEP_X_LINES 0

@@ -186,11 +186,13 @@ FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtDa
 #ifndef FVS_SWEEP_THREADS
 #define FVS_SWEEP_THREADS 128
 #endif
+// 3 resident blocks (168 registers, 12 warps per SM): measured best for the
+// shared-memory pipeline (profiles/r01_tuning.md)
 #ifndef FVS_SWEEP_MIN_BLOCKS
-#define FVS_SWEEP_MIN_BLOCKS 2
+#define FVS_SWEEP_MIN_BLOCKS 3
 #endif
 #ifndef FVS_SWEEP_UNROLL
-#define FVS_SWEEP_UNROLL 2
+#define FVS_SWEEP_UNROLL 1
 #endif
 constexpr int kSweepThreads = FVS_SWEEP_THREADS;
 constexpr int kSweepUnroll = FVS_SWEEP_UNROLL;
@@ -539,7 +541,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 // ---------------------------------------------------------------------------
 // Fused sweep along x: warp per row, shuffle pipeline.
 #ifndef FVS_SWEEP_X_MIN_BLOCKS
-#define FVS_SWEEP_X_MIN_BLOCKS 2
+#define FVS_SWEEP_X_MIN_BLOCKS 4
 #endif
 template <int D, int BASE, int RECON, int LIM>
 __global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_X_MIN_BLOCKS)
