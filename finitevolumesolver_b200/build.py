@@ -38,6 +38,7 @@ def _units():
                           [f"-DFVS_INST_D={d}", f"-DFVS_INST_BASE={b}"]))
     units.append(("generic_kernels.cu", "generic_kernels.o", []))
     units.append(("cutcell.cu", "cutcell.o", []))
+    units.append(("amr.cu", "amr.o", []))
     units.append(("context.cu", "context.o", []))
     return units
 

@@ -42,6 +42,8 @@ SYMBOLS = [
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
     "fvs_eb_array_box", "fvs_download_eb_array", "fvs_cut_cell_flags",
     "fvs_tag_gradient", "fvs_tag_cutcells", "fvs_tag_buffer",
+    "fvs_set_refine_ratio", "fvs_reset_coarse_fine_fluxes", "fvs_accumulate_coarse_fine_fluxes",
+    "fvs_apply_flux_correction", "fvs_coarsen_conservatively", "fvs_fill_ghost_layer_two_levels",
 ]
 
 
@@ -171,19 +173,58 @@ class Context:
                       for lo, hi in boxes]
         self.owner = list(owner) if owner is not None else [0] * len(boxes)
         self.comm_rank = comm_rank
+        self.level = 0
+        self._owns = True
         cfg = Config(rank, gamma, base, recon, limiter, device, comm_rank, comm_size)
         self.h = C.c_void_p()
         _check(lib().fvs_create(C.byref(cfg), C.byref(self.h)))
         lo, hi = _boxes(self.boxes)
         own = (C.c_int * len(boxes))(*self.owner)
-        _check(lib().fvs_level_define(self.h, 0, _i3(domain_lo), _i3(domain_hi), _d3(dx),
+        _check(lib().fvs_level_define(self.h, self.level, _i3(domain_lo), _i3(domain_hi), _d3(dx),
                                       _i3(periodic), len(boxes), lo, hi, own, scratch_gcw,
                                       flux_gcw))
 
     def close(self):
-        if self.h:
+        if self.h and self._owns:
             lib().fvs_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
+
+    def define_level(self, level, domain_lo, domain_hi, dx, boxes, scratch_gcw=4, flux_gcw=2,
+                     periodic=(0, 0, 0)):
+        """Defines a further (finer) level and returns a view of the context
+        whose methods address that level."""
+        import copy
+        v = copy.copy(self)
+        v._owns = False
+        v.level = level
+        v.boxes = [(list(lo) + [0] * (3 - len(lo)), list(hi) + [0] * (3 - len(hi)))
+                   for lo, hi in boxes]
+        v.owner = [self.comm_rank] * len(boxes)
+        lo, hi = _boxes(v.boxes)
+        own = (C.c_int * len(boxes))(*v.owner)
+        _check(lib().fvs_level_define(self.h, level, _i3(domain_lo), _i3(domain_hi), _d3(dx),
+                                      _i3(periodic), len(boxes), lo, hi, own, scratch_gcw,
+                                      flux_gcw))
+        return v
+
+    # ---- coarse-fine (two levels) ---------------------------------------------
+    def set_refine_ratio(self, ratio):
+        _check(lib().fvs_set_refine_ratio(self.h, _i3(ratio, 1)))
+
+    def reset_coarse_fine_fluxes(self, fine, coarse):
+        _check(lib().fvs_reset_coarse_fine_fluxes(self.h, fine, coarse))
+
+    def accumulate_coarse_fine_fluxes(self, level, scale, direction):
+        _check(lib().fvs_accumulate_coarse_fine_fluxes(self.h, level, C.c_double(scale), direction))
+
+    def apply_flux_correction(self, fine, coarse, dt=0.0):
+        _check(lib().fvs_apply_flux_correction(self.h, fine, coarse, C.c_double(dt)))
+
+    def coarsen_conservatively(self, fine, coarse):
+        _check(lib().fvs_coarsen_conservatively(self.h, fine, coarse))
+
+    def fill_ghost_layer_two_levels(self, fine, coarse):
+        _check(lib().fvs_fill_ghost_layer_two_levels(self.h, fine, coarse))
 
     def __del__(self):
         try:
@@ -201,7 +242,7 @@ class Context:
         _check(lib().fvs_set_method(self.h, base, recon, limiter))
 
     def add_bc(self, direction, side, kind):
-        _check(lib().fvs_level_add_boundary(self.h, 0, direction, side, kind))
+        _check(lib().fvs_level_add_boundary(self.h, self.level, direction, side, kind))
 
     def set_regrid_frequency(self, f):
         _check(lib().fvs_set_regrid_frequency(self.h, f))
@@ -216,7 +257,7 @@ class Context:
         bcent = np.ascontiguousarray(geom["bcent"], dtype=np.float64)
         bnorm = np.ascontiguousarray(geom["bnorm"], dtype=np.float64)
         ptrs = (C.POINTER(C.c_double) * 3)(*[_dp(b) for b in betas])
-        _check(lib().fvs_level_set_eb(self.h, 0, box, _dp(alpha), ptrs, _dp(bcent), _dp(bnorm),
+        _check(lib().fvs_level_set_eb(self.h, self.level, box, _dp(alpha), ptrs, _dp(bcent), _dp(bnorm),
                                       fab_type))
 
     def pre_advance_hierarchy(self):
@@ -224,14 +265,14 @@ class Context:
 
     def eb_array(self, box, kind, direction=0):
         lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
-        _check(lib().fvs_eb_array_box(self.h, 0, box, kind, direction, lo, hi, C.byref(nc)))
+        _check(lib().fvs_eb_array_box(self.h, self.level, box, kind, direction, lo, hi, C.byref(nc)))
         out = np.empty(self._shape(list(lo), list(hi), nc.value))
-        _check(lib().fvs_download_eb_array(self.h, 0, box, kind, direction, _dp(out)))
+        _check(lib().fvs_download_eb_array(self.h, self.level, box, kind, direction, _dp(out)))
         return out
 
     def is_cut_cell(self, box):
         out = np.zeros(self.state_shape(box)[1:], dtype=np.uint8)
-        n = lib().fvs_cut_cell_flags(self.h, 0, box, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        n = lib().fvs_cut_cell_flags(self.h, self.level, box, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
         if n < 0:
             raise FvsError(lib().fvs_last_error().decode())
         return out, n
@@ -245,14 +286,14 @@ class Context:
             tags = np.zeros(self._tag_shape(box), dtype=np.int8)
         comps = (C.c_int * len(conditions))(*[c for c, _ in conditions])
         tols = (C.c_double * len(conditions))(*[t for _, t in conditions])
-        _check(lib().fvs_tag_gradient(self.h, 0, box, len(conditions), comps, tols,
+        _check(lib().fvs_tag_gradient(self.h, self.level, box, len(conditions), comps, tols,
                                       1 if use_alpha else 0, tags.ctypes.data_as(C.c_char_p)))
         return tags
 
     def tag_cutcells(self, box, tags=None):
         if tags is None:
             tags = np.zeros(self._tag_shape(box), dtype=np.int8)
-        _check(lib().fvs_tag_cutcells(self.h, 0, box, tags.ctypes.data_as(C.c_char_p)))
+        _check(lib().fvs_tag_cutcells(self.h, self.level, box, tags.ctypes.data_as(C.c_char_p)))
         return tags
 
     def tag_buffer(self, tags, rank, width):
@@ -273,12 +314,12 @@ class Context:
 
     def state_box(self, box):
         lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
-        _check(lib().fvs_state_box(self.h, 0, box, lo, hi, C.byref(nc)))
+        _check(lib().fvs_state_box(self.h, self.level, box, lo, hi, C.byref(nc)))
         return list(lo), list(hi), nc.value
 
     def flux_box(self, box, direction):
         lo, hi, nc = (C.c_int * 3)(), (C.c_int * 3)(), C.c_int()
-        _check(lib().fvs_flux_box(self.h, 0, box, direction, lo, hi, C.byref(nc)))
+        _check(lib().fvs_flux_box(self.h, self.level, box, direction, lo, hi, C.byref(nc)))
         return list(lo), list(hi), nc.value
 
     @staticmethod
@@ -291,54 +332,54 @@ class Context:
     def upload_state(self, box, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         assert arr.shape == self.state_shape(box), (arr.shape, self.state_shape(box))
-        _check(lib().fvs_upload_state(self.h, 0, box, _dp(arr)))
+        _check(lib().fvs_upload_state(self.h, self.level, box, _dp(arr)))
 
     def download_state(self, box, out=None):
         if out is None:
             out = np.empty(self.state_shape(box))
-        _check(lib().fvs_download_state(self.h, 0, box, _dp(out)))
+        _check(lib().fvs_download_state(self.h, self.level, box, _dp(out)))
         return out
 
     def download_fluxes(self, box, direction):
         out = np.empty(self._shape(*self.flux_box(box, direction)))
-        _check(lib().fvs_download_fluxes(self.h, 0, box, direction, _dp(out)))
+        _check(lib().fvs_download_fluxes(self.h, self.level, box, direction, _dp(out)))
         return out
 
     def upload_fluxes(self, box, direction, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float64)
         assert arr.shape == self._shape(*self.flux_box(box, direction))
-        _check(lib().fvs_upload_fluxes(self.h, 0, box, direction, _dp(arr)))
+        _check(lib().fvs_upload_fluxes(self.h, self.level, box, direction, _dp(arr)))
 
     def compute_stable_dt(self, direction):
         out = C.c_double()
-        _check(lib().fvs_compute_stable_dt(self.h, 0, direction, C.byref(out)))
+        _check(lib().fvs_compute_stable_dt(self.h, self.level, direction, C.byref(out)))
         return out.value
 
     def compute_stable_dt_all(self):
         out = C.c_double()
-        _check(lib().fvs_compute_stable_dt_all(self.h, 0, C.byref(out)))
+        _check(lib().fvs_compute_stable_dt_all(self.h, self.level, C.byref(out)))
         return out.value
 
     def compute_numeric_fluxes(self, dt, direction):
-        _check(lib().fvs_compute_numeric_fluxes(self.h, 0, C.c_double(dt), direction))
+        _check(lib().fvs_compute_numeric_fluxes(self.h, self.level, C.c_double(dt), direction))
 
     def update_conservatively(self, dt, direction):
-        _check(lib().fvs_update_conservatively(self.h, 0, C.c_double(dt), direction))
+        _check(lib().fvs_update_conservatively(self.h, self.level, C.c_double(dt), direction))
 
     def complete_from_cons(self):
-        _check(lib().fvs_complete_from_cons(self.h, 0))
+        _check(lib().fvs_complete_from_cons(self.h, self.level))
 
     def sweep(self, dt, direction):
         """Fused sweep. Returns (status, level_dt)."""
         out = C.c_double()
-        rc = _check(lib().fvs_sweep(self.h, 0, C.c_double(dt), direction, C.byref(out)))
+        rc = _check(lib().fvs_sweep(self.h, self.level, C.c_double(dt), direction, C.byref(out)))
         return rc, out.value
 
     def fill_ghost_layer(self):
-        _check(lib().fvs_fill_ghost_layer(self.h, 0))
+        _check(lib().fvs_fill_ghost_layer(self.h, self.level))
 
     def apply_boundary_condition(self, direction):
-        _check(lib().fvs_apply_boundary_condition(self.h, 0, direction))
+        _check(lib().fvs_apply_boundary_condition(self.h, self.level, direction))
 
     def advance_hierarchy(self, dt, split):
         """Returns (ok, failure_dt, sweep_dts)."""

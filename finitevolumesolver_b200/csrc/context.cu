@@ -195,6 +195,15 @@ struct Level {
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::BcDesc>>> bc_cache;
   std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceArray<fvs::PackDesc>>> pack_cache;
   long long max_copy_cells{0};
+  // coarse-fine: the flux register this level holds towards its coarser level
+  struct CfRegister {
+    int patch, dir, side;
+    Box plane; // coarse faces (index of the cell to the right of the face)
+    double* reg{nullptr};
+    unsigned char* open{nullptr};
+  };
+  std::vector<CfRegister> cf_regs;
+  int cf_coarse{-1};
   // embedded boundary
   bool has_eb{false};
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::EbDesc>>> eb_cache;
@@ -214,6 +223,7 @@ struct fvs_ctx {
   double time_point{0.0};
   int regrid_frequency{1};
   int cutcell_riemann{FVS_RIEMANN_HLL_EINFELDT};
+  int ratio[3]{2, 2, 2};
   // stable-dt accumulators
   unsigned long long* d_slots{nullptr};
   unsigned long long* h_slots{nullptr}; // pinned
@@ -277,6 +287,10 @@ void free_level(Level& L) {
   for (PeerExchange& pe : L.peers) {
     if (pe.sendbuf) cudaFree(pe.sendbuf);
     if (pe.recvbuf) cudaFree(pe.recvbuf);
+  }
+  for (Level::CfRegister& r : L.cf_regs) {
+    if (r.reg) cudaFree(r.reg);
+    if (r.open) cudaFree(r.open);
   }
   L = Level();
 }
@@ -941,6 +955,151 @@ void cc_pre_advance(fvs_ctx* ctx, Level& L) {
   const int rc = fvs::launch_cc_reference_states(eb_args(ctx, L, 0, 0.0), ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
+}
+
+
+// ---- coarse-fine ----------------------------------------------------------------
+int coarsen_index(int i, int r) { return i >= 0 ? i / r : -((-i + r - 1) / r); }
+Box coarsen_box(const Box& b, const int ratio[3]) {
+  Box c;
+  for (int d = 0; d < 3; ++d) {
+    c.lo[d] = coarsen_index(b.lo[d], ratio[d]);
+    c.hi[d] = coarsen_index(b.hi[d], ratio[d]);
+  }
+  return c;
+}
+Box refine_box(const Box& b, const int ratio[3]) {
+  Box f;
+  for (int d = 0; d < 3; ++d) {
+    f.lo[d] = b.lo[d] * ratio[d];
+    f.hi[d] = (b.hi[d] + 1) * ratio[d] - 1;
+  }
+  return f;
+}
+bool box_contains(const Box& b, const int p[3]) {
+  return p[0] >= b.lo[0] && p[0] <= b.hi[0] && p[1] >= b.lo[1] && p[1] <= b.hi[1] &&
+         p[2] >= b.lo[2] && p[2] <= b.hi[2];
+}
+fvs::ArrayRef array_ref(double* p, const Box& b, long long sc) {
+  fvs::ArrayRef a{};
+  a.p = p;
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = b.lo[d];
+    a.n[d] = b.len(d);
+  }
+  a.sc = sc;
+  return a;
+}
+void effective_ratio(const fvs_ctx* ctx, int ratio[3]) {
+  for (int d = 0; d < 3; ++d) ratio[d] = d < ctx->cfg.rank ? ctx->ratio[d] : 1;
+}
+void require_single_rank(const Level& L) {
+  for (int o : L.owner)
+    if (o != L.owner[0] || (int)L.patches.size() != (int)L.boxes.size()) {
+      throw Error("coarse-fine operations need both levels on this rank");
+    }
+}
+// FluxRegister of `fine` towards `coarse`: one plane of coarse faces per side
+// of every fine box; ClearInternalBorders = faces whose outside cell lies
+// under another fine box (or outside the domain) are closed.
+void define_flux_register(fvs_ctx* ctx, Level& fine, Level& coarse, int coarse_index) {
+  for (Level::CfRegister& r : fine.cf_regs) {
+    if (r.reg) cudaFree(r.reg);
+    if (r.open) cudaFree(r.open);
+  }
+  fine.cf_regs.clear();
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const int rank = ctx->cfg.rank;
+  for (size_t f = 0; f < fine.patches.size(); ++f) {
+    const Box cb = coarsen_box(fine.patches[f].valid, ratio);
+    for (int d = 0; d < rank; ++d)
+      for (int side = 0; side < 2; ++side) {
+        Level::CfRegister r;
+        r.patch = (int)f;
+        r.dir = d;
+        r.side = side;
+        r.plane = cb;
+        r.plane.lo[d] = r.plane.hi[d] = side == 0 ? cb.lo[d] : cb.hi[d] + 1;
+        const size_t faces = (size_t)r.plane.size();
+        std::vector<unsigned char> open(faces, 1);
+        size_t n = 0;
+        for (int k = r.plane.lo[2]; k <= r.plane.hi[2]; ++k)
+          for (int j = r.plane.lo[1]; j <= r.plane.hi[1]; ++j)
+            for (int i = r.plane.lo[0]; i <= r.plane.hi[0]; ++i, ++n) {
+              int out[3] = {i, j, k};
+              if (side == 0) out[d] -= 1;
+              for (const Patch& g : fine.patches) {
+                if (box_contains(coarsen_box(g.valid, ratio), out)) open[n] = 0;
+              }
+              if (!box_contains(coarse.domain, out)) open[n] = 0;
+            }
+        r.reg = device_alloc_zero<double>(ctx, faces * ctx->ncons());
+        FVS_CUDA(cudaMalloc(&r.open, faces));
+        FVS_CUDA(cudaMemcpy(r.open, open.data(), faces, cudaMemcpyHostToDevice));
+        fine.cf_regs.push_back(r);
+      }
+  }
+  fine.cf_coarse = coarse_index;
+}
+
+// op 0 FineAdd (level = fine), 1 CrseInit (level = coarse), 2 Reflux (level = coarse)
+void run_flux_register(fvs_ctx* ctx, Level& reg_level, Level& level, int op, int dir, double mult,
+                       double vol) {
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  std::vector<fvs::RegisterDesc> host;
+  long long max_faces = 1;
+  for (const Level::CfRegister& r : reg_level.cf_regs) {
+    if (r.dir != dir) continue;
+    fvs::RegisterDesc d{};
+    d.reg = array_ref(r.reg, r.plane, r.plane.size());
+    d.open = r.open;
+    d.side = r.side;
+    if (op == 0) {
+      Patch& p = level.patches[(size_t)r.patch];
+      d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
+      for (int e = 0; e < 3; ++e) {
+        d.lo[e] = r.plane.lo[e];
+        d.len[e] = r.plane.len(e);
+      }
+      max_faces = std::max(max_faces, r.plane.size());
+      host.push_back(d);
+    } else {
+      for (Patch& p : level.patches) {
+        Box faces = r.plane;
+        if (op == 1) {
+          Box nodes = p.valid;
+          nodes.hi[dir] += 1;
+          faces = fvs::intersect(r.plane, nodes);
+          if (!faces.ok()) continue;
+          d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
+        } else {
+          d.other = array_ref(p.buf[level.cur], p.sbox, p.cells);
+        }
+        for (int e = 0; e < 3; ++e) {
+          d.box_lo[e] = p.valid.lo[e];
+          d.box_hi[e] = p.valid.hi[e];
+          d.lo[e] = faces.lo[e];
+          d.len[e] = faces.len(e);
+        }
+        max_faces = std::max(max_faces, faces.size());
+        host.push_back(d);
+      }
+    }
+  }
+  if (host.empty()) return;
+  DeviceArray<fvs::RegisterDesc> dev;
+  dev.upload(host);
+  ctx->launches += fvs::launch_flux_register(dev.ptr, (int)host.size(), op, ctx->ncons(), dir, ratio,
+                                             mult, vol, max_faces, ctx->stream);
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  FVS_CUDA(cudaGetLastError());
+}
+
+double cell_volume(const fvs_ctx* ctx, const Level& L) {
+  const int rank = ctx->cfg.rank;
+  return L.dx[0] * (rank > 1 ? L.dx[1] : 1.0) * (rank > 2 ? L.dx[2] : 1.0);
 }
 
 } // namespace
@@ -1847,6 +2006,153 @@ long fvs_cut_cell_flags(fvs_ctx* ctx, int level, int box, unsigned char* flags) 
     return (int)FVS_OK;
   });
   return rc == FVS_OK ? count : (long)FVS_ERROR;
+}
+
+// ---- coarse-fine operations ---------------------------------------------------------
+int fvs_set_refine_ratio(fvs_ctx* ctx, const int ratio[3]) {
+  return guarded([&] {
+    if (!ctx || !ratio) throw Error("null argument");
+    for (int d = 0; d < ctx->cfg.rank; ++d)
+      if (ratio[d] < 1) throw Error("refinement ratio must be >= 1");
+    for (int d = 0; d < 3; ++d) ctx->ratio[d] = ratio[d];
+    for (Level& L : ctx->levels) L.cf_coarse = -1;
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_reset_coarse_fine_fluxes(fvs_ctx* ctx, int fine, int coarse) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (fine <= coarse || coarse < 0) throw Error("need 0 <= coarse < fine");
+    ctx->use_device();
+    Level& F = ctx->level(fine);
+    Level& Cl = ctx->level(coarse);
+    require_single_rank(F);
+    require_single_rank(Cl);
+    if (F.cf_coarse != coarse) define_flux_register(ctx, F, Cl, coarse);
+    for (Level::CfRegister& r : F.cf_regs) {
+      FVS_CUDA(cudaMemsetAsync(r.reg, 0, (size_t)r.plane.size() * ctx->ncons() * sizeof(double),
+                               ctx->stream));
+    }
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_accumulate_coarse_fine_fluxes(fvs_ctx* ctx, int level, double scale, int dir) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    check_dir(ctx, dir);
+    Level& L = ctx->level(level);
+    ensure_fluxes(ctx, L, dir);
+    const double vol = cell_volume(ctx, L);
+    const double vol_dt_over_dx = vol * scale / L.dx[dir];
+    if (level > 0 && L.cf_coarse >= 0) {
+      run_flux_register(ctx, L, L, 0, dir, vol_dt_over_dx, 1.0);
+    }
+    if (level + 1 < (int)ctx->levels.size() && ctx->levels[level + 1].defined &&
+        ctx->levels[level + 1].cf_coarse == level) {
+      run_flux_register(ctx, ctx->levels[level + 1], L, 1, dir, -vol_dt_over_dx, 1.0);
+    }
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_apply_flux_correction(fvs_ctx* ctx, int fine, int coarse, double /*dt*/) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    Level& F = ctx->level(fine);
+    Level& Cl = ctx->level(coarse);
+    if (F.cf_coarse != coarse) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+    const double vol = cell_volume(ctx, Cl);
+    for (int d = 0; d < ctx->cfg.rank; ++d) run_flux_register(ctx, F, Cl, 2, d, 1.0, vol);
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_coarsen_conservatively(fvs_ctx* ctx, int fine, int coarse) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (fine <= coarse || coarse < 0) throw Error("need 0 <= coarse < fine");
+    ctx->use_device();
+    Level& F = ctx->level(fine);
+    Level& Cl = ctx->level(coarse);
+    require_single_rank(F);
+    require_single_rank(Cl);
+    int ratio[3];
+    effective_ratio(ctx, ratio);
+    std::vector<fvs::AvgDownDesc> host;
+    long long max_cells = 1;
+    for (Patch& f : F.patches) {
+      const Box cf = coarsen_box(f.valid, ratio);
+      for (Patch& c : Cl.patches) {
+        const Box region = fvs::intersect(cf, c.valid);
+        if (!region.ok()) continue;
+        fvs::AvgDownDesc d{};
+        d.fine = array_ref(f.buf[F.cur], f.sbox, f.cells);
+        d.crse = array_ref(c.buf[Cl.cur], c.sbox, c.cells);
+        for (int e = 0; e < 3; ++e) {
+          d.lo[e] = region.lo[e];
+          d.len[e] = region.len(e);
+        }
+        max_cells = std::max(max_cells, region.size());
+        host.push_back(d);
+      }
+    }
+    if (host.empty()) return (int)FVS_OK;
+    DeviceArray<fvs::AvgDownDesc> dev;
+    dev.upload(host);
+    ctx->launches += fvs::launch_average_down(dev.ptr, (int)host.size(), ctx->ncons(), ratio,
+                                              max_cells, ctx->stream);
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    FVS_CUDA(cudaGetLastError());
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_fill_ghost_layer_two_levels(fvs_ctx* ctx, int fine, int coarse) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (fine <= coarse || coarse < 0) throw Error("need 0 <= coarse < fine");
+    ctx->use_device();
+    Level& F = ctx->level(fine);
+    Level& Cl = ctx->level(coarse);
+    require_single_rank(F);
+    require_single_rank(Cl);
+    int ratio[3];
+    effective_ratio(ctx, ratio);
+    std::vector<fvs::InterpDesc> host;
+    long long max_cells = 1;
+    for (Patch& f : F.patches) {
+      for (Patch& c : Cl.patches) {
+        const Box region =
+            fvs::intersect(fvs::intersect(f.sbox, refine_box(c.valid, ratio)), F.domain);
+        if (!region.ok()) continue;
+        fvs::InterpDesc d{};
+        d.fine = array_ref(f.buf[F.cur], f.sbox, f.cells);
+        d.crse = array_ref(c.buf[Cl.cur], c.sbox, c.cells);
+        for (int e = 0; e < 3; ++e) {
+          d.lo[e] = region.lo[e];
+          d.len[e] = region.len(e);
+          d.vlo[e] = f.valid.lo[e];
+          d.vhi[e] = f.valid.hi[e];
+        }
+        max_cells = std::max(max_cells, region.size());
+        host.push_back(d);
+      }
+    }
+    if (!host.empty()) {
+      DeviceArray<fvs::InterpDesc> dev;
+      dev.upload(host);
+      ctx->launches += fvs::launch_pc_interp(dev.ptr, (int)host.size(), ctx->ncomp(), ratio,
+                                             max_cells, ctx->stream);
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+      FVS_CUDA(cudaGetLastError());
+    }
+    fill_ghost_layer(ctx, F);
+    return (int)FVS_OK;
+  });
 }
 
 // ---- tagging ---------------------------------------------------------------------

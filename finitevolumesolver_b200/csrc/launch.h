@@ -131,6 +131,39 @@ int launch_tag_cutcells(const double* alpha, const int n[3], const int lo[3], co
 int launch_tag_buffer(char* tags, char* scratch, int rank, const int n[3], int width,
                       cudaStream_t);
 
+// ---- coarse-fine operations (two levels on one rank) -------------------------
+// All index triples are GLOBAL cell / face indices of the level they refer to;
+// an array is addressed through its lower corner `*_lo` and extents `*_n`.
+struct ArrayRef {
+  double* p;
+  int lo[3], n[3];
+  long long sc; // component stride
+};
+struct AvgDownDesc { // coarse region <- mean of the fine cells, conservative comps
+  ArrayRef fine, crse;
+  int lo[3], len[3]; // coarse region
+};
+struct InterpDesc { // fine ghost region <- coarse parent (pc_interp)
+  ArrayRef fine, crse;
+  int lo[3], len[3];   // fine region
+  int vlo[3], vhi[3];  // the fine box's own valid cells (skipped)
+};
+struct RegisterDesc { // one side of one fine box, coarse faces of direction dir
+  ArrayRef reg;                // plane of ncons components
+  const unsigned char* open;   // Reflux mask
+  int side;
+  ArrayRef other;              // FineAdd: fine flux array; CrseInit: coarse flux; Reflux: coarse state
+  int box_lo[3], box_hi[3];    // CrseInit / Reflux: the coarse box's valid cells
+  int lo[3], len[3];           // faces of the register handled by this descriptor
+};
+int launch_average_down(const AvgDownDesc* d, int n, int ncons, const int ratio[3], long long max_cells,
+                        cudaStream_t);
+int launch_pc_interp(const InterpDesc* d, int n, int ncomp, const int ratio[3], long long max_cells,
+                     cudaStream_t);
+// op: 0 FineAdd, 1 CrseInit, 2 Reflux
+int launch_flux_register(const RegisterDesc* d, int n, int op, int ncons, int dir, const int ratio[3],
+                         double mult, double vol, long long max_faces, cudaStream_t);
+
 // ---- ghost cells -----------------------------------------------------------
 struct CopyDesc {
   const double* src;

@@ -273,6 +273,32 @@ int fvs_download_eb_array(fvs_ctx* ctx, int level, int box, int kind, int dir, d
  * the number of cut cells (the length of the compacted list) or FVS_ERROR. */
 long fvs_cut_cell_flags(fvs_ctx* ctx, int level, int box, unsigned char* flags);
 
+/* ---- coarse-fine operations between two levels ----------------------------- */
+/* Levels are defined with fvs_level_define(level = 0, 1, ...); index spaces
+ * are related by the refinement ratio (default 2 per space dimension,
+ * PatchHierarchyOptions::refine_ratio).  Both levels must be owned by this
+ * rank (cross-rank coarse-fine exchange is listed as next in DESIGN.md).
+ * The flux-register entry points read the per-direction flux arrays that
+ * fvs_compute_numeric_fluxes fills (IntegratorContext::GetFluxes). */
+int fvs_set_refine_ratio(fvs_ctx* ctx, const int ratio[3]);
+/* IntegratorContext::ResetCoarseFineFluxes (src/AMReX/IntegratorContext.cpp:499-512):
+ * (re)builds the flux register of `fine` (one plane of coarse faces per side
+ * of every fine box, internal borders cleared) and zeroes it. */
+int fvs_reset_coarse_fine_fluxes(fvs_ctx* ctx, int fine, int coarse);
+/* IntegratorContext::AccumulateCoarseFineFluxes (:472-497): FineAdd into the
+ * register of `level` (if level > 0) and CrseInit(ADD) with the opposite sign
+ * into the register of level + 1 (if it exists), scaled by vol * scale / dx. */
+int fvs_accumulate_coarse_fine_fluxes(fvs_ctx* ctx, int level, double scale, int dir);
+/* IntegratorContext::ApplyFluxCorrection (:514-531): Reflux in every direction. */
+int fvs_apply_flux_correction(fvs_ctx* ctx, int fine, int coarse, double dt);
+/* IntegratorContext::CoarsenConservatively (:451-470): amrex::average_down of
+ * the conservative components. */
+int fvs_coarsen_conservatively(fvs_ctx* ctx, int fine, int coarse);
+/* IntegratorContext::FillGhostLayerTwoLevels (:380-420): FillPatchTwoLevels
+ * with the piecewise-constant interpolater, then the fine level's own ghost
+ * exchange and physical boundary conditions. */
+int fvs_fill_ghost_layer_two_levels(fvs_ctx* ctx, int fine, int coarse);
+
 /* ---- tagging (patch level) ------------------------------------------------ */
 /* ScalarGradientDetector_::TagCellsForRefinement
  * (include/fub/tagging_method/GradientDetector.hpp:156-232) on the valid cells

@@ -1,0 +1,222 @@
+// TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT PATH.
+//
+// oracle/amr.hpp: CPU restatement of the coarse-fine operations of the
+// reference's IntegratorContext for two levels that live in one process:
+//   CoarsenConservatively      src/AMReX/IntegratorContext.cpp:451-470  (amrex::average_down)
+//   AccumulateCoarseFineFluxes :472-497 (FluxRegister::FineAdd / CrseInit(ADD))
+//   ResetCoarseFineFluxes      :499-512 (ClearInternalBorders + setVal(0))
+//   ApplyFluxCorrection        :514-531 (FluxRegister::Reflux)
+//   FillGhostLayerTwoLevels    :380-420 (FillPatchTwoLevels with pc_interp)
+//
+// PARITY UNPINNED: the arithmetic lives in AMReX (`development`, unpinned,
+// absent from /root/reference: conan/conan-amrex/conanfile.py:29) and the
+// reference has no test with numeric assertions for it.  Restated from the
+// published algorithms: average_down sums the fine cells of a coarse cell in
+// (k, j, i) order and multiplies by 1 / ratio^D; a flux register holds, per
+// fine box and per side, the coarse faces of the box boundary, CrseInit adds
+// mult * coarse flux, FineAdd adds mult * fine flux for every fine face of the
+// coarse face in (k, j, i) order, Reflux adds -+ scale * register / volume to
+// the coarse cell outside the fine box; pc_interp copies the coarse parent.
+#pragma once
+#include "level.hpp"
+
+namespace fvso {
+
+inline int coarsen_index(int i, int r) { return i >= 0 ? i / r : -((-i + r - 1) / r); }
+inline Box coarsen(const Box& b, const int ratio[3]) {
+  Box c;
+  for (int d = 0; d < 3; ++d) {
+    c.lo[d] = coarsen_index(b.lo[d], ratio[d]);
+    c.hi[d] = coarsen_index(b.hi[d], ratio[d]);
+  }
+  return c;
+}
+inline Box refine(const Box& b, const int ratio[3]) {
+  Box f;
+  for (int d = 0; d < 3; ++d) {
+    f.lo[d] = b.lo[d] * ratio[d];
+    f.hi[d] = (b.hi[d] + 1) * ratio[d] - 1;
+  }
+  return f;
+}
+
+// One register: the coarse faces of side `side` (0 lower, 1 upper) of fine box
+// `fine_box` in direction `dir`; face index = index of the cell to its right.
+struct FluxRegisterFab {
+  int fine_box, dir, side;
+  Fab reg;                         // ncons components on the face plane
+  std::vector<unsigned char> open; // 1 where the outside coarse cell is not covered by a fine box
+};
+
+struct CoarseFine {
+  int ratio[3]{2, 2, 2};
+  std::vector<FluxRegisterFab> regs;
+
+  void define(const Level& fine, const Level& coarse) {
+    regs.clear();
+    for (int d = fine.rank; d < 3; ++d) ratio[d] = 1;
+    for (size_t f = 0; f < fine.boxes.size(); ++f) {
+      const Box cb = coarsen(fine.boxes[f], ratio);
+      for (int d = 0; d < fine.rank; ++d)
+        for (int side = 0; side < 2; ++side) {
+          FluxRegisterFab r;
+          r.fine_box = int(f);
+          r.dir = d;
+          r.side = side;
+          Box fb = cb;
+          fb.lo[d] = fb.hi[d] = side == 0 ? cb.lo[d] : cb.hi[d] + 1;
+          r.reg.define(fb, fine.ncons());
+          r.open.assign(size_t(fb.size()), 1);
+          // ClearInternalBorders: faces whose outside cell lies under another fine box
+          size_t n = 0;
+          for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+            for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+              for (int i = fb.lo[0]; i <= fb.hi[0]; ++i, ++n) {
+                int out[3] = {i, j, k};
+                if (side == 0) out[d] -= 1;
+                for (size_t g = 0; g < fine.boxes.size(); ++g) {
+                  if (coarsen(fine.boxes[g], ratio).contains(out[0], out[1], out[2])) r.open[n] = 0;
+                }
+                if (!coarse.domain.contains(out[0], out[1], out[2])) r.open[n] = 0;
+              }
+          regs.push_back(std::move(r));
+        }
+    }
+  }
+
+  void Reset() {
+    for (FluxRegisterFab& r : regs) std::fill(r.reg.data.begin(), r.reg.data.end(), 0.0);
+  }
+
+  // FineAdd: level == fine
+  void FineAdd(const Level& fine, int dir, double mult) {
+    for (FluxRegisterFab& r : regs) {
+      if (r.dir != dir) continue;
+      const Fab& flux = fine.fluxes[dir][size_t(r.fine_box)];
+      const Box& fb = r.reg.box;
+      for (int c = 0; c < r.reg.ncomp; ++c)
+        for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+          for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+            for (int i = fb.lo[0]; i <= fb.hi[0]; ++i) {
+              int lo[3] = {i * ratio[0], j * ratio[1], k * ratio[2]};
+              int hi[3] = {lo[0] + ratio[0] - 1, lo[1] + ratio[1] - 1, lo[2] + ratio[2] - 1};
+              hi[dir] = lo[dir];
+              for (int kk = lo[2]; kk <= hi[2]; ++kk)
+                for (int jj = lo[1]; jj <= hi[1]; ++jj)
+                  for (int ii = lo[0]; ii <= hi[0]; ++ii) {
+                    r.reg(i, j, k, c) += mult * flux(ii, jj, kk, c);
+                  }
+            }
+    }
+  }
+  // CrseInit(..., ADD): level == coarse
+  void CrseInit(const Level& coarse, int dir, double mult) {
+    for (FluxRegisterFab& r : regs) {
+      if (r.dir != dir) continue;
+      const Box& fb = r.reg.box;
+      for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
+        const Fab& flux = coarse.fluxes[dir][cbx];
+        const Box faces = intersect(fb, surrounding_nodes(coarse.boxes[cbx], dir));
+        if (!faces.ok()) continue;
+        for (int c = 0; c < r.reg.ncomp; ++c)
+          for (int k = faces.lo[2]; k <= faces.hi[2]; ++k)
+            for (int j = faces.lo[1]; j <= faces.hi[1]; ++j)
+              for (int i = faces.lo[0]; i <= faces.hi[0]; ++i) {
+                // a face shared by two coarse boxes is initialised by the box
+                // that owns the OUTSIDE cell
+                int out[3] = {i, j, k};
+                if (r.side == 0) out[dir] -= 1;
+                if (!coarse.boxes[cbx].contains(out[0], out[1], out[2])) continue;
+                r.reg(i, j, k, c) += mult * flux(i, j, k, c);
+              }
+      }
+    }
+  }
+  // Reflux into the coarse scratch
+  void Reflux(Level& coarse, int dir, double scale) {
+    const double vol = coarse.dx[0] * (coarse.rank > 1 ? coarse.dx[1] : 1.0) *
+                       (coarse.rank > 2 ? coarse.dx[2] : 1.0);
+    for (FluxRegisterFab& r : regs) {
+      if (r.dir != dir) continue;
+      const Box& fb = r.reg.box;
+      for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
+        Fab& S = coarse.scratch[cbx];
+        size_t n = 0;
+        for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+          for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+            for (int i = fb.lo[0]; i <= fb.hi[0]; ++i, ++n) {
+              if (!r.open[n]) continue;
+              int out[3] = {i, j, k};
+              if (r.side == 0) out[dir] -= 1;
+              if (!coarse.boxes[cbx].contains(out[0], out[1], out[2])) continue;
+              for (int c = 0; c < r.reg.ncomp; ++c) {
+                // lower side: the register face is the right face of the cell
+                const double sign = r.side == 0 ? -1.0 : 1.0;
+                S(out[0], out[1], out[2], c) += sign * scale * r.reg(i, j, k, c) / vol;
+              }
+            }
+      }
+    }
+  }
+};
+
+// src/AMReX/IntegratorContext.cpp:472-497
+inline void AccumulateCoarseFineFluxes(CoarseFine* to_coarser, const Level& level,
+                                       CoarseFine* to_finer, double scale, int dir) {
+  const double vol = level.dx[0] * (level.rank > 1 ? level.dx[1] : 1.0) *
+                     (level.rank > 2 ? level.dx[2] : 1.0);
+  const double vol_dt_over_dx = vol * scale / level.dx[dir];
+  if (to_coarser) to_coarser->FineAdd(level, dir, vol_dt_over_dx);
+  if (to_finer) to_finer->CrseInit(level, dir, -vol_dt_over_dx);
+}
+
+// amrex::average_down on the conservative components
+inline void CoarsenConservatively(const Level& fine, Level& coarse, const int ratio[3]) {
+  const double volfrac = 1.0 / double(ratio[0] * ratio[1] * ratio[2]);
+  for (size_t f = 0; f < fine.boxes.size(); ++f) {
+    const Box cf = coarsen(fine.boxes[f], ratio);
+    for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
+      const Box region = intersect(cf, coarse.boxes[cbx]);
+      if (!region.ok()) continue;
+      const Fab& F = fine.scratch[f];
+      Fab& Cc = coarse.scratch[cbx];
+      for (int n = 0; n < fine.ncons(); ++n)
+        for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+          for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+            for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+              double c = 0.0;
+              for (int kr = 0; kr < ratio[2]; ++kr)
+                for (int jr = 0; jr < ratio[1]; ++jr)
+                  for (int ir = 0; ir < ratio[0]; ++ir) {
+                    c += F(i * ratio[0] + ir, j * ratio[1] + jr, k * ratio[2] + kr, n);
+                  }
+              Cc(i, j, k, n) = volfrac * c;
+            }
+    }
+  }
+}
+
+// FillPatchTwoLevels with pc_interp: ghost cells inside the domain take the
+// coarse parent unless a fine box (or a periodic image) holds them, then the
+// physical boundary conditions of the fine level.
+inline void FillGhostLayerTwoLevels(Level& fine, const Level& coarse, const int ratio[3]) {
+  for (size_t f = 0; f < fine.boxes.size(); ++f) {
+    Fab& F = fine.scratch[f];
+    for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
+      const Box region = intersect(intersect(F.box, refine(coarse.boxes[cbx], ratio)), fine.domain);
+      if (!region.ok()) continue;
+      const Fab& Cc = coarse.scratch[cbx];
+      for (int n = 0; n < fine.ncomp(); ++n)
+        for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+          for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+            for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+              if (fine.boxes[f].contains(i, j, k)) continue;
+              F(i, j, k, n) = Cc(coarsen_index(i, ratio[0]), coarsen_index(j, ratio[1]),
+                                 coarsen_index(k, ratio[2]), n);
+            }
+    }
+  }
+  fine.FillGhostLayerSingleLevel();
+}
+
+} // namespace fvso

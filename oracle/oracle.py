@@ -41,6 +41,7 @@ def lib():
         L.fvso_level_scratch.restype = C.POINTER(C.c_double)
         L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
         L.fvso_level_eb_array.restype = C.POINTER(C.c_double)
+        L.fvso_cf_create.restype = C.c_void_p
         L.fvso_level_cycles.restype = C.c_long
         L.fvso_level_time.restype = C.c_double
         _LIB = L
@@ -221,6 +222,36 @@ class Level:
                                   C.c_long(max_cycles), split, _dp(buf), cap,
                                   C.byref(retries)))
         return buf[:n].copy(), retries.value
+
+
+class CoarseFine:
+    """Coarse-fine operations between two oracle levels (oracle/amr.hpp)."""
+
+    def __init__(self, fine, coarse, ratio=(2, 2, 2)):
+        self.fine, self.coarse = fine, coarse
+        r = [ratio[d] if d < fine.rank else 1 for d in range(3)]
+        self.h = C.c_void_p(lib().fvso_cf_create(fine.h, coarse.h, _ia(r)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().fvso_cf_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        _check(lib().fvso_cf_reset(self.h))
+
+    def accumulate(self, level, scale, direction):
+        _check(lib().fvso_cf_accumulate(self.h, level.h, 1 if level is self.fine else 0,
+                                        C.c_double(scale), direction))
+
+    def apply_flux_correction(self):
+        _check(lib().fvso_cf_apply_flux_correction(self.h, self.coarse.h))
+
+    def coarsen_conservatively(self):
+        _check(lib().fvso_cf_coarsen_conservatively(self.h, self.fine.h, self.coarse.h))
+
+    def fill_ghost_layer_two_levels(self):
+        _check(lib().fvso_cf_fill_ghost_layer_two_levels(self.h, self.fine.h, self.coarse.h))
 
 
 def tag_buffer(tags, rank, width):

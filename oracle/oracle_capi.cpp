@@ -16,6 +16,7 @@
 // boxDiff) is restated from the published algorithms and is "parity
 // unpinned" against a real AMReX build.
 #include "level.hpp"
+#include "amr.hpp"
 
 #include <cstdio>
 #include <cstring>
@@ -265,6 +266,45 @@ int fvso_tag_cutcells(void* h, int box, char* tags) {
 }
 int fvso_tag_buffer(char* tags, int rank, const int* n, int width) {
   return guarded([&] { TagBuffer(tags, rank, n, width); });
+}
+
+// ------------------------------------------------------------ two levels
+void* fvso_cf_create(void* fine, void* coarse, const int* ratio) {
+  CoarseFine* cf = new CoarseFine;
+  for (int d = 0; d < 3; ++d) cf->ratio[d] = ratio[d];
+  cf->define(*static_cast<Level*>(fine), *static_cast<Level*>(coarse));
+  return cf;
+}
+void fvso_cf_destroy(void* cf) { delete static_cast<CoarseFine*>(cf); }
+int fvso_cf_reset(void* cf) {
+  return guarded([&] { static_cast<CoarseFine*>(cf)->Reset(); });
+}
+// level_is_fine != 0: FineAdd with `level` as the fine level, else CrseInit
+int fvso_cf_accumulate(void* cf, void* level, int level_is_fine, double scale, int dir) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(level);
+    CoarseFine* c = static_cast<CoarseFine*>(cf);
+    AccumulateCoarseFineFluxes(level_is_fine ? c : nullptr, *L, level_is_fine ? nullptr : c, scale,
+                               dir);
+  });
+}
+int fvso_cf_apply_flux_correction(void* cf, void* coarse) {
+  return guarded([&] {
+    Level* L = static_cast<Level*>(coarse);
+    for (int d = 0; d < L->rank; ++d) static_cast<CoarseFine*>(cf)->Reflux(*L, d, 1.0);
+  });
+}
+int fvso_cf_coarsen_conservatively(void* cf, void* fine, void* coarse) {
+  return guarded([&] {
+    CoarsenConservatively(*static_cast<Level*>(fine), *static_cast<Level*>(coarse),
+                          static_cast<CoarseFine*>(cf)->ratio);
+  });
+}
+int fvso_cf_fill_ghost_layer_two_levels(void* cf, void* fine, void* coarse) {
+  return guarded([&] {
+    FillGhostLayerTwoLevels(*static_cast<Level*>(fine), *static_cast<Level*>(coarse),
+                            static_cast<CoarseFine*>(cf)->ratio);
+  });
 }
 
 // ----------------------------------------------------- unit-level helpers

@@ -1,0 +1,128 @@
+"""Parity of the coarse-fine kernels (two levels on one GPU) against the CPU
+oracle: pc_interp ghost fill, flux registers (FineAdd, CrseInit, Reflux,
+cleared internal borders), average_down.  Bit-exact; the arithmetic restates
+AMReX's published algorithms ("parity unpinned" against a real AMReX build)."""
+import numpy as np
+import pytest
+
+from helpers import assert_bitwise_equal, smooth_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fvs():
+    from finitevolumesolver_b200 import capi
+    assert capi.device_count() > 0, "no CUDA device"
+    return capi
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as orc
+    orc.build()
+    return orc
+
+
+def two_levels(orc, fvs, rank):
+    if rank == 2:
+        nc = [32, 24, 1]
+        cboxes = [([0, 0, 0], [15, 23, 0]), ([16, 0, 0], [31, 23, 0])]
+        fboxes = [([16, 8, 0], [31, 31, 0]), ([32, 8, 0], [47, 23, 0]), ([32, 24, 0], [47, 39, 0])]
+    else:
+        nc = [16, 12, 12]
+        cboxes = [([0, 0, 0], [15, 11, 11])]
+        fboxes = [([8, 4, 4], [19, 15, 15]), ([20, 4, 4], [27, 15, 19])]
+    dxc = [1.0 / nc[d] if d < rank else 1.0 for d in range(3)]
+    dxf = [0.5 * dxc[d] if d < rank else 1.0 for d in range(3)]
+    chi = [nc[d] - 1 if d < rank else 0 for d in range(3)]
+    fhi = [2 * nc[d] - 1 if d < rank else 0 for d in range(3)]
+    gcw = (4, 2)
+    ccpu = orc.Level(rank, [0] * 3, chi, dxc, cboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    fcpu = orc.Level(rank, [0] * 3, fhi, dxf, fboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    cgpu = fvs.Context(rank, [0] * 3, chi, dxc, cboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    fgpu = cgpu.define_level(1, [0] * 3, fhi, dxf, fboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    for lv in (ccpu, fcpu, cgpu, fgpu):
+        for d in range(rank):
+            for s in (0, 1):
+                lv.add_bc(d, s, 1 if d == 0 else 0)
+    for cpu, gpu, dx, seed in ((ccpu, cgpu, dxc, 1), (fcpu, fgpu, dxf, 2)):
+        for b in range(len(cpu.boxes)):
+            arr, lo, hi = cpu.scratch(b)
+            arr[...] = smooth_state(rank, lo, hi, dx, seed=seed)
+            gpu.upload_state(b, arr)
+    cf = orc.CoarseFine(fcpu, ccpu)
+    return ccpu, fcpu, cgpu, fgpu, cf
+
+
+def compare(cpu, gpu, what):
+    for b in range(len(cpu.boxes)):
+        assert_bitwise_equal(gpu.download_state(b), cpu.scratch(b)[0], f"{what} box {b}")
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_fill_ghost_layer_two_levels(oracle, fvs, rank):
+    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank)
+    ccpu.fill_ghost_layer()
+    cgpu.fill_ghost_layer()
+    cf.fill_ghost_layer_two_levels()
+    cgpu.fill_ghost_layer_two_levels(1, 0)
+    compare(fcpu, fgpu, "pc_interp ghost fill")
+    cgpu.close()
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_coarsen_conservatively(oracle, fvs, rank):
+    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank)
+    before = cgpu.download_state(0).copy()
+    cf.coarsen_conservatively()
+    cgpu.coarsen_conservatively(1, 0)
+    compare(ccpu, cgpu, "average_down")
+    assert (cgpu.download_state(0) != before).any()
+    cgpu.close()
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_flux_register_cycle(oracle, fvs, rank):
+    """One coarse step with two fine subcycles, the order of
+    SubcycleFineFirstSolver::AdvanceLevel: reset, fine fluxes accumulated with
+    FineAdd, coarse fluxes with CrseInit, Reflux, average_down, complete."""
+    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank)
+    ccpu.fill_ghost_layer()
+    cgpu.fill_ghost_layer()
+    cf.fill_ghost_layer_two_levels()
+    cgpu.fill_ghost_layer_two_levels(1, 0)
+    dt = 0.2 * min(min(ccpu.compute_stable_dt(d), fcpu.compute_stable_dt(d)) for d in range(rank))
+    cf.reset()
+    cgpu.reset_coarse_fine_fluxes(1, 0)
+    for sub in range(2):
+        for d in range(rank):
+            fcpu.compute_numeric_fluxes(0.5 * dt, d)
+            fgpu.compute_numeric_fluxes(0.5 * dt, d)
+            fcpu.update_conservatively(0.5 * dt, d)
+            fgpu.update_conservatively(0.5 * dt, d)
+            fcpu.complete_from_cons()
+            fgpu.complete_from_cons()
+            cf.accumulate(fcpu, 0.5 * dt, d)
+            cgpu.accumulate_coarse_fine_fluxes(1, 0.5 * dt, d)
+    for d in range(rank):
+        ccpu.compute_numeric_fluxes(dt, d)
+        cgpu.compute_numeric_fluxes(dt, d)
+        ccpu.update_conservatively(dt, d)
+        cgpu.update_conservatively(dt, d)
+        ccpu.complete_from_cons()
+        cgpu.complete_from_cons()
+        cf.accumulate(ccpu, dt, d)
+        cgpu.accumulate_coarse_fine_fluxes(0, dt, d)
+    before = cgpu.download_state(0).copy()
+    cf.apply_flux_correction()
+    cgpu.apply_flux_correction(1, 0, dt)
+    compare(ccpu, cgpu, "reflux")
+    assert (cgpu.download_state(0) != before).any(), "the flux correction changed nothing"
+    cf.coarsen_conservatively()
+    cgpu.coarsen_conservatively(1, 0)
+    ccpu.complete_from_cons()
+    cgpu.complete_from_cons()
+    compare(ccpu, cgpu, "after average_down + complete")
+    compare(fcpu, fgpu, "fine level")
+    cgpu.close()
