@@ -540,6 +540,9 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 
 // ---------------------------------------------------------------------------
 // Fused sweep along x: warp per row, shuffle pipeline.
+#ifndef FVS_SWEEP_X_PREFETCH
+#define FVS_SWEEP_X_PREFETCH 0
+#endif
 #ifndef FVS_SWEEP_X_MIN_BLOCKS
 #define FVS_SWEEP_X_MIN_BLOCKS 4
 #endif
@@ -574,11 +577,21 @@ fused_sweep_x_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
+#if FVS_SWEEP_X_PREFETCH
+    Complete<D> qnext; // the next chunk's cell, loaded one chunk ahead
+    load_complete<D>(qnext, src + min(max(o_first - 2 + lane, 0), n0 - 1), sc);
+#endif
     for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
       const int c = c0 + lane;
       const int cl = min(max(c, 0), n0 - 1);
       Complete<D> q0;
+#if FVS_SWEEP_X_PREFETCH
+      q0 = qnext;
+      if (c0 + 32 - 2 <= o_last) load_complete<D>(qnext, src + min(max(c + 32, 0), n0 - 1), sc);
+      (void)cl;
+#else
       load_complete<D>(q0, src + cl, sc);
+#endif
       DtData<D, BASE> dt_cur;
       stage_dt_cell<D, BASE>(dt_cur, q0);
       Complete<D> q1 = shfl_up<D>(q0, 1);
