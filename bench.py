@@ -330,13 +330,15 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("fused_sweep_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("size") == args.size and len(my_boxes) == 1:
+                traffic = tj.get("fused_sweep_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
-        "kernel": "fused_sweep_{x,yz}_kernel<3,*,HLLEM-L,MUSCL,VanLeer>",
+        "kernel": "fused_sweep_x_kernel / fused_sweep_yz_smem_kernel<3,*,HLLEM-L,MUSCL,VanLeer>",
         "avg_launch_ms": 1e3 * avg_sweep_s, "launches_timed": n_sweeps,
         "share_of_step": sweep_ms / elapsed_ms if elapsed_ms else None,
         "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,

@@ -44,6 +44,7 @@ SYMBOLS = [
     "fvs_tag_gradient", "fvs_tag_cutcells", "fvs_tag_buffer",
     "fvs_set_refine_ratio", "fvs_reset_coarse_fine_fluxes", "fvs_accumulate_coarse_fine_fluxes",
     "fvs_apply_flux_correction", "fvs_coarsen_conservatively", "fvs_fill_ghost_layer_two_levels",
+    "fvs_compute_stable_dt_hierarchy",
 ]
 
 
@@ -226,6 +227,11 @@ class Context:
     def fill_ghost_layer_two_levels(self, fine, coarse):
         _check(lib().fvs_fill_ghost_layer_two_levels(self.h, fine, coarse))
 
+    def compute_stable_dt_hierarchy(self):
+        out = C.c_double()
+        _check(lib().fvs_compute_stable_dt_hierarchy(self.h, C.byref(out)))
+        return out.value
+
     def __del__(self):
         try:
             self.close()
@@ -384,11 +390,11 @@ class Context:
     def advance_hierarchy(self, dt, split):
         """Returns (ok, failure_dt, sweep_dts)."""
         too = C.c_double()
-        buf = (C.c_double * 16)()
-        n = C.c_int(16)
+        buf = (C.c_double * 64)()
+        n = C.c_int(64)
         rc = _check(lib().fvs_advance_hierarchy(self.h, C.c_double(dt), split, C.byref(too),
                                                 buf, C.byref(n)))
-        return rc == 0, too.value, [buf[i] for i in range(min(n.value, 16))]
+        return rc == 0, too.value, [buf[i] for i in range(min(n.value, 64))]
 
     def run(self, cfl, final_time, max_cycles, split):
         cap = max(int(max_cycles), 1) if max_cycles >= 0 else 100000

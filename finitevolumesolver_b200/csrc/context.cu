@@ -1603,11 +1603,141 @@ int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
   });
 }
 
+namespace {
+int num_levels(const fvs_ctx* ctx) {
+  int n = 0;
+  while (n < (int)ctx->levels.size() && ctx->levels[n].defined) ++n;
+  return n;
+}
+int max_ratio(const fvs_ctx* ctx) {
+  int m = 1;
+  for (int d = 0; d < ctx->cfg.rank; ++d) m = std::max(m, ctx->ratio[d]);
+  return m;
+}
+int total_ratio(const fvs_ctx* ctx, int level) {
+  int r = 1;
+  for (int l = 1; l <= level; ++l) r *= max_ratio(ctx);
+  return r;
+}
+void call(int rc) {
+  if (rc == FVS_ERROR) throw Error(g_error);
+}
+struct TooLarge {
+  double dt;
+};
+
+// SubcycleFineFirstSolver::AdvanceLevel (include/fub/solver/SubcycleFineFirstSolver.hpp:114-175)
+// for a static hierarchy on one rank: finer levels first, `ratio` subcycles
+// each, flux registers, flux correction, conservative coarsening.  Works in
+// place through the per-policy entry points (the registers need the flux
+// arrays); throws TooLarge on a CFL violation.
+void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_kind,
+                   std::vector<double>& sweep_dts) {
+  Level& L = ctx->level(level);
+  const int rank = ctx->cfg.rank;
+  cc_pre_advance(ctx, L); // PreAdvanceLevel
+  const int next = level + 1;
+  const bool has_next = next < num_levels(ctx);
+  if (has_next) {
+    call(fvs_reset_coarse_fine_fluxes(ctx, next, level));
+    const int r = max_ratio(ctx);
+    for (int i = 0; i < r; ++i) advance_level(ctx, next, dt / r, i, split_kind, sweep_dts);
+  }
+  // AdvanceLevelNonRecursively; MakeSplitDirections uses the cycles of level 0
+  const bool is_odd = ((ctx->cycles % 2) + sub_first) % 2 != 0;
+  int dirs[3];
+  for (int i = 0; i < rank; ++i) dirs[i] = is_odd ? (rank - 1 - i) : i;
+  const std::vector<SweepPlanEntry> plan = split_plan(rank, split_kind, dt);
+  int counts[3] = {0, 0, 0};
+  for (const SweepPlanEntry& e : plan) {
+    const int dir = dirs[e.slot];
+    if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir);
+    counts[e.slot] += 1;
+    double level_dt = 0.0;
+    call(fvs_compute_stable_dt(ctx, level, dir, &level_dt));
+    sweep_dts.push_back(level_dt);
+    if (level_dt < e.dt) throw TooLarge{level_dt * total_ratio(ctx, level)};
+    call(fvs_compute_numeric_fluxes(ctx, level, e.dt, dir));
+    call(fvs_update_conservatively(ctx, level, e.dt, dir));
+    call(fvs_complete_from_cons(ctx, level));
+    call(fvs_accumulate_coarse_fine_fluxes(ctx, level, e.dt, dir));
+  }
+  if (has_next) {
+    call(fvs_apply_flux_correction(ctx, next, level, dt));
+    call(fvs_coarsen_conservatively(ctx, next, level));
+    call(fvs_complete_from_cons(ctx, level));
+  }
+}
+
+int advance_hierarchy_multilevel(fvs_ctx* ctx, double dt, int split_kind, double* failure_dt,
+                                 double* sweep_dts, int* n_sweep_dts) {
+  const int nl = num_levels(ctx);
+  std::vector<int> entry(nl);
+  for (int l = 0; l < nl; ++l) {
+    Level& L = ctx->levels[l];
+    require_single_rank(L);
+    entry[l] = L.cur;
+    L.keep = -1;
+    const int work = free_buffer(L, L.cur);
+    ensure_buffer(ctx, L, work);
+    for (Patch& p : L.patches) {
+      FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[L.cur],
+                               (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    L.cur = work;
+  }
+  std::vector<double> dts;
+  int status = FVS_OK;
+  try {
+    advance_level(ctx, 0, dt, 0, split_kind, dts);
+  } catch (const TooLarge& e) {
+    if (failure_dt) *failure_dt = e.dt;
+    status = FVS_TIME_STEP_TOO_LARGE;
+  } catch (...) {
+    for (int l = 0; l < nl; ++l) ctx->levels[l].cur = entry[l];
+    throw;
+  }
+  const int cap = (sweep_dts && n_sweep_dts) ? *n_sweep_dts : 0;
+  for (int i = 0; i < (int)dts.size() && i < cap; ++i) sweep_dts[i] = dts[(size_t)i];
+  if (n_sweep_dts) *n_sweep_dts = (int)dts.size();
+  if (status != FVS_OK) {
+    for (int l = 0; l < nl; ++l) ctx->levels[l].cur = entry[l]; // roll back every level
+    return status;
+  }
+  ctx->cycles += 1;
+  ctx->time_point = ctx->time_point + dt;
+  if (ctx->cycles % ctx->regrid_frequency == 0) { // SubcycleFineFirstSolver.hpp:177-192
+    fill_ghost_layer(ctx, ctx->levels[0]);
+    for (int l = 1; l < nl; ++l) call(fvs_fill_ghost_layer_two_levels(ctx, l, l - 1));
+  }
+  return (int)FVS_OK;
+}
+} // namespace
+
+int fvs_compute_stable_dt_hierarchy(fvs_ctx* ctx, double* dt_out) {
+  return guarded([&] {
+    if (!ctx || !dt_out) throw Error("null argument");
+    double min_dt = std::numeric_limits<double>::max();
+    for (int l = 0; l < num_levels(ctx); ++l) {
+      double d = 0.0;
+      call(fvs_compute_stable_dt_all(ctx, l, &d));
+      min_dt = std::min(min_dt, total_ratio(ctx, l) * d);
+    }
+    *dt_out = min_dt;
+    return (int)FVS_OK;
+  });
+}
+
 int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind, double* failure_dt,
                           double* sweep_dts, int* n_sweep_dts) {
   return guarded([&] {
     if (!ctx) throw Error("null context");
     ctx->use_device();
+    if (split_kind < 0 || split_kind > 2) throw Error("unknown splitting method");
+    if (num_levels(ctx) > 1) {
+      return advance_hierarchy_multilevel(ctx, dt, split_kind, failure_dt, sweep_dts, n_sweep_dts);
+    }
     Level& L = ctx->level(0);
     const int rank = ctx->cfg.rank;
     if (split_kind < 0 || split_kind > 2) throw Error("unknown splitting method");
@@ -1708,7 +1838,7 @@ long fvs_run(fvs_ctx* ctx, double cfl, double final_time, long max_cycles, int s
       double stable_dt;
       if (have_failure) {
         stable_dt = failure_dt;
-      } else if (fvs_compute_stable_dt_all(ctx, 0, &stable_dt) != FVS_OK) {
+      } else if (fvs_compute_stable_dt_hierarchy(ctx, &stable_dt) != FVS_OK) {
         throw Error(g_error);
       }
       const double limited_dt = std::min(final_time - ctx->time_point, cfl * stable_dt);

@@ -299,6 +299,14 @@ int fvs_coarsen_conservatively(fvs_ctx* ctx, int fine, int coarse);
  * exchange and physical boundary conditions. */
 int fvs_fill_ghost_layer_two_levels(fvs_ctx* ctx, int fine, int coarse);
 
+/* SubcycleFineFirstSolver::ComputeStableDt (include/fub/solver/SubcycleFineFirstSolver.hpp:100-112):
+ * min over the levels of (total refinement ratio) * level dt.  With more than
+ * one level defined, fvs_advance_hierarchy runs AdvanceLevel (:114-175) fine
+ * level first with `ratio` subcycles, flux registers, flux correction and
+ * conservative coarsening, and refills all ghost layers afterwards (:177-192);
+ * a CFL violation on any level rolls every level back. */
+int fvs_compute_stable_dt_hierarchy(fvs_ctx* ctx, double* dt_out);
+
 /* ---- tagging (patch level) ------------------------------------------------ */
 /* ScalarGradientDetector_::TagCellsForRefinement
  * (include/fub/tagging_method/GradientDetector.hpp:156-232) on the valid cells

@@ -219,4 +219,95 @@ inline void FillGhostLayerTwoLevels(Level& fine, const Level& coarse, const int 
   fine.FillGhostLayerSingleLevel();
 }
 
+// ---------------------------------------------------------------------------
+// include/fub/solver/SubcycleFineFirstSolver.hpp:100-193 for a static
+// hierarchy (no regridding) held by one process.
+struct Hierarchy {
+  std::vector<Level*> levels;
+  std::vector<CoarseFine> cf; // cf[l] couples level l (fine) with l - 1
+  int ratio[3]{2, 2, 2};
+
+  void define() {
+    cf.assign(levels.size(), CoarseFine());
+    for (size_t l = 1; l < levels.size(); ++l) {
+      for (int d = 0; d < 3; ++d) cf[l].ratio[d] = ratio[d];
+      cf[l].define(*levels[l], *levels[l - 1]);
+    }
+  }
+  int max_ratio() const {
+    int m = 1;
+    for (int d = 0; d < levels[0]->rank; ++d) m = std::max(m, ratio[d]);
+    return m;
+  }
+  int total_ratio(int level) const {
+    int r = 1;
+    for (int l = 1; l <= level; ++l) r *= max_ratio();
+    return r;
+  }
+  // :100-112
+  double ComputeStableDt() const {
+    double min_dt = std::numeric_limits<double>::max();
+    for (size_t l = 0; l < levels.size(); ++l) {
+      min_dt = std::min(min_dt, total_ratio(int(l)) * levels[l]->ComputeStableDtAllDirections());
+    }
+    return min_dt;
+  }
+  // :114-175
+  std::optional<TimeStepTooLarge> AdvanceLevel(int this_level, double dt, int sub_first,
+                                               int split_kind, std::vector<double>* sweep_dts) {
+    Level& L = *levels[size_t(this_level)];
+    L.PreAdvanceHierarchy();
+    const int next = this_level + 1;
+    const bool has_next = next < int(levels.size());
+    if (has_next) {
+      cf[size_t(next)].Reset();
+      const int r = max_ratio();
+      for (int i = 0; i < r; ++i) {
+        if (auto e = AdvanceLevel(next, dt / r, i, split_kind, sweep_dts)) return e;
+      }
+    }
+    L.accumulate_hook = [&, this_level, has_next, next](double scale, int dir) {
+      AccumulateCoarseFineFluxes(this_level > 0 ? &cf[size_t(this_level)] : nullptr, L,
+                                 has_next ? &cf[size_t(next)] : nullptr, scale, dir);
+    };
+    auto result = L.AdvanceLevelNonRecursively(dt, split_kind, sweep_dts, levels[0]->cycles,
+                                               sub_first);
+    L.accumulate_hook = nullptr;
+    if (result) {
+      result->dt *= total_ratio(this_level);
+      return result;
+    }
+    if (has_next) {
+      for (int d = 0; d < L.rank; ++d) cf[size_t(next)].Reflux(L, d, 1.0);
+      CoarsenConservatively(*levels[size_t(next)], L, cf[size_t(next)].ratio);
+      L.CompleteFromCons_();
+    }
+    if (this_level > 0) { // PostAdvanceLevel
+      L.cycles += 1;
+      L.time_point = L.time_point + dt;
+    }
+    return std::nullopt;
+  }
+  // :177-193
+  std::optional<TimeStepTooLarge> AdvanceHierarchy(double dt, int split_kind,
+                                                   std::vector<double>* sweep_dts) {
+    std::vector<Level> backup;
+    for (Level* l : levels) backup.push_back(*l);
+    if (auto e = AdvanceLevel(0, dt, 0, split_kind, sweep_dts)) {
+      for (size_t l = 0; l < levels.size(); ++l) *levels[l] = backup[l];
+      return e;
+    }
+    Level& L0 = *levels[0];
+    L0.cycles += 1;
+    L0.time_point = L0.time_point + dt;
+    if (L0.cycles % L0.regrid_frequency == 0) {
+      L0.FillGhostLayerSingleLevel();
+      for (size_t l = 1; l < levels.size(); ++l) {
+        FillGhostLayerTwoLevels(*levels[l], *levels[l - 1], cf[l].ratio);
+      }
+    }
+    return std::nullopt;
+  }
+};
+
 } // namespace fvso

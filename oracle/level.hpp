@@ -560,12 +560,18 @@ struct Level {
   }
 
   // include/fub/solver/DimensionalSplitLevelIntegrator.hpp:221-276
+  // hook of IntegratorContext::AccumulateCoarseFineFluxes(level, scale, dir),
+  // called after every sweep (DimensionalSplitLevelIntegrator.hpp:258-260)
+  std::function<void(double, int)> accumulate_hook;
+
   std::optional<TimeStepTooLarge>
   AdvanceLevelNonRecursively(double dt, int split_kind,
-                             std::vector<double>* sweep_dts = nullptr) {
-    // MakeSplitDirections, include/fub/split_method/SplittingMethod.hpp:115-126
-    // (single level: subcycle = {0, 1})
-    const int is_odd = int(cycles % 2);
+                             std::vector<double>* sweep_dts = nullptr,
+                             long cycles0 = -1, int subcycle_first = 0) {
+    // MakeSplitDirections, include/fub/split_method/SplittingMethod.hpp:115-126:
+    // the cycle counter of level 0 and the subcycle index
+    const long cyc = cycles0 >= 0 ? cycles0 : cycles;
+    const int is_odd = int((cyc % 2 + subcycle_first) % 2);
     int dirs[3];
     for (int i = 0; i < rank; ++i) dirs[i] = is_odd ? (rank - 1 - i) : i;
     int counts[3] = {0, 0, 0};
@@ -585,6 +591,7 @@ struct Level {
         ComputeNumericFluxes_(split_dt, dir);
         UpdateConservatively_(split_dt, dir);
         CompleteFromCons_();
+        if (accumulate_hook) accumulate_hook(split_dt, dir);
         return std::nullopt;
       };
     };

@@ -42,6 +42,7 @@ def lib():
         L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
         L.fvso_level_eb_array.restype = C.POINTER(C.c_double)
         L.fvso_cf_create.restype = C.c_void_p
+        L.fvso_hierarchy_create.restype = C.c_void_p
         L.fvso_level_cycles.restype = C.c_long
         L.fvso_level_time.restype = C.c_double
         _LIB = L
@@ -252,6 +253,34 @@ class CoarseFine:
 
     def fill_ghost_layer_two_levels(self):
         _check(lib().fvso_cf_fill_ghost_layer_two_levels(self.h, self.fine.h, self.coarse.h))
+
+
+class Hierarchy:
+    """Static multi-level hierarchy with fine-first subcycling (oracle/amr.hpp)."""
+
+    def __init__(self, levels, ratio=(2, 2, 2)):
+        self.levels = list(levels)
+        r = [ratio[d] if d < levels[0].rank else 1 for d in range(3)]
+        arr = (C.c_void_p * len(levels))(*[l.h for l in levels])
+        self.h = C.c_void_p(lib().fvso_hierarchy_create(len(levels), arr, _ia(r)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().fvso_hierarchy_destroy(self.h)
+            self.h = None
+
+    def compute_stable_dt(self):
+        out = C.c_double()
+        _check(lib().fvso_hierarchy_stable_dt(self.h, C.byref(out)))
+        return out.value
+
+    def advance_hierarchy(self, dt, split):
+        too = C.c_double()
+        buf = (C.c_double * 64)()
+        n = C.c_int(64)
+        rc = _check(lib().fvso_hierarchy_advance(self.h, C.c_double(dt), split, C.byref(too), buf,
+                                                 C.byref(n)))
+        return rc == 0, too.value, [buf[i] for i in range(min(n.value, 64))]
 
 
 def tag_buffer(tags, rank, width):

@@ -307,6 +307,37 @@ int fvso_cf_fill_ghost_layer_two_levels(void* cf, void* fine, void* coarse) {
   });
 }
 
+// --------------------------------------------------------------- hierarchy
+void* fvso_hierarchy_create(int nlevels, void** levels, const int* ratio) {
+  Hierarchy* H = new Hierarchy;
+  for (int l = 0; l < nlevels; ++l) H->levels.push_back(static_cast<Level*>(levels[l]));
+  for (int d = 0; d < 3; ++d) H->ratio[d] = ratio[d];
+  H->define();
+  return H;
+}
+void fvso_hierarchy_destroy(void* h) { delete static_cast<Hierarchy*>(h); }
+int fvso_hierarchy_stable_dt(void* h, double* out) {
+  return guarded([&] { *out = static_cast<Hierarchy*>(h)->ComputeStableDt(); });
+}
+int fvso_hierarchy_advance(void* h, double dt, int split_kind, double* too_large_dt,
+                           double* sweep_dts, int* n_sweep_dts) {
+  int status = 0;
+  int rc = guarded([&] {
+    std::vector<double> sd;
+    auto r = static_cast<Hierarchy*>(h)->AdvanceHierarchy(dt, split_kind, &sd);
+    if (r) {
+      status = 1;
+      *too_large_dt = r->dt;
+    }
+    if (sweep_dts && n_sweep_dts) {
+      const int cap = *n_sweep_dts;
+      *n_sweep_dts = int(sd.size());
+      for (int i = 0; i < cap && i < int(sd.size()); ++i) sweep_dts[i] = sd[size_t(i)];
+    }
+  });
+  return rc < 0 ? rc : status;
+}
+
 // ----------------------------------------------------- unit-level helpers
 // UpdateConservatively on a bare array pair: `cells` x-cells, 1 component,
 // direction X (tests/test.HyperbolicSplitPatchIntegrator.cpp).

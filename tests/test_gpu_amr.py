@@ -126,3 +126,84 @@ def test_flux_register_cycle(oracle, fvs, rank):
     compare(ccpu, cgpu, "after average_down + complete")
     compare(fcpu, fgpu, "fine level")
     cgpu.close()
+
+
+def nested_hierarchy(orc, fvs, nlevels):
+    """2-D diagonal Sod problem (examples/AMReX/SodShockTube2d.cpp:57-64) on a
+    static, properly nested hierarchy; reflective boundaries, gcw 8/6."""
+    from helpers import complete_from_prim
+    rank = 2
+    n0 = [32, 24]
+    level_boxes = [
+        [([0, 0, 0], [15, 23, 0]), ([16, 0, 0], [31, 23, 0])],
+        [([16, 8, 0], [31, 39, 0]), ([32, 8, 0], [47, 23, 0]), ([32, 24, 0], [47, 39, 0])],
+        [([48, 40, 0], [71, 63, 0]), ([72, 32, 0], [87, 55, 0])],
+    ][:nlevels]
+    gcw = (8, 6)
+    cpus, gpus = [], []
+    ctx = None
+    for l, boxes in enumerate(level_boxes):
+        f = 2 ** l
+        hi = [n0[0] * f - 1, n0[1] * f - 1, 0]
+        dx = [2.0 / (n0[0] * f), 2.0 / (n0[1] * f), 1.0]
+        cpu = orc.Level(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+        if l == 0:
+            ctx = fvs.Context(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+            gpu = ctx
+        else:
+            gpu = ctx.define_level(l, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+        for lv in (cpu, gpu):
+            for d in range(rank):
+                for s in (0, 1):
+                    lv.add_bc(d, s, 1)
+        for b in range(len(boxes)):
+            arr, lo, hi_b = cpu.scratch(b)
+            x = -1.0 + (np.arange(lo[0], hi_b[0] + 1) + 0.5) * dx[0]
+            y = -1.0 + (np.arange(lo[1], hi_b[1] + 1) + 0.5) * dx[1]
+            upper = (x[None, None, :] + y[None, :, None]) > 0.0
+            rho = np.where(upper, 0.125, 1.0)
+            p = np.where(upper, 10132.5, 101325.0)
+            arr[...] = complete_from_prim(rank, rho, [np.zeros_like(rho)] * 2, p)
+            gpu.upload_state(b, arr)
+        cpus.append(cpu)
+        gpus.append(gpu)
+    hier = orc.Hierarchy(cpus)
+    cpus[0].fill_ghost_layer()
+    gpus[0].fill_ghost_layer()
+    for l in range(1, nlevels):
+        orc.CoarseFine(cpus[l], cpus[l - 1]).fill_ghost_layer_two_levels()
+        ctx.fill_ghost_layer_two_levels(l, l - 1)
+    return hier, cpus, gpus, ctx
+
+
+@pytest.mark.parametrize("nlevels,split", [(2, 1), (3, 1), (3, 0)])
+def test_subcycled_hierarchy_bitwise(oracle, fvs, nlevels, split):
+    """SubcycleFineFirstSolver on a static hierarchy: fine levels first with two
+    subcycles each, flux registers, reflux, average_down, two-level ghost fill;
+    every level bit-identical, identical per-sweep dts and step dt."""
+    hier, cpus, gpus, ctx = nested_hierarchy(oracle, fvs, nlevels)
+    for step in range(4):
+        dt_c = hier.compute_stable_dt()
+        dt_g = ctx.compute_stable_dt_hierarchy()
+        assert dt_c == dt_g, (step, dt_c, dt_g)
+        ok_c, _, dts_c = hier.advance_hierarchy(0.5 * dt_c, split)
+        ok_g, _, dts_g = ctx.advance_hierarchy(0.5 * dt_g, split)
+        assert ok_c and ok_g and dts_c == dts_g, (step, dts_c, dts_g)
+        assert len(dts_c) == (4 if split == 1 else 2) * (2 ** nlevels - 1)
+        for l in range(nlevels):
+            compare(cpus[l], gpus[l], f"step {step} level {l}")
+    ctx.close()
+
+
+def test_hierarchy_cfl_violation_rolls_back_all_levels(oracle, fvs):
+    hier, cpus, gpus, ctx = nested_hierarchy(oracle, fvs, 2)
+    before = [[g.download_state(b) for b in range(len(g.boxes))] for g in gpus]
+    dt = 3.0 * ctx.compute_stable_dt_hierarchy()
+    ok_c, fail_c, _ = hier.advance_hierarchy(dt, 1)
+    ok_g, fail_g, _ = ctx.advance_hierarchy(dt, 1)
+    assert not ok_c and not ok_g and fail_c == fail_g
+    for l, g in enumerate(gpus):
+        for b in range(len(g.boxes)):
+            assert_bitwise_equal(g.download_state(b), before[l][b], f"rollback level {l} box {b}")
+        compare(cpus[l], g, f"rollback vs oracle level {l}")
+    ctx.close()
