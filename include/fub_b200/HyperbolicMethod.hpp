@@ -228,6 +228,30 @@ public:
   }
   long KernelLaunches() const { return fvs_kernel_launches(ctx_.get()); }
 
+  // ---- coarse-fine (src/AMReX/IntegratorContext.cpp:380-533) -----------------
+  bool LevelExists(int level) const {
+    int lo[3], hi[3], nc;
+    return fvs_state_box(ctx_.get(), level, 0, lo, hi, &nc) == FVS_OK;
+  }
+  void SetRefineRatio(const std::array<int, 3>& ratio) {
+    Check(fvs_set_refine_ratio(ctx_.get(), ratio.data()));
+  }
+  void FillGhostLayerTwoLevels(int fine, int coarse) {
+    Check(fvs_fill_ghost_layer_two_levels(ctx_.get(), fine, coarse));
+  }
+  void ResetCoarseFineFluxes(int fine, int coarse) {
+    Check(fvs_reset_coarse_fine_fluxes(ctx_.get(), fine, coarse));
+  }
+  void AccumulateCoarseFineFluxes(int level, double scale, Direction dir) {
+    Check(fvs_accumulate_coarse_fine_fluxes(ctx_.get(), level, scale, static_cast<int>(dir)));
+  }
+  void ApplyFluxCorrection(int fine, int coarse, Duration dt) {
+    Check(fvs_apply_flux_correction(ctx_.get(), fine, coarse, dt.count()));
+  }
+  void CoarsenConservatively(int fine, int coarse) {
+    Check(fvs_coarsen_conservatively(ctx_.get(), fine, coarse));
+  }
+
 private:
   int rank_;
   Options options_;
@@ -250,6 +274,11 @@ struct FluxMethod {
                                      static_cast<int>(dir)));
   }
   int GetStencilWidth() const { return stencil_width; }
+  /// cutcell::FluxMethod::PreAdvanceHierarchy (include/fub/AMReX/cutcell/FluxMethod.hpp:108-133);
+  /// a no-op on levels without an embedded boundary
+  void PreAdvanceHierarchy(IntegratorContext& context) {
+    Check(fvs_pre_advance_hierarchy(context.Handle()));
+  }
   int stencil_width{2};
 };
 
@@ -381,6 +410,8 @@ public:
         return std::nullopt;
       }
     };
+    // cutcell::IntegratorContext::PreAdvanceLevel (src/AMReX/cutcell/IntegratorContext.cpp:802-806)
+    method_.flux_method.PreAdvanceHierarchy(context_);
     const auto dirs =
         MakeSplitDirections<Rank>(static_cast<int>(context_.GetCycles(0)), subcycle);
     std::vector<Op> ops;
@@ -393,6 +424,117 @@ private:
   HyperbolicMethod method_;
   SplitMethod split_;
   bool fused_;
+};
+
+/// fub::SubcycleFineFirstSolver over the device hierarchy
+/// (include/fub/solver/SubcycleFineFirstSolver.hpp:100-193): stable dt over all
+/// levels and one coarse step with fine-first subcycling, flux correction and
+/// conservative coarsening; TimeStepTooLarge leaves every level untouched.
+template <typename SplitKind> struct SplitKindOf;
+template <> struct SplitKindOf<GodunovSplitting> {
+  static constexpr int value = FVS_SPLIT_GODUNOV;
+};
+template <> struct SplitKindOf<StrangSplitting> {
+  static constexpr int value = FVS_SPLIT_STRANG;
+};
+template <> struct SplitKindOf<StrangSplittingLumped> {
+  static constexpr int value = FVS_SPLIT_STRANG_LUMPED;
+};
+template <typename SplitMethod = GodunovSplitting> class SubcycleFineFirstSolver {
+public:
+  explicit SubcycleFineFirstSolver(IntegratorContext context) : context_(std::move(context)) {}
+  IntegratorContext& GetContext() { return context_; }
+  Duration ComputeStableDt() {
+    double dt = 0.0;
+    Check(fvs_compute_stable_dt_hierarchy(context_.Handle(), &dt));
+    return Duration(dt);
+  }
+  AdvanceResult AdvanceHierarchy(Duration dt) {
+    double failure = 0.0;
+    const int rc = fvs_advance_hierarchy(context_.Handle(), dt.count(),
+                                         SplitKindOf<SplitMethod>::value, &failure, nullptr, nullptr);
+    Check(rc);
+    if (rc == FVS_TIME_STEP_TOO_LARGE) return TimeStepTooLarge{Duration(failure), 0};
+    return std::nullopt;
+  }
+
+private:
+  IntegratorContext context_;
+};
+
+// ---- embedded boundary -------------------------------------------------------
+namespace cutcell {
+
+/// The arrays of fub::CutCellData<Rank> that come from amrex::EBFArrayBoxFactory
+/// (include/fub/CutCellData.hpp:48-75, src/AMReX/cutcell/PatchHierarchy.cpp:507-547);
+/// the shielded / unshielded fractions are derived on the device.
+struct CutCellGeometry {
+  const double* volume_fractions{nullptr};            ///< getVolFrac, scratch box
+  std::array<const double*, 3> face_fractions{};      ///< getAreaFrac()[d], one more face along d
+  const double* boundary_centeroids{nullptr};         ///< getBndryCent, Rank components
+  const double* boundary_normals{nullptr};            ///< getBndryNormal, Rank components
+  int fab_type{FVS_FAB_SINGLEVALUED};                 ///< amrex::FabType of the box
+};
+enum class RiemannSolver : int { HllEinfeldt = FVS_RIEMANN_HLL_EINFELDT, Exact = FVS_RIEMANN_EXACT };
+
+/// fub::amrex::cutcell::IntegratorContext: the same policies, cut-cell adapters
+/// once a box has been given its geometry.
+class IntegratorContext : public ::fub::b200::IntegratorContext {
+public:
+  using ::fub::b200::IntegratorContext::IntegratorContext;
+  void SetKbnRiemannSolver(RiemannSolver rs) {
+    Check(fvs_set_cutcell_riemann_solver(Handle(), static_cast<int>(rs)));
+  }
+  /// PatchHierarchy::GetCutCellData(level, mfi) handed to the device
+  void SetEmbeddedBoundary(int level, int box, const CutCellGeometry& g) {
+    const double* beta[3] = {g.face_fractions[0], g.face_fractions[1], g.face_fractions[2]};
+    Check(fvs_level_set_eb(Handle(), level, box, g.volume_fractions, beta, g.boundary_centeroids,
+                           g.boundary_normals, g.fab_type));
+  }
+  /// fub::IsCutCell for every cell of the scratch box; returns the number of cut cells
+  long CutCellFlags(int level, int box, unsigned char* flags) {
+    const long n = fvs_cut_cell_flags(Handle(), level, box, flags);
+    if (n < 0) throw std::runtime_error(fvs_last_error());
+    return n;
+  }
+};
+using FluxMethod = ::fub::b200::FluxMethod;         ///< KbnCutCellMethod behind cutcell::FluxMethod
+using TimeIntegrator = ::fub::b200::TimeIntegrator; ///< cutcell::TimeIntegrator
+using Reconstruction = ::fub::b200::Reconstruction; ///< cutcell::Reconstruction
+
+} // namespace cutcell
+
+// ---- tagging ---------------------------------------------------------------------
+/// fub::GradientDetector(equation, {projection, tolerance}...) with projections
+/// given as component indices of the Complete state
+/// (include/fub/tagging_method/GradientDetector.hpp:156-232).
+struct GradientDetector {
+  std::vector<std::pair<int, double>> conditions;
+  bool use_volume_fractions{false};
+  void TagCellsForRefinement(char* tags, IntegratorContext& context, int level, int box) const {
+    std::vector<int> comps;
+    std::vector<double> tols;
+    for (const auto& c : conditions) {
+      comps.push_back(c.first);
+      tols.push_back(c.second);
+    }
+    Check(fvs_tag_gradient(context.Handle(), level, box, static_cast<int>(comps.size()),
+                           comps.data(), tols.data(), use_volume_fractions ? 1 : 0, tags));
+  }
+};
+/// fub::TagCutCells (src/tagging_method/TagCutCells.cpp:27-35)
+struct TagCutCells {
+  void TagCellsForRefinement(char* tags, IntegratorContext& context, int level, int box) const {
+    Check(fvs_tag_cutcells(context.Handle(), level, box, tags));
+  }
+};
+/// fub::TagBuffer (src/tagging_method/TagBuffer.cpp:27-86) on a dense view
+struct TagBuffer {
+  int buffer_width{1};
+  void TagCellsForRefinement(char* tags, IntegratorContext& context, int rank,
+                             const std::array<int, 3>& extents) const {
+    Check(fvs_tag_buffer(context.Handle(), rank, tags, extents.data(), buffer_width));
+  }
 };
 
 } // namespace b200
