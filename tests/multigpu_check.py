@@ -83,10 +83,61 @@ def main():
     assert v == 3.0, v
     ctx.close()
     dist.barrier()
+    eb_check(capi, orc, rank, world, local)
+    dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: {world} ranks, halo + 6 Strang steps bit-identical to the "
-              f"oracle, identical dt sequence, min_all ok")
+              f"oracle, identical dt sequence, min_all ok; cut-cell level over {world} ranks "
+              f"bit-identical too")
     dist.destroy_process_group()
+
+
+def eb_check(capi, orc, rank, world, local):
+    """A 2-D cut-cell level (wedge) whose boxes are spread over the ranks:
+    KbnCutCellMethod + NCCL halo + dt all-reduce, against the oracle."""
+    from helpers import complete_from_prim, eb_fab_type, eb_geometry, polygon_phi
+    nbx = world
+    n = (24 * nbx, 32)
+    dx = [0.15 / n[0], 0.10 / n[1], 1.0]
+    boxes = [([24 * b, 0, 0], [24 * b + 23, n[1] - 1, 0]) for b in range(nbx)]
+    ctx = capi.Context(2, [0] * 3, [n[0] - 1, n[1] - 1, 0], dx, boxes, scratch_gcw=8, flux_gcw=6,
+                       device=local, comm_rank=rank, comm_size=world, owner=list(range(world)))
+    idt = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    cpu = orc.Level(2, [0] * 3, [n[0] - 1, n[1] - 1, 0], dx, boxes, scratch_gcw=8, flux_gcw=6)
+    cpu.set_method(0, 1, 2)
+    cpu.enable_eb()
+    ctx.enable_eb()
+    phi = polygon_phi([(0.04, 0.05), (0.10, 0.075), (0.10, 0.025)])
+    for d in range(2):
+        for s in (0, 1):
+            ctx.add_bc(d, s, capi.BC_TRANSMISSIVE)
+            cpu.add_bc(d, s, orc.BC_TRANSMISSIVE)
+    for b in range(nbx):
+        arr, lo, hi = cpu.scratch(b)
+        g = eb_geometry(2, lo, hi, dx, [0.0] * 3, phi)
+        cpu.set_eb(b, g, eb_fab_type(g))
+        x = (np.arange(lo[0], hi[0] + 1) + 0.5) * dx[0]
+        rho = np.ones(arr.shape[1:])
+        p = np.where(x < 0.02, 5 * 101325.0, 101325.0)[None, None, :] + np.zeros_like(rho)
+        arr[...] = complete_from_prim(2, rho, [np.zeros_like(rho)] * 2, p) * (g["alpha"][0] > 0)
+        if b == rank:
+            ctx.set_eb(b, g, eb_fab_type(g))
+            ctx.upload_state(b, arr)
+    cpu.fill_ghost_layer()
+    ctx.fill_ghost_layer()
+    for step in range(8):
+        dt_c = min(cpu.compute_stable_dt(q) for q in range(2))
+        dt_g = ctx.compute_stable_dt_all()
+        assert dt_c == dt_g, (rank, step, dt_c, dt_g)
+        ok_c, _, dts_c = cpu.advance_hierarchy(0.4 * dt_c, orc.SPLIT_STRANG)
+        ok_g, _, dts_g = ctx.advance_hierarchy(0.4 * dt_g, capi.SPLIT_STRANG)
+        assert ok_c and ok_g and dts_c == dts_g, (rank, step, dts_c, dts_g)
+    assert_bitwise_equal(ctx.download_state(rank), cpu.scratch(rank)[0], f"rank {rank}: EB level")
+    ctx.close()
 
 
 if __name__ == "__main__":
