@@ -239,7 +239,7 @@ struct fvs_ctx {
   // comm
   Nccl::comm_t comm{nullptr};
 
-  int stencil_width() const { return method.recon == fvs::kReconMusclHancock ? 2 : 1; }
+  int stencil_width() const { return method.recon == fvs::kReconFirstOrder ? 1 : 2; }
   int ncomp() const { return cfg.rank + 4; }
   int ncons() const { return cfg.rank + 2; }
 
@@ -1185,9 +1185,13 @@ int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limite
   return guarded([&] {
     if (!ctx) throw Error("null context");
     if (base_method < 0 || base_method > 3) throw Error("unknown base method");
-    if (reconstruction < 0 || reconstruction > 1) throw Error("unknown reconstruction");
+    if (reconstruction < 0 || reconstruction > 2) throw Error("unknown reconstruction");
+    if (reconstruction == FVS_RECON_MUSCL_HANCOCK_PRIM && base_method != FVS_BASE_HLLEM_LARROUTUROU) {
+      // src/equations/perfect_gas/MusclHancockPrimMethod.hpp:175
+      throw Error("MusclHancockPrim is defined over HLLEM (Larrouturou) only");
+    }
     if (limiter < 0 || limiter > 2) throw Error("unknown limiter");
-    const int w = reconstruction == FVS_RECON_MUSCL_HANCOCK ? 2 : 1;
+    const int w = reconstruction == FVS_RECON_FIRST_ORDER ? 1 : 2;
     for (Level& L : ctx->levels) {
       if (L.defined && L.scratch_gcw < L.flux_gcw + w) {
         throw Error("scratch_gcw must be >= flux_gcw + stencil width");

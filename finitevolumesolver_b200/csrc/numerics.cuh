@@ -23,7 +23,7 @@
 namespace fvs {
 
 enum : int { kBaseHllemLarrouturou = 0, kBaseHllem = 1, kBaseHllEinfeldt = 2, kBaseGodunovExact = 3 };
-enum : int { kReconFirstOrder = 0, kReconMusclHancock = 1 };
+enum : int { kReconFirstOrder = 0, kReconMusclHancock = 1, kReconMusclHancockPrim = 2 };
 enum : int { kLimiterNone = 0, kLimiterMinMod = 1, kLimiterVanLeer = 2 };
 
 // PerfectGas equation constants (include/fub/equations/PerfectGas.hpp:216-219):
@@ -203,6 +203,123 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   recR.rc = M::rcp(recR.q.rho);
   complete_edge<M, D, MASKED>(eq, recL.q, recL.rc, fl);
   complete_edge<M, D, MASKED>(eq, recR.q, recR.rc, fl);
+}
+
+// ---------------------------------------------------------------------------
+// perfect_gas::MusclHancockPrim, src/equations/perfect_gas/MusclHancockPrimMethod.hpp:59-179:
+// MUSCL-Hancock on the primitive variables (rho, u, p) with its own limiter;
+// the base method is always HLLEM with the Larrouturou modification (:175).
+template <int D> struct PrimCell {
+  double rho, p, a;
+  double u[D];
+};
+template <class M, int D, typename State>
+FVS_DEV void prim_cell(PrimCell<D>& c, const State& q, Flag& fl) {
+  const Rcp rc = M::rcp(q.rho);
+  M::check(rc, fl);
+  c.rho = q.rho;
+  c.p = q.p;
+  c.a = q.a;
+#pragma unroll
+  for (int i = 0; i < D; ++i) c.u[i] = M::div(q.mom[i], rc, fl);
+}
+// the limiter lambda of :70-86
+template <class M> FVS_DEV double prim_limited_slope(double qL, double qM, double qR, Flag& fl) {
+  const double delta_q = 0.5 * (qR - qL);
+  const bool is_relevant = fabs(delta_q) > 1e-12;
+  const double dq = is_relevant ? delta_q : 1.0;
+  const Rcp rc = M::rcp(dq);
+  M::check(rc, fl);
+  const double qLq = M::div(qM - qL, rc, fl, is_relevant);
+  const double qRq = M::div(qR - qM, rc, fl, is_relevant);
+  const double rL = is_relevant ? qLq : 0.0;
+  const double rR = is_relevant ? qRq : 0.0;
+  const bool is_positive = rL > 0.0 && rR > 0.0;
+  const double r = is_positive ? vmin(rL, rR) : 0.0;
+  const double r_1 = M::div(2 * r, 1.0 + r, fl);
+  const double r_2 = 0.5 * (r + 1.0);
+  const double sigma = r < 1.0 ? r_1 : r_2;
+  return sigma * delta_q;
+}
+template <int D> struct PrimSlopes {
+  double drho, dp;
+  double du[D];
+};
+template <class M, int D>
+FVS_DEV void prim_slopes(PrimSlopes<D>& s, const PrimCell<D>& m, const PrimCell<D>& c,
+                         const PrimCell<D>& p, Flag& fl) {
+  s.drho = prim_limited_slope<M>(m.rho, c.rho, p.rho, fl);
+  s.dp = prim_limited_slope<M>(m.p, c.p, p.p, fl);
+#pragma unroll
+  for (int i = 0; i < D; ++i) s.du[i] = prim_limited_slope<M>(m.u[i], c.u[i], p.u[i], fl);
+}
+// One predicted edge state of cell `c`: RIGHT = its upper edge (w[0] of the
+// face above, :108-119), else its lower edge (w[1] of the face below, :121-132);
+// then the Complete state of :139-158.
+template <class M, int D, int DIR, bool RIGHT>
+FVS_DEV void prim_edge(const EqM& eq, Edge<D>& out, const PrimCell<D>& c, const PrimSlopes<D>& s,
+                       double lambda, Flag& fl) {
+  const double ud = c.u[DIR];
+  double rec_rho, rec_p, rec_u[D];
+  if constexpr (RIGHT) {
+    rec_rho = c.rho + 0.5 * (s.drho - lambda * (ud * s.drho + c.rho * s.du[DIR]));
+    rec_p = c.p + 0.5 * (s.dp - lambda * (c.rho * c.a * c.a * s.du[DIR] + ud * s.dp));
+#pragma unroll
+    for (int i = 0; i < D; ++i) rec_u[i] = c.u[i] + 0.5 * (s.du[i] - lambda * (ud * s.du[i]));
+  } else {
+    rec_rho = c.rho - 0.5 * (s.drho + lambda * (ud * s.drho + c.rho * s.du[DIR]));
+    rec_p = c.p - 0.5 * (s.dp + lambda * (c.rho * c.a * c.a * s.du[DIR] + ud * s.dp));
+#pragma unroll
+    for (int i = 0; i < D; ++i) rec_u[i] = c.u[i] - 0.5 * (s.du[i] + lambda * (ud * s.du[i]));
+  }
+  rec_u[DIR] = rec_u[DIR] - M::div(0.5 * lambda * s.dp, c.rho, fl);
+  out.q.rho = rec_rho;
+#pragma unroll
+  for (int i = 0; i < D; ++i) out.q.mom[i] = rec_rho * rec_u[i];
+  out.q.p = rec_p;
+  out.rc = M::rcp(rec_rho);
+  M::check(out.rc, fl);
+  out.q.a = M::sqrt(M::div(eq.gamma * rec_p, out.rc, fl), fl);
+  out.q.E = 0.5 * rec_rho * squared_norm<D>(rec_u) + rec_p * eq.gm1_inv.b;
+}
+// both edge states of the cell with neighbours qm, qp (regular grid: every
+// cell predictor is shared by the two faces of the cell)
+template <class M, int D, int DIR, typename S0, typename S1, typename S2>
+FVS_DEV void muscl_prim_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp,
+                                double lambda, Edge<D>& recL, Edge<D>& recR, Flag& fl) {
+  PrimCell<D> m, c, p;
+  prim_cell<M, D>(m, qm, fl);
+  prim_cell<M, D>(c, q0, fl);
+  prim_cell<M, D>(p, qp, fl);
+  PrimSlopes<D> s;
+  prim_slopes<M, D>(s, m, c, p, fl);
+  prim_edge<M, D, DIR, false>(eq, recL, c, s, lambda, fl);
+  prim_edge<M, D, DIR, true>(eq, recR, c, s, lambda, fl);
+}
+// masked face of a cut-cell fab (:185-329): an outer stencil cell whose volume
+// fraction is not positive is replaced by its inner neighbour
+template <class M, int D, int DIR, typename S>
+FVS_DEV void muscl_prim_face_masked(const EqM& eq, const S& s0, const S& s1, const S& s2,
+                                    const S& s3, bool left_ok, bool right_ok, double lambda,
+                                    Edge<D>& left, Edge<D>& right, Flag& fl) {
+  PrimCell<D> ll, l, r, rr;
+  prim_cell<M, D>(l, s1, fl);
+  prim_cell<M, D>(r, s2, fl);
+  if (left_ok) {
+    prim_cell<M, D>(ll, s0, fl);
+  } else {
+    ll = l;
+  }
+  if (right_ok) {
+    prim_cell<M, D>(rr, s3, fl);
+  } else {
+    rr = r;
+  }
+  PrimSlopes<D> sl, sr;
+  prim_slopes<M, D>(sl, ll, l, r, fl);
+  prim_slopes<M, D>(sr, l, r, rr, fl);
+  prim_edge<M, D, DIR, true>(eq, left, l, sl, lambda, fl);
+  prim_edge<M, D, DIR, false>(eq, right, r, sr, lambda, fl);
 }
 
 // ---------------------------------------------------------------------------

@@ -100,9 +100,10 @@ int cc_stable_dt(const SweepArgs& A, cudaStream_t s) {
   return 1;
 }
 
-template <int DIR, typename F0, typename F1, typename F2, typename F3>
-int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer) {
+template <int DIR, typename F0, typename F1, typename F2, typename F3, typename F4>
+int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim) {
   if (k.recon == kReconFirstOrder) return fo();
+  if (k.recon == kReconMusclHancockPrim) return prim();
   switch (k.limiter) {
   case kLimiterNone: return none();
   case kLimiterMinMod: return minmod();
@@ -116,14 +117,30 @@ template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStr
       k, [&] { return fused<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fused<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
       [&] { return fused<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
-      [&] { return fused<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+      [&] { return fused<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); },
+      [&] {
+        // perfect_gas::MusclHancockPrim exists over HLLEM-Larrouturou only
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return fused<DIR, kReconMusclHancockPrim, kLimiterNone>(A, s);
+        } else {
+          return -1;
+        }
+      });
 }
 template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
   return by_recon<DIR>(
       k, [&] { return fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
       [&] { return fluxes<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
-      [&] { return fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+      [&] { return fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); },
+      [&] {
+        // perfect_gas::MusclHancockPrim exists over HLLEM-Larrouturou only
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return fluxes<DIR, kReconMusclHancockPrim, kLimiterNone>(A, s);
+        } else {
+          return -1;
+        }
+      });
 }
 
 template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
@@ -131,7 +148,15 @@ template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cud
       k, [&] { return cc_fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
       [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterMinMod>(A, s); },
-      [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); });
+      [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s); },
+      [&] {
+        // perfect_gas::MusclHancockPrim exists over HLLEM-Larrouturou only
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return cc_fluxes<DIR, kReconMusclHancockPrim, kLimiterNone>(A, s);
+        } else {
+          return -1;
+        }
+      });
 }
 
 } // namespace

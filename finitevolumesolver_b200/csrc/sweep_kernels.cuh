@@ -132,6 +132,11 @@ FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const S1& q0, const S2& 
     with_fallback([&](auto M, Flag& fl) {
       muscl_predict<decltype(M), D, DIR, LIM>(eq.m, qm, q0, qp, lambda_half, recL, recR, fl);
     });
+  } else if constexpr (RECON == kReconMusclHancockPrim) {
+    // MusclHancockPrim uses lambda = dt / dx (MusclHancockPrimMethod.hpp:101)
+    with_fallback([&](auto M, Flag& fl) {
+      muscl_prim_predict<decltype(M), D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
+    });
   } else {
     recL.q = q0;
     recL.rc = FastMath::rcp(q0.rho);
@@ -231,7 +236,8 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     const unsigned char* dtmask = B.dtmask;
 
     Complete<D> q0, q1, qn; // cells j, j-1 and the prefetched cell j+1
-    Cons<D> q2;             // cell j-2
+    // cell j-2: the primitive-variable predictor also needs its pressure
+    std::conditional_t<RECON == kReconMusclHancockPrim, Complete<D>, Cons<D>> q2;
     Edge<D> recR_prev;      // upper edge state of cell j-2
     Cons<D> F_prev;         // flux through face j-2
     DtData<D, BASE> dt_prev, dt_cur;
@@ -240,7 +246,11 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     qn = q0;
     if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
     q1 = q0;
-    copy_cons<D>(q2, q0);
+    if constexpr (RECON == kReconMusclHancockPrim) {
+      q2 = q0;
+    } else {
+      copy_cons<D>(q2, q0);
+    }
     recR_prev.q = q0;
     recR_prev.rc = FastMath::rcp(q0.rho);
     copy_cons<D>(F_prev, q0);
@@ -269,6 +279,8 @@ fused_sweep_yz_kernel(const SweepArgs A) {
           using MM = decltype(M);
           if constexpr (RECON == kReconMusclHancock) {
             muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, A.lambda_half, recL, recR, fl);
+          } else if constexpr (RECON == kReconMusclHancockPrim) {
+            muscl_prim_predict<MM, D, DIR>(eq.m, q2, q1, q0, A.lambda, recL, recR, fl);
           } else {
             recL.q = q1;
             recL.rc = MM::rcp(q1.rho);
@@ -288,7 +300,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
         store_complete<D>(dst + stride * (j - 2), sc, out);
       } else {
         // stage A: cell j-1
-        if (j >= jstart + (RECON == kReconMusclHancock ? 2 : 1) && j - 1 >= ulo - 1 &&
+        if (j >= jstart + (RECON != kReconFirstOrder ? 2 : 1) && j - 1 >= ulo - 1 &&
             j - 1 <= uhi + 1) {
           stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
         } else {
@@ -296,7 +308,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
           recR = recR_prev;
         }
         // stage B: face j-1
-        if (j >= jstart + (RECON == kReconMusclHancock ? 3 : 2) && j - 1 >= ulo &&
+        if (j >= jstart + (RECON != kReconFirstOrder ? 3 : 2) && j - 1 >= ulo &&
             j - 1 <= uhi + 1) {
           stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
         } else {
@@ -314,7 +326,11 @@ fused_sweep_yz_kernel(const SweepArgs A) {
         const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
         maxsig = s > maxsig ? s : maxsig;
       }
-      copy_cons<D>(q2, q1);
+      if constexpr (RECON == kReconMusclHancockPrim) {
+        q2 = q1;
+      } else {
+        copy_cons<D>(q2, q1);
+      }
       q1 = q0;
       recR_prev = recR;
       F_prev = F;
@@ -689,7 +705,7 @@ __global__ void __launch_bounds__(128) numeric_flux_kernel(const SweepArgs A) {
     const Eqs eq(A.eq);
     Cons<D> F;
     Edge<D> unused, left, right;
-    if constexpr (RECON == kReconMusclHancock) {
+    if constexpr (RECON != kReconFirstOrder) {
       Complete<D> s0, s1, s2, s3;
       load_complete<D>(s0, p - 2 * stride, B.sc);
       load_complete<D>(s1, p - stride, B.sc);
@@ -846,7 +862,21 @@ __global__ void __launch_bounds__(128) cc_numeric_flux_kernel(const SweepArgs A)
     } else {
       Flag fl;
       Edge<D> unused, left, right;
-      if constexpr (RECON == kReconMusclHancock) {
+      if constexpr (RECON == kReconMusclHancockPrim) {
+        Complete<D> s0, s1, s2, s3;
+        load_complete<D>(s0, p - 2 * stride, B.sc);
+        load_complete<D>(s1, p - stride, B.sc);
+        load_complete<D>(s2, p, B.sc);
+        load_complete<D>(s3, p + stride, B.sc);
+        if (single) {
+          const double* al = B.alpha + cell;
+          muscl_prim_face_masked<SafeMath, D, DIR>(eq.m, s0, s1, s2, s3, al[-2 * stride] > 0.0,
+                                                   al[stride] > 0.0, A.lambda, left, right, fl);
+        } else {
+          muscl_prim_predict<SafeMath, D, DIR>(eq.m, s0, s1, s2, A.lambda, unused, left, fl);
+          muscl_prim_predict<SafeMath, D, DIR>(eq.m, s1, s2, s3, A.lambda, right, unused, fl);
+        }
+      } else if constexpr (RECON == kReconMusclHancock) {
         Complete<D> s0, s1, s2, s3;
         load_complete<D>(s0, p - 2 * stride, B.sc);
         load_complete<D>(s1, p - stride, B.sc);

@@ -40,8 +40,11 @@ enum {
   FVS_BASE_HLL_EINFELDT = 2,
   FVS_BASE_GODUNOV_EXACT = 3
 };
-/* include/fub/flux_method/MusclHancockMethod.hpp:189-571 */
-enum { FVS_RECON_FIRST_ORDER = 0, FVS_RECON_MUSCL_HANCOCK = 1 };
+/* include/fub/flux_method/MusclHancockMethod.hpp:189-571;
+ * perfect_gas::MusclHancockPrim (src/equations/perfect_gas/MusclHancockPrimMethod.hpp:25-333):
+ * primitive-variable MUSCL-Hancock with its own limiter, base method HLLEM
+ * (Larrouturou) only, the limiter argument is ignored */
+enum { FVS_RECON_FIRST_ORDER = 0, FVS_RECON_MUSCL_HANCOCK = 1, FVS_RECON_MUSCL_HANCOCK_PRIM = 2 };
 /* include/fub/flux_method/MusclHancockMethod.hpp:31-187 */
 enum { FVS_LIMITER_NONE = 0, FVS_LIMITER_MINMOD = 1, FVS_LIMITER_VANLEER = 2 };
 /* src/AMReX/boundary_condition/TransmissiveBoundary.cpp,

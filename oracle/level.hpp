@@ -18,7 +18,7 @@
 namespace fvso {
 
 enum BaseKind { kHllemLarrouturou = 0, kHllem = 1, kHllEinfeldt = 2, kGodunovExact = 3 };
-enum ReconKind { kFirstOrder = 0, kMusclHancock = 1 };
+enum ReconKind { kFirstOrder = 0, kMusclHancock = 1, kMusclHancockPrim = 2 };
 enum LimiterKind { kNoLimiter = 0, kMinMod = 1, kVanLeer = 2 };
 enum BcKind { kTransmissive = 0, kReflective = 1 };
 enum SplitKind { kGodunovSplitting = 0, kStrangSplitting = 1, kStrangSplittingLumped = 2 };
@@ -27,7 +27,7 @@ struct MethodSpec {
   int base{kHllemLarrouturou};
   int recon{kMusclHancock};
   int limiter{kVanLeer};
-  int stencil_width() const { return recon == kMusclHancock ? 2 : 1; }
+  int stencil_width() const { return recon == kFirstOrder ? 1 : 2; }
 };
 
 struct BoundaryCondition {
@@ -49,7 +49,11 @@ void with_method(const MethodSpec& ms, const PerfectGasEq& eq, F&& f) {
     default: throw std::runtime_error("unknown base method");
     }
   };
-  if (ms.recon == kFirstOrder) {
+  if (ms.recon == kMusclHancockPrim) {
+    // perfect_gas::MusclHancockPrim is a complete method: own limiter, HLLEM
+    // with the Larrouturou modification (MusclHancockPrimMethod.hpp:175)
+    f(MusclHancockPrim<D>(eq));
+  } else if (ms.recon == kFirstOrder) {
     with_base([&](auto base) { f(base); });
   } else {
     with_base([&](auto base) {

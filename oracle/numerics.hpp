@@ -1170,4 +1170,132 @@ template <typename Base, typename Limiter> struct MusclHancock {
   }
 };
 
+// ---------------------------------------------------------------------------
+// perfect_gas::MusclHancockPrim: MUSCL-Hancock on primitive variables with its
+// own limiter over HLLEM (Larrouturou).
+// src/equations/perfect_gas/MusclHancockPrimMethod.hpp:25-333
+template <int D> struct MusclHancockPrim {
+  static constexpr int kWidth = 2;
+  static constexpr int kDim = D;
+  using T = A8;
+  using Lane = A8;
+  PerfectGasEq eq;
+  Hllem<D, true> hllem;
+  explicit MusclHancockPrim(const PerfectGasEq& e) : eq(e), hllem(e) {}
+
+  // :70-86
+  static T limiter(const T& qL, const T& qM, const T& qR) {
+    const T delta_q = 0.5 * (qR - qL);
+    const M8 is_relevant = vabs(delta_q) > 1e-12;
+    const T delta_q_if_relevant = select(is_relevant, delta_q, 1.0);
+    const T rL = select(is_relevant, (qM - qL) / delta_q_if_relevant, 0.0);
+    const T rR = select(is_relevant, (qR - qM) / delta_q_if_relevant, 0.0);
+    const M8 is_positive = (rL > 0.0) && (rR > 0.0);
+    const T r = select(is_positive, vmin(rL, rR), 0.0);
+    const M8 less_than_one = r < 1.0;
+    const T r_1 = 2 * r / (A8(1.0) + r);
+    const T r_2 = 0.5 * (r + A8(1.0));
+    const T sigma = select(less_than_one, r_1, r_2);
+    return sigma * delta_q;
+  }
+
+  // :33-38
+  T ComputeStableDt(const Complete<T, D>* states, double dx, int dir) const {
+    return hllem.ComputeStableDt(states + 1, dx, dir);
+  }
+  // :40-47
+  T ComputeStableDt(const Complete<T, D>* states, const T& face_fraction, const T* vols,
+                    double dx, int dir) const {
+    return hllem.ComputeStableDt(states + 1, face_fraction, vols + 1, dx, dir);
+  }
+
+  // the part of :59-179 / :185-329 after the (masked) inputs have been chosen
+  void Reconstruct(Complete<T, D> (&w)[2], const T& rho_ll, const T& rho_l, const T& rho_r,
+                   const T& rho_rr, const T& p_ll, const T& p_l, const T& p_r, const T& p_rr,
+                   const T& a_l, const T& a_r, const T (&u_ll)[D], const T (&u_l)[D],
+                   const T (&u_r)[D], const T (&u_rr)[D], double dt, double dx, int d) const {
+    const T lambda(dt / dx);
+    const T drho_l = limiter(rho_ll, rho_l, rho_r);
+    const T dp_l = limiter(p_ll, p_l, p_r);
+    T du_l[D];
+    for (int i = 0; i < D; ++i) du_l[i] = limiter(u_ll[i], u_l[i], u_r[i]);
+    const T drho_r = limiter(rho_l, rho_r, rho_rr);
+    const T dp_r = limiter(p_l, p_r, p_rr);
+    T du_r[D];
+    for (int i = 0; i < D; ++i) du_r[i] = limiter(u_l[i], u_r[i], u_rr[i]);
+
+    const T rec_rho_l = rho_l + 0.5 * (drho_l - lambda * (u_l[d] * drho_l + rho_l * du_l[d]));
+    const T rec_p_l = p_l + 0.5 * (dp_l - lambda * (rho_l * a_l * a_l * du_l[d] + u_l[d] * dp_l));
+    T rec_u_l[D];
+    for (int i = 0; i < D; ++i) {
+      rec_u_l[i] = u_l[i] + 0.5 * (du_l[i] - lambda * (u_l[d] * du_l[i]));
+    }
+    rec_u_l[d] = rec_u_l[d] - 0.5 * lambda * dp_l / rho_l;
+
+    const T rec_rho_r = rho_r - 0.5 * (drho_r + lambda * (u_r[d] * drho_r + rho_r * du_r[d]));
+    const T rec_p_r = p_r - 0.5 * (dp_r + lambda * (rho_r * a_r * a_r * du_r[d] + u_r[d] * dp_r));
+    T rec_u_r[D];
+    for (int i = 0; i < D; ++i) {
+      rec_u_r[i] = u_r[i] - 0.5 * (du_r[i] + lambda * (u_r[d] * du_r[i]));
+    }
+    rec_u_r[d] = rec_u_r[d] - 0.5 * lambda * dp_r / rho_r;
+
+    auto fill = [&](Complete<T, D>& q, const T& rho, const T (&u)[D], const T& p) {
+      q.rho = rho;
+      for (int i = 0; i < D; ++i) q.mom[i] = rho * u[i];
+      q.p = p;
+      q.a = vsqrt(eq.gamma * p / rho);
+      q.E = 0.5 * rho * squared_norm<T, D>(u) + p * eq.gamma_minus_1_inv;
+    };
+    fill(w[0], rec_rho_l, rec_u_l, rec_p_l);
+    fill(w[1], rec_rho_r, rec_u_r, rec_p_r);
+  }
+
+  // :59-179
+  void ComputeNumericFlux(Cons<T, D>& flux, const Complete<T, D>* st, double dt, double dx,
+                          int dir) const {
+    T u[4][D];
+    for (int s = 0; s < 4; ++s)
+      for (int i = 0; i < D; ++i) u[s][i] = st[s].mom[i] / st[s].rho;
+    Complete<T, D> w[2];
+    Reconstruct(w, st[0].rho, st[1].rho, st[2].rho, st[3].rho, st[0].p, st[1].p, st[2].p, st[3].p,
+                st[1].a, st[2].a, u[0], u[1], u[2], u[3], dt, dx, dir);
+    hllem.ComputeNumericFlux(flux, w, dt, dx, dir);
+  }
+
+  // :185-329 (masked)
+  void ComputeNumericFlux(Cons<T, D>& flux, const T& face_fractions, const Complete<T, D>* st,
+                          const T* volume_fractions, double dt, double dx, int dir) const {
+    const M8 mask = face_fractions > 0.0;
+    if (!any(mask)) return; // the reference leaves `flux` untouched
+    const M8 left_mask = volume_fractions[0] > 0.0;
+    const M8 right_mask = volume_fractions[3] > 0.0;
+    const T rho_l = select(mask, st[1].rho, 1.0);
+    const T rho_r = select(mask, st[2].rho, 1.0);
+    const T rho_ll = select(left_mask, st[0].rho, rho_l);
+    const T rho_rr = select(right_mask, st[3].rho, rho_r);
+    const T p_l = select(mask, st[1].p, 1.0);
+    const T p_r = select(mask, st[2].p, 1.0);
+    const T p_ll = select(left_mask, st[0].p, p_l);
+    const T p_rr = select(right_mask, st[3].p, p_r);
+    const T a_l = select(mask, st[1].a, 1.0);
+    const T a_r = select(mask, st[2].a, 1.0);
+    T u_ll[D], u_l[D], u_r[D], u_rr[D];
+    for (int i = 0; i < D; ++i) {
+      const T rho_u_l = select(mask, st[1].mom[i], 0.0);
+      const T rho_u_r = select(mask, st[2].mom[i], 0.0);
+      const T rho_u_ll = select(left_mask, st[0].mom[i], rho_u_l);
+      const T rho_u_rr = select(right_mask, st[3].mom[i], rho_u_r);
+      u_ll[i] = rho_u_ll / rho_ll;
+      u_l[i] = rho_u_l / rho_l;
+      u_r[i] = rho_u_r / rho_r;
+      u_rr[i] = rho_u_rr / rho_rr;
+    }
+    Complete<T, D> w[2];
+    Reconstruct(w, rho_ll, rho_l, rho_r, rho_rr, p_ll, p_l, p_r, p_rr, a_l, a_r, u_ll, u_l, u_r,
+                u_rr, dt, dx, dir);
+    hllem.ComputeNumericFlux(flux, face_fractions, w, volume_fractions + 1, dt, dx, dir);
+  }
+};
+
 } // namespace fvso

@@ -91,14 +91,14 @@ def test_fill_cutcell_data_and_flags_bitwise(oracle, fvs):
     pair.close()
 
 
-METHODS = [(0, 1, 2), (0, 0, 0), (1, 1, 1), (2, 1, 1), (2, 0, 0), (2, 1, 2)]
+METHODS = [(0, 1, 2), (0, 0, 0), (1, 1, 1), (2, 1, 1), (2, 0, 0), (2, 1, 2), (0, 2, 0)]
 
 
 @pytest.mark.parametrize("method", METHODS)
 def test_cutcell_policies_bitwise(oracle, fvs, method):
     """PreAdvanceHierarchy, ComputeStableDt, ComputeNumericFluxes (boundary,
     regular, stabilised, shielded), UpdateConservatively, CompleteFromCons."""
-    gcw = (4, 2) if method[1] == 1 else (3, 2)
+    gcw = (4, 2) if method[1] != 0 else (3, 2)
     pair, dx, geoms = wedge_pair(oracle, fvs, method=method, gcw=gcw)
     pair.cpu.pre_advance_hierarchy()
     pair.gpu.pre_advance_hierarchy()

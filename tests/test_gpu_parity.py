@@ -29,6 +29,7 @@ BITWISE_METHODS = [
     (0, 1, 1), (0, 1, 0), (0, 0, 0),
     (1, 1, 2), (1, 0, 0),
     (2, 1, 1), (2, 1, 2), (2, 0, 0),
+    (0, 2, 0),  # perfect_gas::MusclHancockPrim (over HLLEM Larrouturou)
 ]
 
 

@@ -195,3 +195,31 @@ def test_kinetic_energy_reduction_order(oracle):
     q = oracle.complete_from_cons(3, [1.7, *m, 9.0])
     ke = 0.5 * (m[0] * m[0] + (m[1] * m[1] + m[2] * m[2])) / 1.7
     assert q[5] == (9.0 - ke) / (1.0 / (1.4 - 1.0))
+
+
+def test_muscl_hancock_prim_sod_star_state(oracle):
+    """perfect_gas::MusclHancockPrim (the reference has no test for it): the
+    oracle's restatement must resolve the Sod problem -- star density 0.42632
+    and contact / shock positions of Toro, section 4.3.3."""
+    import numpy as np
+    from helpers import complete_from_prim
+    n = 400
+    dx = [2.0 / n]
+    lvl = oracle.Level(1, [0], [n - 1], dx, [([0], [n - 1])], scratch_gcw=2, flux_gcw=0)
+    lvl.set_method(oracle.BASE_HLLEM_LARROUTUROU, oracle.RECON_MUSCL_HANCOCK_PRIM, 0)
+    lvl.add_bc(0, 0, oracle.BC_TRANSMISSIVE)
+    lvl.add_bc(0, 1, oracle.BC_TRANSMISSIVE)
+    arr, lo, hi = lvl.scratch(0)
+    x = -1.0 + (np.arange(lo[0], hi[0] + 1) + 0.5) * dx[0]
+    rho = np.where(x < 0.0, 1.0, 0.125)[None, None, :]
+    p = np.where(x < 0.0, 1.0, 0.1)[None, None, :]
+    arr[...] = complete_from_prim(1, rho, [np.zeros_like(rho)], p)
+    lvl.fill_ghost_layer()
+    lvl.run(0.5, 0.25, -1, oracle.SPLIT_GODUNOV)
+    r = arr[0, 0, 0]
+    assert not np.isnan(arr).any()
+    star = r[(x > 0.08) & (x < 0.20)]           # between contact (0.232) and rarefaction tail
+    assert abs(star.mean() - 0.42632) < 3e-3
+    post_shock = r[(x > 0.27) & (x < 0.41)]     # between contact and shock (0.438)
+    assert abs(post_shock.mean() - 0.26557) < 3e-3
+    assert abs(r[x > 0.5].mean() - 0.125) < 1e-12
