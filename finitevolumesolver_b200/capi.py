@@ -45,6 +45,7 @@ SYMBOLS = [
     "fvs_set_refine_ratio", "fvs_reset_coarse_fine_fluxes", "fvs_accumulate_coarse_fine_fluxes",
     "fvs_apply_flux_correction", "fvs_coarsen_conservatively", "fvs_fill_ghost_layer_two_levels",
     "fvs_compute_stable_dt_hierarchy",
+    "fvs_upload_state_async", "fvs_download_state_async", "fvs_synchronize",
 ]
 
 
@@ -345,6 +346,19 @@ class Context:
             out = np.empty(self.state_shape(box))
         _check(lib().fvs_download_state(self.h, self.level, box, _dp(out)))
         return out
+
+    def upload_state_async(self, box, arr):
+        """arr must be a C-contiguous float64 array in page-locked memory."""
+        assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        assert arr.shape == self.state_shape(box), (arr.shape, self.state_shape(box))
+        _check(lib().fvs_upload_state_async(self.h, self.level, box, _dp(arr)))
+
+    def download_state_async(self, box, out):
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        _check(lib().fvs_download_state_async(self.h, self.level, box, _dp(out)))
+
+    def synchronize(self):
+        _check(lib().fvs_synchronize(self.h))
 
     def download_fluxes(self, box, direction):
         out = np.empty(self._shape(*self.flux_box(box, direction)))

@@ -1379,6 +1379,39 @@ int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab) {
   });
 }
 
+int fvs_upload_state_async(fvs_ctx* ctx, int level, int box, const double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(p.buf[L.cur], host_fab, (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_download_state_async(fvs_ctx* ctx, int level, int box, double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    Patch& p = ctx->patch(L, box);
+    FVS_CUDA(cudaMemcpyAsync(host_fab, p.buf[L.cur], (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_synchronize(fvs_ctx* ctx) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->use_device();
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int)FVS_OK;
+  });
+}
+
 int fvs_upload_fluxes(fvs_ctx* ctx, int level, int box, int dir, const double* host_fab) {
   return guarded([&] {
     if (!ctx || !host_fab) throw Error("null argument");

@@ -139,6 +139,13 @@ int fvs_flux_box(const fvs_ctx* ctx, int level, int box, int dir, int lo[3],
  * host_fab holds (rank+4) components over fvs_state_box in FAB layout. */
 int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab);
 int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab);
+/* Stream-ordered variants for callers that pipeline several contexts (one per
+ * batch of boxes): the copy is enqueued on the context's stream and the call
+ * returns; host_fab must be page-locked and stay valid until
+ * fvs_synchronize(ctx) (or any entry point that returns a host value). */
+int fvs_upload_state_async(fvs_ctx* ctx, int level, int box, const double* host_fab);
+int fvs_download_state_async(fvs_ctx* ctx, int level, int box, double* host_fab);
+int fvs_synchronize(fvs_ctx* ctx);
 /* IntegratorContext::GetFluxes(level, dir), src/AMReX/IntegratorContext.cpp:233-236 */
 int fvs_upload_fluxes(fvs_ctx* ctx, int level, int box, int dir, const double* host_fab);
 int fvs_download_fluxes(fvs_ctx* ctx, int level, int box, int dir, double* host_fab);
