@@ -7,6 +7,9 @@
 #ifndef FVS_SWEEP_SMEM
 #define FVS_SWEEP_SMEM 1
 #endif
+#ifndef FVS_SWEEP_X_SMEM
+#define FVS_SWEEP_X_SMEM 1
+#endif
 #ifndef FVS_SWEEP_X_LINES
 #define FVS_SWEEP_X_LINES 0
 #endif
@@ -48,7 +51,11 @@ int fused(const SweepArgs& A, cudaStream_t s) {
     const long long rows = (long long)A.max_n[1] * A.max_n[2];
     const int nseg = (A.max_n[0] + A.seg_len - 1) / A.seg_len;
     dim3 grid(cdiv(rows * nseg, kSweepThreads / 32), A.nboxes, 1);
+#if FVS_SWEEP_X_SMEM
+    fused_sweep_x_smem_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+#else
     fused_sweep_x_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+#endif
   } else {
     const long long lines = (long long)A.max_n[0] * (DIR == 1 ? A.max_n[2] : A.max_n[1]);
     const int nseg = (A.max_n[DIR] + A.seg_len - 1) / A.seg_len;

@@ -38,6 +38,14 @@ template <int D> FVS_DEV void load_complete(Complete<D>& q, const double* p, lon
   q.p = __ldg(p + sc * (2 + D));
   q.a = __ldg(p + sc * (3 + D));
 }
+// prefetch.global.L1 of the D + 4 component values of one cell: hides the
+// load latency of the next pipeline step without holding registers
+template <int D> FVS_DEV void prefetch_complete(const double* p, long long sc) {
+#pragma unroll
+  for (int c = 0; c < D + 4; ++c) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + sc * c));
+  }
+}
 template <int D> FVS_DEV void store_complete(double* p, long long sc, const Complete<D>& q) {
   p[0] = q.rho;
 #pragma unroll
@@ -361,8 +369,13 @@ template <typename T> struct Slot<T, false> {
 };
 #define FVS_STAGE_BARRIER() asm volatile("" ::: "memory")
 
+// 0: none, 1: cell j+1 held in registers, 2: prefetch.global.L1 of cell
+// j + FVS_SWEEP_PREFETCH_DIST
 #ifndef FVS_SWEEP_PREFETCH
 #define FVS_SWEEP_PREFETCH 1
+#endif
+#ifndef FVS_SWEEP_PREFETCH_DIST
+#define FVS_SWEEP_PREFETCH_DIST 1
 #endif
 
 template <int D, int DIR, int BASE, int RECON, int LIM>
@@ -411,13 +424,13 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
     const unsigned char* dtmask = B.dtmask;
 
     Complete<D> q0; // cell j
-#if FVS_SWEEP_PREFETCH
+#if FVS_SWEEP_PREFETCH == 1
     Complete<D> qn; // prefetched cell j+1
 #endif
     DtData<D, BASE> dt_cur;
     const int jstart = max(o_first - 2, 0);
     load_complete<D>(q0, src + stride * jstart, sc);
-#if FVS_SWEEP_PREFETCH
+#if FVS_SWEEP_PREFETCH == 1
     qn = q0;
     if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
 #endif
@@ -449,15 +462,19 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 #pragma unroll 1
     for (int j = jstart; j <= jend; ++j) {
       if (j > jstart) {
-#if FVS_SWEEP_PREFETCH
+#if FVS_SWEEP_PREFETCH == 1
         q0 = qn;
 #else
         if (j < nd) load_complete<D>(q0, src + stride * j, sc);
 #endif
         if (j < nd) stage_dt_cell<D, BASE>(dt_cur, q0);
       }
-#if FVS_SWEEP_PREFETCH
+#if FVS_SWEEP_PREFETCH == 1
       if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
+#elif FVS_SWEEP_PREFETCH == 2
+      if (j + FVS_SWEEP_PREFETCH_DIST < nd) {
+        prefetch_complete<D>(src + stride * (j + FVS_SWEEP_PREFETCH_DIST), sc);
+      }
 #endif
       const int i1 = m3 == 0 ? 2 : m3 - 1;  // (j - 1) % 3
       const int i2 = i1 == 0 ? 2 : i1 - 1;  // (j - 2) % 3
@@ -672,6 +689,125 @@ fused_sweep_x_kernel(const SweepArgs A) {
         const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
         maxsig = s > maxsig ? s : maxsig;
       }
+      first = false;
+    }
+  }
+  reduce_max_signal(maxsig, A.max_signal);
+  if (failed) *A.fail_flag = 1;
+}
+
+// ---------------------------------------------------------------------------
+// Fused sweep along x, shared-memory exchange: warp per row, lane = cell, like
+// fused_sweep_x_kernel, but a lane hands its results to its right neighbour
+// through per-warp shared-memory slots instead of warp shuffles, and the
+// stages are separated by __syncwarp().  Slot i + 1 of a stage array belongs to
+// lane i, slot 0 carries lane 31 of the previous 32-cell chunk (two carry slots
+// for the cell states): no shuffle / select carry logic, and -- as in the y/z
+// kernel -- a register budget of one stage instead of the whole pipeline.
+#ifndef FVS_SWEEP_XS_MIN_BLOCKS
+#define FVS_SWEEP_XS_MIN_BLOCKS 4
+#endif
+#ifndef FVS_SWEEP_XS_PREFETCH
+#define FVS_SWEEP_XS_PREFETCH 1
+#endif
+template <int D, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_XS_MIN_BLOCKS)
+fused_sweep_x_smem_kernel(const SweepArgs A) {
+  constexpr int DIR = 0;
+  constexpr int kWarps = kSweepThreads / 32;
+  using QT = std::conditional_t<RECON == kReconMusclHancock, Cons<D>, Complete<D>>;
+  __shared__ Slot<QT> s_q[kWarps][34];              // slot i + 2 <- cell of lane i
+  __shared__ Slot<Edge<D>> s_rec[kWarps][33];       // slot i + 1 <- recR of lane i (cell c - 1)
+  __shared__ Slot<Cons<D>> s_F[kWarps][33];         // slot i + 1 <- flux of lane i (face c - 1)
+  __shared__ Slot<DtData<D, BASE>> s_dt[kWarps][33]; // slot i + 1 <- dt data of lane i's cell
+  const BoxDesc& B = A.boxes[blockIdx.y];
+  const int n0 = B.n[0];
+  const long long nrows = (long long)B.n[1] * B.n[2];
+  const int nseg = (n0 + A.seg_len - 1) / A.seg_len;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * kWarps + warp;
+  double maxsig = 0.0;
+  int failed = 0;
+  if (w < nrows * nseg) {
+    const Eqs eq(A.eq);
+    const long long row = w / nseg;
+    const int seg = (int)(w % nseg);
+    const int o_first = seg * A.seg_len;
+    const int o_last = min(n0, o_first + A.seg_len) - 1;
+    const double* src = B.src + row * n0;
+    double* dst = B.dst + row * n0;
+    const long long sc = B.sc;
+    const int ulo = B.ulo, uhi = B.uhi;
+    const unsigned char* dtmask = B.dtmask;
+    bool first = true;
+    for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
+      const int c = c0 + lane;
+      const int cl = min(max(c, 0), n0 - 1);
+      // ---- load: cell c, its dt data
+      Complete<D> q0;
+      load_complete<D>(q0, src + cl, sc);
+#if FVS_SWEEP_XS_PREFETCH
+      if (c0 + 32 - 2 <= o_last) prefetch_complete<D>(src + min(c + 32, n0 - 1), sc);
+#endif
+      DtData<D, BASE> dt_cur;
+      stage_dt_cell<D, BASE>(dt_cur, q0);
+      {
+        QT mine;
+        if constexpr (RECON == kReconMusclHancock) {
+          copy_cons<D>(mine, q0);
+        } else {
+          mine = q0;
+        }
+        s_q[warp][lane + 2].v = mine;
+        s_dt[warp][lane + 1].v = dt_cur;
+        if (first && lane == 0) {
+          // no carry yet: lanes 0..3 produce no output in the first chunk; give
+          // their missing neighbours real data to keep the arithmetic benign
+          s_q[warp][0].v = mine;
+          s_q[warp][1].v = mine;
+          s_dt[warp][0].v = dt_cur;
+        }
+      }
+      __syncwarp();
+      // ---- stage A: cell c-1 from cells c-2, c-1, c
+      Edge<D> recL;
+      {
+        Edge<D> recR;
+        stage_predict<D, DIR, RECON, LIM>(eq, s_q[warp][lane].v, s_q[warp][lane + 1].v, q0,
+                                          A.lambda_half, recL, recR);
+        s_rec[warp][lane + 1].v = recR;
+        if (first && lane == 0) s_rec[warp][0].v = recR;
+      }
+      __syncwarp();
+      // ---- stage B: face c-1 = (c-2 | c-1)
+      Cons<D> F;
+      stage_flux<D, DIR, BASE>(eq, F, s_rec[warp][lane].v, recL, failed);
+      s_F[warp][lane + 1].v = F;
+      if (first && lane == 0) s_F[warp][0].v = F;
+      __syncwarp();
+      // ---- stage C: cell c-2
+      const int o = c - 2;
+      if ((!first || lane >= 4) && o >= o_first && o <= o_last) {
+        Complete<D> out;
+        stage_update<D>(eq, out, s_q[warp][lane].v, s_F[warp][lane].v, F, A.lambda,
+                        o >= ulo && o <= uhi);
+        store_complete<D>(dst + o, sc, out);
+      }
+      // ---- stage D: face (c-1 | c) of the stored states
+      if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+        const double sgn = stage_dt_face<D, DIR, BASE>(eq, s_dt[warp][lane].v, dt_cur, failed);
+        maxsig = sgn > maxsig ? sgn : maxsig;
+      }
+      __syncwarp();
+      // ---- carry of lanes 30, 31 into slots 0, 1 for the next chunk
+      if (lane >= 30) s_q[warp][lane - 30].v = s_q[warp][lane + 2].v;
+      if (lane == 31) {
+        s_rec[warp][0].v = s_rec[warp][32].v;
+        s_F[warp][0].v = F;
+        s_dt[warp][0].v = dt_cur;
+      }
+      __syncwarp();
       first = false;
     }
   }
