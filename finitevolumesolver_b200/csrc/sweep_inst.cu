@@ -7,12 +7,6 @@
 #ifndef FVS_SWEEP_SMEM
 #define FVS_SWEEP_SMEM 1
 #endif
-#ifndef FVS_SWEEP_X_SMEM
-#define FVS_SWEEP_X_SMEM 1
-#endif
-#ifndef FVS_SWEEP_X_LINES
-#define FVS_SWEEP_X_LINES 0
-#endif
 #include <algorithm>
 #ifndef FVS_INST_D
 #error "define FVS_INST_D"
@@ -35,27 +29,11 @@ inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) /
 
 template <int DIR, int RECON, int LIM>
 int fused(const SweepArgs& A, cudaStream_t s) {
-  if constexpr (DIR == 0 && FVS_SWEEP_X_LINES != 0 && RECON == kReconMusclHancock) {
-    // thread per row: segment the rows like the y / z sweeps do
-    SweepArgs X = A;
-    const long long lines = (long long)A.max_n[1] * A.max_n[2];
-    const long long target = 148LL * 2048;
-    int nseg = (int)std::min<long long>((target + lines * A.nboxes - 1) / (lines * A.nboxes),
-                                        std::max(A.max_n[0] / 32, 1));
-    nseg = std::max(nseg, 1);
-    X.seg_len = std::max((A.max_n[0] + nseg - 1) / nseg, 1);
-    nseg = (A.max_n[0] + X.seg_len - 1) / X.seg_len;
-    dim3 grid(cdiv(lines, kSweepThreads), A.nboxes, nseg);
-    fused_sweep_yz_smem_kernel<D, 0, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(X);
-  } else if constexpr (DIR == 0) {
+  if constexpr (DIR == 0) {
     const long long rows = (long long)A.max_n[1] * A.max_n[2];
     const int nseg = (A.max_n[0] + A.seg_len - 1) / A.seg_len;
     dim3 grid(cdiv(rows * nseg, kSweepThreads / 32), A.nboxes, 1);
-#if FVS_SWEEP_X_SMEM
     fused_sweep_x_smem_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
-#else
-    fused_sweep_x_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
-#endif
   } else {
     const long long lines = (long long)A.max_n[0] * (DIR == 1 ? A.max_n[2] : A.max_n[1]);
     const int nseg = (A.max_n[DIR] + A.seg_len - 1) / A.seg_len;

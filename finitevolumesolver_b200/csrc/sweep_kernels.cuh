@@ -19,10 +19,11 @@
 //   stage D (face j-1|j): signal speeds of the STORED states -> stable dt
 // * y / z sweeps: one thread per grid line; threads of a warp are adjacent in
 //   x, so every load and store is a coalesced 256-byte row segment; the
-//   pipeline state lives in registers.
-// * x sweeps: one warp per grid row; lane l holds cell c0+l; neighbours come
-//   from warp shuffles and the two-cell carry between 32-cell chunks goes
-//   through shared memory.
+//   loop-carried pipeline state lives in thread-private shared-memory slots
+//   (MUSCL-Hancock) or in registers (first order, MusclHancockPrim).
+// * x sweeps: one warp per grid row; lane l holds cell c0+l; a lane hands its
+//   stage results to its right neighbour through per-warp shared-memory slots
+//   (slot 0 carries the last lane of the previous 32-cell chunk).
 #pragma once
 #include <type_traits>
 
@@ -59,47 +60,6 @@ template <int D> FVS_DEV void copy_cons(Cons<D>& c, const Complete<D>& q) {
 #pragma unroll
   for (int d = 0; d < D; ++d) c.mom[d] = q.mom[d];
   c.E = q.E;
-}
-
-FVS_DEV double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
-template <int D> FVS_DEV Complete<D> shfl_up(const Complete<D>& q, int delta) {
-  Complete<D> r;
-  r.rho = shfl_up_d(q.rho, delta);
-#pragma unroll
-  for (int d = 0; d < D; ++d) r.mom[d] = shfl_up_d(q.mom[d], delta);
-  r.E = shfl_up_d(q.E, delta);
-  r.p = shfl_up_d(q.p, delta);
-  r.a = shfl_up_d(q.a, delta);
-  return r;
-}
-template <int D> FVS_DEV Cons<D> shfl_up(const Cons<D>& q, int delta) {
-  Cons<D> r;
-  r.rho = shfl_up_d(q.rho, delta);
-#pragma unroll
-  for (int d = 0; d < D; ++d) r.mom[d] = shfl_up_d(q.mom[d], delta);
-  r.E = shfl_up_d(q.E, delta);
-  return r;
-}
-template <int D> FVS_DEV Edge<D> shfl_up(const Edge<D>& e, int delta) {
-  Edge<D> r;
-  r.q = shfl_up<D>(e.q, delta);
-  r.rc.b = r.q.rho;
-  r.rc.r = shfl_up_d(e.rc.r, delta);
-  return r;
-}
-template <int D> FVS_DEV DtCell<D> shfl_up(const DtCell<D>& c, int delta) {
-  DtCell<D> r;
-#pragma unroll
-  for (int d = 0; d < D; ++d) r.u[d] = shfl_up_d(c.u[d], delta);
-  r.h = shfl_up_d(c.h, delta);
-  r.sq_rho = shfl_up_d(c.sq_rho, delta);
-  r.a = shfl_up_d(c.a, delta);
-  return r;
-}
-template <int D, int BASE> FVS_DEV DtData<D, BASE> shfl_up(const DtData<D, BASE>& c, int delta) {
-  DtData<D, BASE> r;
-  r.c = shfl_up<D>(c.c, delta);
-  return r;
 }
 
 // Block-wide max of a non-negative double, then one atomic per block.  The
@@ -381,7 +341,7 @@ template <typename T> struct Slot<T, false> {
 template <int D, int DIR, int BASE, int RECON, int LIM>
 __global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
 fused_sweep_yz_smem_kernel(const SweepArgs A) {
-  static_assert(DIR >= 0 && DIR < D, "sweep direction");
+  static_assert(DIR >= 1 && DIR < D, "y/z sweep");
   // first order needs the stored p and a of the neighbour, MUSCL only its
   // conservative part
   using QT = std::conditional_t<RECON == kReconMusclHancock, Cons<D>, Complete<D>>;
@@ -391,11 +351,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
   __shared__ Slot<DtData<D, BASE>> s_dt[kSweepThreads]; // dt data of cell j-1
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
-  // DIR == 0: one thread per grid ROW (lanes of a warp are adjacent in y);
-  // every 8-byte load then touches its own 32-byte sector, which L1 serves
-  // again for the next three cells of the row
-  const long long nlines = DIR == 0 ? (long long)B.n[1] * B.n[2]
-                                    : (long long)n0 * ((DIR == 1) ? B.n[2] : B.n[1]);
+  const long long nlines = (long long)n0 * ((DIR == 1) ? B.n[2] : B.n[1]);
   const long long line = (long long)blockIdx.x * kSweepThreads + threadIdx.x;
   const int nd = B.n[DIR];
   const int o_first = blockIdx.z * A.seg_len;
@@ -405,12 +361,9 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
   if (line < nlines && o_first < nd) {
     const Eqs eq(A.eq);
     const int o_last = min(nd, o_first + A.seg_len) - 1;
-    const long long stride =
-        DIR == 0 ? 1 : ((DIR == 1) ? (long long)n0 : (long long)n0 * B.n[1]);
+    const long long stride = (DIR == 1) ? (long long)n0 : (long long)n0 * B.n[1];
     long long base;
-    if (DIR == 0) {
-      base = line * n0;
-    } else if (DIR == 1) {
+    if (DIR == 1) {
       const int x = (int)(line % n0);
       const int z = (int)(line / n0);
       base = x + (long long)n0 * B.n[1] * z;
@@ -565,131 +518,6 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       s_dt[tid].v = dt_cur;
       FVS_STAGE_BARRIER();
       m3 = m3 == 2 ? 0 : m3 + 1;
-    }
-  }
-  reduce_max_signal(maxsig, A.max_signal);
-  if (failed) *A.fail_flag = 1;
-}
-
-// ---------------------------------------------------------------------------
-// Fused sweep along x: warp per row, shuffle pipeline.
-#ifndef FVS_SWEEP_X_PREFETCH
-#define FVS_SWEEP_X_PREFETCH 0
-#endif
-#ifndef FVS_SWEEP_X_MIN_BLOCKS
-#define FVS_SWEEP_X_MIN_BLOCKS 4
-#endif
-template <int D, int BASE, int RECON, int LIM>
-__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_X_MIN_BLOCKS)
-fused_sweep_x_kernel(const SweepArgs A) {
-  constexpr int DIR = 0;
-  constexpr int kWarps = kSweepThreads / 32;
-  const BoxDesc& B = A.boxes[blockIdx.y];
-  const int n0 = B.n[0];
-  const long long nrows = (long long)B.n[1] * B.n[2];
-  const int nseg = (n0 + A.seg_len - 1) / A.seg_len;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const long long w = (long long)blockIdx.x * kWarps + warp;
-  // carry between consecutive 32-cell chunks of a row (per warp)
-  __shared__ Complete<D> carry_q[kWarps][2];        // cells of lanes 30, 31
-  __shared__ Edge<D> carry_rec[kWarps];             // recR of lane 31
-  __shared__ Cons<D> carry_F[kWarps];               // F of lane 31
-  __shared__ DtData<D, BASE> carry_dt[kWarps];      // dt data of lane 31
-  double maxsig = 0.0;
-  int failed = 0;
-  if (w < nrows * nseg) {
-    const Eqs eq(A.eq);
-    const long long row = w / nseg;
-    const int seg = (int)(w % nseg);
-    const int o_first = seg * A.seg_len;
-    const int o_last = min(n0, o_first + A.seg_len) - 1;
-    const double* src = B.src + row * n0;
-    double* dst = B.dst + row * n0;
-    const long long sc = B.sc;
-    const int ulo = B.ulo, uhi = B.uhi;
-    const unsigned char* dtmask = B.dtmask;
-    bool first = true;
-#if FVS_SWEEP_X_PREFETCH
-    Complete<D> qnext; // the next chunk's cell, loaded one chunk ahead
-    load_complete<D>(qnext, src + min(max(o_first - 2 + lane, 0), n0 - 1), sc);
-#endif
-    for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
-      const int c = c0 + lane;
-      const int cl = min(max(c, 0), n0 - 1);
-      Complete<D> q0;
-#if FVS_SWEEP_X_PREFETCH
-      q0 = qnext;
-      if (c0 + 32 - 2 <= o_last) load_complete<D>(qnext, src + min(max(c + 32, 0), n0 - 1), sc);
-      (void)cl;
-#else
-      load_complete<D>(q0, src + cl, sc);
-#endif
-      DtData<D, BASE> dt_cur;
-      stage_dt_cell<D, BASE>(dt_cur, q0);
-      Complete<D> q1 = shfl_up<D>(q0, 1);
-      Complete<D> q2 = shfl_up<D>(q0, 2);
-      DtData<D, BASE> dt_prev = shfl_up<D, BASE>(dt_cur, 1);
-      if (first) {
-        // no carry yet: lanes 0..3 produce no output in the first chunk; give
-        // their missing neighbours real data to keep the arithmetic benign
-        if (lane < 1) {
-          q1 = q0;
-          dt_prev = dt_cur;
-        }
-        if (lane < 2) q2 = q0;
-      } else {
-        if (lane == 0) {
-          q1 = carry_q[warp][1];
-          q2 = carry_q[warp][0];
-          dt_prev = carry_dt[warp];
-        } else if (lane == 1) {
-          q2 = carry_q[warp][1];
-        }
-      }
-      // stage A: cell c-1
-      Edge<D> recL, recR;
-      stage_predict<D, DIR, RECON, LIM>(eq, q2, q1, q0, A.lambda_half, recL, recR);
-      // stage B: face c-1 = (c-2 | c-1)
-      Edge<D> recR_prev = shfl_up<D>(recR, 1);
-      if (lane == 0) {
-        if (first) {
-          recR_prev = recR;
-        } else {
-          recR_prev = carry_rec[warp];
-        }
-      }
-      Cons<D> F;
-      stage_flux<D, DIR, BASE>(eq, F, recR_prev, recL, failed);
-      // stage C: cell c-2
-      Cons<D> F_prev = shfl_up<D>(F, 1);
-      if (lane == 0) {
-        if (first) {
-          F_prev = F;
-        } else {
-          F_prev = carry_F[warp];
-        }
-      }
-      __syncwarp();
-      if (lane >= 30) carry_q[warp][lane - 30] = q0;
-      if (lane == 31) {
-        carry_rec[warp] = recR;
-        carry_F[warp] = F;
-        carry_dt[warp] = dt_cur;
-      }
-      __syncwarp();
-      const int o = c - 2;
-      if ((!first || lane >= 4) && o >= o_first && o <= o_last) {
-        Complete<D> out;
-        stage_update<D>(eq, out, q2, F_prev, F, A.lambda, o >= ulo && o <= uhi);
-        store_complete<D>(dst + o, sc, out);
-      }
-      // stage D: face (c-1 | c) of the stored states
-      if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
-        const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
-        maxsig = s > maxsig ? s : maxsig;
-      }
-      first = false;
     }
   }
   reduce_max_signal(maxsig, A.max_signal);
