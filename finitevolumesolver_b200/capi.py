@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FVS_B200_LIB") or os.path.join(_HERE, "libfvs_b200.so")
 
 BASE_HLLEM_LARROUTUROU, BASE_HLLEM, BASE_HLL_EINFELDT, BASE_GODUNOV_EXACT = 0, 1, 2, 3
-RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK, RECON_MUSCL_HANCOCK_PRIM = 0, 1, 2
+RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK, RECON_MUSCL_HANCOCK_PRIM, RECON_MUSCL_HANCOCK_CHAR = 0, 1, 2, 3
 LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
 BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
 SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2

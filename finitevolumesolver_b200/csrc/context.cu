@@ -1185,10 +1185,11 @@ int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limite
   return guarded([&] {
     if (!ctx) throw Error("null context");
     if (base_method < 0 || base_method > 3) throw Error("unknown base method");
-    if (reconstruction < 0 || reconstruction > 2) throw Error("unknown reconstruction");
-    if (reconstruction == FVS_RECON_MUSCL_HANCOCK_PRIM && base_method != FVS_BASE_HLLEM_LARROUTUROU) {
-      // src/equations/perfect_gas/MusclHancockPrimMethod.hpp:175
-      throw Error("MusclHancockPrim is defined over HLLEM (Larrouturou) only");
+    if (reconstruction < 0 || reconstruction > 3) throw Error("unknown reconstruction");
+    if (reconstruction >= FVS_RECON_MUSCL_HANCOCK_PRIM && base_method != FVS_BASE_HLLEM_LARROUTUROU) {
+      // src/equations/perfect_gas/MusclHancockPrimMethod.hpp:175,
+      // include/fub/equations/perfect_gas/MusclHancockCharactersticMethod.hpp:174
+      throw Error("MusclHancockPrim / MusclHancockChar are defined over HLLEM (Larrouturou) only");
     }
     if (limiter < 0 || limiter > 2) throw Error("unknown limiter");
     const int w = reconstruction == FVS_RECON_FIRST_ORDER ? 1 : 2;

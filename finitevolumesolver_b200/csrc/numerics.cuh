@@ -23,7 +23,12 @@
 namespace fvs {
 
 enum : int { kBaseHllemLarrouturou = 0, kBaseHllem = 1, kBaseHllEinfeldt = 2, kBaseGodunovExact = 3 };
-enum : int { kReconFirstOrder = 0, kReconMusclHancock = 1, kReconMusclHancockPrim = 2 };
+enum : int {
+  kReconFirstOrder = 0,
+  kReconMusclHancock = 1,
+  kReconMusclHancockPrim = 2,
+  kReconMusclHancockChar = 3
+};
 enum : int { kLimiterNone = 0, kLimiterMinMod = 1, kLimiterVanLeer = 2 };
 
 // PerfectGas equation constants (include/fub/equations/PerfectGas.hpp:216-219):
@@ -320,6 +325,98 @@ FVS_DEV void muscl_prim_face_masked(const EqM& eq, const S& s0, const S& s1, con
   prim_slopes<M, D>(sr, l, r, rr, fl);
   prim_edge<M, D, DIR, true>(eq, left, l, sl, lambda, fl);
   prim_edge<M, D, DIR, false>(eq, right, r, sr, lambda, fl);
+}
+
+// ---------------------------------------------------------------------------
+// perfect_gas::MusclHancockCharacteristic,
+// src/equations/perfect_gas/MusclHancockCharacteristicMethod.hpp:28-359: slopes of
+// the characteristic wave amplitudes (VanLeer), half time step, recombination
+// to primitive variables; base method HLLEM with the Larrouturou modification.
+template <int D> struct CharAmpl {
+  double minus, zero, plus, t[2]; // t: the transverse velocity differences (iy, iz)
+};
+// VanLeer::operator()(sL, sR), MusclHancockMethod.hpp:144-149
+template <class M> FVS_DEV double vanleer2(double sL, double sR, Flag& fl) {
+  const double r = 2.0 * sL * sR;
+  const bool pos = r > 0.0;
+  const double q = M::div(r, sL + sR, fl, pos);
+  return pos ? q : 0.0;
+}
+template <int D, int DIR>
+FVS_DEV void char_amplitudes(CharAmpl<D>& a, const PrimCell<D>& l, const PrimCell<D>& r,
+                             double rhoc, double ooc2) {
+  constexpr int iy = (DIR + 1) % 3, iz = (iy + 1) % 3;
+  const double dp = r.p - l.p;
+  const double du = r.u[DIR] - l.u[DIR];
+  const double drho = r.rho - l.rho;
+  a.minus = dp - rhoc * du;
+  a.zero = drho - ooc2 * dp;
+  a.plus = dp + rhoc * du;
+  if constexpr (iy < D) a.t[0] = r.u[iy] - l.u[iy];
+  if constexpr (iz < D) a.t[1] = r.u[iz] - l.u[iz];
+}
+// one edge state: SIGN = +1 upper edge (is_right_side = 0), -1 lower edge
+template <class M, int D, int DIR, int SIGN, bool MASKED>
+FVS_DEV void char_edge(const EqM& eq, Edge<D>& out, const PrimCell<D>& c, const CharAmpl<D>& slope,
+                       double lambda, double rhoc, double ooc2, Flag& fl) {
+  constexpr int iy = (DIR + 1) % 3, iz = (iy + 1) % 3;
+  const double u = c.u[DIR];
+  const double sg = (double)SIGN;
+  const double minus = sg * 0.5 * slope.minus * (1.0 - sg * lambda * (u - c.a));
+  const double zero = sg * 0.5 * slope.zero * (1.0 - sg * lambda * u);
+  const double plus = sg * 0.5 * slope.plus * (1.0 - sg * lambda * (u + c.a));
+  double dp = 0.5 * (minus + plus);
+  double drho = ooc2 * dp + zero;
+  double du[D];
+  du[DIR] = M::div(0.5 * (plus - minus), rhoc, fl);
+  if constexpr (iy < D) du[iy] = sg * 0.5 * slope.t[0] * (1.0 - sg * lambda * u);
+  if constexpr (iz < D) du[iz] = sg * 0.5 * slope.t[1] * (1.0 - sg * lambda * u);
+  drho = drho + c.rho;
+#pragma unroll
+  for (int d = 0; d < D; ++d) du[d] = du[d] + c.u[d];
+  dp = dp + c.p;
+  // PerfectGas::CompleteFromPrim, src/equations/PerfectGas.cpp:160-174
+  out.q.rho = drho;
+#pragma unroll
+  for (int d = 0; d < D; ++d) out.q.mom[d] = drho * du[d];
+  out.q.p = dp;
+  out.rc = M::rcp(drho);
+  M::check(out.rc, fl);
+  const double e_kin = M::div(0.5 * squared_norm<D>(out.q.mom), out.rc, fl);
+  out.q.E = e_kin + dp * eq.gm1_inv.b;
+  out.q.a = M::sqrt(M::div(eq.gamma * dp, out.rc, fl), fl);
+  (void)MASKED;
+}
+template <class M, int D, int DIR, bool MASKED = false, typename S0, typename S1, typename S2>
+FVS_DEV void muscl_char_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp,
+                                double lambda, Edge<D>& recL, Edge<D>& recR, Flag& fl,
+                                bool slope_ok = true) {
+  PrimCell<D> m, c, p;
+  prim_cell<M, D>(m, qm, fl);
+  prim_cell<M, D>(c, q0, fl);
+  prim_cell<M, D>(p, qp, fl);
+  const double rhoc = c.rho * c.a;
+  const double ooc2 = M::div(1.0, c.a * c.a, fl);
+  CharAmpl<D> al, ar, slope;
+  char_amplitudes<D, DIR>(al, m, c, rhoc, ooc2);
+  char_amplitudes<D, DIR>(ar, c, p, rhoc, ooc2);
+  if constexpr (MASKED) {
+    if (!slope_ok) { // :147-152: only the LEFT amplitudes are zeroed
+      al.minus = 0.0;
+      al.zero = 0.0;
+      al.plus = 0.0;
+      al.t[0] = 0.0;
+      al.t[1] = 0.0;
+    }
+  }
+  constexpr int iy = (DIR + 1) % 3, iz = (iy + 1) % 3;
+  slope.minus = vanleer2<M>(al.minus, ar.minus, fl);
+  slope.zero = vanleer2<M>(al.zero, ar.zero, fl);
+  slope.plus = vanleer2<M>(al.plus, ar.plus, fl);
+  if constexpr (iy < D) slope.t[0] = vanleer2<M>(al.t[0], ar.t[0], fl);
+  if constexpr (iz < D) slope.t[1] = vanleer2<M>(al.t[1], ar.t[1], fl);
+  char_edge<M, D, DIR, -1, MASKED>(eq, recL, c, slope, lambda, rhoc, ooc2, fl);
+  char_edge<M, D, DIR, +1, MASKED>(eq, recR, c, slope, lambda, rhoc, ooc2, fl);
 }
 
 // ---------------------------------------------------------------------------

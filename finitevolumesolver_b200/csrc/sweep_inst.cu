@@ -85,10 +85,11 @@ int cc_stable_dt(const SweepArgs& A, cudaStream_t s) {
   return 1;
 }
 
-template <int DIR, typename F0, typename F1, typename F2, typename F3, typename F4>
-int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim) {
+template <int DIR, typename F0, typename F1, typename F2, typename F3, typename F4, typename F5>
+int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim, F5 chr) {
   if (k.recon == kReconFirstOrder) return fo();
   if (k.recon == kReconMusclHancockPrim) return prim();
+  if (k.recon == kReconMusclHancockChar) return chr();
   switch (k.limiter) {
   case kLimiterNone: return none();
   case kLimiterMinMod: return minmod();
@@ -110,6 +111,14 @@ template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStr
         } else {
           return -1;
         }
+      },
+      [&] {
+        // perfect_gas::MusclHancockCharacteristic: VanLeer amplitudes over HLLEM-Larrouturou
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return fused<DIR, kReconMusclHancockChar, kLimiterVanLeer>(A, s);
+        } else {
+          return -1;
+        }
       });
 }
 template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
@@ -122,6 +131,14 @@ template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaSt
         // perfect_gas::MusclHancockPrim exists over HLLEM-Larrouturou only
         if constexpr (BASE == kBaseHllemLarrouturou) {
           return fluxes<DIR, kReconMusclHancockPrim, kLimiterNone>(A, s);
+        } else {
+          return -1;
+        }
+      },
+      [&] {
+        // perfect_gas::MusclHancockCharacteristic: VanLeer amplitudes over HLLEM-Larrouturou
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return fluxes<DIR, kReconMusclHancockChar, kLimiterVanLeer>(A, s);
         } else {
           return -1;
         }
@@ -138,6 +155,14 @@ template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cud
         // perfect_gas::MusclHancockPrim exists over HLLEM-Larrouturou only
         if constexpr (BASE == kBaseHllemLarrouturou) {
           return cc_fluxes<DIR, kReconMusclHancockPrim, kLimiterNone>(A, s);
+        } else {
+          return -1;
+        }
+      },
+      [&] {
+        // perfect_gas::MusclHancockCharacteristic: VanLeer amplitudes over HLLEM-Larrouturou
+        if constexpr (BASE == kBaseHllemLarrouturou) {
+          return cc_fluxes<DIR, kReconMusclHancockChar, kLimiterVanLeer>(A, s);
         } else {
           return -1;
         }

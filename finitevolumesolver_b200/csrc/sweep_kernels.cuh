@@ -101,9 +101,14 @@ FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const S1& q0, const S2& 
       muscl_predict<decltype(M), D, DIR, LIM>(eq.m, qm, q0, qp, lambda_half, recL, recR, fl);
     });
   } else if constexpr (RECON == kReconMusclHancockPrim) {
-    // MusclHancockPrim uses lambda = dt / dx (MusclHancockPrimMethod.hpp:101)
+    // MusclHancockPrim uses lambda = dt / dx (MusclHancockPrimMethod.hpp:101);
+    // 2 * (0.5 * dt / dx) is that value exactly
     with_fallback([&](auto M, Flag& fl) {
       muscl_prim_predict<decltype(M), D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
+    });
+  } else if constexpr (RECON == kReconMusclHancockChar) {
+    with_fallback([&](auto M, Flag& fl) {
+      muscl_char_predict<decltype(M), D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
     });
   } else {
     recL.q = q0;
@@ -205,7 +210,9 @@ fused_sweep_yz_kernel(const SweepArgs A) {
 
     Complete<D> q0, q1, qn; // cells j, j-1 and the prefetched cell j+1
     // cell j-2: the primitive-variable predictor also needs its pressure
-    std::conditional_t<RECON == kReconMusclHancockPrim, Complete<D>, Cons<D>> q2;
+    std::conditional_t<RECON == kReconMusclHancock || RECON == kReconFirstOrder, Cons<D>,
+                       Complete<D>>
+        q2;
     Edge<D> recR_prev;      // upper edge state of cell j-2
     Cons<D> F_prev;         // flux through face j-2
     DtData<D, BASE> dt_prev, dt_cur;
@@ -214,7 +221,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
     qn = q0;
     if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
     q1 = q0;
-    if constexpr (RECON == kReconMusclHancockPrim) {
+    if constexpr (std::is_same_v<decltype(q2), Complete<D>>) {
       q2 = q0;
     } else {
       copy_cons<D>(q2, q0);
@@ -249,6 +256,8 @@ fused_sweep_yz_kernel(const SweepArgs A) {
             muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, A.lambda_half, recL, recR, fl);
           } else if constexpr (RECON == kReconMusclHancockPrim) {
             muscl_prim_predict<MM, D, DIR>(eq.m, q2, q1, q0, A.lambda, recL, recR, fl);
+          } else if constexpr (RECON == kReconMusclHancockChar) {
+            muscl_char_predict<MM, D, DIR>(eq.m, q2, q1, q0, A.lambda, recL, recR, fl);
           } else {
             recL.q = q1;
             recL.rc = MM::rcp(q1.rho);
@@ -294,7 +303,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
         const double s = stage_dt_face<D, DIR, BASE>(eq, dt_prev, dt_cur, failed);
         maxsig = s > maxsig ? s : maxsig;
       }
-      if constexpr (RECON == kReconMusclHancockPrim) {
+      if constexpr (std::is_same_v<decltype(q2), Complete<D>>) {
         q2 = q1;
       } else {
         copy_cons<D>(q2, q1);
@@ -839,6 +848,24 @@ __global__ void __launch_bounds__(128) cc_numeric_flux_kernel(const SweepArgs A)
         } else {
           muscl_prim_predict<SafeMath, D, DIR>(eq.m, s0, s1, s2, A.lambda, unused, left, fl);
           muscl_prim_predict<SafeMath, D, DIR>(eq.m, s1, s2, s3, A.lambda, right, unused, fl);
+        }
+      } else if constexpr (RECON == kReconMusclHancockChar) {
+        Complete<D> s0, s1, s2, s3;
+        load_complete<D>(s0, p - 2 * stride, B.sc);
+        load_complete<D>(s1, p - stride, B.sc);
+        load_complete<D>(s2, p, B.sc);
+        load_complete<D>(s3, p + stride, B.sc);
+        if (single) {
+          const double* al = B.alpha + cell;
+          const bool a0 = al[-2 * stride] > 0.0, a1 = al[-stride] > 0.0, a2 = al[0] > 0.0,
+                     a3 = al[stride] > 0.0;
+          muscl_char_predict<SafeMath, D, DIR, true>(eq.m, s0, s1, s2, A.lambda, unused, left, fl,
+                                                     a0 && a1 && a2);
+          muscl_char_predict<SafeMath, D, DIR, true>(eq.m, s1, s2, s3, A.lambda, right, unused, fl,
+                                                     a1 && a2 && a3);
+        } else {
+          muscl_char_predict<SafeMath, D, DIR>(eq.m, s0, s1, s2, A.lambda, unused, left, fl);
+          muscl_char_predict<SafeMath, D, DIR>(eq.m, s1, s2, s3, A.lambda, right, unused, fl);
         }
       } else if constexpr (RECON == kReconMusclHancock) {
         Complete<D> s0, s1, s2, s3;

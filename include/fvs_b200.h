@@ -43,8 +43,16 @@ enum {
 /* include/fub/flux_method/MusclHancockMethod.hpp:189-571;
  * perfect_gas::MusclHancockPrim (src/equations/perfect_gas/MusclHancockPrimMethod.hpp:25-333):
  * primitive-variable MUSCL-Hancock with its own limiter, base method HLLEM
- * (Larrouturou) only, the limiter argument is ignored */
-enum { FVS_RECON_FIRST_ORDER = 0, FVS_RECON_MUSCL_HANCOCK = 1, FVS_RECON_MUSCL_HANCOCK_PRIM = 2 };
+ * (Larrouturou) only, the limiter argument is ignored;
+ * perfect_gas::MusclHancockCharacteristic (MusclHancockCharMethod,
+ * src/equations/perfect_gas/MusclHancockCharacteristicMethod.hpp:28-359): characteristic
+ * amplitudes limited with VanLeer, HLLEM (Larrouturou) only */
+enum {
+  FVS_RECON_FIRST_ORDER = 0,
+  FVS_RECON_MUSCL_HANCOCK = 1,
+  FVS_RECON_MUSCL_HANCOCK_PRIM = 2,
+  FVS_RECON_MUSCL_HANCOCK_CHAR = 3
+};
 /* include/fub/flux_method/MusclHancockMethod.hpp:31-187 */
 enum { FVS_LIMITER_NONE = 0, FVS_LIMITER_MINMOD = 1, FVS_LIMITER_VANLEER = 2 };
 /* src/AMReX/boundary_condition/TransmissiveBoundary.cpp,

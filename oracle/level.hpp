@@ -18,7 +18,7 @@
 namespace fvso {
 
 enum BaseKind { kHllemLarrouturou = 0, kHllem = 1, kHllEinfeldt = 2, kGodunovExact = 3 };
-enum ReconKind { kFirstOrder = 0, kMusclHancock = 1, kMusclHancockPrim = 2 };
+enum ReconKind { kFirstOrder = 0, kMusclHancock = 1, kMusclHancockPrim = 2, kMusclHancockChar = 3 };
 enum LimiterKind { kNoLimiter = 0, kMinMod = 1, kVanLeer = 2 };
 enum BcKind { kTransmissive = 0, kReflective = 1 };
 enum SplitKind { kGodunovSplitting = 0, kStrangSplitting = 1, kStrangSplittingLumped = 2 };
@@ -53,6 +53,8 @@ void with_method(const MethodSpec& ms, const PerfectGasEq& eq, F&& f) {
     // perfect_gas::MusclHancockPrim is a complete method: own limiter, HLLEM
     // with the Larrouturou modification (MusclHancockPrimMethod.hpp:175)
     f(MusclHancockPrim<D>(eq));
+  } else if (ms.recon == kMusclHancockChar) {
+    f(MusclHancockChar<D>(eq));
   } else if (ms.recon == kFirstOrder) {
     with_base([&](auto base) { f(base); });
   } else {

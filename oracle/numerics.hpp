@@ -1298,4 +1298,147 @@ template <int D> struct MusclHancockPrim {
   }
 };
 
+// ---------------------------------------------------------------------------
+// perfect_gas::MusclHancockCharacteristic (MusclHancockCharMethod): MUSCL-Hancock
+// on characteristic variables, VanLeer limiter on the wave amplitudes, base
+// method HLLEM (Larrouturou).
+// src/equations/perfect_gas/MusclHancockCharacteristicMethod.hpp:28-359,
+// include/fub/equations/perfect_gas/MusclHancockCharactersticMethod.hpp:34-175
+template <int D> struct MusclHancockChar {
+  static constexpr int kWidth = 2;
+  static constexpr int kDim = D;
+  using T = A8;
+  using Lane = A8;
+  PerfectGasEq eq;
+  Hllem<D, true> hllem;
+  explicit MusclHancockChar(const PerfectGasEq& e) : eq(e), hllem(e) {}
+
+  struct Prim {
+    T rho, p;
+    T u[3];
+  };
+  struct Chars {
+    T minus, zero, plus, v, w;
+  };
+  static Prim prim_of(const Complete<T, D>& q) { // PrimitivesArray, header :88-113
+    Prim w;
+    w.rho = q.rho;
+    w.p = q.p;
+    for (int d = 0; d < 3; ++d) w.u[d] = A8(0.0);
+    for (int d = 0; d < D; ++d) w.u[d] = q.mom[d] / q.rho;
+    return w;
+  }
+  // fub::VanLeer::operator()(Array1d, Array1d), MusclHancockMethod.hpp:144-149
+  static T limiter(const T& sL, const T& sR) {
+    const T r = 2.0 * sL * sR;
+    return select(r > 0.0, r / (sL + sR), 0.0);
+  }
+  static Chars amplitudes(const Prim& l, const Prim& r, const T& rhoc, const T& ooc2, int ix,
+                          int iy, int iz) { // :50-66
+    const T dp = r.p - l.p;
+    const T du = r.u[ix] - l.u[ix];
+    const T drho = r.rho - l.rho;
+    Chars a;
+    a.minus = dp - rhoc * du;
+    a.zero = drho - ooc2 * dp;
+    a.plus = dp + rhoc * du;
+    a.v = r.u[iy] - l.u[iy];
+    a.w = r.u[iz] - l.u[iz];
+    return a;
+  }
+  // Reconstruct, :228-253 (masked :255-285): `slope_mask` zeroes the left
+  // amplitudes, `valid_face` masks CompleteFromPrim; both null = unmasked
+  void Reconstruct(Complete<T, D>& rec, int is_right_side, const Complete<T, D>* st,
+                   const T& lambda, int dir, const M8* slope_mask, const M8* valid_face) const {
+    const int ix = dir, iy = (ix + 1) % 3, iz = (iy + 1) % 3;
+    const Complete<T, D>& q = st[1];
+    const T rho = q.rho;
+    const T u = q.mom[dir] / rho;
+    const T c = q.a;
+    const T rhoc = rho * c;
+    const T ooc2 = 1.0 / (c * c);
+    const Prim pL = prim_of(st[0]), pM = prim_of(st[1]), pR = prim_of(st[2]);
+    Chars al = amplitudes(pL, pM, rhoc, ooc2, ix, iy, iz);
+    const Chars ar = amplitudes(pM, pR, rhoc, ooc2, ix, iy, iz);
+    if (slope_mask) {
+      al.minus = select(*slope_mask, al.minus, 0.0);
+      al.zero = select(*slope_mask, al.zero, 0.0);
+      al.plus = select(*slope_mask, al.plus, 0.0);
+      al.v = select(*slope_mask, al.v, 0.0);
+      al.w = select(*slope_mask, al.w, 0.0);
+    }
+    Chars slope;
+    slope.minus = limiter(al.minus, ar.minus);
+    slope.zero = limiter(al.zero, ar.zero);
+    slope.plus = limiter(al.plus, ar.plus);
+    slope.v = limiter(al.v, ar.v);
+    slope.w = limiter(al.w, ar.w);
+    // DoTimeStep, :178-190
+    const int sign = 1 - 2 * is_right_side;
+    Chars am;
+    am.minus = sign * 0.5 * slope.minus * (1.0 - sign * lambda * (u - c));
+    am.zero = sign * 0.5 * slope.zero * (1.0 - sign * lambda * u);
+    am.plus = sign * 0.5 * slope.plus * (1.0 - sign * lambda * (u + c));
+    am.v = sign * 0.5 * slope.v * (1.0 - sign * lambda * u);
+    am.w = sign * 0.5 * slope.w * (1.0 - sign * lambda * u);
+    // Recombine, :79-88
+    Prim diffs;
+    diffs.p = 0.5 * (am.minus + am.plus);
+    diffs.rho = ooc2 * diffs.p + am.zero;
+    for (int d = 0; d < 3; ++d) diffs.u[d] = A8(0.0);
+    diffs.u[ix] = 0.5 * (am.plus - am.minus) / rhoc;
+    diffs.u[iy] = am.v;
+    diffs.u[iz] = am.w;
+    diffs.rho = diffs.rho + rho;
+    for (int d = 0; d < D; ++d) diffs.u[d] = diffs.u[d] + (q.mom[d] / q.rho);
+    diffs.p = diffs.p + q.p;
+    // PerfectGas::CompleteFromPrim (array), src/equations/PerfectGas.cpp:160-191
+    if (!valid_face) {
+      rec.rho = diffs.rho;
+      for (int d = 0; d < D; ++d) rec.mom[d] = diffs.rho * diffs.u[d];
+      rec.p = diffs.p;
+      const T e_kin = KineticEnergy<T, D>(rec.rho, rec.mom);
+      rec.E = e_kin + diffs.p * eq.gamma_minus_1_inv;
+      rec.a = vsqrt(eq.gamma * rec.p / rec.rho);
+    } else {
+      const M8& mask = *valid_face;
+      rec.rho = select(mask, diffs.rho, 0.0);
+      for (int d = 0; d < D; ++d) rec.mom[d] = select(mask, diffs.rho * diffs.u[d], 0.0);
+      rec.p = select(mask, diffs.p, 0.0);
+      const T e_kin = select(mask, KineticEnergy<T, D>(diffs.rho, rec.mom), 0.0);
+      rec.E = e_kin + rec.p * eq.gamma_minus_1_inv;
+      rec.a = vsqrt(select(mask, eq.gamma * rec.p / rec.rho, 0.0));
+    }
+  }
+
+  T ComputeStableDt(const Complete<T, D>* states, double dx, int dir) const {
+    return hllem.ComputeStableDt(states + 1, dx, dir);
+  }
+  T ComputeStableDt(const Complete<T, D>* states, const T& face_fraction, const T* vols,
+                    double dx, int dir) const {
+    return hllem.ComputeStableDt(states + 1, face_fraction, vols + 1, dx, dir);
+  }
+  // :301-314
+  void ComputeNumericFlux(Cons<T, D>& flux, const Complete<T, D>* st, double dt, double dx,
+                          int dir) const {
+    const T lambda(dt / dx);
+    Complete<T, D> rec[2];
+    Reconstruct(rec[0], 0, st, lambda, dir, nullptr, nullptr);
+    Reconstruct(rec[1], 1, st + 1, lambda, dir, nullptr, nullptr);
+    hllem.ComputeNumericFlux(flux, rec, dt, dx, dir);
+  }
+  // :316-334
+  void ComputeNumericFlux(Cons<T, D>& flux, const T& face_fractions, const Complete<T, D>* st,
+                          const T* vols, double dt, double dx, int dir) const {
+    const T lambda(dt / dx);
+    const M8 valid_face = face_fractions > 0.0;
+    const M8 left_mask = (vols[0] > 0.0) && (vols[1] > 0.0) && (vols[2] > 0.0);
+    const M8 right_mask = (vols[1] > 0.0) && (vols[2] > 0.0) && (vols[3] > 0.0);
+    Complete<T, D> rec[2];
+    Reconstruct(rec[0], 0, st, lambda, dir, &left_mask, &valid_face);
+    Reconstruct(rec[1], 1, st + 1, lambda, dir, &right_mask, &valid_face);
+    hllem.ComputeNumericFlux(flux, face_fractions, rec, vols + 1, dt, dx, dir);
+  }
+};
+
 } // namespace fvso

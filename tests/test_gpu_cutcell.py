@@ -91,7 +91,7 @@ def test_fill_cutcell_data_and_flags_bitwise(oracle, fvs):
     pair.close()
 
 
-METHODS = [(0, 1, 2), (0, 0, 0), (1, 1, 1), (2, 1, 1), (2, 0, 0), (2, 1, 2), (0, 2, 0)]
+METHODS = [(0, 1, 2), (0, 0, 0), (1, 1, 1), (2, 1, 1), (2, 0, 0), (2, 1, 2), (0, 2, 0), (0, 3, 2)]
 
 
 @pytest.mark.parametrize("method", METHODS)
@@ -160,6 +160,26 @@ def test_multibox_regular_cut_and_covered_fabs(oracle, fvs):
         ok_g, _, dts_g = pair.gpu.advance_hierarchy(0.4 * dt_c, 1)
         assert ok_c and ok_g and dts_c == dts_g
     pair.compare_states("multibox EB, 6 steps")
+    pair.close()
+
+
+def test_schardin_config_size_bitwise(oracle, fvs):
+    """BASELINE config 4 stand-in at the size of examples/AMReX/EB/2D/Schardin.cpp:87-130:
+    200 x 140 cells on [0, 0.15] x [0, 0.10], triangular wedge, shock at x = 0.015 with a
+    five-fold energy jump, KbnCutCellMethod(MusclHancock<HLLEM, VanLeer>, HLL), gcw 8/6,
+    Strang splitting, CFL 0.4."""
+    pair, dx, geoms = wedge_pair(oracle, fvs, gcw=(8, 6), n=(200, 140),
+                                 boxes=[([0, 0, 0], [99, 139, 0]), ([100, 0, 0], [199, 139, 0])])
+    for step in range(12):
+        dt_c = min(pair.cpu.compute_stable_dt(d) for d in range(2))
+        dt_g = pair.gpu.compute_stable_dt_all()
+        assert dt_c == dt_g, (step, dt_c, dt_g)
+        ok_c, _, dts_c = pair.cpu.advance_hierarchy(0.4 * dt_c, 1)
+        ok_g, _, dts_g = pair.gpu.advance_hierarchy(0.4 * dt_g, 1)
+        assert ok_c and ok_g and dts_c == dts_g
+    pair.compare_states("Schardin 200 x 140, 12 steps")
+    flags, count = pair.gpu.is_cut_cell(0)
+    assert np.array_equal(flags, pair.cpu.is_cut_cell(0)) and count > 40
     pair.close()
 
 

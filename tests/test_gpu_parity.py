@@ -30,6 +30,7 @@ BITWISE_METHODS = [
     (1, 1, 2), (1, 0, 0),
     (2, 1, 1), (2, 1, 2), (2, 0, 0),
     (0, 2, 0),  # perfect_gas::MusclHancockPrim (over HLLEM Larrouturou)
+    (0, 3, 2),  # perfect_gas::MusclHancockCharacteristic (VanLeer, HLLEM Larrouturou)
 ]
 
 

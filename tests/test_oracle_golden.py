@@ -197,16 +197,21 @@ def test_kinetic_energy_reduction_order(oracle):
     assert q[5] == (9.0 - ke) / (1.0 / (1.4 - 1.0))
 
 
-def test_muscl_hancock_prim_sod_star_state(oracle):
-    """perfect_gas::MusclHancockPrim (the reference has no test for it): the
-    oracle's restatement must resolve the Sod problem -- star density 0.42632
-    and contact / shock positions of Toro, section 4.3.3."""
+import pytest as _pytest
+
+
+@_pytest.mark.parametrize("recon", [2, 3])
+def test_muscl_hancock_prim_and_char_sod_star_state(oracle, recon):
+    """perfect_gas::MusclHancockPrim (2) and MusclHancockCharacteristic (3): the
+    reference has no test for them; the oracle's restatement must resolve the
+    Sod problem -- star density 0.42632, post-contact density 0.26557 (Toro,
+    section 4.3.3) at the right positions."""
     import numpy as np
     from helpers import complete_from_prim
     n = 400
     dx = [2.0 / n]
     lvl = oracle.Level(1, [0], [n - 1], dx, [([0], [n - 1])], scratch_gcw=2, flux_gcw=0)
-    lvl.set_method(oracle.BASE_HLLEM_LARROUTUROU, oracle.RECON_MUSCL_HANCOCK_PRIM, 0)
+    lvl.set_method(oracle.BASE_HLLEM_LARROUTUROU, recon, 2)
     lvl.add_bc(0, 0, oracle.BC_TRANSMISSIVE)
     lvl.add_bc(0, 1, oracle.BC_TRANSMISSIVE)
     arr, lo, hi = lvl.scratch(0)
