@@ -192,7 +192,7 @@ class Context:
         self.h = C.c_void_p()
 
     def define_level(self, level, domain_lo, domain_hi, dx, boxes, scratch_gcw=4, flux_gcw=2,
-                     periodic=(0, 0, 0)):
+                     periodic=(0, 0, 0), owner=None):
         """Defines a further (finer) level and returns a view of the context
         whose methods address that level."""
         import copy
@@ -201,7 +201,7 @@ class Context:
         v.level = level
         v.boxes = [(list(lo) + [0] * (3 - len(lo)), list(hi) + [0] * (3 - len(hi)))
                    for lo, hi in boxes]
-        v.owner = [self.comm_rank] * len(boxes)
+        v.owner = list(owner) if owner is not None else [self.comm_rank] * len(boxes)
         lo, hi = _boxes(v.boxes)
         own = (C.c_int * len(boxes))(*v.owner)
         _check(lib().fvs_level_define(self.h, level, _i3(domain_lo), _i3(domain_hi), _d3(dx),

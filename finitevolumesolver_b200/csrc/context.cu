@@ -959,6 +959,14 @@ void cc_pre_advance(fvs_ctx* ctx, Level& L) {
 
 
 // ---- coarse-fine ----------------------------------------------------------------
+// All five operations enumerate the GLOBAL (fine box, coarse box) pairs in the
+// same order on every rank.  A pair whose two boxes live on this rank is
+// handled by one kernel on the arrays themselves; otherwise the producing
+// rank packs (or computes into) a contiguous staging buffer, the buffers of a
+// call travel in one grouped ncclSend / ncclRecv (the halo's pattern), and the
+// consuming rank runs the SAME kernel with the staging buffer standing in for
+// the remote array -- so the arithmetic, and the result, does not depend on
+// the distribution of the boxes.
 int coarsen_index(int i, int r) { return i >= 0 ? i / r : -((-i + r - 1) / r); }
 Box coarsen_box(const Box& b, const int ratio[3]) {
   Box c;
@@ -993,15 +1001,128 @@ fvs::ArrayRef array_ref(double* p, const Box& b, long long sc) {
 void effective_ratio(const fvs_ctx* ctx, int ratio[3]) {
   for (int d = 0; d < 3; ++d) ratio[d] = d < ctx->cfg.rank ? ctx->ratio[d] : 1;
 }
-void require_single_rank(const Level& L) {
-  for (int o : L.owner)
-    if (o != L.owner[0] || (int)L.patches.size() != (int)L.boxes.size()) {
-      throw Error("coarse-fine operations need both levels on this rank");
-    }
+double cell_volume(const fvs_ctx* ctx, const Level& L) {
+  const int rank = ctx->cfg.rank;
+  return L.dx[0] * (rank > 1 ? L.dx[1] : 1.0) * (rank > 2 ? L.dx[2] : 1.0);
 }
-// FluxRegister of `fine` towards `coarse`: one plane of coarse faces per side
-// of every fine box; ClearInternalBorders = faces whose outside cell lies
-// under another fine box (or outside the domain) are closed.
+Patch* local_patch(Level& L, int global_box) {
+  const int loc = L.local_of_global[(size_t)global_box];
+  return loc < 0 ? nullptr : &L.patches[(size_t)loc];
+}
+
+// staging buffers and the transfers of one coarse-fine call
+struct Transfers {
+  fvs_ctx* ctx;
+  struct X {
+    int src, dst;
+    size_t count;
+    double* ptr; // the local end (send buffer on src, receive buffer on dst)
+  };
+  std::vector<X> list;
+  std::vector<double*> owned;
+  explicit Transfers(fvs_ctx* c) : ctx(c) {}
+  Transfers(const Transfers&) = delete;
+  ~Transfers() {
+    cudaStreamSynchronize(ctx->stream);
+    for (double* p : owned) cudaFree(p);
+  }
+  double* buffer(size_t count) {
+    double* p = nullptr;
+    FVS_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(double)));
+    owned.push_back(p);
+    return p;
+  }
+  // registers a transfer this rank takes part in; returns its local buffer
+  double* add(int src, int dst, size_t count) {
+    double* p = buffer(count);
+    list.push_back({src, dst, count, p});
+    return p;
+  }
+  void run() {
+    if (list.empty()) return;
+    if (!ctx->comm) throw Error("levels span several ranks but fvs_comm_init was not called");
+    Nccl& n = Nccl::get();
+    const int me = ctx->cfg.comm_rank;
+    n.check(n.GroupStart(), "ncclGroupStart");
+    for (const X& x : list) {
+      if (x.src == me) {
+        n.check(n.Send(x.ptr, x.count, Nccl::kDouble, x.dst, ctx->comm, ctx->stream), "ncclSend");
+      } else {
+        n.check(n.Recv(x.ptr, x.count, Nccl::kDouble, x.src, ctx->comm, ctx->stream), "ncclRecv");
+      }
+    }
+    n.check(n.GroupEnd(), "ncclGroupEnd");
+  }
+};
+
+// copies `region` (ncomp components) between two arrays; used to pack a region
+// into a staging buffer (whose box is the region itself) and to unpack it
+struct RegionCopies {
+  std::vector<fvs::CopyDesc> descs;
+  long long max_cells{1};
+  void add(const fvs::ArrayRef& dst, const fvs::ArrayRef& src, const Box& region) {
+    fvs::CopyDesc d{};
+    d.src = src.p;
+    d.dst = dst.p;
+    for (int e = 0; e < 3; ++e) {
+      d.sn[e] = src.n[e];
+      d.dn[e] = dst.n[e];
+      d.slo[e] = region.lo[e] - src.lo[e];
+      d.dlo[e] = region.lo[e] - dst.lo[e];
+      d.len[e] = region.len(e);
+    }
+    d.ssc = src.sc;
+    d.dsc = dst.sc;
+    max_cells = std::max(max_cells, region.size());
+    descs.push_back(d);
+  }
+  void run(fvs_ctx* ctx, int ncomp, Transfers& keep_alive) {
+    if (descs.empty()) return;
+    fvs::CopyDesc* dev = nullptr;
+    FVS_CUDA(cudaMalloc(&dev, descs.size() * sizeof(fvs::CopyDesc)));
+    keep_alive.owned.push_back(reinterpret_cast<double*>(dev));
+    FVS_CUDA(cudaMemcpyAsync(dev, descs.data(), descs.size() * sizeof(fvs::CopyDesc),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream)); // descs is a host temporary
+    ctx->launches += fvs::launch_copy_regions(dev, (int)descs.size(), ncomp, max_cells, ctx->stream);
+  }
+};
+template <typename Desc> Desc* upload_descs(fvs_ctx* ctx, const std::vector<Desc>& host, Transfers& keep) {
+  Desc* dev = nullptr;
+  FVS_CUDA(cudaMalloc(&dev, std::max<size_t>(host.size(), 1) * sizeof(Desc)));
+  keep.owned.push_back(reinterpret_cast<double*>(dev));
+  FVS_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(Desc), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return dev;
+}
+
+// plane of coarse faces of one side of a fine box, and its Reflux mask
+// (ClearInternalBorders: closed where the outside cell lies under a fine box
+// or outside the domain)
+Box register_plane(const Box& fine_valid, const int ratio[3], int dir, int side) {
+  Box plane = coarsen_box(fine_valid, ratio);
+  plane.lo[dir] = plane.hi[dir] = side == 0 ? plane.lo[dir] : plane.hi[dir] + 1;
+  return plane;
+}
+std::vector<unsigned char> register_open(const Level& fine, const Level& coarse, const int ratio[3],
+                                         const Box& faces, int dir, int side) {
+  std::vector<unsigned char> open((size_t)faces.size(), 1);
+  size_t n = 0;
+  for (int k = faces.lo[2]; k <= faces.hi[2]; ++k)
+    for (int j = faces.lo[1]; j <= faces.hi[1]; ++j)
+      for (int i = faces.lo[0]; i <= faces.hi[0]; ++i, ++n) {
+        int out[3] = {i, j, k};
+        if (side == 0) out[dir] -= 1;
+        for (const Box& g : fine.boxes) {
+          if (box_contains(coarsen_box(g, ratio), out)) open[n] = 0;
+        }
+        if (!box_contains(coarse.domain, out)) open[n] = 0;
+      }
+  return open;
+}
+// FluxRegister of `fine` towards `coarse`: one plane per side of every OWNED
+// fine box
 void define_flux_register(fvs_ctx* ctx, Level& fine, Level& coarse, int coarse_index) {
   for (Level::CfRegister& r : fine.cf_regs) {
     if (r.reg) cudaFree(r.reg);
@@ -1012,74 +1133,107 @@ void define_flux_register(fvs_ctx* ctx, Level& fine, Level& coarse, int coarse_i
   effective_ratio(ctx, ratio);
   const int rank = ctx->cfg.rank;
   for (size_t f = 0; f < fine.patches.size(); ++f) {
-    const Box cb = coarsen_box(fine.patches[f].valid, ratio);
     for (int d = 0; d < rank; ++d)
       for (int side = 0; side < 2; ++side) {
         Level::CfRegister r;
         r.patch = (int)f;
         r.dir = d;
         r.side = side;
-        r.plane = cb;
-        r.plane.lo[d] = r.plane.hi[d] = side == 0 ? cb.lo[d] : cb.hi[d] + 1;
-        const size_t faces = (size_t)r.plane.size();
-        std::vector<unsigned char> open(faces, 1);
-        size_t n = 0;
-        for (int k = r.plane.lo[2]; k <= r.plane.hi[2]; ++k)
-          for (int j = r.plane.lo[1]; j <= r.plane.hi[1]; ++j)
-            for (int i = r.plane.lo[0]; i <= r.plane.hi[0]; ++i, ++n) {
-              int out[3] = {i, j, k};
-              if (side == 0) out[d] -= 1;
-              for (const Patch& g : fine.patches) {
-                if (box_contains(coarsen_box(g.valid, ratio), out)) open[n] = 0;
-              }
-              if (!box_contains(coarse.domain, out)) open[n] = 0;
-            }
-        r.reg = device_alloc_zero<double>(ctx, faces * ctx->ncons());
-        FVS_CUDA(cudaMalloc(&r.open, faces));
-        FVS_CUDA(cudaMemcpy(r.open, open.data(), faces, cudaMemcpyHostToDevice));
+        r.plane = register_plane(fine.patches[f].valid, ratio, d, side);
+        const std::vector<unsigned char> open = register_open(fine, coarse, ratio, r.plane, d, side);
+        r.reg = device_alloc_zero<double>(ctx, open.size() * ctx->ncons());
+        FVS_CUDA(cudaMalloc(&r.open, open.size()));
+        FVS_CUDA(cudaMemcpy(r.open, open.data(), open.size(), cudaMemcpyHostToDevice));
         fine.cf_regs.push_back(r);
       }
   }
   fine.cf_coarse = coarse_index;
 }
+Level::CfRegister* find_register(Level& fine, int local_patch_index, int dir, int side) {
+  for (Level::CfRegister& r : fine.cf_regs) {
+    if (r.patch == local_patch_index && r.dir == dir && r.side == side) return &r;
+  }
+  return nullptr;
+}
 
-// op 0 FineAdd (level = fine), 1 CrseInit (level = coarse), 2 Reflux (level = coarse)
-void run_flux_register(fvs_ctx* ctx, Level& reg_level, Level& level, int op, int dir, double mult,
-                       double vol) {
+void launch_registers(fvs_ctx* ctx, const std::vector<fvs::RegisterDesc>& host, int op, int dir,
+                      double mult, double vol, long long max_faces, Transfers& keep) {
+  if (host.empty()) return;
   int ratio[3];
   effective_ratio(ctx, ratio);
+  const fvs::RegisterDesc* dev = upload_descs(ctx, host, keep);
+  ctx->launches += fvs::launch_flux_register(dev, (int)host.size(), op, ctx->ncons(), dir, ratio,
+                                             mult, vol, max_faces, ctx->stream);
+  FVS_CUDA(cudaGetLastError());
+}
+
+// FineAdd: registers and fine fluxes are both local to the owner of the fine box
+void fine_add(fvs_ctx* ctx, Level& fine, int dir, double mult) {
+  Transfers keep(ctx);
   std::vector<fvs::RegisterDesc> host;
   long long max_faces = 1;
-  for (const Level::CfRegister& r : reg_level.cf_regs) {
+  for (const Level::CfRegister& r : fine.cf_regs) {
     if (r.dir != dir) continue;
+    Patch& p = fine.patches[(size_t)r.patch];
     fvs::RegisterDesc d{};
     d.reg = array_ref(r.reg, r.plane, r.plane.size());
     d.open = r.open;
     d.side = r.side;
-    if (op == 0) {
-      Patch& p = level.patches[(size_t)r.patch];
-      d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
-      for (int e = 0; e < 3; ++e) {
-        d.lo[e] = r.plane.lo[e];
-        d.len[e] = r.plane.len(e);
-      }
-      max_faces = std::max(max_faces, r.plane.size());
-      host.push_back(d);
-    } else {
-      for (Patch& p : level.patches) {
-        Box faces = r.plane;
-        if (op == 1) {
-          Box nodes = p.valid;
-          nodes.hi[dir] += 1;
-          faces = fvs::intersect(r.plane, nodes);
-          if (!faces.ok()) continue;
-          d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
+    d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
+    for (int e = 0; e < 3; ++e) {
+      d.lo[e] = r.plane.lo[e];
+      d.len[e] = r.plane.len(e);
+    }
+    max_faces = std::max(max_faces, r.plane.size());
+    host.push_back(d);
+  }
+  launch_registers(ctx, host, 0, dir, mult, 1.0, max_faces, keep);
+}
+
+// CrseInit(ADD): the coarse fluxes on the register planes travel to the owner
+// of the fine box
+void crse_init(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double mult) {
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const int me = ctx->cfg.comm_rank;
+  const int ncons = ctx->ncons();
+  Transfers xf(ctx);
+  RegionCopies packs;
+  std::vector<fvs::RegisterDesc> host;
+  long long max_faces = 1;
+  for (size_t f = 0; f < fine.boxes.size(); ++f)
+    for (int side = 0; side < 2; ++side) {
+      const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
+      for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+        Box nodes = coarse.boxes[c];
+        nodes.hi[dir] += 1;
+        const Box faces = fvs::intersect(plane, nodes);
+        if (!faces.ok()) continue;
+        const int rf = fine.owner[f], rc = coarse.owner[c];
+        if (rf != me && rc != me) continue;
+        Patch* fp = local_patch(fine, (int)f);
+        Patch* cp = local_patch(coarse, (int)c);
+        fvs::ArrayRef flux_ref;
+        if (rf == me && rc == me) {
+          flux_ref = array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size());
         } else {
-          d.other = array_ref(p.buf[level.cur], p.sbox, p.cells);
+          double* buf = xf.add(rc, rf, (size_t)faces.size() * ncons);
+          flux_ref = array_ref(buf, faces, faces.size());
+          if (rc == me) {
+            packs.add(flux_ref, array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), faces);
+            continue;
+          }
         }
+        Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+        if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+        fvs::RegisterDesc d{};
+        d.reg = array_ref(r->reg, r->plane, r->plane.size());
+        d.open = r->open;
+        d.side = side;
+        d.other = flux_ref;
         for (int e = 0; e < 3; ++e) {
-          d.box_lo[e] = p.valid.lo[e];
-          d.box_hi[e] = p.valid.hi[e];
+          d.box_lo[e] = coarse.boxes[c].lo[e];
+          d.box_hi[e] = coarse.boxes[c].hi[e];
           d.lo[e] = faces.lo[e];
           d.len[e] = faces.len(e);
         }
@@ -1087,19 +1241,181 @@ void run_flux_register(fvs_ctx* ctx, Level& reg_level, Level& level, int op, int
         host.push_back(d);
       }
     }
-  }
-  if (host.empty()) return;
-  DeviceArray<fvs::RegisterDesc> dev;
-  dev.upload(host);
-  ctx->launches += fvs::launch_flux_register(dev.ptr, (int)host.size(), op, ctx->ncons(), dir, ratio,
-                                             mult, vol, max_faces, ctx->stream);
-  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-  FVS_CUDA(cudaGetLastError());
+  packs.run(ctx, ncons, xf);
+  xf.run();
+  launch_registers(ctx, host, 1, dir, mult, 1.0, max_faces, xf);
 }
 
-double cell_volume(const fvs_ctx* ctx, const Level& L) {
-  const int rank = ctx->cfg.rank;
-  return L.dx[0] * (rank > 1 ? L.dx[1] : 1.0) * (rank > 2 ? L.dx[2] : 1.0);
+// Reflux: the registers travel to the owners of the coarse boxes
+void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const int me = ctx->cfg.comm_rank;
+  const int ncons = ctx->ncons();
+  const double vol = cell_volume(ctx, coarse);
+  Transfers xf(ctx);
+  RegionCopies packs;
+  std::vector<fvs::RegisterDesc> host;
+  long long max_faces = 1;
+  for (size_t f = 0; f < fine.boxes.size(); ++f)
+    for (int side = 0; side < 2; ++side) {
+      const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
+      for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+        // faces of the plane whose OUTSIDE cell belongs to coarse box c
+        Box cells = coarse.boxes[c];
+        if (side == 0) {
+          cells.lo[dir] += 1;
+          cells.hi[dir] += 1;
+        }
+        const Box faces = fvs::intersect(plane, cells);
+        if (!faces.ok()) continue;
+        const int rf = fine.owner[f], rc = coarse.owner[c];
+        if (rf != me && rc != me) continue;
+        Patch* cp = local_patch(coarse, (int)c);
+        fvs::ArrayRef reg_ref;
+        const unsigned char* open = nullptr;
+        if (rf == me && rc == me) {
+          Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+          if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+          reg_ref = array_ref(r->reg, r->plane, r->plane.size());
+          open = r->open;
+        } else {
+          double* buf = xf.add(rf, rc, (size_t)faces.size() * ncons);
+          reg_ref = array_ref(buf, faces, faces.size());
+          if (rf == me) {
+            Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+            if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+            packs.add(reg_ref, array_ref(r->reg, r->plane, r->plane.size()), faces);
+            continue;
+          }
+          const std::vector<unsigned char> mask = register_open(fine, coarse, ratio, faces, dir, side);
+          unsigned char* dmask = reinterpret_cast<unsigned char*>(xf.buffer((mask.size() + 7) / 8 + 1));
+          FVS_CUDA(cudaMemcpy(dmask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
+          open = dmask;
+        }
+        fvs::RegisterDesc d{};
+        d.reg = reg_ref;
+        d.open = open;
+        d.side = side;
+        d.other = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+        for (int e = 0; e < 3; ++e) {
+          d.box_lo[e] = coarse.boxes[c].lo[e];
+          d.box_hi[e] = coarse.boxes[c].hi[e];
+          d.lo[e] = faces.lo[e];
+          d.len[e] = faces.len(e);
+        }
+        max_faces = std::max(max_faces, faces.size());
+        host.push_back(d);
+      }
+    }
+  packs.run(ctx, ncons, xf);
+  xf.run();
+  launch_registers(ctx, host, 2, dir, scale, vol, max_faces, xf);
+}
+
+// amrex::average_down: the owner of the fine box averages, the result travels
+void average_down(fvs_ctx* ctx, Level& fine, Level& coarse) {
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const int me = ctx->cfg.comm_rank;
+  const int ncons = ctx->ncons();
+  Transfers xf(ctx);
+  RegionCopies unpacks;
+  std::vector<fvs::AvgDownDesc> host;
+  long long max_cells = 1;
+  for (size_t f = 0; f < fine.boxes.size(); ++f) {
+    const Box cf = coarsen_box(fine.boxes[f], ratio);
+    for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+      const Box region = fvs::intersect(cf, coarse.boxes[c]);
+      if (!region.ok()) continue;
+      const int rf = fine.owner[f], rc = coarse.owner[c];
+      if (rf != me && rc != me) continue;
+      Patch* fp = local_patch(fine, (int)f);
+      Patch* cp = local_patch(coarse, (int)c);
+      fvs::ArrayRef target;
+      if (rf == me && rc == me) {
+        target = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+      } else {
+        double* buf = xf.add(rf, rc, (size_t)region.size() * ncons);
+        target = array_ref(buf, region, region.size());
+        if (rc == me) {
+          unpacks.add(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), target, region);
+          continue;
+        }
+      }
+      fvs::AvgDownDesc d{};
+      d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
+      d.crse = target;
+      for (int e = 0; e < 3; ++e) {
+        d.lo[e] = region.lo[e];
+        d.len[e] = region.len(e);
+      }
+      max_cells = std::max(max_cells, region.size());
+      host.push_back(d);
+    }
+  }
+  if (!host.empty()) {
+    const fvs::AvgDownDesc* dev = upload_descs(ctx, host, xf);
+    ctx->launches += fvs::launch_average_down(dev, (int)host.size(), ncons, ratio, max_cells, ctx->stream);
+    FVS_CUDA(cudaGetLastError());
+  }
+  xf.run();
+  unpacks.run(ctx, ncons, xf);
+}
+
+// FillPatchTwoLevels with pc_interp: the coarse parents travel to the owner of
+// the fine box
+void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const int me = ctx->cfg.comm_rank;
+  const int ncomp = ctx->ncomp();
+  Transfers xf(ctx);
+  RegionCopies packs;
+  std::vector<fvs::InterpDesc> host;
+  long long max_cells = 1;
+  for (size_t f = 0; f < fine.boxes.size(); ++f) {
+    const Box fsbox = fvs::state_box(fine.boxes[f], ctx->cfg.rank, fine.scratch_gcw);
+    for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+      const Box region =
+          fvs::intersect(fvs::intersect(fsbox, refine_box(coarse.boxes[c], ratio)), fine.domain);
+      if (!region.ok()) continue;
+      const int rf = fine.owner[f], rc = coarse.owner[c];
+      if (rf != me && rc != me) continue;
+      Patch* fp = local_patch(fine, (int)f);
+      Patch* cp = local_patch(coarse, (int)c);
+      fvs::ArrayRef source;
+      if (rf == me && rc == me) {
+        source = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+      } else {
+        const Box parents = coarsen_box(region, ratio);
+        double* buf = xf.add(rc, rf, (size_t)parents.size() * ncomp);
+        source = array_ref(buf, parents, parents.size());
+        if (rc == me) {
+          packs.add(source, array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), parents);
+          continue;
+        }
+      }
+      fvs::InterpDesc d{};
+      d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
+      d.crse = source;
+      for (int e = 0; e < 3; ++e) {
+        d.lo[e] = region.lo[e];
+        d.len[e] = region.len(e);
+        d.vlo[e] = fine.boxes[f].lo[e];
+        d.vhi[e] = fine.boxes[f].hi[e];
+      }
+      max_cells = std::max(max_cells, region.size());
+      host.push_back(d);
+    }
+  }
+  packs.run(ctx, ncomp, xf);
+  xf.run();
+  if (!host.empty()) {
+    const fvs::InterpDesc* dev = upload_descs(ctx, host, xf);
+    ctx->launches += fvs::launch_pc_interp(dev, (int)host.size(), ncomp, ratio, max_cells, ctx->stream);
+    FVS_CUDA(cudaGetLastError());
+  }
 }
 
 } // namespace
@@ -1713,7 +2029,6 @@ int advance_hierarchy_multilevel(fvs_ctx* ctx, double dt, int split_kind, double
   std::vector<int> entry(nl);
   for (int l = 0; l < nl; ++l) {
     Level& L = ctx->levels[l];
-    require_single_rank(L);
     entry[l] = L.cur;
     L.keep = -1;
     const int work = free_buffer(L, L.cur);
@@ -2195,8 +2510,6 @@ int fvs_reset_coarse_fine_fluxes(fvs_ctx* ctx, int fine, int coarse) {
     ctx->use_device();
     Level& F = ctx->level(fine);
     Level& Cl = ctx->level(coarse);
-    require_single_rank(F);
-    require_single_rank(Cl);
     if (F.cf_coarse != coarse) define_flux_register(ctx, F, Cl, coarse);
     for (Level::CfRegister& r : F.cf_regs) {
       FVS_CUDA(cudaMemsetAsync(r.reg, 0, (size_t)r.plane.size() * ctx->ncons() * sizeof(double),
@@ -2215,12 +2528,10 @@ int fvs_accumulate_coarse_fine_fluxes(fvs_ctx* ctx, int level, double scale, int
     ensure_fluxes(ctx, L, dir);
     const double vol = cell_volume(ctx, L);
     const double vol_dt_over_dx = vol * scale / L.dx[dir];
-    if (level > 0 && L.cf_coarse >= 0) {
-      run_flux_register(ctx, L, L, 0, dir, vol_dt_over_dx, 1.0);
-    }
+    if (level > 0 && L.cf_coarse >= 0) fine_add(ctx, L, dir, vol_dt_over_dx);
     if (level + 1 < (int)ctx->levels.size() && ctx->levels[level + 1].defined &&
         ctx->levels[level + 1].cf_coarse == level) {
-      run_flux_register(ctx, ctx->levels[level + 1], L, 1, dir, -vol_dt_over_dx, 1.0);
+      crse_init(ctx, ctx->levels[level + 1], L, dir, -vol_dt_over_dx);
     }
     return (int)FVS_OK;
   });
@@ -2233,8 +2544,7 @@ int fvs_apply_flux_correction(fvs_ctx* ctx, int fine, int coarse, double /*dt*/)
     Level& F = ctx->level(fine);
     Level& Cl = ctx->level(coarse);
     if (F.cf_coarse != coarse) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
-    const double vol = cell_volume(ctx, Cl);
-    for (int d = 0; d < ctx->cfg.rank; ++d) run_flux_register(ctx, F, Cl, 2, d, 1.0, vol);
+    for (int d = 0; d < ctx->cfg.rank; ++d) reflux(ctx, F, Cl, d, 1.0);
     return (int)FVS_OK;
   });
 }
@@ -2244,37 +2554,7 @@ int fvs_coarsen_conservatively(fvs_ctx* ctx, int fine, int coarse) {
     if (!ctx) throw Error("null context");
     if (fine <= coarse || coarse < 0) throw Error("need 0 <= coarse < fine");
     ctx->use_device();
-    Level& F = ctx->level(fine);
-    Level& Cl = ctx->level(coarse);
-    require_single_rank(F);
-    require_single_rank(Cl);
-    int ratio[3];
-    effective_ratio(ctx, ratio);
-    std::vector<fvs::AvgDownDesc> host;
-    long long max_cells = 1;
-    for (Patch& f : F.patches) {
-      const Box cf = coarsen_box(f.valid, ratio);
-      for (Patch& c : Cl.patches) {
-        const Box region = fvs::intersect(cf, c.valid);
-        if (!region.ok()) continue;
-        fvs::AvgDownDesc d{};
-        d.fine = array_ref(f.buf[F.cur], f.sbox, f.cells);
-        d.crse = array_ref(c.buf[Cl.cur], c.sbox, c.cells);
-        for (int e = 0; e < 3; ++e) {
-          d.lo[e] = region.lo[e];
-          d.len[e] = region.len(e);
-        }
-        max_cells = std::max(max_cells, region.size());
-        host.push_back(d);
-      }
-    }
-    if (host.empty()) return (int)FVS_OK;
-    DeviceArray<fvs::AvgDownDesc> dev;
-    dev.upload(host);
-    ctx->launches += fvs::launch_average_down(dev.ptr, (int)host.size(), ctx->ncons(), ratio,
-                                              max_cells, ctx->stream);
-    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-    FVS_CUDA(cudaGetLastError());
+    average_down(ctx, ctx->level(fine), ctx->level(coarse));
     return (int)FVS_OK;
   });
 }
@@ -2285,39 +2565,7 @@ int fvs_fill_ghost_layer_two_levels(fvs_ctx* ctx, int fine, int coarse) {
     if (fine <= coarse || coarse < 0) throw Error("need 0 <= coarse < fine");
     ctx->use_device();
     Level& F = ctx->level(fine);
-    Level& Cl = ctx->level(coarse);
-    require_single_rank(F);
-    require_single_rank(Cl);
-    int ratio[3];
-    effective_ratio(ctx, ratio);
-    std::vector<fvs::InterpDesc> host;
-    long long max_cells = 1;
-    for (Patch& f : F.patches) {
-      for (Patch& c : Cl.patches) {
-        const Box region =
-            fvs::intersect(fvs::intersect(f.sbox, refine_box(c.valid, ratio)), F.domain);
-        if (!region.ok()) continue;
-        fvs::InterpDesc d{};
-        d.fine = array_ref(f.buf[F.cur], f.sbox, f.cells);
-        d.crse = array_ref(c.buf[Cl.cur], c.sbox, c.cells);
-        for (int e = 0; e < 3; ++e) {
-          d.lo[e] = region.lo[e];
-          d.len[e] = region.len(e);
-          d.vlo[e] = f.valid.lo[e];
-          d.vhi[e] = f.valid.hi[e];
-        }
-        max_cells = std::max(max_cells, region.size());
-        host.push_back(d);
-      }
-    }
-    if (!host.empty()) {
-      DeviceArray<fvs::InterpDesc> dev;
-      dev.upload(host);
-      ctx->launches += fvs::launch_pc_interp(dev.ptr, (int)host.size(), ctx->ncomp(), ratio,
-                                             max_cells, ctx->stream);
-      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-      FVS_CUDA(cudaGetLastError());
-    }
+    pc_interp(ctx, F, ctx->level(coarse));
     fill_ghost_layer(ctx, F);
     return (int)FVS_OK;
   });

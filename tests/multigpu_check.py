@@ -85,11 +85,84 @@ def main():
     dist.barrier()
     eb_check(capi, orc, rank, world, local)
     dist.barrier()
+    amr_check(capi, orc, rank, world, local)
+    dist.barrier()
     if rank == 0:
         print(f"multigpu_check ok: {world} ranks, halo + 6 Strang steps bit-identical to the "
               f"oracle, identical dt sequence, min_all ok; cut-cell level over {world} ranks "
-              f"bit-identical too")
+              f"bit-identical too; 3-level subcycled hierarchy with coarse and fine boxes on "
+              f"different ranks bit-identical")
     dist.destroy_process_group()
+
+
+def amr_check(capi, orc, rank, world, local):
+    """Three nested levels whose boxes are dealt round robin over the ranks, so
+    that average_down, pc_interp, CrseInit and Reflux all cross rank borders;
+    fine-first subcycling against the oracle's hierarchy."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import complete_from_prim
+    n0 = [32, 24]
+    level_boxes = [
+        [([0, 0, 0], [15, 23, 0]), ([16, 0, 0], [31, 23, 0])],
+        [([16, 8, 0], [31, 39, 0]), ([32, 8, 0], [47, 23, 0]), ([32, 24, 0], [47, 39, 0])],
+        [([48, 40, 0], [71, 63, 0]), ([72, 32, 0], [87, 55, 0])],
+    ]
+    owners = [[b % world for b in range(2)], [(b + 1) % world for b in range(3)],
+              [b % world for b in range(2)]]
+    cpus, gpus = [], []
+    ctx = None
+    for l, boxes in enumerate(level_boxes):
+        f = 2 ** l
+        hi = [n0[0] * f - 1, n0[1] * f - 1, 0]
+        dx = [2.0 / (n0[0] * f), 2.0 / (n0[1] * f), 1.0]
+        cpu = orc.Level(2, [0] * 3, hi, dx, boxes, scratch_gcw=8, flux_gcw=6)
+        if l == 0:
+            ctx = capi.Context(2, [0] * 3, hi, dx, boxes, scratch_gcw=8, flux_gcw=6, device=local,
+                               comm_rank=rank, comm_size=world, owner=owners[0])
+            idt = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            ctx.comm_init(bytes(idt.cpu().numpy().tobytes()))
+            gpu = ctx
+        else:
+            gpu = ctx.define_level(l, [0] * 3, hi, dx, boxes, scratch_gcw=8, flux_gcw=6,
+                                   owner=owners[l])
+        for lv in (cpu, gpu):
+            for d in range(2):
+                for s in (0, 1):
+                    lv.add_bc(d, s, 1)
+        for b in range(len(boxes)):
+            arr, lo, hi_b = cpu.scratch(b)
+            x = -1.0 + (np.arange(lo[0], hi_b[0] + 1) + 0.5) * dx[0]
+            y = -1.0 + (np.arange(lo[1], hi_b[1] + 1) + 0.5) * dx[1]
+            upper = (x[None, None, :] + y[None, :, None]) > 0.0
+            rho = np.where(upper, 0.125, 1.0)
+            p = np.where(upper, 10132.5, 101325.0)
+            arr[...] = complete_from_prim(2, rho, [np.zeros_like(rho)] * 2, p)
+            if owners[l][b] == rank:
+                gpu.upload_state(b, arr)
+        cpus.append(cpu)
+        gpus.append(gpu)
+    hier = orc.Hierarchy(cpus)
+    cpus[0].fill_ghost_layer()
+    gpus[0].fill_ghost_layer()
+    for l in range(1, 3):
+        orc.CoarseFine(cpus[l], cpus[l - 1]).fill_ghost_layer_two_levels()
+        ctx.fill_ghost_layer_two_levels(l, l - 1)
+    for step in range(3):
+        dt_c = hier.compute_stable_dt()
+        dt_g = ctx.compute_stable_dt_hierarchy()
+        assert dt_c == dt_g, (rank, step, dt_c, dt_g)
+        ok_c, _, dts_c = hier.advance_hierarchy(0.5 * dt_c, orc.SPLIT_STRANG)
+        ok_g, _, dts_g = ctx.advance_hierarchy(0.5 * dt_g, capi.SPLIT_STRANG)
+        assert ok_c and ok_g and dts_c == dts_g, (rank, step, dts_c, dts_g)
+        for l in range(3):
+            for b in range(len(level_boxes[l])):
+                if owners[l][b] == rank:
+                    assert_bitwise_equal(gpus[l].download_state(b), cpus[l].scratch(b)[0],
+                                         f"rank {rank} step {step} level {l} box {b}")
+    ctx.close()
 
 
 def eb_check(capi, orc, rank, world, local):
