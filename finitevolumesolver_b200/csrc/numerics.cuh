@@ -138,7 +138,10 @@ template <int D> struct Edge {
 // Masked CompleteFromCons of the cut-cell path (PerfectGas.cpp:126-144 on a
 // valid face): a state whose density is not positive becomes all zeros, and
 // the masked Flux (PerfectGas.cpp:79-93) then divides by 1 instead.
-template <class M, int D, bool MASKED>
+// NEED_A = false: the caller only uses the pressure (the trial states q_L, q_R
+// of the predictor feed Flux(), which does not read the speed of sound), so
+// the division and square root behind `a` are not evaluated at all.
+template <class M, int D, bool MASKED, bool NEED_A = true>
 FVS_DEV void complete_edge(const EqM& eq, Complete<D>& q, Rcp& rc, Flag& fl) {
   if constexpr (MASKED) {
     if (!(q.rho > 0.0)) {
@@ -153,7 +156,14 @@ FVS_DEV void complete_edge(const EqM& eq, Complete<D>& q, Rcp& rc, Flag& fl) {
     }
   }
   M::check(rc, fl);
-  complete_from_cons<M, D>(eq, q, rc, fl);
+  if constexpr (NEED_A) {
+    complete_from_cons<M, D>(eq, q, rc, fl);
+  } else {
+    const double e_kin = M::div(0.5 * squared_norm<D>(q.mom), rc, fl);
+    const double e_int = q.E - e_kin;
+    q.p = M::div(e_int, eq.gm1_inv, fl);
+    q.a = 0.0;
+  }
 }
 
 template <class M, int D, int DIR, int LIM, bool MASKED = false, typename S0, typename S1,
@@ -183,8 +193,8 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   }
   Rcp rcL = M::rcp(qL.rho);
   Rcp rcR = M::rcp(qR.rho);
-  complete_edge<M, D, MASKED>(eq, qL, rcL, fl);
-  complete_edge<M, D, MASKED>(eq, qR, rcR, fl);
+  complete_edge<M, D, MASKED, false>(eq, qL, rcL, fl);
+  complete_edge<M, D, MASKED, false>(eq, qR, rcR, fl);
   Cons<D> fL, fR;
   euler_flux_v<D, DIR>(fL, qL, M::div(qL.mom[DIR], rcL, fl));
   euler_flux_v<D, DIR>(fR, qR, M::div(qR.mom[DIR], rcR, fl));
