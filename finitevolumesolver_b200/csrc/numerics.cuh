@@ -526,8 +526,15 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
       M::div(bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho), rcDb, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    hlle.mom[d] = M::div(
-        bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]), rcDb, fl);
+    // with the Larrouturou modification the tangential momentum fluxes are
+    // upwinded below (:994-1004) and the HLLE values of those components,
+    // which the reference computes and discards, are never read
+    if (LARROUTUROU && D > 1 && d != DIR) {
+      hlle.mom[d] = 0.0;
+    } else {
+      hlle.mom[d] = M::div(
+          bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]), rcDb, fl);
+    }
   }
   hlle.E = M::div(bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E), rcDb, fl);
 
