@@ -46,6 +46,7 @@ SYMBOLS = [
     "fvs_apply_flux_correction", "fvs_coarsen_conservatively", "fvs_fill_ghost_layer_two_levels",
     "fvs_compute_stable_dt_hierarchy",
     "fvs_upload_state_async", "fvs_download_state_async", "fvs_synchronize",
+    "fvs_copy_data_to_scratch_async", "fvs_copy_scratch_to_data_async",
 ]
 
 
@@ -356,6 +357,21 @@ class Context:
     def download_state_async(self, box, out):
         assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
         _check(lib().fvs_download_state_async(self.h, self.level, box, _dp(out)))
+
+    def data_shape(self, box):
+        """[ncomp, z, y, x] of the level data of a box: valid cells, no ghosts."""
+        lo, hi = self.boxes[box]
+        return (self.ncomp, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+
+    def copy_data_to_scratch_async(self, box, arr):
+        assert arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"]
+        assert arr.shape == self.data_shape(box), (arr.shape, self.data_shape(box))
+        _check(lib().fvs_copy_data_to_scratch_async(self.h, self.level, box, _dp(arr)))
+
+    def copy_scratch_to_data_async(self, box, out):
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        assert out.shape == self.data_shape(box), (out.shape, self.data_shape(box))
+        _check(lib().fvs_copy_scratch_to_data_async(self.h, self.level, box, _dp(out)))
 
     def synchronize(self):
         _check(lib().fvs_synchronize(self.h))

@@ -1720,6 +1720,52 @@ int fvs_download_state_async(fvs_ctx* ctx, int level, int box, double* host_fab)
   });
 }
 
+namespace {
+// valid cells of a patch <-> a dense host array, one 3-D copy per component
+void copy_valid(fvs_ctx* ctx, Level& L, Patch& p, double* host, bool to_device) {
+  const int g[3] = {p.valid.lo[0] - p.sbox.lo[0], p.valid.lo[1] - p.sbox.lo[1],
+                    p.valid.lo[2] - p.sbox.lo[2]};
+  const size_t vx = (size_t)p.valid.len(0), vy = (size_t)p.valid.len(1), vz = (size_t)p.valid.len(2);
+  for (int c = 0; c < ctx->ncomp(); ++c) {
+    cudaMemcpy3DParms parms{};
+    double* dev = p.buf[L.cur] + (size_t)p.cells * c;
+    double* hst = host + vx * vy * vz * c;
+    const cudaPitchedPtr dptr =
+        make_cudaPitchedPtr(dev, (size_t)p.n[0] * sizeof(double), (size_t)p.n[0], (size_t)p.n[1]);
+    const cudaPitchedPtr hptr = make_cudaPitchedPtr(hst, vx * sizeof(double), vx, vy);
+    const cudaPos dpos = make_cudaPos((size_t)g[0] * sizeof(double), (size_t)g[1], (size_t)g[2]);
+    const cudaPos hpos = make_cudaPos(0, 0, 0);
+    parms.srcPtr = to_device ? hptr : dptr;
+    parms.srcPos = to_device ? hpos : dpos;
+    parms.dstPtr = to_device ? dptr : hptr;
+    parms.dstPos = to_device ? dpos : hpos;
+    parms.extent = make_cudaExtent(vx * sizeof(double), vy, vz);
+    parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    FVS_CUDA(cudaMemcpy3DAsync(&parms, ctx->stream));
+  }
+}
+} // namespace
+
+int fvs_copy_data_to_scratch_async(fvs_ctx* ctx, int level, int box, const double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    copy_valid(ctx, L, ctx->patch(L, box), const_cast<double*>(host_fab), true);
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_copy_scratch_to_data_async(fvs_ctx* ctx, int level, int box, double* host_fab) {
+  return guarded([&] {
+    if (!ctx || !host_fab) throw Error("null argument");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    copy_valid(ctx, L, ctx->patch(L, box), host_fab, false);
+    return (int)FVS_OK;
+  });
+}
+
 int fvs_synchronize(fvs_ctx* ctx) {
   return guarded([&] {
     if (!ctx) throw Error("null context");

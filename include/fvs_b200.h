@@ -147,6 +147,15 @@ int fvs_flux_box(const fvs_ctx* ctx, int level, int box, int dir, int lo[3],
  * host_fab holds (rank+4) components over fvs_state_box in FAB layout. */
 int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab);
 int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab);
+/* IntegratorContext::CopyDataToScratch / CopyScratchToData
+ * (src/AMReX/IntegratorContext.cpp:629-651): the level data of the patch
+ * hierarchy carries NO ghost cells; host_fab holds (rank+4) components over
+ * the box's valid cells only (FAB layout).  Copying data to scratch leaves the
+ * ghost cells to fvs_fill_ghost_layer (FillMultiFabFromLevel = the same data
+ * plus the ghost fill).  Stream ordered like the *_async calls: page-locked
+ * buffers, valid until fvs_synchronize. */
+int fvs_copy_data_to_scratch_async(fvs_ctx* ctx, int level, int box, const double* host_fab);
+int fvs_copy_scratch_to_data_async(fvs_ctx* ctx, int level, int box, double* host_fab);
 /* Stream-ordered variants for callers that pipeline several contexts (one per
  * batch of boxes): the copy is enqueued on the context's stream and the call
  * returns; host_fab must be page-locked and stay valid until

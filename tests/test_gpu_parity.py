@@ -307,3 +307,27 @@ def test_no_cpu_fallback_symbols(fvs):
     import subprocess
     out = subprocess.run(["nm", "-D", fvs.LIB_PATH], capture_output=True, text=True).stdout
     assert "fvso_" not in out
+
+
+def test_copy_data_to_scratch_and_back(fvs):
+    """CopyDataToScratch / CopyScratchToData: level data without ghost cells."""
+    n = (13, 9, 7)
+    ctx = fvs.Context(3, [0] * 3, [n[0] - 1, n[1] - 1, n[2] - 1], [1.0 / v for v in n],
+                      [([0] * 3, [n[0] - 1, n[1] - 1, n[2] - 1])], scratch_gcw=4, flux_gcw=2,
+                      periodic=(1, 1, 1))
+    rng = np.random.default_rng(3)
+    data = rng.random(ctx.data_shape(0)) + 1.0
+    ctx.upload_state(0, np.zeros(ctx.state_shape(0)))
+    ctx.copy_data_to_scratch_async(0, data)
+    ctx.synchronize()
+    full = ctx.download_state(0)
+    assert_bitwise_equal(full[:, 4:-4, 4:-4, 4:-4], data, "valid cells")
+    assert not full[:, :4].any() and not full[:, :, :, -4:].any()
+    ctx.fill_ghost_layer()  # periodic images
+    full = ctx.download_state(0)
+    assert_bitwise_equal(full[:, 4:-4, 4:-4, 0:4], data[:, :, :, -4:], "periodic ghost cells")
+    back = np.empty_like(data)
+    ctx.copy_scratch_to_data_async(0, back)
+    ctx.synchronize()
+    assert_bitwise_equal(back, data, "scratch to data")
+    ctx.close()
