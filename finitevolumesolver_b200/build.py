@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-fmad=false", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
 ]
 
-HEADERS = ["numerics.cuh", "launch.h", "sweep_kernels.cuh", "boxes.hpp",
+HEADERS = ["numerics.cuh", "fastmath.cuh", "launch.h", "sweep_kernels.cuh", "boxes.hpp",
            os.path.join(INCLUDE, "fvs_b200.h")]
 
 
@@ -36,6 +36,13 @@ def _units():
         for b in (0, 1, 2, 3):
             units.append(("sweep_inst.cu", f"sweep_D{d}_B{b}.o",
                           [f"-DFVS_INST_D={d}", f"-DFVS_INST_BASE={b}"]))
+    # the fused sweep once more with the tolerance arithmetic (fvs_set_arithmetic):
+    # the only units with FMA contraction; no build for the exact Riemann solver
+    for d in (1, 2, 3):
+        for b in (0, 1, 2):
+            units.append(("sweep_inst.cu", f"sweep_tol_D{d}_B{b}.o",
+                          [f"-DFVS_INST_D={d}", f"-DFVS_INST_BASE={b}", "-DFVS_TOLERANCE_UNIT=1",
+                           "-fmad=true"]))
     units.append(("generic_kernels.cu", "generic_kernels.o", []))
     units.append(("cutcell.cu", "cutcell.o", []))
     units.append(("amr.cu", "amr.o", []))
@@ -58,7 +65,8 @@ def _compile(unit, force, verbose, extra):
     if (not force and os.path.exists(obj_p)
             and os.path.getmtime(obj_p) > max(os.path.getmtime(src_p), _newest_header())):
         return obj_p, ""
-    cmd = [NVCC] + NVCC_FLAGS + extra + defs + ["-I", INCLUDE, "-c", src_p, "-o", obj_p]
+    flags = [f for f in NVCC_FLAGS if not (f == "-fmad=false" and "-fmad=true" in defs)]
+    cmd = [NVCC] + flags + extra + defs + ["-I", INCLUDE, "-c", src_p, "-o", obj_p]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

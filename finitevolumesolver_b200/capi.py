@@ -22,6 +22,7 @@ SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
 OK, ERROR, TIME_STEP_TOO_LARGE = 0, -1, 1
 FAB_COVERED, FAB_REGULAR, FAB_SINGLEVALUED = -1, 0, 1
 RIEMANN_HLL_EINFELDT, RIEMANN_EXACT = 0, 1
+ARITH_IEEE, ARITH_TOLERANCE = 0, 1
 (EB_ALPHA, EB_BETA, EB_BCENT, EB_BNORM, EB_US, EB_SL, EB_SR, EB_DS, EB_REFERENCE,
  EB_BOUNDARY_FLUX, EB_STABILIZED, EB_SHIELDED_LEFT, EB_SHIELDED_RIGHT) = range(13)
 UNIQUE_ID_BYTES = 128
@@ -29,7 +30,7 @@ UNIQUE_ID_BYTES = 128
 # every symbol include/fvs_b200.h declares
 SYMBOLS = [
     "fvs_last_error", "fvs_version", "fvs_device_count", "fvs_create", "fvs_destroy",
-    "fvs_set_method", "fvs_stencil_width", "fvs_level_define", "fvs_level_add_boundary",
+    "fvs_set_method", "fvs_set_arithmetic", "fvs_stencil_width", "fvs_level_define", "fvs_level_add_boundary",
     "fvs_state_box", "fvs_flux_box", "fvs_upload_state", "fvs_download_state",
     "fvs_upload_fluxes", "fvs_download_fluxes", "fvs_state_device_ptr",
     "fvs_compute_stable_dt", "fvs_compute_numeric_fluxes", "fvs_update_conservatively",
@@ -248,6 +249,9 @@ class Context:
 
     def set_method(self, base, recon, limiter):
         _check(lib().fvs_set_method(self.h, base, recon, limiter))
+
+    def set_arithmetic(self, arithmetic):
+        _check(lib().fvs_set_arithmetic(self.h, arithmetic))
 
     def add_bc(self, direction, side, kind):
         _check(lib().fvs_level_add_boundary(self.h, self.level, direction, side, kind))

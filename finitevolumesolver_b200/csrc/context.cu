@@ -223,6 +223,7 @@ struct fvs_ctx {
   double time_point{0.0};
   int regrid_frequency{1};
   int cutcell_riemann{FVS_RIEMANN_HLL_EINFELDT};
+  int arithmetic{FVS_ARITH_IEEE};
   int ratio[3]{2, 2, 2};
   // stable-dt accumulators
   unsigned long long* d_slots{nullptr};
@@ -497,7 +498,9 @@ int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out) {
   fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot);
   if (!L.patches.empty()) {
     EventTimer t(ctx);
-    const int rc = fvs::launch_fused_sweep(ctx->method, dir, A, ctx->stream);
+    const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
+                       ? fvs::launch_fused_sweep_tolerance(ctx->method, dir, A, ctx->stream)
+                       : fvs::launch_fused_sweep(ctx->method, dir, A, ctx->stream);
     check_launch(rc);
     ctx->launches += rc;
     t.stop();
@@ -1508,6 +1511,9 @@ int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limite
       throw Error("MusclHancockPrim / MusclHancockChar are defined over HLLEM (Larrouturou) only");
     }
     if (limiter < 0 || limiter > 2) throw Error("unknown limiter");
+    if (ctx->arithmetic == FVS_ARITH_TOLERANCE && base_method == FVS_BASE_GODUNOV_EXACT) {
+      throw Error("the exact Riemann solver has no tolerance-arithmetic build");
+    }
     const int w = reconstruction == FVS_RECON_FIRST_ORDER ? 1 : 2;
     for (Level& L : ctx->levels) {
       if (L.defined && L.scratch_gcw < L.flux_gcw + w) {
@@ -1515,6 +1521,20 @@ int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limite
       }
     }
     ctx->method = fvs::MethodKey{ctx->cfg.rank, base_method, reconstruction, limiter};
+    return (int)FVS_OK;
+  });
+}
+
+int fvs_set_arithmetic(fvs_ctx* ctx, int arithmetic) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (arithmetic != FVS_ARITH_IEEE && arithmetic != FVS_ARITH_TOLERANCE) {
+      throw Error("unknown arithmetic");
+    }
+    if (arithmetic == FVS_ARITH_TOLERANCE && ctx->method.base == FVS_BASE_GODUNOV_EXACT) {
+      throw Error("the exact Riemann solver has no tolerance-arithmetic build");
+    }
+    ctx->arithmetic = arithmetic;
     return (int)FVS_OK;
   });
 }

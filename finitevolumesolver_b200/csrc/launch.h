@@ -51,6 +51,8 @@ using SweepLauncher = int (*)(const MethodKey&, int dir, const SweepArgs&, cudaS
 
 // fused: stable dt + numeric flux + conservative update + complete, src -> dst
 int launch_fused_sweep(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
+// the same with the tolerance arithmetic (fvs_set_arithmetic); -1 for the exact Riemann solver
+int launch_fused_sweep_tolerance(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
 // unfused policies (operate on src in place, fluxes through BoxDesc::flux)
 int launch_stable_dt(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);
 int launch_numeric_fluxes(const MethodKey&, int dir, const SweepArgs&, cudaStream_t);

@@ -1035,7 +1035,11 @@ FVS_DEV double base_max_signal(const Eqs& eq, const DtData<D, BASE>& left,
 template <typename F> FVS_DEV void with_fallback(F&& f) {
 #if FVS_FASTMATH
   Flag fl;
+#if FVS_FASTMATH == 2
+  f(ToleranceMath{}, fl);
+#else
   f(FastMath{}, fl);
+#endif
   if (fl.any()) {
     Flag unused;
     f(SafeMath{}, unused);

@@ -2,6 +2,18 @@
 // dimension (FVS_INST_D) and ONE base method (FVS_INST_BASE); compiled twelve
 // times by the build (3 dimensions x 4 base methods) so the translation
 // units build in parallel.
+//
+// FVS_TOLERANCE_UNIT: the same fused-sweep kernels built a second time with the
+// tolerance arithmetic (fastmath.cuh ToleranceMath, FMA contraction on) for
+// contexts that opted in with fvs_set_arithmetic(FVS_ARITH_TOLERANCE).  The
+// whole header stack is compiled into namespace fvs_tol so the two builds of
+// the templates never meet at link time; only the fused launcher is exported,
+// through plain pointers (the descriptors are the same PODs in both
+// namespaces).
+#ifdef FVS_TOLERANCE_UNIT
+#define FVS_FASTMATH 2
+#define fvs fvs_tol
+#endif
 #include "sweep_kernels.cuh"
 
 #ifndef FVS_SWEEP_SMEM
@@ -49,6 +61,7 @@ int fused(const SweepArgs& A, cudaStream_t s) {
   return 1;
 }
 
+#ifndef FVS_TOLERANCE_UNIT
 template <int DIR, int RECON, int LIM>
 int fluxes(const SweepArgs& A, cudaStream_t s) {
   long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
@@ -84,6 +97,8 @@ int cc_stable_dt(const SweepArgs& A, cudaStream_t s) {
   cc_stable_dt_kernel<D, DIR, BASE><<<grid, 256, 0, s>>>(A);
   return 1;
 }
+
+#endif // !FVS_TOLERANCE_UNIT
 
 template <int DIR, typename F0, typename F1, typename F2, typename F3, typename F4, typename F5>
 int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim, F5 chr) {
@@ -121,6 +136,7 @@ template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStr
         }
       });
 }
+#ifndef FVS_TOLERANCE_UNIT
 template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
   return by_recon<DIR>(
       k, [&] { return fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
@@ -169,9 +185,11 @@ template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cud
       });
 }
 
+#endif // !FVS_TOLERANCE_UNIT
+
 } // namespace
 
-#if FVS_INST_D >= 2
+#if FVS_INST_D >= 2 && !defined(FVS_TOLERANCE_UNIT)
 int FVS_FN(launch_cc_numeric_fluxes)(const MethodKey& k, int dir, const SweepArgs& A,
                                      cudaStream_t s) {
   if (dir == 0) return cc_fluxes_dir<0>(k, A, s);
@@ -203,6 +221,7 @@ int FVS_FN(launch_fused_sweep)(const MethodKey& k, int dir, const SweepArgs& A,
   return -1;
 }
 
+#ifndef FVS_TOLERANCE_UNIT
 int FVS_FN(launch_numeric_fluxes)(const MethodKey& k, int dir, const SweepArgs& A,
                                   cudaStream_t s) {
   if (dir == 0) return fluxes_dir<0>(k, A, s);
@@ -232,5 +251,17 @@ int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStrea
   stable_dt_all_kernel<D, BASE><<<grid, 256, 0, s>>>(A);
   return 1;
 }
+#endif // !FVS_TOLERANCE_UNIT
 
 } // namespace fvs
+
+#ifdef FVS_TOLERANCE_UNIT
+#undef fvs
+namespace fvs {
+// called by launch_fused_sweep_tolerance (generic_kernels.cu)
+int FVS_FN(launch_fused_sweep_tol)(const void* key, int dir, const void* args, cudaStream_t s) {
+  return fvs_tol::FVS_FN(launch_fused_sweep)(*static_cast<const fvs_tol::MethodKey*>(key), dir,
+                                             *static_cast<const fvs_tol::SweepArgs*>(args), s);
+}
+} // namespace fvs
+#endif

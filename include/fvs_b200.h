@@ -82,6 +82,18 @@ enum {
   FVS_EB_SHIELDED_RIGHT_FLUXES = 12
 };
 
+/* Arithmetic of the fused sweep (fvs_set_arithmetic).
+ * FVS_ARITH_IEEE (default): every fp64 operation correctly rounded, no FMA
+ *   contraction, operation order of the reference's array code path -- results
+ *   are bit-identical to the CPU restatement of the reference.
+ * FVS_ARITH_TOLERANCE: quotients as a * (1 / b) with a reciprocal refined to
+ *   below one ulp, uncorrected square-root refinement, FMA contraction (what
+ *   `g++ -O3 -march=native` does to the reference too): each operation within
+ *   ~2 ulp of IEEE, conserved variables within 1e-12 relative L-inf per step of
+ *   the reference (BASELINE.json north_star), the dt sequence equal to that
+ *   relative accuracy rather than bit for bit. */
+enum { FVS_ARITH_IEEE = 0, FVS_ARITH_TOLERANCE = 1 };
+
 /* status codes */
 enum {
   FVS_OK = 0,
@@ -116,6 +128,11 @@ void fvs_destroy(fvs_ctx* ctx);
 /* Change the numerical method of an existing context (HyperbolicMethod is a
  * value that can be swapped, include/fub/HyperbolicMethod.hpp:155-159). */
 int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limiter);
+/* Select the arithmetic of the fused sweep (fvs_sweep, fvs_advance_hierarchy on
+ * levels without flux registers / cut cells); all other entry points always
+ * compute in FVS_ARITH_IEEE.  No counterpart in the reference (its arithmetic
+ * is fixed by the compiler flags of the build, CMakeLists.txt). */
+int fvs_set_arithmetic(fvs_ctx* ctx, int arithmetic);
 /* FluxMethod::GetStencilWidth(), README.md:882-892 */
 int fvs_stencil_width(const fvs_ctx* ctx);
 

@@ -3,7 +3,7 @@
 # body) of the 3-D MUSCL-Hancock<HLLEM-L, VanLeer> z-sweep kernel for a given
 # set of -D flags:  tools/count_steady.sh [-DNAME=VALUE ...]
 cd "$(dirname "$0")/../finitevolumesolver_b200/csrc"
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -ccbin /usr/bin/g++ -I ../../include -DFVS_INST_D=3 -DFVS_INST_BASE=0 "$@" -c sweep_inst.cu -o /tmp/cs.o 2>/dev/null || exit 1
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=${FMAD:-false} -ccbin /usr/bin/g++ -I ../../include -DFVS_INST_D=3 -DFVS_INST_BASE=0 "$@" -c sweep_inst.cu -o /tmp/cs.o 2>/dev/null || exit 1
 for fn in _ZN3fvs26fused_sweep_yz_smem_kernelILi3ELi2ELi0ELi1ELi2EEEvNS_9SweepArgsE _ZN3fvs25fused_sweep_x_smem_kernelILi3ELi0ELi1ELi2EEEvNS_9SweepArgsE; do
 cuobjdump -sass -fun $fn /tmp/cs.o | grep -E '^\s+/\*[0-9a-f]{4,5}\*/' > /tmp/cs.sass
 python3 - <<'PY'
