@@ -177,7 +177,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512, help="cells per box edge (one box per GPU)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=24,
+                    help="independent batches timed end to end; the three-stage pipeline needs "
+                         "about two batches to fill and drain, so few batches understate its rate")
     ap.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
                     help="one context, upload / step / download strictly in sequence")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -402,7 +404,7 @@ def main():
         for c in pipe:
             c.synchronize()
 
-    run_e2e(min(n_pipe, 2))                                  # warm the extra contexts up
+    run_e2e(n_pipe)                                          # every context once: buffers allocated
     barrier()
     t0 = time.perf_counter()
     run_e2e(e2e_steps)

@@ -26,6 +26,10 @@ NVCC_FLAGS = [
     "-fmad=false", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
 ]
 
+# launch shape of the tolerance-arithmetic kernels, measured best (profiles/r01_tuning.md):
+# the x sweep holds the next chunk in registers at 3 resident blocks of 128 threads
+TOLERANCE_TUNING = ["-DFVS_SWEEP_XS_PREFETCH=2", "-DFVS_SWEEP_XS_MIN_BLOCKS=3"]
+
 HEADERS = ["numerics.cuh", "fastmath.cuh", "launch.h", "sweep_kernels.cuh", "boxes.hpp",
            os.path.join(INCLUDE, "fvs_b200.h")]
 
@@ -42,7 +46,7 @@ def _units():
         for b in (0, 1, 2):
             units.append(("sweep_inst.cu", f"sweep_tol_D{d}_B{b}.o",
                           [f"-DFVS_INST_D={d}", f"-DFVS_INST_BASE={b}", "-DFVS_TOLERANCE_UNIT=1",
-                           "-fmad=true"]))
+                           "-fmad=true"] + TOLERANCE_TUNING))
     units.append(("generic_kernels.cu", "generic_kernels.o", []))
     units.append(("cutcell.cu", "cutcell.o", []))
     units.append(("amr.cu", "amr.o", []))

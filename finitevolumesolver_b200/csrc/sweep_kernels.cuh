@@ -172,6 +172,12 @@ FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtDa
 #ifndef FVS_SWEEP_UNROLL
 #define FVS_SWEEP_UNROLL 1
 #endif
+// tuning builds may cap the registers directly instead of through the resident-block count
+#ifdef FVS_SWEEP_MAXNREG
+#define FVS_SWEEP_BOUNDS __maxnreg__(FVS_SWEEP_MAXNREG)
+#else
+#define FVS_SWEEP_BOUNDS __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
+#endif
 constexpr int kSweepThreads = FVS_SWEEP_THREADS;
 constexpr int kSweepUnroll = FVS_SWEEP_UNROLL;
 
@@ -348,7 +354,7 @@ template <typename T> struct Slot<T, false> {
 #endif
 
 template <int D, int DIR, int BASE, int RECON, int LIM>
-__global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_MIN_BLOCKS)
+__global__ void FVS_SWEEP_BOUNDS
 fused_sweep_yz_smem_kernel(const SweepArgs A) {
   static_assert(DIR >= 1 && DIR < D, "y/z sweep");
   // first order needs the stored p and a of the neighbour, MUSCL only its
@@ -578,13 +584,24 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
+#if FVS_SWEEP_XS_PREFETCH == 2
+    // the next chunk's cell is loaded into registers one chunk ahead
+    Complete<D> qn;
+    load_complete<D>(qn, src + min(max(o_first - 2 + lane, 0), n0 - 1), sc);
+#endif
     for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
       const int c = c0 + lane;
       const int cl = min(max(c, 0), n0 - 1);
       // ---- load: cell c, its dt data
       Complete<D> q0;
+#if FVS_SWEEP_XS_PREFETCH == 2
+      q0 = qn;
+      (void)cl;
+      if (c0 + 32 - 2 <= o_last) load_complete<D>(qn, src + min(c + 32, n0 - 1), sc);
+#else
       load_complete<D>(q0, src + cl, sc);
-#if FVS_SWEEP_XS_PREFETCH
+#endif
+#if FVS_SWEEP_XS_PREFETCH == 1
       if (c0 + 32 - 2 <= o_last) prefetch_complete<D>(src + min(c + 32, n0 - 1), sc);
 #endif
       DtData<D, BASE> dt_cur;

@@ -178,6 +178,10 @@ public:
                                  static_cast<int>(kind)));
   }
 
+  /// Arithmetic of the fused sweep: FVS_ARITH_IEEE (default, bit-identical to the
+  /// reference's array code path) or FVS_ARITH_TOLERANCE (within 1e-12 per step).
+  void SetArithmetic(int arithmetic) { Check(fvs_set_arithmetic(Handle(), arithmetic)); }
+
   int Rank() const { return rank_; }
   int NumBoxes() const { return nboxes_; }
   double GetDx(int /*level*/, Direction dir) const { return dx_[static_cast<int>(dir)]; }

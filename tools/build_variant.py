@@ -13,18 +13,12 @@ sys.path.insert(0, ROOT)
 from finitevolumesolver_b200 import build as b  # noqa: E402
 
 
-def main():
-    tag, flags = sys.argv[1], sys.argv[2:]
-    tol = "--tol" in flags  # vary the tolerance-arithmetic unit instead of the IEEE one
-    flags = [f for f in flags if f != "--tol"]
-    b.build()
-    obj = os.path.join(b.OBJ, f"variant_{tag}.o")
+def compile_unit(tag, flags, tol):
+    obj = os.path.join(b.OBJ, f"variant_{tag}_{'tol' if tol else 'ieee'}.o")
     base_flags = list(b.NVCC_FLAGS)
-    replaced = "sweep_D3_B0.o"
     if tol:
         base_flags = [f for f in base_flags if f != "-fmad=false"] + ["-fmad=true",
                                                                       "-DFVS_TOLERANCE_UNIT=1"]
-        replaced = "sweep_tol_D3_B0.o"
     cmd = [b.NVCC] + base_flags + flags + ["-DFVS_INST_D=3", "-DFVS_INST_BASE=0", "-Xptxas", "-v",
            "-I", b.INCLUDE, "-c", os.path.join(b.CSRC, "sweep_inst.cu"), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -33,8 +27,21 @@ def main():
     lines = r.stderr.splitlines()
     for i, l in enumerate(lines):
         if "fused_sweep" in l and "ELi1ELi2E" in l and "Function properties" in l:
-            print(tag, l.split()[-1][:48], "|", lines[i + 1].strip(), "|", lines[i + 2].strip())
-    objs = [os.path.join(b.OBJ, u[1]) for u in b._units() if u[1] != replaced] + [obj]
+            print(tag, "tol " if tol else "ieee", l.split()[-1][:48], "|", lines[i + 1].strip(), "|",
+                  lines[i + 2].strip())
+    return obj
+
+
+def main():
+    # --tol: vary the tolerance-arithmetic unit, --both: both units, default: the IEEE unit
+    tag, flags = sys.argv[1], sys.argv[2:]
+    which = [True] if "--tol" in flags else [False, True] if "--both" in flags else [False]
+    flags = [f for f in flags if f not in ("--tol", "--both")]
+    b.build()
+    replaced = {True: "sweep_tol_D3_B0.o", False: "sweep_D3_B0.o"}
+    objs = [os.path.join(b.OBJ, u[1]) for u in b._units()
+            if u[1] not in [replaced[w] for w in which]]
+    objs += [compile_unit(tag, flags, w) for w in which]
     lib = os.path.join(b.HERE, f"libfvs_b200_{tag}.so")
     subprocess.check_call([b.NVCC, "-shared", "-o", lib, "-ccbin", "/usr/bin/g++"] + objs + ["-ldl"])
     print(lib)
