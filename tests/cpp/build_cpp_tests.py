@@ -29,5 +29,22 @@ def build(force=False):
     return out
 
 
+def build_fastmath_check(force=False):
+    """tests/cuda/fastmath_check: FastMath vs the IEEE operators bit for bit,
+    ToleranceMath's error bound (nvcc cross-compiles without a GPU)."""
+    cuda = os.path.join(os.path.dirname(HERE), "cuda")
+    out = os.path.join(cuda, "fastmath_check")
+    src = os.path.join(cuda, "fastmath_check.cu")
+    deps = [src, os.path.join(PKG, "csrc", "fastmath.cuh")]
+    if (not force and os.path.exists(out)
+            and os.path.getmtime(out) > max(os.path.getmtime(d) for d in deps)):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
+                           "-fmad=false", "-ccbin", CXX, "-o", out, src])
+    return out
+
+
 if __name__ == "__main__":
+    print(build_fastmath_check(force=True))
     print(build(force=True))

@@ -1,6 +1,8 @@
 // Compares FastMath::div / FastMath::sqrt (finitevolumesolver_b200/csrc/fastmath.cuh)
 // bit for bit against the IEEE operators on random and edge-case operands.
-// Usage: fastmath_check [n_blocks]   prints "mismatch_div M mismatch_sqrt M flagged_div F flagged_sqrt F tested N"
+// ToleranceMath (the opt-in arithmetic) is checked for its error bound instead: the largest error
+// of its quotients / square roots in ulps of the IEEE result over moderate operands.
+// Usage: fastmath_check [n_blocks]   prints "mismatch_div M mismatch_sqrt M flagged_div F flagged_sqrt F tested N tol_div_ulp U tol_sqrt_ulp U"
 #include <cstdio>
 #include <cstdlib>
 #include "../../finitevolumesolver_b200/csrc/fastmath.cuh"
@@ -25,9 +27,16 @@ __device__ double draw(unsigned long long& s, int mode) {
   return __longlong_as_double((long long)(sign | ((unsigned long long)e << 52) | mant));
 }
 
+__device__ unsigned long long ulp_distance(double got, double ref) {
+  const long long a = __double_as_longlong(got), b = __double_as_longlong(ref);
+  if ((a < 0) != (b < 0)) return ~0ull;
+  return (unsigned long long)(a > b ? a - b : b - a);
+}
+
 __global__ void check(unsigned long long seed, int iters, unsigned long long* out) {
   unsigned long long s = seed + 0x1234567ull * (blockIdx.x * blockDim.x + threadIdx.x);
   unsigned long long bad_div = 0, bad_sqrt = 0, fl_div = 0, fl_sqrt = 0, n = 0;
+  unsigned long long tol_div = 0, tol_sqrt = 0;
   const double specials[12] = {0.0, -0.0, 1.0, -1.0, 2.2250738585072014e-308, 4.9e-324,
                                1.7976931348623157e308, 1e-300, 1e300, 0.5, 3.0,
                                __longlong_as_double(0x7ff0000000000000ll)};
@@ -67,8 +76,22 @@ __global__ void check(unsigned long long seed, int iters, unsigned long long* ou
     } else {
       fl_sqrt++;
     }
+    if (mode != 0 && (it & 63) != 0 && (it & 127) != 1) {
+      // moderate operands: inside the domain, no over- / underflow
+      Flag t;
+      const Rcp rt = ToleranceMath::rcp(b);
+      ToleranceMath::check(rt, t);
+      const unsigned long long ud = ulp_distance(ToleranceMath::div(a, rt, t), r1);
+      const unsigned long long us = ulp_distance(ToleranceMath::sqrt(x, t), sr);
+      if (!t.bad) {
+        tol_div = ud > tol_div ? ud : tol_div;
+        tol_sqrt = us > tol_sqrt ? us : tol_sqrt;
+      }
+    }
     n++;
   }
+  atomicMax(out + 5, tol_div);
+  atomicMax(out + 6, tol_sqrt);
   atomicAdd(out + 0, bad_div);
   atomicAdd(out + 1, bad_sqrt);
   atomicAdd(out + 2, fl_div);
@@ -79,15 +102,16 @@ __global__ void check(unsigned long long seed, int iters, unsigned long long* ou
 int main(int argc, char** argv) {
   const int blocks = argc > 1 ? atoi(argv[1]) : 148 * 8;
   unsigned long long* d;
-  cudaMalloc(&d, 5 * sizeof(unsigned long long));
-  cudaMemset(d, 0, 5 * sizeof(unsigned long long));
+  cudaMalloc(&d, 7 * sizeof(unsigned long long));
+  cudaMemset(d, 0, 7 * sizeof(unsigned long long));
   check<<<blocks, 256>>>(42ull, 20000, d);
-  unsigned long long h[5];
+  unsigned long long h[7];
   if (cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
     printf("cuda error\n");
     return 2;
   }
-  printf("mismatch_div %llu mismatch_sqrt %llu flagged_div %llu flagged_sqrt %llu tested %llu\n",
-         h[0], h[1], h[2], h[3], h[4]);
-  return (h[0] || h[1]) ? 1 : 0;
+  printf("mismatch_div %llu mismatch_sqrt %llu flagged_div %llu flagged_sqrt %llu tested %llu "
+         "tol_div_ulp %llu tol_sqrt_ulp %llu\n",
+         h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+  return (h[0] || h[1] || h[5] > 2 || h[6] > 2) ? 1 : 0;
 }
