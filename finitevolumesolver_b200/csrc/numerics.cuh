@@ -454,6 +454,10 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
     uL[i] = vL_[i];
     uR[i] = vR_[i];
   }
+  // Tolerance arithmetic with the Larrouturou modification: the tangential
+  // momenta, velocities, Roe velocities and momentum jumps are zero, so every
+  // term they enter is dropped instead of being evaluated to a signed zero.
+  constexpr bool kDropTangential = LARROUTUROU && !M::kExact;
   if constexpr (LARROUTUROU) {
     // :729-745 -- tangential momenta are multiplied by 0.0 (keeps their sign
     // bit) and their kinetic energy is taken out of E.
@@ -462,10 +466,17 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
       if (i != DIR) {
         eKinRL += vL_[i] * vL_[i];
         eKinRR += vR_[i] * vR_[i];
-        left.mom[i] *= 0.0;
-        right.mom[i] *= 0.0;
-        uL[i] = M::div_zero(left.mom[i], rcL); // (+-0) / rho, :774-775
-        uR[i] = M::div_zero(right.mom[i], rcR);
+        if constexpr (kDropTangential) {
+          left.mom[i] = 0.0;
+          right.mom[i] = 0.0;
+          uL[i] = 0.0;
+          uR[i] = 0.0;
+        } else {
+          left.mom[i] *= 0.0;
+          right.mom[i] *= 0.0;
+          uL[i] = M::div_zero(left.mom[i], rcL); // (+-0) / rho, :774-775
+          uR[i] = M::div_zero(right.mom[i], rcR);
+        }
       }
     }
     eKinRL *= 0.5;
@@ -495,14 +506,30 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   const double sqRhoR_over_Sum = M::div(sqRhoR, rcSum, fl);
   double roeU[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) roeU[i] = sqRhoL_over_Sum * uL[i] + sqRhoR_over_Sum * uR[i];
+  for (int i = 0; i < D; ++i) {
+    if (kDropTangential && i != DIR) {
+      roeU[i] = 0.0;
+    } else {
+      roeU[i] = sqRhoL_over_Sum * uL[i] + sqRhoR_over_Sum * uR[i];
+    }
+  }
   const double roeH = sqRhoL_over_Sum * hL + sqRhoR_over_Sum * hR;
   double squaredNormRoeU = 0.0;
+  if constexpr (kDropTangential) {
+    squaredNormRoeU = roeU[DIR] * roeU[DIR];
+  } else {
 #pragma unroll
-  for (int i = 0; i < D; ++i) squaredNormRoeU += roeU[i] * roeU[i];
+    for (int i = 0; i < D; ++i) squaredNormRoeU += roeU[i] * roeU[i];
+  }
   const double squaredNormRoeU_half = 0.5 * squaredNormRoeU;
-  const double roeGamma = M::div(sqRhoL * eq.gamma + sqRhoR * eq.gamma, rcSum, fl);
-  const double gm1 = roeGamma - 1.0;
+  // (sqrt(rhoL) gamma + sqrt(rhoR) gamma) / (sqrt(rhoL) + sqrt(rhoR)) is gamma up to rounding
+  double gm1;
+  if constexpr (M::kExact) {
+    const double roeGamma = M::div(sqRhoL * eq.gamma + sqRhoR * eq.gamma, rcSum, fl);
+    gm1 = roeGamma - 1.0;
+  } else {
+    gm1 = eq.gamma_minus_1;
+  }
   const double roeA2 = gm1 * (roeH - squaredNormRoeU_half);
   const double roeA = M::sqrt(roeA2, fl);
   const double maxA = vmax(aL, aR);
@@ -564,11 +591,15 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
     // :892-923
     constexpr int ix = DIR;
     constexpr int iy = (ix == 0) ? 1 : 0;
-    const double l22 = gm1_over_roeA2 * roeU[0];
-    const double l23 = gm1_over_roeA2 * roeU[1];
     const double l24 = -gm1_over_roeA2;
-    const double alpha_2 =
-        l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] + l24 * deltaRhoE;
+    double alpha_2;
+    if constexpr (kDropTangential) {
+      alpha_2 = l21 * deltaRho + (gm1_over_roeA2 * roeU[ix]) * deltaRhoU[ix] + l24 * deltaRhoE;
+    } else {
+      const double l22 = gm1_over_roeA2 * roeU[0];
+      const double l23 = gm1_over_roeA2 * roeU[1];
+      alpha_2 = l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] + l24 * deltaRhoE;
+    }
     const double b_delta = b * delta;
     const double b_delta_alpha_2 = b_delta * alpha_2;
     flux.rho = hlle.rho - b_delta_alpha_2;
@@ -590,17 +621,27 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
     constexpr int ix = DIR;
     constexpr int iy = (ix + 1) % 3;
     constexpr int iz = (iy + 1) % 3;
-    const double l22 = gm1_over_roeA2 * roeU[0];
-    const double l23 = gm1_over_roeA2 * roeU[1];
-    const double l24 = gm1_over_roeA2 * roeU[2];
     const double l25 = -gm1_over_roeA2;
-    const double alpha_2 = l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] +
-                           l24 * deltaRhoU[2] + l25 * deltaRhoE;
+    double alpha_2;
+    if constexpr (kDropTangential) {
+      alpha_2 = l21 * deltaRho + (gm1_over_roeA2 * roeU[ix]) * deltaRhoU[ix] + l25 * deltaRhoE;
+    } else {
+      const double l22 = gm1_over_roeA2 * roeU[0];
+      const double l23 = gm1_over_roeA2 * roeU[1];
+      const double l24 = gm1_over_roeA2 * roeU[2];
+      alpha_2 = l21 * deltaRho + l22 * deltaRhoU[0] + l23 * deltaRhoU[1] + l24 * deltaRhoU[2] +
+                l25 * deltaRhoE;
+    }
     const double b_delta = b * delta;
     const double b_delta_alpha_2 = b_delta * alpha_2;
     flux.rho = hlle.rho - b_delta_alpha_2;
     // :991-992 uses roeU.row(iy), not row(ix): reference behaviour, reproduced
-    flux.mom[ix] = hlle.mom[ix] - b_delta_alpha_2 * roeU[iy];
+    // (with the Larrouturou modification roeU[iy] is zero)
+    if constexpr (kDropTangential) {
+      flux.mom[ix] = hlle.mom[ix];
+    } else {
+      flux.mom[ix] = hlle.mom[ix] - b_delta_alpha_2 * roeU[iy];
+    }
     if constexpr (LARROUTUROU) {
       const bool upwind = flux.rho > 0.0;
       flux.mom[iy] = flux.rho * (upwind ? vL_[iy] : vR_[iy]);
