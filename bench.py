@@ -429,13 +429,15 @@ def main():
         try:
             tj = json.load(open(tpath))
             if tj.get("size") == args.size and len(my_boxes) == 1:
-                traffic = tj.get("fused_sweep_bytes_per_launch")
+                traffic = tj.get("fused_sweep_bytes_per_launch" if args.arithmetic == "ieee"
+                                 else "fused_sweep_bytes_per_launch_tolerance")
         except Exception:
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
-        "kernel": "fused_sweep_x_kernel / fused_sweep_yz_smem_kernel<3,*,HLLEM-L,MUSCL,VanLeer>",
+        "kernel": ("fvs::" if args.arithmetic == "ieee" else "fvs_tol::") +
+                  "fused_sweep_x_smem_kernel / fused_sweep_yz_smem_kernel<3,*,HLLEM-L,MUSCL,VanLeer>",
         "avg_launch_ms": 1e3 * avg_sweep_s, "launches_timed": n_sweeps,
         "share_of_step": sweep_ms / elapsed_ms if elapsed_ms else None,
         "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
