@@ -467,8 +467,9 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
-                "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
+        # whole job: every rank moves its own boxes (one 512^3 box per rank)
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state * max(world, 1),
+                "d2h_bytes_per_step": bytes_state * max(world, 1), "steps": e2e_steps,
                 "pipeline": f"{n_pipe} context(s); every step is an independent batch "
                             "(pinned level data = valid cells in, ghost fill + dt pass + 6 sweeps on the "
                             "device, level data out: CopyDataToScratch / CopyScratchToData); "
