@@ -2009,7 +2009,9 @@ int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
     A.max_signal = ctx->d_slots + slot;
     A.fail_flag = ctx->d_fail;
     if (!L.patches.empty()) {
-      const int rc = fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
+      const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
+                         ? fvs::launch_stable_dt_all_tolerance(ctx->method, A, ctx->stream)
+                         : fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
       check_launch(rc);
       ctx->launches += rc;
     }

@@ -42,7 +42,8 @@ int launch_fused_sweep(const MethodKey& k, int dir, const SweepArgs& A, cudaStre
 // tolerance-arithmetic build of the fused sweep (sweep_inst.cu, FVS_TOLERANCE_UNIT);
 // the exact Riemann solver (libm pow, Newton) has no such build
 #define FVS_DECL_TOL(D, B)                                                                    \
-  int launch_fused_sweep_tol_D##D##_##B(const void*, int, const void*, cudaStream_t);
+  int launch_fused_sweep_tol_D##D##_##B(const void*, int, const void*, cudaStream_t);         \
+  int launch_stable_dt_all_tol_D##D##_##B(const void*, const void*, cudaStream_t);
 #define FVS_DECL_TOL_D(D) FVS_DECL_TOL(D, 0) FVS_DECL_TOL(D, 1) FVS_DECL_TOL(D, 2)
 FVS_DECL_TOL_D(1)
 FVS_DECL_TOL_D(2)
@@ -53,6 +54,14 @@ int launch_fused_sweep_tolerance(const MethodKey& k, int dir, const SweepArgs& A
   FVS_CASE_TOL(1, 0) FVS_CASE_TOL(1, 1) FVS_CASE_TOL(1, 2)
   FVS_CASE_TOL(2, 0) FVS_CASE_TOL(2, 1) FVS_CASE_TOL(2, 2)
   FVS_CASE_TOL(3, 0) FVS_CASE_TOL(3, 1) FVS_CASE_TOL(3, 2)
+  return -1;
+}
+int launch_stable_dt_all_tolerance(const MethodKey& k, const DtAllArgs& A, cudaStream_t s) {
+#define FVS_CASE_TOL_DT(D, B)                                                                 \
+  if (k.rank == D && k.base == B) return launch_stable_dt_all_tol_D##D##_##B(&k, &A, s);
+  FVS_CASE_TOL_DT(1, 0) FVS_CASE_TOL_DT(1, 1) FVS_CASE_TOL_DT(1, 2)
+  FVS_CASE_TOL_DT(2, 0) FVS_CASE_TOL_DT(2, 1) FVS_CASE_TOL_DT(2, 2)
+  FVS_CASE_TOL_DT(3, 0) FVS_CASE_TOL_DT(3, 1) FVS_CASE_TOL_DT(3, 2)
   return -1;
 }
 int launch_numeric_fluxes(const MethodKey& k, int dir, const SweepArgs& A, cudaStream_t s) {

@@ -68,6 +68,8 @@ struct DtAllArgs {
   int* fail_flag;
 };
 int launch_stable_dt_all(const MethodKey&, const DtAllArgs&, cudaStream_t);
+// the same with the tolerance arithmetic (regular levels of a context that opted in)
+int launch_stable_dt_all_tolerance(const MethodKey&, const DtAllArgs&, cudaStream_t);
 
 // ---- cut cells (embedded boundary) ------------------------------------------
 // masked regular fluxes (KbnCutCellMethod::ComputeRegularFluxes) and the

@@ -245,23 +245,28 @@ int FVS_FN(launch_stable_dt)(const MethodKey&, int dir, const SweepArgs& A, cuda
   return -1;
 }
 
+#endif // !FVS_TOLERANCE_UNIT
+
 int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStream_t s) {
   const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
   dim3 grid(cdiv(total, 256), A.nboxes, 1);
   stable_dt_all_kernel<D, BASE><<<grid, 256, 0, s>>>(A);
   return 1;
 }
-#endif // !FVS_TOLERANCE_UNIT
 
 } // namespace fvs
 
 #ifdef FVS_TOLERANCE_UNIT
 #undef fvs
 namespace fvs {
-// called by launch_fused_sweep_tolerance (generic_kernels.cu)
+// called by launch_fused_sweep_tolerance / launch_stable_dt_all_tolerance (generic_kernels.cu)
 int FVS_FN(launch_fused_sweep_tol)(const void* key, int dir, const void* args, cudaStream_t s) {
   return fvs_tol::FVS_FN(launch_fused_sweep)(*static_cast<const fvs_tol::MethodKey*>(key), dir,
                                              *static_cast<const fvs_tol::SweepArgs*>(args), s);
+}
+int FVS_FN(launch_stable_dt_all_tol)(const void* key, const void* args, cudaStream_t s) {
+  return fvs_tol::FVS_FN(launch_stable_dt_all)(*static_cast<const fvs_tol::MethodKey*>(key),
+                                               *static_cast<const fvs_tol::DtAllArgs*>(args), s);
 }
 } // namespace fvs
 #endif

