@@ -342,7 +342,11 @@ template <typename T> struct Slot<T, false> {
   T v;
   double pad;
 };
+#ifdef FVS_NO_STAGE_BARRIER
+#define FVS_STAGE_BARRIER()
+#else
 #define FVS_STAGE_BARRIER() asm volatile("" ::: "memory")
+#endif
 
 // 0: none, 1: cell j+1 held in registers, 2: prefetch.global.L1 of cell
 // j + FVS_SWEEP_PREFETCH_DIST
