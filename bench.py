@@ -388,14 +388,27 @@ def main():
         for b in my_boxes:
             c.copy_data_to_scratch_async(b, data_in[b].numpy())   # H2D from pinned memory
 
+    trace = os.environ.get("FVS_E2E_TRACE")                  # host time line of every batch (debug)
+    skip_compute = os.environ.get("FVS_E2E_SKIP_COMPUTE")    # transfers only (debug, not a bench value)
+
     def run_e2e(nsteps):
         upload(pipe[0])
+        t_prev = time.perf_counter()
         for k in range(nsteps):
             cur = pipe[k % n_pipe]
             if k + 1 < nsteps and n_pipe > 1:
                 upload(pipe[(k + 1) % n_pipe])               # overlaps cur's compute
-            cur.fill_ghost_layer()
-            step_of(cur)                                     # synchronises cur's stream (dt)
+            if trace:
+                cur.synchronize()
+                t_up = time.perf_counter()
+            if not skip_compute:
+                cur.fill_ghost_layer()
+                step_of(cur)                                 # synchronises cur's stream (dt)
+            if trace and rank == 0:
+                t_now = time.perf_counter()
+                print(f"e2e batch {k}: waited for upload {1e3 * (t_up - t_prev):.1f} ms, "
+                      f"compute {1e3 * (t_now - t_up):.1f} ms", file=sys.stderr)
+                t_prev = t_now
             for b in my_boxes:
                 cur.copy_scratch_to_data_async(b, outs[k % n_pipe][b].numpy())   # D2H of the result
             if n_pipe == 1 and k + 1 < nsteps:

@@ -227,7 +227,9 @@ struct fvs_ctx {
   int ratio[3]{2, 2, 2};
   // stable-dt accumulators
   unsigned long long* d_slots{nullptr};
-  unsigned long long* h_slots{nullptr}; // pinned
+  unsigned long long* h_slots{nullptr}; // pinned, mapped
+  unsigned long long* h_slots_dev{nullptr}; // device address of h_slots
+  int* h_fail_dev{nullptr};                 // device address of h_fail
   int* d_fail{nullptr};
   int* h_fail{nullptr}; // pinned
   int next_slot{0};
@@ -419,6 +421,19 @@ void check_launch(int rc) {
   FVS_CUDA(cudaGetLastError());
 }
 
+// Copies the accumulators and the failure flag into mapped pinned host memory
+// with plain stores from an SM.  A cudaMemcpyAsync would queue behind whatever
+// the device-to-host copy engine is busy with -- a 7.5 GB download of another
+// context in the end-to-end pipeline of bench.py delayed each of these 8-byte
+// read-backs by up to 160 ms.
+__global__ void publish_results_kernel(const unsigned long long* d_slots,
+                                       unsigned long long* h_slots, int count, const int* d_fail,
+                                       int* h_fail) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) h_slots[i] = d_slots[i];
+  if (threadIdx.x == 0) *h_fail = *d_fail;
+  __threadfence_system();
+}
+
 // read `count` accumulators back (max over ranks), one synchronisation
 void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out) {
   if (ctx->comm && ctx->cfg.comm_size > 1) {
@@ -430,11 +445,10 @@ void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out) {
                         ctx->stream),
             "ncclAllReduce(fail flag)");
   }
-  FVS_CUDA(cudaMemcpyAsync(ctx->h_slots + slot, ctx->d_slots + slot,
-                           sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost,
-                           ctx->stream));
-  FVS_CUDA(cudaMemcpyAsync(ctx->h_fail, ctx->d_fail, sizeof(int), cudaMemcpyDeviceToHost,
-                           ctx->stream));
+  publish_results_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_slots + slot, ctx->h_slots_dev + slot,
+                                                    count, ctx->d_fail, ctx->h_fail_dev);
+  FVS_CUDA(cudaGetLastError());
+  ctx->launches += 1;
   FVS_CUDA(cudaStreamSynchronize(ctx->stream));
   if (*ctx->h_fail) {
     FVS_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), ctx->stream));
@@ -1461,10 +1475,13 @@ int fvs_create(const fvs_config* config, fvs_ctx** out) {
     FVS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     FVS_CUDA(cudaMalloc(&ctx->d_slots, sizeof(unsigned long long) * kDtSlots));
     FVS_CUDA(cudaMemset(ctx->d_slots, 0, sizeof(unsigned long long) * kDtSlots));
-    FVS_CUDA(cudaMallocHost(&ctx->h_slots, sizeof(unsigned long long) * kDtSlots));
+    FVS_CUDA(cudaHostAlloc(&ctx->h_slots, sizeof(unsigned long long) * kDtSlots,
+                           cudaHostAllocMapped));
+    FVS_CUDA(cudaHostGetDevicePointer(&ctx->h_slots_dev, ctx->h_slots, 0));
     FVS_CUDA(cudaMalloc(&ctx->d_fail, sizeof(int)));
     FVS_CUDA(cudaMemset(ctx->d_fail, 0, sizeof(int)));
-    FVS_CUDA(cudaMallocHost(&ctx->h_fail, sizeof(int)));
+    FVS_CUDA(cudaHostAlloc(&ctx->h_fail, sizeof(int), cudaHostAllocMapped));
+    FVS_CUDA(cudaHostGetDevicePointer(&ctx->h_fail_dev, ctx->h_fail, 0));
     *ctx->h_fail = 0;
     fvs_ctx* raw = ctx.release();
     *out = raw;
