@@ -249,7 +249,7 @@ int FVS_FN(launch_stable_dt)(const MethodKey&, int dir, const SweepArgs& A, cuda
 
 int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStream_t s) {
   const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
-  dim3 grid(cdiv(total, 256), A.nboxes, 1);
+  dim3 grid(cdiv(total, 256 * kDtAllCellsPerThread), A.nboxes, 1);
   stable_dt_all_kernel<D, BASE><<<grid, 256, 0, s>>>(A);
   return 1;
 }

@@ -757,22 +757,32 @@ __global__ void __launch_bounds__(256) stable_dt_kernel(const SweepArgs A) {
   if (failed) *A.fail_flag = 1;
 }
 
-// stable dt in all directions, one pass (DimensionalSplitLevelIntegrator.hpp:204-219)
+// stable dt in all directions, one pass (DimensionalSplitLevelIntegrator.hpp:204-219).
+// A thread visits kDtAllCellsPerThread cells (block-strided, so a warp still reads
+// consecutive cells) before the three block reductions: with one cell per thread
+// their barriers were 15 % of the kernel's stall samples.
+#ifndef FVS_DT_ALL_CELLS
+#define FVS_DT_ALL_CELLS 4
+#endif
+constexpr int kDtAllCellsPerThread = FVS_DT_ALL_CELLS;
 template <int D, int BASE>
 __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
   const BoxDesc& B = A.boxes[0][blockIdx.y];
   const long long total = (long long)B.n[0] * B.n[1] * B.n[2];
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double maxsig[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) maxsig[d] = 0.0;
   int failed = 0;
-  if (t < total) {
+  const Eqs eq(A.eq);
+#pragma unroll 1
+  for (int k = 0; k < kDtAllCellsPerThread; ++k) {
+    const long long t =
+        ((long long)blockIdx.x * kDtAllCellsPerThread + k) * blockDim.x + threadIdx.x;
+    if (t >= total) break;
     int idx[3];
     idx[0] = (int)(t % B.n[0]);
     idx[1] = (int)((t / B.n[0]) % B.n[1]);
     idx[2] = (int)(t / ((long long)B.n[0] * B.n[1]));
-    const Eqs eq(A.eq);
     Complete<D> l;
     load_complete<D>(l, B.src + t, B.sc);
     DtData<D, BASE> dl, dr;
@@ -782,7 +792,7 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
       load_complete<D>(r, B.src + t + 1, B.sc);
       stage_dt_cell<D, BASE>(dr, r);
       const double s = stage_dt_face<D, 0, BASE>(eq, dl, dr, failed);
-      maxsig[0] = s > 0.0 ? s : 0.0;
+      maxsig[0] = s > maxsig[0] ? s : maxsig[0];
     }
     if constexpr (D >= 2) {
       if (idx[1] + 1 < B.n[1] && A.boxes[1][blockIdx.y].dtmask[idx[1]]) {
@@ -790,7 +800,7 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
         load_complete<D>(r, B.src + t + B.n[0], B.sc);
         stage_dt_cell<D, BASE>(dr, r);
         const double s = stage_dt_face<D, 1, BASE>(eq, dl, dr, failed);
-        maxsig[1] = s > 0.0 ? s : 0.0;
+        maxsig[1] = s > maxsig[1] ? s : maxsig[1];
       }
     }
     if constexpr (D >= 3) {
@@ -799,7 +809,7 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
         load_complete<D>(r, B.src + t + (long long)B.n[0] * B.n[1], B.sc);
         stage_dt_cell<D, BASE>(dr, r);
         const double s = stage_dt_face<D, 2, BASE>(eq, dl, dr, failed);
-        maxsig[2] = s > 0.0 ? s : 0.0;
+        maxsig[2] = s > maxsig[2] ? s : maxsig[2];
       }
     }
   }
