@@ -39,6 +39,7 @@ SYMBOLS = [
     "fvs_run", "fvs_set_regrid_frequency", "fvs_set_cycles", "fvs_cycles", "fvs_time_point",
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
+    "fvs_set_dt_hints", "fvs_dt_hint_redos",
     "fvs_enable_timing", "fvs_sweep_time_ms",
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
     "fvs_eb_array_box", "fvs_download_eb_array", "fvs_cut_cell_flags",
@@ -81,6 +82,7 @@ def lib():
         L.fvs_run.restype = C.c_long
         L.fvs_halo_plan.restype = C.c_long
         L.fvs_kernel_launches.restype = C.c_long
+        L.fvs_dt_hint_redos.restype = C.c_long
         L.fvs_cut_cell_flags.restype = C.c_long
         L.fvs_stream.restype = C.c_void_p
         _LIB = L
@@ -447,6 +449,13 @@ class Context:
     @property
     def kernel_launches(self):
         return lib().fvs_kernel_launches(self.h)
+
+    def set_dt_hints(self, on):
+        _check(lib().fvs_set_dt_hints(self.h, 1 if on else 0))
+
+    @property
+    def dt_hint_redos(self):
+        return lib().fvs_dt_hint_redos(self.h)
 
     @property
     def stream(self):

@@ -207,6 +207,9 @@ struct Level {
   // embedded boundary
   bool has_eb{false};
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::EbDesc>>> eb_cache;
+  // lazy stable dt: the last max signal speed evaluated per direction (all ranks
+  // hold the same value, it comes out of the all-reduce); 0 = none yet
+  double last_sig[3]{0.0, 0.0, 0.0};
 };
 
 } // namespace
@@ -233,6 +236,11 @@ struct fvs_ctx {
   int* d_fail{nullptr};
   int* h_fail{nullptr}; // pinned
   int next_slot{0};
+  // lazy stable dt (numerics.cuh): hints are derived from Level::last_sig and
+  // verified after every evaluation; a failed verification repeats the work
+  // without a hint
+  bool dt_hints{true};
+  long hint_redos{0};
   // timing
   bool timing{false};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
@@ -389,8 +397,20 @@ int pick_seg_len(int rank, int dir, const int max_n[3], int nboxes) {
   return std::max(seg, 1);
 }
 
+// The hint of a lazy stable-dt evaluation: kHintFactor times the last known max
+// signal speed of the direction.  Valid iff the evaluation returns at least the
+// hint (verify_hint); the max signal speed of a level changes by a fraction of a
+// percent from sweep to sweep, so a violated hint is the exception (a redo).
+constexpr double kHintFactor = 0.97;
+double dt_hint(const fvs_ctx* ctx, const Level& L, int dir) {
+  return ctx->dt_hints ? kHintFactor * L.last_sig[dir] : 0.0;
+}
+// true iff an evaluation with `hint` that returned `sig` is exact: every face
+// that was skipped has a signal speed below max(hint, sig) (numerics.cuh)
+bool verify_hint(double hint, double sig) { return sig >= hint; }
+
 fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxDesc* boxes,
-                          int slot) {
+                          int slot, double hint = 0.0) {
   fvs::SweepArgs A{};
   A.eq = ctx->eq;
   A.lambda = dt / L.dx[dir];
@@ -399,8 +419,10 @@ fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxD
   A.nboxes = (int)L.patches.size();
   for (int d = 0; d < 3; ++d) A.max_n[d] = L.max_n[d];
   A.seg_len = pick_seg_len(ctx->cfg.rank, dir, L.max_n, A.nboxes);
-  A.max_signal = ctx->d_slots + slot;
-  A.fail_flag = ctx->d_fail;
+  // slot < 0: a kernel without a stable-dt accumulator (general failure flag)
+  A.max_signal = ctx->d_slots + std::max(slot, 0);
+  A.fail_flag = ctx->d_fail + (slot >= 0 ? slot : kDtSlots);
+  A.sig_hint = hint;
   return A;
 }
 
@@ -409,6 +431,7 @@ int take_slot(fvs_ctx* ctx, int count = 1) {
   const int s = ctx->next_slot;
   ctx->next_slot += count;
   FVS_CUDA(cudaMemsetAsync(ctx->d_slots + s, 0, sizeof(unsigned long long) * count, ctx->stream));
+  FVS_CUDA(cudaMemsetAsync(ctx->d_fail + s, 0, sizeof(int) * count, ctx->stream));
   return s;
 }
 
@@ -426,40 +449,58 @@ void check_launch(int rc) {
 // the device-to-host copy engine is busy with -- a 7.5 GB download of another
 // context in the end-to-end pipeline of bench.py delayed each of these 8-byte
 // read-backs by up to 160 ms.
+// d_fail / h_fail: one Newton-failure flag per accumulator slot plus a general
+// one (index kDtSlots) for the kernels that have no slot (cut-cell states).
 __global__ void publish_results_kernel(const unsigned long long* d_slots,
                                        unsigned long long* h_slots, int count, const int* d_fail,
-                                       int* h_fail) {
-  for (int i = threadIdx.x; i < count; i += blockDim.x) h_slots[i] = d_slots[i];
-  if (threadIdx.x == 0) *h_fail = *d_fail;
+                                       int* h_fail, const int* d_general, int* h_general) {
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    h_slots[i] = d_slots[i];
+    h_fail[i] = d_fail[i];
+  }
+  if (threadIdx.x == 0) *h_general = *d_general;
   __threadfence_system();
 }
 
-// read `count` accumulators back (max over ranks), one synchronisation
-void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out) {
+[[noreturn]] void throw_newton() {
+  // include/fub/NewtonIteration.hpp:44-50
+  throw Error("Newton Iteration did not converge.");
+}
+
+// Reads `count` accumulators back (max over ranks), one synchronisation.
+// fails == nullptr: throws if a Newton iteration failed in any of the kernels;
+// otherwise the per-slot flags are returned and the caller decides (a sweep
+// behind a CFL violation never ran in the reference).
+void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out, int* fails = nullptr) {
   if (ctx->comm && ctx->cfg.comm_size > 1) {
     Nccl& n = Nccl::get();
     n.check(n.AllReduce(ctx->d_slots + slot, ctx->d_slots + slot, (size_t)count, Nccl::kDouble,
                         Nccl::kMax, ctx->comm, ctx->stream),
             "ncclAllReduce(max signal)");
-    n.check(n.AllReduce(ctx->d_fail, ctx->d_fail, 1, 2 /* ncclInt32 */, Nccl::kMax, ctx->comm,
-                        ctx->stream),
-            "ncclAllReduce(fail flag)");
+    n.check(n.AllReduce(ctx->d_fail, ctx->d_fail, (size_t)kDtSlots + 1, 2 /* ncclInt32 */,
+                        Nccl::kMax, ctx->comm, ctx->stream),
+            "ncclAllReduce(fail flags)");
   }
-  publish_results_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_slots + slot, ctx->h_slots_dev + slot,
-                                                    count, ctx->d_fail, ctx->h_fail_dev);
+  publish_results_kernel<<<1, 32, 0, ctx->stream>>>(
+      ctx->d_slots + slot, ctx->h_slots_dev + slot, count, ctx->d_fail + slot,
+      ctx->h_fail_dev + slot, ctx->d_fail + kDtSlots, ctx->h_fail_dev + kDtSlots);
   FVS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (*ctx->h_fail) {
-    FVS_CUDA(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), ctx->stream));
-    // include/fub/NewtonIteration.hpp:44-50
-    throw Error("Newton Iteration did not converge.");
+  const bool general = ctx->h_fail[kDtSlots] != 0;
+  if (general) {
+    FVS_CUDA(cudaMemsetAsync(ctx->d_fail + kDtSlots, 0, sizeof(int), ctx->stream));
   }
+  bool any = general;
   for (int i = 0; i < count; ++i) {
     double v;
     std::memcpy(&v, ctx->h_slots + slot + i, sizeof(double));
     out[i] = v;
+    const int f = ctx->h_fail[slot + i] != 0 || general;
+    if (fails) fails[i] = f;
+    any = any || f;
   }
+  if (!fails && any) throw_newton();
 }
 
 // FluxMethodAdapter.hpp:78,96: min over faces of dx / max|s|, starting from DBL_MAX
@@ -502,14 +543,15 @@ void drain_events(fvs_ctx* ctx) {
   ctx->pending_events.clear();
 }
 
-// launches the fused sweep cur -> free buffer; does NOT flip
-int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out) {
+// launches the fused sweep cur -> free buffer; does NOT flip.  `hint`: see
+// SweepArgs::sig_hint -- the caller verifies it against the fetched result.
+int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, double hint = 0.0) {
   const int src = L.cur;
   const int dst = free_buffer(L, src);
   ensure_buffer(ctx, L, dst);
   const BoxDesc* boxes = box_descs(ctx, L, dir, src, dst, false);
   const int slot = take_slot(ctx);
-  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot);
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot, hint);
   if (!L.patches.empty()) {
     EventTimer t(ctx);
     const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
@@ -921,7 +963,7 @@ fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt) {
     A.max_cells = std::max(A.max_cells, p.cells + p.cells / p.n[dir]);
     A.max_cut = std::max(A.max_cut, p.eb.n_cut);
   }
-  A.fail_flag = ctx->d_fail;
+  A.fail_flag = ctx->d_fail + kDtSlots;
   return A;
 }
 
@@ -947,7 +989,7 @@ void cc_numeric_fluxes(fvs_ctx* ctx, Level& L, double dt, int dir) {
   check_launch(rc);
   ctx->launches += rc;
   const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
-  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, -1);
   rc = fvs::launch_cc_numeric_fluxes(ctx->method, dir, A, ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
@@ -1478,11 +1520,11 @@ int fvs_create(const fvs_config* config, fvs_ctx** out) {
     FVS_CUDA(cudaHostAlloc(&ctx->h_slots, sizeof(unsigned long long) * kDtSlots,
                            cudaHostAllocMapped));
     FVS_CUDA(cudaHostGetDevicePointer(&ctx->h_slots_dev, ctx->h_slots, 0));
-    FVS_CUDA(cudaMalloc(&ctx->d_fail, sizeof(int)));
-    FVS_CUDA(cudaMemset(ctx->d_fail, 0, sizeof(int)));
-    FVS_CUDA(cudaHostAlloc(&ctx->h_fail, sizeof(int), cudaHostAllocMapped));
+    FVS_CUDA(cudaMalloc(&ctx->d_fail, sizeof(int) * (kDtSlots + 1)));
+    FVS_CUDA(cudaMemset(ctx->d_fail, 0, sizeof(int) * (kDtSlots + 1)));
+    FVS_CUDA(cudaHostAlloc(&ctx->h_fail, sizeof(int) * (kDtSlots + 1), cudaHostAllocMapped));
     FVS_CUDA(cudaHostGetDevicePointer(&ctx->h_fail_dev, ctx->h_fail, 0));
-    *ctx->h_fail = 0;
+    std::memset(ctx->h_fail, 0, sizeof(int) * (kDtSlots + 1));
     fvs_ctx* raw = ctx.release();
     *out = raw;
     const int rc = fvs_set_method(raw, config->base_method, config->reconstruction, config->limiter);
@@ -1894,7 +1936,7 @@ int fvs_compute_numeric_fluxes(fvs_ctx* ctx, int level, double dt, int dir) {
     }
     ensure_fluxes(ctx, L, dir);
     const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
-    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, -1);
     if (!L.patches.empty()) {
       const int rc = fvs::launch_numeric_fluxes(ctx->method, dir, A, ctx->stream);
       check_launch(rc);
@@ -1916,7 +1958,7 @@ int fvs_update_conservatively(fvs_ctx* ctx, int level, double dt, int dir) {
     }
     ensure_fluxes(ctx, L, dir);
     const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
-    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, 0);
+    fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, -1);
     if (!L.patches.empty()) {
       const int rc = fvs::launch_update_conservatively(ctx->cfg.rank, dir, A, ctx->stream);
       check_launch(rc);
@@ -1936,7 +1978,7 @@ int fvs_complete_from_cons(fvs_ctx* ctx, int level) {
       return (int)FVS_OK;
     }
     const BoxDesc* boxes = box_descs(ctx, L, 0, L.cur, L.cur, false);
-    fvs::SweepArgs A = sweep_args(ctx, L, 0, 0.0, boxes, 0);
+    fvs::SweepArgs A = sweep_args(ctx, L, 0, 0.0, boxes, -1);
     if (!L.patches.empty()) {
       const int rc = fvs::launch_complete_from_cons(ctx->cfg.rank, A, ctx->stream);
       check_launch(rc);
@@ -1968,9 +2010,16 @@ int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out)
       return (int)FVS_OK;
     }
     int dst;
-    const int slot = launch_sweep(ctx, L, dt, dir, &dst);
+    double hint = dt_hint(ctx, L, dir);
+    int slot = launch_sweep(ctx, L, dt, dir, &dst, hint);
     double sig;
     fetch_slots(ctx, slot, 1, &sig);
+    if (!verify_hint(hint, sig)) { // the source buffer is untouched: once more, eagerly
+      ctx->hint_redos += 1;
+      slot = launch_sweep(ctx, L, dt, dir, &dst, 0.0);
+      fetch_slots(ctx, slot, 1, &sig);
+    }
+    L.last_sig[dir] = sig;
     const double level_dt = dt_from_signal(L.dx[dir], sig);
     if (level_dt_out) *level_dt_out = level_dt;
     // DimensionalSplitLevelIntegrator.hpp:243-245
@@ -2022,18 +2071,26 @@ int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
       A.max_n[d] = L.max_n[d];
     }
     A.nboxes = (int)L.patches.size();
-    const int slot = take_slot(ctx, 3);
-    A.max_signal = ctx->d_slots + slot;
-    A.fail_flag = ctx->d_fail;
-    if (!L.patches.empty()) {
-      const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
-                         ? fvs::launch_stable_dt_all_tolerance(ctx->method, A, ctx->stream)
-                         : fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
-      check_launch(rc);
-      ctx->launches += rc;
-    }
     double sig[3];
-    fetch_slots(ctx, slot, 3, sig);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      const int slot = take_slot(ctx, 3);
+      A.max_signal = ctx->d_slots + slot;
+      A.fail_flag = ctx->d_fail + slot;
+      for (int d = 0; d < 3; ++d) A.sig_hint[d] = attempt == 0 && d < rank ? dt_hint(ctx, L, d) : 0.0;
+      if (!L.patches.empty()) {
+        const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
+                           ? fvs::launch_stable_dt_all_tolerance(ctx->method, A, ctx->stream)
+                           : fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
+        check_launch(rc);
+        ctx->launches += rc;
+      }
+      fetch_slots(ctx, slot, 3, sig);
+      bool ok = true;
+      for (int d = 0; d < rank; ++d) ok = ok && verify_hint(A.sig_hint[d], sig[d]);
+      if (ok) break;
+      ctx->hint_redos += 1;
+    }
+    for (int d = 0; d < rank; ++d) L.last_sig[d] = sig[d];
     // DimensionalSplitLevelIntegrator.hpp:204-219
     double min_dt = std::numeric_limits<double>::max();
     for (int d = 0; d < rank; ++d) min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
@@ -2187,73 +2244,112 @@ int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind, double* failu
     if ((int)plan.size() > kDtSlots) throw Error("too many sweeps");
     const int entry = L.cur;
     const int old_keep = L.keep;
-    L.keep = entry; // the state at entry survives until the step is accepted
-    int counts[3] = {0, 0, 0};
-    std::vector<int> slots;
-    ctx->next_slot = 0;
-    try {
-      if (L.has_eb) {
-        // cut-cell levels work in place on a copy of the entry state
-        const int work = free_buffer(L, entry);
-        ensure_buffer(ctx, L, work);
-        for (Patch& p : L.patches) {
-          FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[entry],
-                                   (size_t)p.cells * ctx->ncomp() * sizeof(double),
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        L.cur = work;
-        cc_pre_advance(ctx, L); // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
-      }
-      for (const SweepPlanEntry& e : plan) {
-        const int dir = dirs[e.slot];
-        if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir); // :228-234
-        counts[e.slot] += 1;
+    // Speculative step: all sweeps are launched back to back (each also evaluates
+    // the stable dt of its input state, which the reference checks before the
+    // sweep), read back with ONE synchronisation and checked in order.  The lazy
+    // stable dt runs with hints first; a hint that turns out too high (the max
+    // signal speed fell by more than 3 % since its last evaluation) invalidates
+    // the result of that sweep, and the step is repeated from the entry buffer
+    // without hints.
+    for (int attempt = 0;; ++attempt) {
+      const bool use_hints = attempt == 0;
+      L.keep = entry; // the state at entry survives until the step is accepted
+      int counts[3] = {0, 0, 0};
+      std::vector<int> slots;
+      std::vector<double> hints;
+      ctx->next_slot = 0;
+      try {
         if (L.has_eb) {
-          const int slot = take_slot(ctx);
-          cc_stable_dt(ctx, L, dir, slot);
-          cc_numeric_fluxes(ctx, L, e.dt, dir);
-          cc_update(ctx, L, e.dt, dir);
-          cc_complete(ctx, L);
-          slots.push_back(slot);
-          continue;
+          // cut-cell levels work in place on a copy of the entry state
+          const int work = free_buffer(L, entry);
+          ensure_buffer(ctx, L, work);
+          for (Patch& p : L.patches) {
+            FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[entry],
+                                     (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+          }
+          L.cur = work;
+          cc_pre_advance(ctx, L); // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
         }
-        int dst;
-        slots.push_back(launch_sweep(ctx, L, e.dt, dir, &dst));
-        L.cur = dst;
+        for (const SweepPlanEntry& e : plan) {
+          const int dir = dirs[e.slot];
+          if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir); // :228-234
+          counts[e.slot] += 1;
+          if (L.has_eb) {
+            const int slot = take_slot(ctx);
+            cc_stable_dt(ctx, L, dir, slot);
+            cc_numeric_fluxes(ctx, L, e.dt, dir);
+            cc_update(ctx, L, e.dt, dir);
+            cc_complete(ctx, L);
+            slots.push_back(slot);
+            hints.push_back(0.0);
+            continue;
+          }
+          int dst;
+          const double hint = use_hints ? dt_hint(ctx, L, dir) : 0.0;
+          slots.push_back(launch_sweep(ctx, L, e.dt, dir, &dst, hint));
+          hints.push_back(hint);
+          L.cur = dst;
+        }
+      } catch (...) {
+        L.cur = entry;
+        L.keep = old_keep;
+        throw;
       }
-    } catch (...) {
-      L.cur = entry;
-      L.keep = old_keep;
-      throw;
-    }
-    // one synchronisation for all sweeps of the step
-    std::vector<double> sig(plan.size());
-    // slots are consecutive (next_slot was reset above)
-    try {
-      fetch_slots(ctx, slots.front(), (int)plan.size(), sig.data());
-    } catch (...) {
-      L.cur = entry;
-      L.keep = old_keep;
-      throw;
-    }
-    int n_out = 0;
-    const int cap = (sweep_dts && n_sweep_dts) ? *n_sweep_dts : 0;
-    int status = FVS_OK;
-    for (size_t i = 0; i < plan.size(); ++i) {
-      const double level_dt = dt_from_signal(L.dx[dirs[plan[i].slot]], sig[i]);
-      if (n_out < cap) sweep_dts[n_out] = level_dt;
-      ++n_out;
-      if (level_dt < plan[i].dt) { // :243-245
-        if (failure_dt) *failure_dt = level_dt;
-        status = FVS_TIME_STEP_TOO_LARGE;
-        break;
+      // one synchronisation for all sweeps of the step
+      std::vector<double> sig(plan.size());
+      std::vector<int> fails(plan.size());
+      // slots are consecutive (next_slot was reset above)
+      try {
+        fetch_slots(ctx, slots.front(), (int)plan.size(), sig.data(), fails.data());
+      } catch (...) {
+        L.cur = entry;
+        L.keep = old_keep;
+        throw;
       }
-    }
-    if (n_sweep_dts) *n_sweep_dts = n_out;
-    L.keep = old_keep;
-    if (status != FVS_OK) {
-      L.cur = entry; // roll back: the entry buffer was never written
-      return status;
+      int n_out = 0;
+      const int cap = (sweep_dts && n_sweep_dts) ? *n_sweep_dts : 0;
+      int status = FVS_OK;
+      bool redo = false;
+      bool newton = false;
+      for (size_t i = 0; i < plan.size(); ++i) {
+        const int dir = dirs[plan[i].slot];
+        if (!verify_hint(hints[i], sig[i])) {
+          redo = true;
+          break;
+        }
+        L.last_sig[dir] = sig[i];
+        const double level_dt = dt_from_signal(L.dx[dir], sig[i]);
+        if (n_out < cap) sweep_dts[n_out] = level_dt;
+        ++n_out;
+        if (level_dt < plan[i].dt) { // :243-245
+          // the reference stops here: nothing behind this check ever ran, so a
+          // Newton failure of this or a later sweep is not an error
+          if (failure_dt) *failure_dt = level_dt;
+          status = FVS_TIME_STEP_TOO_LARGE;
+          break;
+        }
+        if (fails[i]) {
+          newton = true;
+          break;
+        }
+      }
+      L.keep = old_keep;
+      if (redo) {
+        ctx->hint_redos += 1;
+        L.cur = entry;
+        continue;
+      }
+      if (newton) {
+        L.cur = entry;
+        throw_newton();
+      }
+      if (n_sweep_dts) *n_sweep_dts = n_out;
+      if (status != FVS_OK) {
+        L.cur = entry; // roll back: the entry buffer was never written
+        return status;
+      }
+      break;
     }
     // SubcycleFineFirstSolver.hpp:164-174,177-192
     ctx->cycles += 1;
@@ -2743,6 +2839,14 @@ int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width
 }
 
 long fvs_kernel_launches(const fvs_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int fvs_set_dt_hints(fvs_ctx* ctx, int on) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    ctx->dt_hints = on != 0;
+    return (int)FVS_OK;
+  });
+}
+long fvs_dt_hint_redos(const fvs_ctx* ctx) { return ctx ? ctx->hint_redos : -1; }
 void* fvs_stream(fvs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int fvs_enable_timing(fvs_ctx* ctx, int on) {

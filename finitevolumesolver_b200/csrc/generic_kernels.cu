@@ -135,7 +135,7 @@ template <int D> __global__ void __launch_bounds__(256) complete_kernel(const Sw
   const Eqs eq(A.eq);
   with_fallback([&](auto M, Flag& fl) {
     const Rcp rc = decltype(M)::rcp(q.rho);
-    decltype(M)::check(rc, fl);
+    decltype(M)::check_window(rc, fl);
     complete_from_cons<decltype(M), D>(eq.m, q, rc, fl);
   });
   u[B.sc * (2 + D)] = q.p;

@@ -39,6 +39,11 @@ struct SweepArgs {
   int seg_len;        // output cells per segment along the sweep direction
   unsigned long long* max_signal; // device: bit pattern of the max signal speed (non-negative double)
   int* fail_flag;     // device: set to 1 if a Newton iteration failed
+  // lazy stable dt (numerics.cuh "Lazy stable dt"): a value the caller believes
+  // to be <= the max signal speed of this sweep; faces whose cheap bound stays
+  // below it are not evaluated.  The caller MUST verify result >= sig_hint
+  // afterwards and repeat with 0 otherwise.  0 = no hint.
+  double sig_hint;
 };
 
 struct MethodKey {
@@ -66,6 +71,7 @@ struct DtAllArgs {
   int max_n[3];
   unsigned long long* max_signal; // [3] one accumulator per direction
   int* fail_flag;
+  double sig_hint[3]; // per direction, see SweepArgs::sig_hint
 };
 int launch_stable_dt_all(const MethodKey&, const DtAllArgs&, cudaStream_t);
 // the same with the tolerance arithmetic (regular levels of a context that opted in)

@@ -94,10 +94,11 @@ FVS_DEV void euler_flux_v(Cons<D>& f, const State& s, double velocity) {
 }
 
 // src/equations/PerfectGas.cpp:31-37,112-124: fills p and a of `q` from its
-// conservative part; rc = rcp(q.rho).
+// conservative part; rc = rcp(q.rho), checked with M::check_window by the caller
+// (the kinetic energy of a gas at rest is a zero numerator).
 template <class M, int D>
 FVS_DEV void complete_from_cons(const EqM& eq, Complete<D>& q, const Rcp& rc, Flag& fl) {
-  const double e_kin = M::div(0.5 * squared_norm<D>(q.mom), rc, fl);
+  const double e_kin = M::divz(0.5 * squared_norm<D>(q.mom), rc, fl);
   const double e_int = q.E - e_kin;
   q.p = M::div(e_int, eq.gm1_inv, fl);
   q.a = M::sqrt(M::div(eq.gamma * q.p, rc, fl), fl);
@@ -155,11 +156,11 @@ FVS_DEV void complete_edge(const EqM& eq, Complete<D>& q, Rcp& rc, Flag& fl) {
       return;
     }
   }
-  M::check(rc, fl);
+  M::check_window(rc, fl);
   if constexpr (NEED_A) {
     complete_from_cons<M, D>(eq, q, rc, fl);
   } else {
-    const double e_kin = M::div(0.5 * squared_norm<D>(q.mom), rc, fl);
+    const double e_kin = M::divz(0.5 * squared_norm<D>(q.mom), rc, fl);
     const double e_int = q.E - e_kin;
     q.p = M::div(e_int, eq.gm1_inv, fl);
     q.a = 0.0;
@@ -196,8 +197,8 @@ FVS_DEV void muscl_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& 
   complete_edge<M, D, MASKED, false>(eq, qL, rcL, fl);
   complete_edge<M, D, MASKED, false>(eq, qR, rcR, fl);
   Cons<D> fL, fR;
-  euler_flux_v<D, DIR>(fL, qL, M::div(qL.mom[DIR], rcL, fl));
-  euler_flux_v<D, DIR>(fR, qR, M::div(qR.mom[DIR], rcR, fl));
+  euler_flux_v<D, DIR>(fL, qL, M::divz(qL.mom[DIR], rcL, fl));
+  euler_flux_v<D, DIR>(fR, qR, M::divz(qR.mom[DIR], rcR, fl));
   {
     const double c = lambda_half * (fL.rho - fR.rho);
     recL.q.rho = qL.rho + c;
@@ -231,12 +232,12 @@ template <int D> struct PrimCell {
 template <class M, int D, typename State>
 FVS_DEV void prim_cell(PrimCell<D>& c, const State& q, Flag& fl) {
   const Rcp rc = M::rcp(q.rho);
-  M::check(rc, fl);
+  M::check_window(rc, fl);
   c.rho = q.rho;
   c.p = q.p;
   c.a = q.a;
 #pragma unroll
-  for (int i = 0; i < D; ++i) c.u[i] = M::div(q.mom[i], rc, fl);
+  for (int i = 0; i < D; ++i) c.u[i] = M::divz(q.mom[i], rc, fl);
 }
 // the limiter lambda of :70-86
 template <class M> FVS_DEV double prim_limited_slope(double qL, double qM, double qR, Flag& fl) {
@@ -245,13 +246,14 @@ template <class M> FVS_DEV double prim_limited_slope(double qL, double qM, doubl
   const double dq = is_relevant ? delta_q : 1.0;
   const Rcp rc = M::rcp(dq);
   M::check(rc, fl);
-  const double qLq = M::div(qM - qL, rc, fl, is_relevant);
-  const double qRq = M::div(qR - qM, rc, fl, is_relevant);
+  const double qLq = M::div_any(qM - qL, rc, fl, is_relevant);
+  const double qRq = M::div_any(qR - qM, rc, fl, is_relevant);
   const double rL = is_relevant ? qLq : 0.0;
   const double rR = is_relevant ? qRq : 0.0;
   const bool is_positive = rL > 0.0 && rR > 0.0;
   const double r = is_positive ? vmin(rL, rR) : 0.0;
-  const double r_1 = M::div(2 * r, 1.0 + r, fl);
+  const Rcp rc1 = M::rcp(1.0 + r); // in [1, 2): inside the window
+  const double r_1 = M::divz(2 * r, rc1, fl);
   const double r_2 = 0.5 * (r + 1.0);
   const double sigma = r < 1.0 ? r_1 : r_2;
   return sigma * delta_q;
@@ -287,7 +289,11 @@ FVS_DEV void prim_edge(const EqM& eq, Edge<D>& out, const PrimCell<D>& c, const 
 #pragma unroll
     for (int i = 0; i < D; ++i) rec_u[i] = c.u[i] - 0.5 * (s.du[i] + lambda * (ud * s.du[i]));
   }
-  rec_u[DIR] = rec_u[DIR] - M::div(0.5 * lambda * s.dp, c.rho, fl);
+  {
+    const Rcp rcc = M::rcp(c.rho);
+    M::check_window(rcc, fl);
+    rec_u[DIR] = rec_u[DIR] - M::divz(0.5 * lambda * s.dp, rcc, fl);
+  }
   out.q.rho = rec_rho;
 #pragma unroll
   for (int i = 0; i < D; ++i) out.q.mom[i] = rec_rho * rec_u[i];
@@ -378,7 +384,11 @@ FVS_DEV void char_edge(const EqM& eq, Edge<D>& out, const PrimCell<D>& c, const 
   double dp = 0.5 * (minus + plus);
   double drho = ooc2 * dp + zero;
   double du[D];
-  du[DIR] = M::div(0.5 * (plus - minus), rhoc, fl);
+  {
+    const Rcp rcc = M::rcp(rhoc);
+    M::check_window(rcc, fl);
+    du[DIR] = M::divz(0.5 * (plus - minus), rcc, fl);
+  }
   if constexpr (iy < D) du[iy] = sg * 0.5 * slope.t[0] * (1.0 - sg * lambda * u);
   if constexpr (iz < D) du[iz] = sg * 0.5 * slope.t[1] * (1.0 - sg * lambda * u);
   drho = drho + c.rho;
@@ -391,8 +401,8 @@ FVS_DEV void char_edge(const EqM& eq, Edge<D>& out, const PrimCell<D>& c, const 
   for (int d = 0; d < D; ++d) out.q.mom[d] = drho * du[d];
   out.q.p = dp;
   out.rc = M::rcp(drho);
-  M::check(out.rc, fl);
-  const double e_kin = M::div(0.5 * squared_norm<D>(out.q.mom), out.rc, fl);
+  M::check_window(out.rc, fl);
+  const double e_kin = M::divz(0.5 * squared_norm<D>(out.q.mom), out.rc, fl);
   out.q.E = e_kin + dp * eq.gm1_inv.b;
   out.q.a = M::sqrt(M::div(eq.gamma * dp, out.rc, fl), fl);
   (void)MASKED;
@@ -440,8 +450,8 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   Complete<D> right = eR.q;
   const Rcp& rcL = eL.rc;
   const Rcp& rcR = eR.rc;
-  M::check(rcL, fl);
-  M::check(rcR, fl);
+  M::check_window(rcL, fl);
+  M::check_window(rcR, fl);
   const double rhoL = left.rho;
   const double rhoR = right.rho;
   double vL_[D], vR_[D]; // velocities of the unmodified states
@@ -449,8 +459,8 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   double eKinRL = 0.0, eKinRR = 0.0;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
-    vL_[i] = M::div(left.mom[i], rcL, fl);
-    vR_[i] = M::div(right.mom[i], rcR, fl);
+    vL_[i] = M::divz(left.mom[i], rcL, fl);
+    vR_[i] = M::divz(right.mom[i], rcR, fl);
     uL[i] = vL_[i];
     uR[i] = vR_[i];
   }
@@ -547,10 +557,12 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   const double db = bR - bL;
   const double db_positive = db > 0.0 ? db : 1.0;
   const Rcp rcDb = M::rcp(db_positive);
-  M::check(rcDb, fl);
+  M::check_window(rcDb, fl);
   Cons<D> hlle;
+  // the mass and energy fluxes of a uniform gas at rest are zero numerators; the
+  // normal momentum flux carries the pressure
   hlle.rho =
-      M::div(bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho), rcDb, fl);
+      M::divz(bR * fluxL.rho - bL * fluxR.rho + bLbR * (right.rho - left.rho), rcDb, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     // with the Larrouturou modification the tangential momentum fluxes are
@@ -559,17 +571,18 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
     if (LARROUTUROU && D > 1 && d != DIR) {
       hlle.mom[d] = 0.0;
     } else {
-      hlle.mom[d] = M::div(
-          bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]), rcDb, fl);
+      const double num =
+          bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]);
+      hlle.mom[d] = d == DIR ? M::div(num, rcDb, fl) : M::divz(num, rcDb, fl);
     }
   }
-  hlle.E = M::div(bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E), rcDb, fl);
+  hlle.E = M::divz(bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E), rcDb, fl);
 
   // :813-823
   const double u_bar = 0.5 * (sR + sL);
   const double u_bar_abs = fabs(u_bar);
   const double delta = M::div(roeA, roeA + u_bar_abs, fl);
-  const double b = M::div(bLbR, rcDb, fl);
+  const double b = M::divz(bLbR, rcDb, fl);
   const double deltaRho = rhoR - rhoL;
   double deltaRhoU[D];
 #pragma unroll
@@ -676,11 +689,11 @@ template <int D> struct DtCell {
 template <class M, int D, typename State>
 FVS_DEV void dt_cell(DtCell<D>& c, const State& q, Flag& fl) {
   const Rcp rc = M::rcp(q.rho);
-  M::check(rc, fl);
+  M::check_window(rc, fl);
   c.h = M::div(q.E + q.p, rc, fl);
   c.sq_rho = M::sqrt(q.rho, fl);
 #pragma unroll
-  for (int i = 0; i < D; ++i) c.u[i] = M::div(q.mom[i], rc, fl);
+  for (int i = 0; i < D; ++i) c.u[i] = M::divz(q.mom[i], rc, fl);
   c.a = q.a;
 }
 
@@ -708,6 +721,67 @@ FVS_DEV double hllem_max_signal(const EqM& eq, const DtCell<D>& L, const DtCell<
   const double sL = vmin(L.u[DIR] - maxA, roeU[DIR] - roeA);
   const double sR = vmax(roeU[DIR] + roeA, R.u[DIR] + maxA);
   return vmax(fabs(sL), fabs(sR));
+}
+
+// ---------------------------------------------------------------------------
+// Lazy stable dt.  The stable dt of a sweep is dx / max over faces of the signal
+// speed S = max(|sL|, |sR|); only the faces near the maximum decide it.  For
+// HLLEM and HLL-Einfeldt
+//   |sL|, |sR| <= max(|uL|, |uR|) + max(aL, aR, roeA),  roeA^2 <= (gamma-1) max(hL, hR)
+// up to a few roundings (the Roe averages are convex combinations whose weights
+// sum to 1 within 2 ulp), so  B = max(|u|) + max(a, sqrt((gamma-1) h))  over the
+// two cells bounds S from above.  B is evaluated from the 20-bit MUFU seeds
+// (6 fp64 instructions per cell instead of ~85) and compared in the high words;
+// the exact signal speed is only evaluated where B exceeds kLazyKeep times a
+// known lower bound of the final maximum (the thread's running maximum, or the
+// hint the host derives from the previous evaluation and verifies afterwards,
+// context.cu: verify_hint).  All approximation errors (seeds 2^-19, high-word
+// truncation 2^-19, roundings) stay far inside the 2^-10 margin, and anything
+// that is not an ordinary positive number (NaN, infinity, negative density)
+// turns B into NaN or infinity, which takes the exact path: the maximum is
+// bit-identical to the eager evaluation.
+struct SigBound {
+  int u; // high word of an approximation of |u_DIR|
+  int c; // high word of an approximation of max(a, sqrt((gamma-1) h))
+};
+template <int D> struct SigBoundAll {
+  int u[D];
+  int c;
+};
+constexpr double kLazyKeep = 1.0 - 0.0009765625; // 1 - 2^-10
+
+FVS_DEV int imax(int a, int b) { return a > b ? a : b; }
+
+// rs * rs ~ 1 / rho; NaN for a negative density, infinity for zero
+template <int D, typename State>
+FVS_DEV int sig_bound_c(const EqM& eq, const State& q, double r0) {
+  const double hs = ((q.E + q.p) * r0) * eq.gamma_minus_1;
+  const double ch = hs * mufu_rsq64h(hs); // sqrt((gamma-1) h); NaN for h <= 0
+  return imax(hi32(q.a) & 0x7fffffff, hi32(ch));
+}
+template <int D, int DIR, typename State>
+FVS_DEV SigBound sig_bound(const EqM& eq, const State& q) {
+  const double rs = mufu_rsq64h(q.rho);
+  const double r0 = rs * rs;
+  SigBound b;
+  b.u = hi32(fabs(q.mom[DIR]) * r0);
+  b.c = sig_bound_c<D>(eq, q, r0);
+  return b;
+}
+template <int D, typename State>
+FVS_DEV SigBoundAll<D> sig_bound_all(const EqM& eq, const State& q) {
+  const double rs = mufu_rsq64h(q.rho);
+  const double r0 = rs * rs;
+  SigBoundAll<D> b;
+#pragma unroll
+  for (int d = 0; d < D; ++d) b.u[d] = hi32(fabs(q.mom[d]) * r0);
+  b.c = sig_bound_c<D>(eq, q, r0);
+  return b;
+}
+// true iff the face between two cells may carry a signal speed above thr / kLazyKeep
+FVS_DEV bool sig_bound_exceeds(int ul, int cl, int ur, int cr, double thr) {
+  const double s = hilo(imax(ul, ur), 0) + hilo(imax(cl, cr), 0);
+  return !(s <= thr);
 }
 
 // ---------------------------------------------------------------------------
@@ -752,10 +826,10 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
                                const Edge<D>& eR, Flag& fl) {
   const Complete<D>& left = eL.q;
   const Complete<D>& right = eR.q;
-  M::check(eL.rc, fl);
-  M::check(eR.rc, fl);
-  const double uL = M::div(left.mom[DIR], eL.rc, fl);
-  const double uR = M::div(right.mom[DIR], eR.rc, fl);
+  M::check_window(eL.rc, fl);
+  M::check_window(eR.rc, fl);
+  const double uL = M::divz(left.mom[DIR], eL.rc, fl);
+  const double uR = M::divz(right.mom[DIR], eR.rc, fl);
   const double hL = M::div(left.E + left.p, eL.rc, fl);
   const double hR = M::div(right.E + right.p, eR.rc, fl);
   double s0, s1;
@@ -775,14 +849,14 @@ FVS_DEV void hll_einfeldt_flux(const EqM& eq, Cons<D>& nf, const Edge<D>& eL,
   double ds = sR - sL;
   if constexpr (!MASKED) ds = ds > 0.0 ? ds : 1.0;
   const Rcp rcDs = M::rcp(ds);
-  M::check(rcDs, fl);
-  nf.rho = M::div(sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho), rcDs, fl);
+  M::check_window(rcDs, fl);
+  nf.rho = M::divz(sR * fL.rho - sL * fR.rho + sLsR * (right.rho - left.rho), rcDs, fl);
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    nf.mom[d] =
-        M::div(sR * fL.mom[d] - sL * fR.mom[d] + sLsR * (right.mom[d] - left.mom[d]), rcDs, fl);
+    const double num = sR * fL.mom[d] - sL * fR.mom[d] + sLsR * (right.mom[d] - left.mom[d]);
+    nf.mom[d] = d == DIR ? M::div(num, rcDs, fl) : M::divz(num, rcDs, fl);
   }
-  nf.E = M::div(sR * fL.E - sL * fR.E + sLsR * (right.E - left.E), rcDs, fl);
+  nf.E = M::divz(sR * fL.E - sL * fR.E + sLsR * (right.E - left.E), rcDs, fl);
 }
 
 // include/fub/flux_method/HllMethod.hpp:337-347: max(0, |s0|, |s1|)

@@ -114,6 +114,14 @@ int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim,
 }
 
 template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+#ifdef FVS_INST_MINIMAL
+  // tuning builds (tools/build_variant.py --minimal, tools/count_steady.sh): only the
+  // bench configuration, MUSCL-Hancock with VanLeer, is instantiated
+  if (k.recon == kReconMusclHancock && k.limiter == kLimiterVanLeer) {
+    return fused<DIR, kReconMusclHancock, kLimiterVanLeer>(A, s);
+  }
+  return -1;
+#else
   return by_recon<DIR>(
       k, [&] { return fused<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fused<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
@@ -135,9 +143,13 @@ template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStr
           return -1;
         }
       });
+#endif
 }
 #ifndef FVS_TOLERANCE_UNIT
 template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+#ifdef FVS_INST_MINIMAL
+  return -1;
+#else
   return by_recon<DIR>(
       k, [&] { return fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
@@ -159,9 +171,13 @@ template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaSt
           return -1;
         }
       });
+#endif
 }
 
 template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
+#ifdef FVS_INST_MINIMAL
+  return -1;
+#else
   return by_recon<DIR>(
       k, [&] { return cc_fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
@@ -183,6 +199,7 @@ template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cud
           return -1;
         }
       });
+#endif
 }
 
 #endif // !FVS_TOLERANCE_UNIT
@@ -247,11 +264,24 @@ int FVS_FN(launch_stable_dt)(const MethodKey&, int dir, const SweepArgs& A, cuda
 
 #endif // !FVS_TOLERANCE_UNIT
 
-int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStream_t s) {
-  const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
-  dim3 grid(cdiv(total, 256 * kDtAllCellsPerThread), A.nboxes, 1);
-  stable_dt_all_kernel<D, BASE><<<grid, 256, 0, s>>>(A);
+namespace {
+// a template, so that only the kernel of the taken branch is instantiated
+template <int B> int dt_all(const DtAllArgs& A, cudaStream_t s) {
+  if constexpr (kLazyDt<B>) {
+    dim3 grid(cdiv(A.max_n[0], 32) * cdiv(A.max_n[1], 8), A.nboxes,
+              cdiv(A.max_n[2], kDtAllSegment));
+    stable_dt_all_lazy_kernel<D, B><<<grid, 256, 0, s>>>(A);
+  } else {
+    const long long total = (long long)A.max_n[0] * A.max_n[1] * A.max_n[2];
+    dim3 grid(cdiv(total, 256 * kDtAllCellsPerThread), A.nboxes, 1);
+    stable_dt_all_kernel<D, B><<<grid, 256, 0, s>>>(A);
+  }
   return 1;
+}
+} // namespace
+
+int FVS_FN(launch_stable_dt_all)(const MethodKey&, const DtAllArgs& A, cudaStream_t s) {
+  return dt_all<BASE>(A, s);
 }
 
 } // namespace fvs

@@ -142,7 +142,7 @@ FVS_DEV void stage_update(const Eqs& eq, Complete<D>& out, const S& q, const Con
   }
   with_fallback([&](auto M, Flag& fl) {
     const Rcp rc = decltype(M)::rcp(out.rho);
-    decltype(M)::check(rc, fl);
+    decltype(M)::check_window(rc, fl);
     complete_from_cons<decltype(M), D>(eq.m, out, rc, fl);
   });
 }
@@ -159,6 +159,27 @@ FVS_DEV double stage_dt_face(const Eqs& eq, const DtData<D, BASE>& l, const DtDa
     s = base_max_signal<decltype(M), D, DIR, BASE>(eq, l, r, fl, failed);
   });
   return s;
+}
+
+// stage D, lazy (numerics.cuh "Lazy stable dt"): the exact signal speed of the
+// face between the stored states at pl and pr is only evaluated where the
+// cheap bound exceeds `thr`; the exact path reloads the two states (cache hits).
+template <int BASE> constexpr bool kLazyDt = BASE != kBaseGodunovExact;
+template <int D, int DIR, int BASE>
+FVS_DEV void stage_dt_exact(const Eqs& eq, const double* pl, const double* pr, long long sc,
+                            double& maxsig, double& thr, int& failed) {
+  Complete<D> l, r;
+  load_complete<D>(l, pl, sc);
+  load_complete<D>(r, pr, sc);
+  DtData<D, BASE> dl, dr;
+  stage_dt_cell<D, BASE>(dl, l);
+  stage_dt_cell<D, BASE>(dr, r);
+  const double s = stage_dt_face<D, DIR, BASE>(eq, dl, dr, failed);
+  if (s > maxsig) {
+    maxsig = s;
+    const double t = s * kLazyKeep;
+    thr = t > thr ? t : thr;
+  }
 }
 
 #ifndef FVS_SWEEP_THREADS
@@ -277,7 +298,7 @@ fused_sweep_yz_kernel(const SweepArgs A) {
           }
           out.E = q2.E + A.lambda * (F_prev.E - F.E);
           const Rcp rc = MM::rcp(out.rho);
-          MM::check(rc, fl);
+          MM::check_window(rc, fl);
           complete_from_cons<MM, D>(eq.m, out, rc, fl);
         });
         store_complete<D>(dst + stride * (j - 2), sc, out);
@@ -367,7 +388,8 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
   __shared__ Slot<QT> s_q[3][kSweepThreads];        // ring: slot j % 3 holds cell j
   __shared__ Slot<Edge<D>> s_rec[2][kSweepThreads]; // ring: slot j & 1 holds recR of cell j-1
   __shared__ Slot<Cons<D>> s_F[kSweepThreads];      // flux through face j-2
-  __shared__ Slot<DtData<D, BASE>> s_dt[kSweepThreads]; // dt data of cell j-1
+  // eager stable dt (exact Riemann solver): dt data of cell j-1
+  __shared__ Slot<DtData<D, BASE>> s_dt[kLazyDt<BASE> ? 1 : kSweepThreads];
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
   const long long nlines = (long long)n0 * ((DIR == 1) ? B.n[2] : B.n[1]);
@@ -400,6 +422,8 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
     Complete<D> qn; // prefetched cell j+1
 #endif
     DtData<D, BASE> dt_cur;
+    SigBound sb_prev{0, 0}, sb_cur{0, 0};
+    double thr = A.sig_hint * kLazyKeep;
     const int jstart = max(o_first - 2, 0);
     load_complete<D>(q0, src + stride * jstart, sc);
 #if FVS_SWEEP_PREFETCH == 1
@@ -424,8 +448,12 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       s_rec[0][tid].v = e0;
       s_rec[1][tid].v = e0;
       s_F[tid].v = c0;
-      stage_dt_cell<D, BASE>(dt_cur, q0);
-      s_dt[tid].v = dt_cur;
+      if constexpr (kLazyDt<BASE>) {
+        sb_cur = sig_bound<D, DIR>(eq.m, q0);
+      } else {
+        stage_dt_cell<D, BASE>(dt_cur, q0);
+        s_dt[tid].v = dt_cur;
+      }
     }
     const int jend = o_last + 2;
     const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
@@ -439,7 +467,14 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 #else
         if (j < nd) load_complete<D>(q0, src + stride * j, sc);
 #endif
-        if (j < nd) stage_dt_cell<D, BASE>(dt_cur, q0);
+        if (j < nd) {
+          if constexpr (kLazyDt<BASE>) {
+            sb_prev = sb_cur;
+            sb_cur = sig_bound<D, DIR>(eq.m, q0);
+          } else {
+            stage_dt_cell<D, BASE>(dt_cur, q0);
+          }
+        }
       }
 #if FVS_SWEEP_PREFETCH == 1
       if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
@@ -484,7 +519,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
           }
           out.E = q2.E + A.lambda * (F_prev.E - F.E);
           const Rcp rc = MM::rcp(out.rho);
-          MM::check(rc, fl);
+          MM::check_window(rc, fl);
           complete_from_cons<MM, D>(eq.m, out, rc, fl);
         });
         store_complete<D>(dst + stride * (j - 2), sc, out);
@@ -524,8 +559,15 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       FVS_STAGE_BARRIER();
       // stage D: face (j-1 | j) of the stored states
       if (j > jstart && j < nd && dtmask[j - 1]) {
-        const double s = stage_dt_face<D, DIR, BASE>(eq, s_dt[tid].v, dt_cur, failed);
-        maxsig = s > maxsig ? s : maxsig;
+        if constexpr (kLazyDt<BASE>) {
+          if (sig_bound_exceeds(sb_prev.u, sb_prev.c, sb_cur.u, sb_cur.c, thr)) {
+            stage_dt_exact<D, DIR, BASE>(eq, src + stride * (j - 1), src + stride * j, sc, maxsig,
+                                         thr, failed);
+          }
+        } else {
+          const double s = stage_dt_face<D, DIR, BASE>(eq, s_dt[tid].v, dt_cur, failed);
+          maxsig = s > maxsig ? s : maxsig;
+        }
       }
       // rotate: slot j % 3 <- cell j, flux and dt slots
       if constexpr (RECON == kReconMusclHancock) {
@@ -534,7 +576,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
         s_q[m3][tid].v = q0;
       }
       F_prev = F;
-      s_dt[tid].v = dt_cur;
+      if constexpr (!kLazyDt<BASE>) s_dt[tid].v = dt_cur;
       FVS_STAGE_BARRIER();
       m3 = m3 == 2 ? 0 : m3 + 1;
     }
@@ -566,7 +608,8 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
   __shared__ Slot<QT> s_q[kWarps][34];              // slot i + 2 <- cell of lane i
   __shared__ Slot<Edge<D>> s_rec[kWarps][33];       // slot i + 1 <- recR of lane i (cell c - 1)
   __shared__ Slot<Cons<D>> s_F[kWarps][33];         // slot i + 1 <- flux of lane i (face c - 1)
-  __shared__ Slot<DtData<D, BASE>> s_dt[kWarps][33]; // slot i + 1 <- dt data of lane i's cell
+  // eager stable dt (exact Riemann solver): slot i + 1 <- dt data of lane i's cell
+  __shared__ Slot<DtData<D, BASE>> s_dt[kLazyDt<BASE> ? 1 : kWarps][kLazyDt<BASE> ? 1 : 33];
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
   const long long nrows = (long long)B.n[1] * B.n[2];
@@ -588,6 +631,8 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
+    double thr = A.sig_hint * kLazyKeep;
+    int carry_u = 0, carry_c = 0; // signal bound of lane 31 of the previous chunk
 #if FVS_SWEEP_XS_PREFETCH == 2
     // the next chunk's cell is loaded into registers one chunk ahead
     Complete<D> qn;
@@ -609,7 +654,12 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       if (c0 + 32 - 2 <= o_last) prefetch_complete<D>(src + min(c + 32, n0 - 1), sc);
 #endif
       DtData<D, BASE> dt_cur;
-      stage_dt_cell<D, BASE>(dt_cur, q0);
+      SigBound sb{0, 0};
+      if constexpr (kLazyDt<BASE>) {
+        sb = sig_bound<D, DIR>(eq.m, q0);
+      } else {
+        stage_dt_cell<D, BASE>(dt_cur, q0);
+      }
       {
         QT mine;
         if constexpr (RECON == kReconMusclHancock) {
@@ -618,13 +668,13 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
           mine = q0;
         }
         s_q[warp][lane + 2].v = mine;
-        s_dt[warp][lane + 1].v = dt_cur;
+        if constexpr (!kLazyDt<BASE>) s_dt[warp][lane + 1].v = dt_cur;
         if (first && lane == 0) {
           // no carry yet: lanes 0..3 produce no output in the first chunk; give
           // their missing neighbours real data to keep the arithmetic benign
           s_q[warp][0].v = mine;
           s_q[warp][1].v = mine;
-          s_dt[warp][0].v = dt_cur;
+          if constexpr (!kLazyDt<BASE>) s_dt[warp][0].v = dt_cur;
         }
       }
       __syncwarp();
@@ -653,9 +703,25 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
         store_complete<D>(dst + o, sc, out);
       }
       // ---- stage D: face (c-1 | c) of the stored states
-      if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
-        const double sgn = stage_dt_face<D, DIR, BASE>(eq, s_dt[warp][lane].v, dt_cur, failed);
-        maxsig = sgn > maxsig ? sgn : maxsig;
+      if constexpr (kLazyDt<BASE>) {
+        int lu = __shfl_up_sync(0xffffffffu, sb.u, 1);
+        int lc = __shfl_up_sync(0xffffffffu, sb.c, 1);
+        if (lane == 0) {
+          lu = carry_u;
+          lc = carry_c;
+        }
+        carry_u = __shfl_sync(0xffffffffu, sb.u, 31);
+        carry_c = __shfl_sync(0xffffffffu, sb.c, 31);
+        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+          if (sig_bound_exceeds(lu, lc, sb.u, sb.c, thr)) {
+            stage_dt_exact<D, DIR, BASE>(eq, src + (c - 1), src + c, sc, maxsig, thr, failed);
+          }
+        }
+      } else {
+        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+          const double sgn = stage_dt_face<D, DIR, BASE>(eq, s_dt[warp][lane].v, dt_cur, failed);
+          maxsig = sgn > maxsig ? sgn : maxsig;
+        }
       }
       __syncwarp();
       // ---- carry of lanes 30, 31 into slots 0, 1 for the next chunk
@@ -663,7 +729,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       if (lane == 31) {
         s_rec[warp][0].v = s_rec[warp][32].v;
         s_F[warp][0].v = F;
-        s_dt[warp][0].v = dt_cur;
+        if constexpr (!kLazyDt<BASE>) s_dt[warp][0].v = dt_cur;
       }
       __syncwarp();
       first = false;
@@ -810,6 +876,81 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
         stage_dt_cell<D, BASE>(dr, r);
         const double s = stage_dt_face<D, 2, BASE>(eq, dl, dr, failed);
         maxsig[2] = s > maxsig[2] ? s : maxsig[2];
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    reduce_max_signal(maxsig[d], A.max_signal + d);
+    __syncthreads();
+  }
+  if (failed) *A.fail_flag = 1;
+}
+
+// The same with the lazy evaluation (numerics.cuh "Lazy stable dt"), HLLEM and
+// HLL-Einfeldt: a block covers 32 x 8 (x, y) columns and marches kDtAllSegment
+// cells along z; per cell one bound of the stored state and of its +x and +y
+// neighbours (cache hits: they are the block's own cells), three high-word
+// compares, and the exact signal speeds only where a bound exceeds the
+// threshold -- a read pass at HBM speed instead of 800 instructions per cell.
+constexpr int kDtAllSegment = 16;
+template <int D, int BASE>
+__global__ void __launch_bounds__(256) stable_dt_all_lazy_kernel(const DtAllArgs A) {
+  const BoxDesc& B = A.boxes[0][blockIdx.y];
+  const int n0 = B.n[0], n1 = B.n[1], n2 = B.n[2];
+  const int tiles_x = (n0 + 31) / 32;
+  const int x = (blockIdx.x % tiles_x) * 32 + (threadIdx.x & 31);
+  const int y = (blockIdx.x / tiles_x) * 8 + (threadIdx.x >> 5);
+  const int z0 = blockIdx.z * kDtAllSegment;
+  double maxsig[D], thr[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    maxsig[d] = 0.0;
+    thr[d] = A.sig_hint[d] * kLazyKeep;
+  }
+  int failed = 0;
+  if (x < n0 && y < n1 && z0 < n2) {
+    const Eqs eq(A.eq);
+    const long long sc = B.sc;
+    const long long plane = (long long)n0 * n1;
+    const double* p = B.src + x + (long long)n0 * y + plane * z0;
+    const unsigned char* mx = A.boxes[0][blockIdx.y].dtmask;
+    const unsigned char* my = D >= 2 ? A.boxes[1][blockIdx.y].dtmask : nullptr;
+    const unsigned char* mz = D >= 3 ? A.boxes[2][blockIdx.y].dtmask : nullptr;
+    const bool face_x = x + 1 < n0 && mx[x];
+    const bool face_y = D >= 2 && y + 1 < n1 && my[y];
+    const int z_end = min(z0 + kDtAllSegment, n2 - 1); // last cell read: the +z neighbour of the segment
+    SigBoundAll<D> prev{};
+#pragma unroll 1
+    for (int z = z0; z <= z_end; ++z, p += plane) {
+      Complete<D> q;
+      load_complete<D>(q, p, sc);
+      const SigBoundAll<D> cur = sig_bound_all<D>(eq.m, q);
+      if constexpr (D >= 3) {
+        if (z > z0 && mz[z - 1] &&
+            sig_bound_exceeds(prev.u[2], prev.c, cur.u[2], cur.c, thr[2])) {
+          stage_dt_exact<D, 2, BASE>(eq, p - plane, p, sc, maxsig[2], thr[2], failed);
+        }
+      }
+      prev = cur;
+      if (z == z0 + kDtAllSegment) break; // the +z neighbour belongs to the next segment
+      if (face_x) {
+        Complete<D> r;
+        load_complete<D>(r, p + 1, sc);
+        const SigBound b = sig_bound<D, 0>(eq.m, r);
+        if (sig_bound_exceeds(cur.u[0], cur.c, b.u, b.c, thr[0])) {
+          stage_dt_exact<D, 0, BASE>(eq, p, p + 1, sc, maxsig[0], thr[0], failed);
+        }
+      }
+      if constexpr (D >= 2) {
+        if (face_y) {
+          Complete<D> r;
+          load_complete<D>(r, p + n0, sc);
+          const SigBound b = sig_bound<D, 1>(eq.m, r);
+          if (sig_bound_exceeds(cur.u[1], cur.c, b.u, b.c, thr[1])) {
+            stage_dt_exact<D, 1, BASE>(eq, p, p + n0, sc, maxsig[1], thr[1], failed);
+          }
+        }
       }
     }
   }

@@ -371,6 +371,17 @@ int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width
 /* ---- statistics ---------------------------------------------------------- */
 /* Number of kernels this context has launched so far. */
 long fvs_kernel_launches(const fvs_ctx* ctx);
+/* Lazy stable dt.  The fused sweep and fvs_compute_stable_dt_all evaluate the
+ * signal speeds of FluxMethod<>::ComputeStableDt (include/fub/flux_method/
+ * FluxMethod.hpp:341-382) exactly only on faces whose cheap upper bound comes
+ * near the maximum; the bound is compared with a hint taken from the previous
+ * evaluation of that direction and the result is verified against the hint
+ * afterwards (a violated hint repeats the evaluation without one), so the
+ * returned dt is bit-identical either way.  on = 0 disables the hints (every
+ * evaluation starts from zero).  No reference counterpart.  Default: on. */
+int fvs_set_dt_hints(fvs_ctx* ctx, int on);
+/* Number of evaluations that had to be repeated because a hint was violated. */
+long fvs_dt_hint_redos(const fvs_ctx* ctx);
 /* The CUDA stream (cudaStream_t) all work of the context is ordered on. */
 void* fvs_stream(fvs_ctx* ctx);
 /* Elapsed device time (ms) of the most recent fvs_sweep / sweep inside

@@ -35,7 +35,7 @@ def build_fastmath_check(force=False):
     cuda = os.path.join(os.path.dirname(HERE), "cuda")
     out = os.path.join(cuda, "fastmath_check")
     src = os.path.join(cuda, "fastmath_check.cu")
-    deps = [src, os.path.join(PKG, "csrc", "fastmath.cuh")]
+    deps = [src, os.path.join(PKG, "csrc", "fastmath.cuh"), os.path.join(cuda, "fastmath_cases.h")]
     if (not force and os.path.exists(out)
             and os.path.getmtime(out) > max(os.path.getmtime(d) for d in deps)):
         return out
@@ -45,6 +45,21 @@ def build_fastmath_check(force=False):
     return out
 
 
+def build_fastmath_host(force=False):
+    """tests/cpp/fastmath_host: csrc/fastmath.cuh compiled for the CPU (hardware FMA,
+    emulated MUFU seeds) against `/` and sqrt()."""
+    out = os.path.join(HERE, "fastmath_host")
+    src = os.path.join(HERE, "fastmath_host.cpp")
+    deps = [src, os.path.join(PKG, "csrc", "fastmath.cuh"),
+            os.path.join(os.path.dirname(HERE), "cuda", "fastmath_cases.h")]
+    if (not force and os.path.exists(out)
+            and os.path.getmtime(out) > max(os.path.getmtime(d) for d in deps)):
+        return out
+    subprocess.check_call([CXX, "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-o", out, src])
+    return out
+
+
 if __name__ == "__main__":
+    print(build_fastmath_host(force=True))
     print(build_fastmath_check(force=True))
     print(build(force=True))

@@ -20,6 +20,7 @@ def test_fastmath_bitwise_and_tolerance_bound():
     assert r.returncode == 0, r.stdout + r.stderr
     fields = r.stdout.split()
     vals = dict(zip(fields[0::2], map(int, fields[1::2])))
-    assert vals["mismatch_div"] == 0 and vals["mismatch_sqrt"] == 0
+    assert vals["mismatch_div"] == 0 and vals["mismatch_sqrt"] == 0 and vals["mismatch_divz"] == 0
+    assert vals["zero_divz"] > 0.2 * vals["tested"]
     assert vals["tested"] > 1e9
     assert vals["tol_div_ulp"] <= 2 and vals["tol_sqrt_ulp"] <= 2, vals
