@@ -268,7 +268,9 @@ namespace {
 // a template, so that only the kernel of the taken branch is instantiated
 template <int B> int dt_all(const DtAllArgs& A, cudaStream_t s) {
   if constexpr (kLazyDt<B>) {
-    dim3 grid(cdiv(A.max_n[0], 32) * cdiv(A.max_n[1], 8), A.nboxes,
+    // overlapping tiles: 31 (x) by 7 (y; 1 for a 1-D level) owned columns per block
+    const int step_y = D >= 2 ? kDtTileY - 1 : 1;
+    dim3 grid(cdiv(A.max_n[0], kDtTileX - 1) * cdiv(A.max_n[1], step_y), A.nboxes,
               cdiv(A.max_n[2], kDtAllSegment));
     stable_dt_all_lazy_kernel<D, B><<<grid, 256, 0, s>>>(A);
   } else {

@@ -888,19 +888,54 @@ __global__ void __launch_bounds__(256) stable_dt_all_kernel(const DtAllArgs A) {
 }
 
 // The same with the lazy evaluation (numerics.cuh "Lazy stable dt"), HLLEM and
-// HLL-Einfeldt: a block covers 32 x 8 (x, y) columns and marches kDtAllSegment
-// cells along z; per cell one bound of the stored state and of its +x and +y
-// neighbours (cache hits: they are the block's own cells), three high-word
-// compares, and the exact signal speeds only where a bound exceeds the
-// threshold -- a read pass at HBM speed instead of 800 instructions per cell.
+// HLL-Einfeldt: a read pass at HBM speed instead of 800 instructions per cell.
+// A block covers a tile of 32 x 8 (x, y) columns and marches kDtAllSegment cells
+// along z.  Per step every thread
+// evaluates the bound of its own cell ONCE and publishes it in shared memory
+// (double buffered, one barrier per step); the +x / +y faces read the
+// neighbour's bound from there, the +z face keeps the previous step's.  Tiles
+// overlap by one column and one row (the last column / row of a tile only
+// supplies bounds), so no thread ever evaluates a neighbour's bound.  The exact
+// signal speeds are evaluated only where a bound exceeds the threshold, out of
+// line so that the march stays small.
 constexpr int kDtAllSegment = 16;
+constexpr int kDtTileX = 32, kDtTileY = 8, kDtPlanes = 2;
+// exact signal speed of the face between the stored states at pl and pr (the
+// lazy bases never set the Newton failure flag)
+template <int D, int DIR, int BASE>
+__device__ __noinline__ double dt_all_exact(const EqConst ec, const double* pl, const double* pr,
+                                            long long sc) {
+  const Eqs eq(ec);
+  Complete<D> l, r;
+  load_complete<D>(l, pl, sc);
+  load_complete<D>(r, pr, sc);
+  DtData<D, BASE> dl, dr;
+  stage_dt_cell<D, BASE>(dl, l);
+  stage_dt_cell<D, BASE>(dr, r);
+  int failed = 0;
+  return stage_dt_face<D, DIR, BASE>(eq, dl, dr, failed);
+}
+FVS_DEV void dt_all_take(double s, double& maxsig, double& thr) {
+  if (s > maxsig) {
+    maxsig = s;
+    const double t = s * kLazyKeep;
+    thr = t > thr ? t : thr;
+  }
+}
+#ifndef FVS_DT_ALL_MIN_BLOCKS
+#define FVS_DT_ALL_MIN_BLOCKS 4
+#endif
 template <int D, int BASE>
-__global__ void __launch_bounds__(256) stable_dt_all_lazy_kernel(const DtAllArgs A) {
+__global__ void __launch_bounds__(256, FVS_DT_ALL_MIN_BLOCKS) stable_dt_all_lazy_kernel(const DtAllArgs A) {
+  __shared__ int4 s_b[2][kDtPlanes][kDtTileY][kDtTileX];
   const BoxDesc& B = A.boxes[0][blockIdx.y];
   const int n0 = B.n[0], n1 = B.n[1], n2 = B.n[2];
-  const int tiles_x = (n0 + 31) / 32;
-  const int x = (blockIdx.x % tiles_x) * 32 + (threadIdx.x & 31);
-  const int y = (blockIdx.x / tiles_x) * 8 + (threadIdx.x >> 5);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // tiles advance by 31 / 7 cells (2-D and 3-D; a 1-D level has a single row)
+  const int step_y = D >= 2 ? kDtTileY - 1 : 1;
+  const int tiles_x = (n0 + kDtTileX - 2) / (kDtTileX - 1);
+  const int x = (blockIdx.x % tiles_x) * (kDtTileX - 1) + tx;
+  const int y = (blockIdx.x / tiles_x) * step_y + ty;
   const int z0 = blockIdx.z * kDtAllSegment;
   double maxsig[D], thr[D];
 #pragma unroll
@@ -908,47 +943,71 @@ __global__ void __launch_bounds__(256) stable_dt_all_lazy_kernel(const DtAllArgs
     maxsig[d] = 0.0;
     thr[d] = A.sig_hint[d] * kLazyKeep;
   }
-  int failed = 0;
-  if (x < n0 && y < n1 && z0 < n2) {
-    const Eqs eq(A.eq);
+  if (z0 < n2) { // block uniform
+    const EqM eq(A.eq);
     const long long sc = B.sc;
     const long long plane = (long long)n0 * n1;
-    const double* p = B.src + x + (long long)n0 * y + plane * z0;
+    const bool in_box = x < n0 && y < n1;
+    // cells outside the box read the last cell (their bounds are never used)
+    const double* p = B.src + min(x, n0 - 1) + (long long)n0 * min(y, n1 - 1) + plane * z0;
     const unsigned char* mx = A.boxes[0][blockIdx.y].dtmask;
     const unsigned char* my = D >= 2 ? A.boxes[1][blockIdx.y].dtmask : nullptr;
     const unsigned char* mz = D >= 3 ? A.boxes[2][blockIdx.y].dtmask : nullptr;
-    const bool face_x = x + 1 < n0 && mx[x];
-    const bool face_y = D >= 2 && y + 1 < n1 && my[y];
+    // faces owned by this thread: not in the last column / row of the tile
+    const bool owner = in_box && tx < kDtTileX - 1 && (D < 2 || ty < kDtTileY - 1);
+    const bool face_x = owner && x + 1 < n0 && mx[x];
+    const bool face_y = D >= 2 && owner && y + 1 < n1 && my[y];
     const int z_end = min(z0 + kDtAllSegment, n2 - 1); // last cell read: the +z neighbour of the segment
     SigBoundAll<D> prev{};
+    // kDtPlanes planes per step: their loads are issued together (memory-level
+    // parallelism without a register prefetch), one barrier per step
 #pragma unroll 1
-    for (int z = z0; z <= z_end; ++z, p += plane) {
-      Complete<D> q;
-      load_complete<D>(q, p, sc);
-      const SigBoundAll<D> cur = sig_bound_all<D>(eq.m, q);
-      if constexpr (D >= 3) {
-        if (z > z0 && mz[z - 1] &&
-            sig_bound_exceeds(prev.u[2], prev.c, cur.u[2], cur.c, thr[2])) {
-          stage_dt_exact<D, 2, BASE>(eq, p - plane, p, sc, maxsig[2], thr[2], failed);
-        }
+    for (int zb = z0; zb <= z_end; zb += kDtPlanes, p += plane * kDtPlanes) {
+      Complete<D> q[kDtPlanes];
+#pragma unroll
+      for (int i = 0; i < kDtPlanes; ++i) {
+        // planes past the end re-read the last one; their results are not used
+        load_complete<D>(q[i], p + plane * min(i, z_end - zb), sc);
       }
-      prev = cur;
-      if (z == z0 + kDtAllSegment) break; // the +z neighbour belongs to the next segment
-      if (face_x) {
-        Complete<D> r;
-        load_complete<D>(r, p + 1, sc);
-        const SigBound b = sig_bound<D, 0>(eq.m, r);
-        if (sig_bound_exceeds(cur.u[0], cur.c, b.u, b.c, thr[0])) {
-          stage_dt_exact<D, 0, BASE>(eq, p, p + 1, sc, maxsig[0], thr[0], failed);
-        }
+      SigBoundAll<D> cur[kDtPlanes];
+      const int buf = ((zb - z0) / kDtPlanes) & 1;
+#pragma unroll
+      for (int i = 0; i < kDtPlanes; ++i) {
+        cur[i] = sig_bound_all<D>(eq, q[i]);
+        int4 mine;
+        mine.x = cur[i].u[0];
+        mine.y = D >= 2 ? cur[i].u[1] : 0;
+        mine.z = D >= 3 ? cur[i].u[2] : 0;
+        mine.w = cur[i].c;
+        s_b[buf][i][ty][tx] = mine;
       }
-      if constexpr (D >= 2) {
-        if (face_y) {
-          Complete<D> r;
-          load_complete<D>(r, p + n0, sc);
-          const SigBound b = sig_bound<D, 1>(eq.m, r);
-          if (sig_bound_exceeds(cur.u[1], cur.c, b.u, b.c, thr[1])) {
-            stage_dt_exact<D, 1, BASE>(eq, p, p + n0, sc, maxsig[1], thr[1], failed);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kDtPlanes; ++i) {
+        const int z = zb + i;
+        if (z > z_end) break;
+        const double* pz = p + plane * i;
+        if constexpr (D >= 3) {
+          if (owner && z > z0 && mz[z - 1] &&
+              sig_bound_exceeds(prev.u[2], prev.c, cur[i].u[2], cur[i].c, thr[2])) {
+            dt_all_take(dt_all_exact<D, 2, BASE>(A.eq, pz - plane, pz, sc), maxsig[2], thr[2]);
+          }
+        }
+        prev = cur[i];
+        if (z < z0 + kDtAllSegment) { // the +z neighbour of the segment only closes the z face
+          if (face_x) {
+            const int4 r = s_b[buf][i][ty][tx + 1];
+            if (sig_bound_exceeds(cur[i].u[0], cur[i].c, r.x, r.w, thr[0])) {
+              dt_all_take(dt_all_exact<D, 0, BASE>(A.eq, pz, pz + 1, sc), maxsig[0], thr[0]);
+            }
+          }
+          if constexpr (D >= 2) {
+            if (face_y) {
+              const int4 r = s_b[buf][i][ty + 1][tx];
+              if (sig_bound_exceeds(cur[i].u[1], cur[i].c, r.y, r.w, thr[1])) {
+                dt_all_take(dt_all_exact<D, 1, BASE>(A.eq, pz, pz + n0, sc), maxsig[1], thr[1]);
+              }
+            }
           }
         }
       }
@@ -959,7 +1018,6 @@ __global__ void __launch_bounds__(256) stable_dt_all_lazy_kernel(const DtAllArgs
     reduce_max_signal(maxsig[d], A.max_signal + d);
     __syncthreads();
   }
-  if (failed) *A.fail_flag = 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def compile_unit(tag, flags, tol):
     if tol:
         base_flags = [f for f in base_flags if f != "-fmad=false"] + ["-fmad=true",
                                                                       "-DFVS_TOLERANCE_UNIT=1"]
-    cmd = [b.NVCC] + base_flags + flags + ["-DFVS_INST_D=3", "-DFVS_INST_BASE=0", "-Xptxas", "-v",
+    cmd = [b.NVCC] + base_flags + flags + ["-DFVS_INST_D=3", "-DFVS_INST_BASE=0", "-DFVS_INST_MINIMAL", "-Xptxas", "-v",
            "-I", b.INCLUDE, "-c", os.path.join(b.CSRC, "sweep_inst.cu"), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
