@@ -39,7 +39,7 @@ SYMBOLS = [
     "fvs_run", "fvs_set_regrid_frequency", "fvs_set_cycles", "fvs_cycles", "fvs_time_point",
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
-    "fvs_set_dt_hints", "fvs_dt_hint_redos",
+    "fvs_set_dt_hints", "fvs_dt_hint_redos", "fvs_download_state_region",
     "fvs_enable_timing", "fvs_sweep_time_ms",
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
     "fvs_eb_array_box", "fvs_download_eb_array", "fvs_cut_cell_flags",
@@ -352,6 +352,13 @@ class Context:
         if out is None:
             out = np.empty(self.state_shape(box))
         _check(lib().fvs_download_state(self.h, self.level, box, _dp(out)))
+        return out
+
+    def download_state_region(self, box, lo, hi):
+        """[ncomp, z, y, x] copy of the cells lo..hi (global indices) of the box's state array."""
+        lo3, hi3 = list(lo) + [0] * (3 - len(lo)), list(hi) + [0] * (3 - len(hi))
+        out = np.empty((self.ncomp, hi3[2] - lo3[2] + 1, hi3[1] - lo3[1] + 1, hi3[0] - lo3[0] + 1))
+        _check(lib().fvs_download_state_region(self.h, self.level, box, _i3(lo3), _i3(hi3), _dp(out)))
         return out
 
     def upload_state_async(self, box, arr):

@@ -165,6 +165,13 @@ int fvs_flux_box(const fvs_ctx* ctx, int level, int box, int dir, int lo[3],
  * host_fab holds (rank+4) components over fvs_state_box in FAB layout. */
 int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab);
 int fvs_download_state(fvs_ctx* ctx, int level, int box, double* host_fab);
+/* A sub-box [lo, hi] (global cell indices, inside the state array of the box incl.
+ * its ghost cells) of the current state into host[ncomp][hi2-lo2+1][hi1-lo1+1][hi0-lo0+1]:
+ * what amrex::FArrayBox::copy of a sub-box does on the host side
+ * (the reference reads sub-boxes of GetScratch(level) in its output and tagging code,
+ * src/AMReX/IntegratorContext.cpp:303-331). */
+int fvs_download_state_region(fvs_ctx* ctx, int level, int box, const int lo[3], const int hi[3],
+                              double* host);
 /* IntegratorContext::CopyDataToScratch / CopyScratchToData
  * (src/AMReX/IntegratorContext.cpp:629-651): the level data of the patch
  * hierarchy carries NO ghost cells; host_fab holds (rank+4) components over

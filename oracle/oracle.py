@@ -29,24 +29,62 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
+def build_timing():
+    """Timing-only builds (oracle/Makefile `timing`): {name: path} of the ones that exist."""
+    try:
+        subprocess.check_call(["make", "-s", "-j2", "-C", _HERE, "timing"])
+    except (subprocess.CalledProcessError, OSError):
+        pass
+    out = {}
+    for name in ("v3fma", "v4"):
+        path = os.path.join(_HERE, "_native", f"liboracle_{name}.so")
+        if os.path.exists(path):
+            out[name] = path
+    return out
+
+
+def unload():
+    """Forget the loaded build so that use_library() can bind another one (the old
+    handle stays mapped; Level objects created from it keep working)."""
+    global _LIB
+    _LIB = None
+
+
+def use_library(path):
+    """Binds this module to another build of the oracle (bench.py: the native timing
+    build).  Must be called before the first lib()."""
+    global _LIB
+    assert _LIB is None, "oracle library already loaded"
+    _LIB = _load(path)
+    return _LIB
+
+
+def set_num_threads(n):
+    return lib().fvso_set_num_threads(int(n))
+
+
 def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(path):
             build()
-        L = C.CDLL(path)
-        L.fvso_last_error.restype = C.c_char_p
-        L.fvso_level_create.restype = C.c_void_p
-        L.fvso_level_scratch.restype = C.POINTER(C.c_double)
-        L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
-        L.fvso_level_eb_array.restype = C.POINTER(C.c_double)
-        L.fvso_cf_create.restype = C.c_void_p
-        L.fvso_hierarchy_create.restype = C.c_void_p
-        L.fvso_level_cycles.restype = C.c_long
-        L.fvso_level_time.restype = C.c_double
-        _LIB = L
+        _LIB = _load(path)
     return _LIB
+
+
+def _load(path):
+    L = C.CDLL(path)
+    L.fvso_last_error.restype = C.c_char_p
+    L.fvso_level_create.restype = C.c_void_p
+    L.fvso_level_scratch.restype = C.POINTER(C.c_double)
+    L.fvso_level_fluxes.restype = C.POINTER(C.c_double)
+    L.fvso_level_eb_array.restype = C.POINTER(C.c_double)
+    L.fvso_cf_create.restype = C.c_void_p
+    L.fvso_hierarchy_create.restype = C.c_void_p
+    L.fvso_level_cycles.restype = C.c_long
+    L.fvso_level_time.restype = C.c_double
+    return L
 
 
 def _ia(x):

@@ -15,6 +15,9 @@
 // Third-party arithmetic (Eigen reduction order, AMReX tiling / FillBoundary /
 // boxDiff) is restated from the published algorithms and is "parity
 // unpinned" against a real AMReX build.
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "level.hpp"
 #include "amr.hpp"
 
@@ -48,6 +51,18 @@ Box make_box(const int* lo, const int* hi) {
 extern "C" {
 
 const char* fvso_last_error() { return g_error.c_str(); }
+
+// Threads of the OpenMP tile loops (the reference: OMP_NUM_THREADS).  bench.py sets
+// it explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers.
+int fvso_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 // ------------------------------------------------------------------ level
 void* fvso_level_create(int rank, const int* dom_lo, const int* dom_hi,

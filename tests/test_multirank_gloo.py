@@ -129,15 +129,21 @@ def test_two_ranks_halo_exchange_and_dt_min_match_single_process_oracle(tmp_path
 
 
 def test_bench_box_layout_is_one_box_per_rank():
-    """bench.py --gpus N: N boxes, box b on rank b, domain grows with N (weak scaling)."""
+    """bench.py --gpus N: N boxes, box b on rank b; weak scaling grows the domain with N,
+    strong scaling cuts the same domain into N boxes; the parity sub-box of bench.py lies
+    inside the domain and touches every rank boundary it can."""
     import importlib
     bench = importlib.import_module("bench")
     for n in (1, 2, 4, 8):
-        domain_n, boxes = bench.grid_of_boxes(n, 16)
-        assert len(boxes) == n
+        domain_n, boxes, parts, box_n = bench.grid_of_boxes(n, 16)
+        assert len(boxes) == n and parts[0] * parts[1] * parts[2] == n
         assert domain_n[0] * domain_n[1] * domain_n[2] == n * 16 ** 3
         cells = set()
         for lo, hi in boxes:
             assert all(hi[d] - lo[d] + 1 == 16 for d in range(3))
             cells.add(tuple(lo))
         assert len(cells) == n
+        sdom, sboxes, sparts, sbox_n = bench.grid_of_boxes(n, 16, strong=True)
+        assert sdom == [16, 16, 16] and len(sboxes) == n
+        assert sum((hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)
+                   for lo, hi in sboxes) == 16 ** 3
