@@ -458,7 +458,7 @@ class Context:
         return lib().fvs_kernel_launches(self.h)
 
     def set_dt_hints(self, on):
-        _check(lib().fvs_set_dt_hints(self.h, 1 if on else 0))
+        _check(lib().fvs_set_dt_hints(self.h, int(on)))
 
     @property
     def dt_hint_redos(self):

@@ -240,6 +240,7 @@ struct fvs_ctx {
   // verified after every evaluation; a failed verification repeats the work
   // without a hint
   bool dt_hints{true};
+  bool keep_hints_on_upload{false}; // fvs_set_dt_hints(ctx, 2): lets the tests plant a stale hint
   long hint_redos{0};
   // timing
   bool timing{false};
@@ -410,6 +411,11 @@ double dt_hint(const fvs_ctx* ctx, const Level& L, int dir) {
 // true iff an evaluation with `hint` that returned `sig` is exact: every face
 // that was skipped has a signal speed below max(hint, sig) (numerics.cuh)
 bool verify_hint(double hint, double sig) { return sig >= hint; }
+// new data from outside: what is known about the old state says nothing about it
+void drop_hints(const fvs_ctx* ctx, Level& L) {
+  if (ctx->keep_hints_on_upload) return;
+  for (double& s : L.last_sig) s = 0.0;
+}
 
 fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxDesc* boxes,
                           int slot, double hint = 0.0) {
@@ -1756,6 +1762,7 @@ int fvs_upload_state(fvs_ctx* ctx, int level, int box, const double* host_fab) {
     if (!ctx || !host_fab) throw Error("null argument");
     ctx->use_device();
     Level& L = ctx->level(level);
+    drop_hints(ctx, L);
     Patch& p = ctx->patch(L, box);
     FVS_CUDA(cudaMemcpyAsync(p.buf[L.cur], host_fab, (size_t)p.cells * ctx->ncomp() * sizeof(double),
                              cudaMemcpyHostToDevice, ctx->stream));
@@ -1815,6 +1822,7 @@ int fvs_upload_state_async(fvs_ctx* ctx, int level, int box, const double* host_
     if (!ctx || !host_fab) throw Error("null argument");
     ctx->use_device();
     Level& L = ctx->level(level);
+    drop_hints(ctx, L);
     Patch& p = ctx->patch(L, box);
     FVS_CUDA(cudaMemcpyAsync(p.buf[L.cur], host_fab, (size_t)p.cells * ctx->ncomp() * sizeof(double),
                              cudaMemcpyHostToDevice, ctx->stream));
@@ -1865,6 +1873,7 @@ int fvs_copy_data_to_scratch_async(fvs_ctx* ctx, int level, int box, const doubl
     if (!ctx || !host_fab) throw Error("null argument");
     ctx->use_device();
     Level& L = ctx->level(level);
+    drop_hints(ctx, L);
     copy_valid(ctx, L, ctx->patch(L, box), const_cast<double*>(host_fab), true);
     return (int)FVS_OK;
   });
@@ -2878,6 +2887,7 @@ int fvs_set_dt_hints(fvs_ctx* ctx, int on) {
   return guarded([&] {
     if (!ctx) throw Error("null context");
     ctx->dt_hints = on != 0;
+    ctx->keep_hints_on_upload = on == 2;
     return (int)FVS_OK;
   });
 }

@@ -385,7 +385,9 @@ long fvs_kernel_launches(const fvs_ctx* ctx);
  * evaluation of that direction and the result is verified against the hint
  * afterwards (a violated hint repeats the evaluation without one), so the
  * returned dt is bit-identical either way.  on = 0 disables the hints (every
- * evaluation starts from zero).  No reference counterpart.  Default: on. */
+ * evaluation starts from zero).  Uploading a state drops the hints of its level;
+ * on = 2 keeps them (the tests use it to plant a stale hint and exercise the
+ * repeat).  No reference counterpart.  Default: 1. */
 int fvs_set_dt_hints(fvs_ctx* ctx, int on);
 /* Number of evaluations that had to be repeated because a hint was violated. */
 long fvs_dt_hint_redos(const fvs_ctx* ctx);

@@ -362,6 +362,15 @@ def numeric_flux_scalar_hll(rank, recon, limiter, states, dt, dx, direction, gam
     return out
 
 
+def hllem_scalar(rank, larrouturou, states, direction, gamma=1.4):
+    """The reference's scalar HLLEM code path (scalar_hllem.hpp), Rank 1 and 2."""
+    states = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.zeros(rank + 2)
+    _check(lib().fvso_unit_hllem_scalar(rank, C.c_double(gamma), int(larrouturou), _dp(states),
+                                        direction, _dp(out)))
+    return out
+
+
 def exact_riemann(rank, left, right, direction=0, gamma=1.4):
     left = np.ascontiguousarray(left, dtype=np.float64)
     right = np.ascontiguousarray(right, dtype=np.float64)

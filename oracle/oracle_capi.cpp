@@ -18,6 +18,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "scalar_hllem.hpp"
 #include "level.hpp"
 #include "amr.hpp"
 
@@ -445,6 +446,34 @@ int fvso_unit_numeric_flux(int rank, double gamma, int base, int recon,
     if (rank == 1) run(std::integral_constant<int, 1>{});
     else if (rank == 2) run(std::integral_constant<int, 2>{});
     else run(std::integral_constant<int, 3>{});
+  });
+}
+
+// The reference's scalar HLLEM code path (scalar_hllem.hpp; Rank 1 and 2), restated
+// independently of the array path: 2 Complete states -> Conservative flux.
+int fvso_unit_hllem_scalar(int rank, double gamma, int larrouturou, const double* states, int dir,
+                           double* flux_out) {
+  return guarded([&] {
+    auto run = [&](auto Dc) {
+      constexpr int D = decltype(Dc)::value;
+      fvso_scalar::State<D> st[2];
+      for (int k = 0; k < 2; ++k) {
+        const double* p = states + k * (D + 4);
+        st[k].rho = p[0];
+        for (int d = 0; d < D; ++d) st[k].mom[d] = p[1 + d];
+        st[k].E = p[1 + D];
+        st[k].p = p[2 + D];
+        st[k].a = p[3 + D];
+      }
+      fvso_scalar::Flux<D> f;
+      fvso_scalar::HllemScalar<D>(f, st[0], st[1], gamma, dir, larrouturou != 0);
+      flux_out[0] = f.rho;
+      for (int d = 0; d < D; ++d) flux_out[1 + d] = f.mom[d];
+      flux_out[1 + D] = f.E;
+    };
+    if (rank == 1) run(std::integral_constant<int, 1>{});
+    else if (rank == 2) run(std::integral_constant<int, 2>{});
+    else throw std::runtime_error("the reference's scalar HLLEM path is complete for Rank 1 and 2 only");
   });
 }
 

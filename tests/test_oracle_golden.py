@@ -228,3 +228,195 @@ def test_muscl_hancock_prim_and_char_sod_star_state(oracle, recon):
     post_shock = r[(x > 0.27) & (x < 0.41)]     # between contact and shock (0.438)
     assert abs(post_shock.mean() - 0.26557) < 3e-3
     assert abs(r[x > 0.5].mean() - 0.125) < 1e-12
+
+
+# --- HLLEM: the reference's two code paths against each other ---------------------
+# The reference cross-checks its scalar and array paths for HLL only
+# (tests/test.simd_FluxMethod.cpp:54-105).  oracle/scalar_hllem.hpp restates the
+# scalar HLLEM path (src/equations/perfect_gas/HllemMethod.hpp:371-640)
+# independently of the array restatement the product is compared with
+# (oracle/numerics.hpp <- :711-1072); the two differ upstream in the order of the
+# Roe averages (equal up to rounding) and in the Larrouturou upwinding of a flux
+# towards the left (quirk Q6, scalar_hllem.hpp header).
+def _random_states(orc, rank, rng, supersonic=False):
+    out = []
+    for _ in range(2):
+        rho = 0.2 + 2.0 * rng.random()
+        p = 0.1 + 3.0 * rng.random()
+        a = math.sqrt(GAMMA * p / rho)
+        u = (rng.random(rank) - 0.5) * (6.0 if supersonic else 1.0) * a
+        e = p / (GAMMA - 1.0) + 0.5 * rho * float(np.dot(u, u))
+        out.append(complete(orc, rank, rho, list(rho * u), e))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("rank", [1, 2])
+@pytest.mark.parametrize("supersonic", [False, True])
+def test_hllem_scalar_path_agrees_with_array_path(oracle, rank, supersonic):
+    orc = oracle
+    rng = np.random.default_rng(17 + rank)
+    worst = 0.0
+    for _ in range(400):
+        states = _random_states(orc, rank, rng, supersonic)
+        for direction in range(rank):
+            scalar = orc.hllem_scalar(rank, False, states, direction)
+            array = orc.numeric_flux(rank, orc.BASE_HLLEM, orc.RECON_FIRST_ORDER,
+                                     orc.LIMITER_NONE, states, 1.0, 1.0, direction)
+            scale = np.max(np.abs(array)) + 1e-300
+            worst = max(worst, float(np.max(np.abs(scalar - array)) / scale))
+    # only the order of the Roe averages differs: a few ulp, amplified by the
+    # cancellation in roeH - |roeU|^2 / 2
+    assert worst < 2e-14, worst
+
+
+def test_hllem_scalar_equals_array_bitwise_for_equal_densities(oracle):
+    """With rhoL == rhoR both Roe weights are exactly 1/2 and every product with them is
+    exact, so the two operation orders round identically: bit-for-bit equality of two
+    independent restatements of the same formulas."""
+    orc = oracle
+    rng = np.random.default_rng(5)
+    for rank in (1, 2):
+        for _ in range(300):
+            rho = 4.0 ** rng.integers(-2, 3)   # sqrt(rho) exact
+            cells = []
+            for _ in range(2):
+                p = 0.1 + 3.0 * rng.random()
+                u = (rng.random(rank) - 0.5)
+                e = p / (GAMMA - 1.0) + 0.5 * rho * float(np.dot(u, u))
+                cells.append(complete(orc, rank, rho, list(rho * u), e))
+            states = np.concatenate(cells)
+            for direction in range(rank):
+                scalar = orc.hllem_scalar(rank, False, states, direction)
+                array = orc.numeric_flux(rank, orc.BASE_HLLEM, orc.RECON_FIRST_ORDER,
+                                         orc.LIMITER_NONE, states, 1.0, 1.0, direction)
+                assert np.array_equal(scalar, array), (rank, direction, scalar, array)
+
+
+def test_hllem_larrouturou_scalar_vs_array_upwinding(oracle):
+    """Q6: for a mass flux towards the right the scalar and the array path agree (to the
+    rounding of the Roe averages); towards the left the scalar path carries MINUS the
+    upwinded tangential momentum flux (HllemMethod.hpp:543-546 vs :907-910)."""
+    orc = oracle
+    rng = np.random.default_rng(23)
+    seen = {True: 0, False: 0}
+    for _ in range(600):
+        states = _random_states(orc, 2, rng)
+        for direction in (0, 1):
+            iy = 1 - direction
+            scalar = orc.hllem_scalar(2, True, states, direction)
+            array = orc.numeric_flux(2, orc.BASE_HLLEM_LARROUTUROU, orc.RECON_FIRST_ORDER,
+                                     orc.LIMITER_NONE, states, 1.0, 1.0, direction)
+            scale = np.max(np.abs(array)) + 1e-300
+            assert abs(scalar[0] - array[0]) / scale < 2e-14
+            assert abs(scalar[1 + direction] - array[1 + direction]) / scale < 2e-14
+            towards_right = array[0] > 0.0
+            seen[towards_right] += 1
+            if towards_right:
+                assert np.max(np.abs(scalar - array)) / scale < 2e-14
+            else:
+                assert abs(scalar[1 + iy] + array[1 + iy]) / scale < 2e-14
+    assert seen[True] > 100 and seen[False] > 100
+
+
+# --- known answers of the HLLEM flux and of the limiter ---------------------------
+@pytest.mark.parametrize("base", [0, 1])
+@pytest.mark.parametrize("rank", [1, 2, 3])
+def test_hllem_keeps_a_stationary_contact_exactly(oracle, rank, base):
+    """The point of the HLLEM anti-diffusion (Einfeldt 1991): across a contact at rest
+    (jump in density, equal pressure, zero velocity) the numeric flux is the physical
+    one, (0, p e_d, 0) -- no mass or energy flux, where plain HLLE smears the contact.
+    Powers of four keep sqrt(rho) and the Roe weights exact, so 'exactly' means bits."""
+    orc = oracle
+    p = 1.0
+    left = complete(orc, rank, 4.0, [0.0] * rank, p / (GAMMA - 1.0))
+    right = complete(orc, rank, 1.0, [0.0] * rank, p / (GAMMA - 1.0))
+    for direction in range(rank):
+        f = orc.numeric_flux(rank, base, orc.RECON_FIRST_ORDER, orc.LIMITER_NONE,
+                             np.concatenate([left, right]), 1.0, 1.0, direction)
+        hll = orc.numeric_flux(rank, orc.BASE_HLL_EINFELDT, orc.RECON_FIRST_ORDER,
+                               orc.LIMITER_NONE, np.concatenate([left, right]), 1.0, 1.0, direction)
+        assert abs(f[0]) < 1e-15 and abs(f[rank + 1]) < 1e-15, f
+        assert abs(f[1 + direction] - p) < 1e-15
+        assert hll[0] > 0.1, "plain HLLE diffuses the contact (mass flux towards the light gas)"
+
+
+def test_q1_3d_normal_momentum_antidiffusion_vanishes(oracle):
+    """Quirk Q1 (HllemMethod.hpp:991-992): the array 3-D path subtracts
+    b_delta_alpha_2 * roeU.row(iy) from the NORMAL momentum flux.  With the Larrouturou
+    modification roeU[iy] is zero, so in 3-D the normal momentum flux of HLLEM-L equals
+    the HLLE value, while the same states in 2-D (which uses row(ix)) get the correction."""
+    orc = oracle
+    rng = np.random.default_rng(3)
+    differs_2d = 0
+    for _ in range(50):
+        rho = [0.5 + rng.random(), 0.5 + rng.random()]
+        p = [0.5 + rng.random(), 0.5 + rng.random()]
+        u = [0.3 * (rng.random() - 0.5), 0.3 * (rng.random() - 0.5)]
+        def cells(rank):
+            out = []
+            for k in range(2):
+                vel = [u[k]] + [0.0] * (rank - 1)
+                e = p[k] / (GAMMA - 1.0) + 0.5 * rho[k] * u[k] * u[k]
+                out.append(complete(orc, rank, rho[k], [rho[k] * v for v in vel], e))
+            return np.concatenate(out)
+        f3 = orc.numeric_flux(3, orc.BASE_HLLEM_LARROUTUROU, orc.RECON_FIRST_ORDER,
+                              orc.LIMITER_NONE, cells(3), 1.0, 1.0, 0)
+        # the HLLE value of the normal momentum flux with HLLEM's signal speeds (:752-811)
+        a = [math.sqrt(GAMMA * p[k] / rho[k]) for k in range(2)]
+        en = [p[k] / (GAMMA - 1.0) + 0.5 * rho[k] * u[k] * u[k] for k in range(2)]
+        h = [(en[k] + p[k]) / rho[k] for k in range(2)]
+        sq = [math.sqrt(r) for r in rho]
+        w = [sq[k] / (sq[0] + sq[1]) for k in range(2)]
+        roe_u = w[0] * u[0] + w[1] * u[1]
+        roe_a = math.sqrt((GAMMA - 1.0) * (w[0] * h[0] + w[1] * h[1] - 0.5 * roe_u * roe_u))
+        b_l = min(min(u[0] - max(a), roe_u - roe_a), 0.0)
+        b_r = max(max(roe_u + roe_a, u[1] + max(a)), 0.0)
+        m = [rho[k] * u[k] for k in range(2)]
+        fm = [u[k] * m[k] + p[k] for k in range(2)]
+        h3 = [None, (b_r * fm[0] - b_l * fm[1] + b_l * b_r * (m[1] - m[0])) / (b_r - b_l)]
+        f2 = orc.numeric_flux(2, orc.BASE_HLLEM_LARROUTUROU, orc.RECON_FIRST_ORDER,
+                              orc.LIMITER_NONE, cells(2), 1.0, 1.0, 0)
+        f1 = orc.numeric_flux(1, orc.BASE_HLLEM_LARROUTUROU, orc.RECON_FIRST_ORDER,
+                              orc.LIMITER_NONE, cells(1), 1.0, 1.0, 0)
+        assert abs(f3[1] - h3[1]) <= 1e-14 * abs(h3[1])
+        # mass and energy flux are the same in every dimension; the normal momentum
+        # flux of 1-D and 2-D carries the anti-diffusion term that 3-D loses
+        assert abs(f3[0] - f2[0]) <= 1e-15 and abs(f2[0] - f1[0]) <= 1e-15
+        assert abs(f2[1] - f1[1]) <= 1e-15
+        differs_2d += abs(f2[1] - f3[1]) > 1e-6
+    assert differs_2d > 40
+
+
+def test_vanleer_and_minmod_known_values(oracle):
+    """MusclHancockMethod.hpp:92-187: VanLeer(sL, sR) = 2 sL sR / (sL + sR) for sL sR > 0,
+    else 0; MinMod picks the smaller slope.  Read off the reconstructed density: with a
+    uniform velocity-free state only rho varies, q0 - q_L(edge) = slope / 2 ... probed through
+    the first-order-in-time limit dt -> 0 of MUSCL-Hancock over HLL: the flux through the
+    face between cells 1 and 2 is then the HLL flux of (q1 + s1/2, q2 - s2/2)."""
+    orc = oracle
+    p = 1.0
+
+    def cell(rho):
+        return complete(orc, 1, rho, [0.0], p / (GAMMA - 1.0))
+
+    def face_flux(limiter, rhos, dt=0.0):
+        states = np.concatenate([cell(r) for r in rhos])
+        return orc.numeric_flux(1, orc.BASE_HLL_EINFELDT, orc.RECON_MUSCL_HANCOCK, limiter,
+                                states, dt, 1.0, 0)
+
+    def hll(rho_l, rho_r):
+        return orc.numeric_flux(1, orc.BASE_HLL_EINFELDT, orc.RECON_FIRST_ORDER, orc.LIMITER_NONE,
+                                np.concatenate([cell(rho_l), cell(rho_r)]), 0.0, 1.0, 0)
+
+    # densities 1, 2, 5, 7: slopes of cell 1 are (1, 3), of cell 2 (3, 2)
+    rhos = [1.0, 2.0, 5.0, 7.0]
+    # VanLeer(1, 3) = 1.5, VanLeer(3, 2) = 2.4 -> edge states 2.75 | 3.8
+    assert np.array_equal(face_flux(orc.LIMITER_VANLEER, rhos), hll(2.0 + 0.75, 5.0 - 1.2))
+    # MinMod(1, 3) = 1, MinMod(3, 2) = 2 -> 2.5 | 4
+    assert np.array_equal(face_flux(orc.LIMITER_MINMOD, rhos), hll(2.5, 4.0))
+    # NoLimiter: central slopes (1 + 3) / 2 = 2, (3 + 2) / 2 = 2.5 -> 3 | 3.75
+    assert np.array_equal(face_flux(orc.LIMITER_NONE, rhos), hll(3.0, 3.75))
+    # an extremum: slopes of opposite sign -> VanLeer and MinMod give 0 (first order)
+    rhos = [1.0, 3.0, 2.0, 4.0]
+    assert np.array_equal(face_flux(orc.LIMITER_VANLEER, rhos), hll(3.0, 2.0))
+    assert np.array_equal(face_flux(orc.LIMITER_MINMOD, rhos), hll(3.0, 2.0))
