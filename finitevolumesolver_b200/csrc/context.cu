@@ -1172,15 +1172,41 @@ Box register_plane(const Box& fine_valid, const int ratio[3], int dir, int side)
   plane.lo[dir] = plane.hi[dir] = side == 0 ? plane.lo[dir] : plane.hi[dir] + 1;
   return plane;
 }
+// Periodic images of a level's boxes: the index shifts (multiples of the domain
+// length in the periodic directions, the zero shift first) under which a box of
+// the level is seen from across a periodic boundary.  amrex::FluxRegister::
+// CrseInit / Reflux and FillPatchTwoLevels copy with geom.periodicity().
+std::vector<std::array<int, 3>> period_shifts(const Level& L, int rank) {
+  std::vector<std::array<int, 3>> out;
+  out.push_back({0, 0, 0});
+  int r[3];
+  for (int d = 0; d < 3; ++d) r[d] = (d < rank && L.periodic[d]) ? 1 : 0;
+  for (int sz = -r[2]; sz <= r[2]; ++sz)
+    for (int sy = -r[1]; sy <= r[1]; ++sy)
+      for (int sx = -r[0]; sx <= r[0]; ++sx) {
+        if (sx == 0 && sy == 0 && sz == 0) continue;
+        out.push_back({sx * L.domain.len(0), sy * L.domain.len(1), sz * L.domain.len(2)});
+      }
+  return out;
+}
+fvs::ArrayRef shifted_ref(fvs::ArrayRef a, const std::array<int, 3>& s) {
+  for (int d = 0; d < 3; ++d) a.lo[d] += s[(size_t)d];
+  return a;
+}
 std::vector<unsigned char> register_open(const Level& fine, const Level& coarse, const int ratio[3],
                                          const Box& faces, int dir, int side) {
   std::vector<unsigned char> open((size_t)faces.size(), 1);
   size_t n = 0;
+  const int len = coarse.domain.len(dir);
   for (int k = faces.lo[2]; k <= faces.hi[2]; ++k)
     for (int j = faces.lo[1]; j <= faces.hi[1]; ++j)
       for (int i = faces.lo[0]; i <= faces.hi[0]; ++i, ++n) {
         int out[3] = {i, j, k};
         if (side == 0) out[dir] -= 1;
+        if (coarse.periodic[dir]) { // the outside cell across a periodic boundary
+          if (out[dir] < coarse.domain.lo[dir]) out[dir] += len;
+          if (out[dir] > coarse.domain.hi[dir]) out[dir] -= len;
+        }
         for (const Box& g : fine.boxes) {
           if (box_contains(coarsen_box(g, ratio), out)) open[n] = 0;
         }
@@ -1268,26 +1294,31 @@ void crse_init(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double mult) {
   RegionCopies packs;
   std::vector<fvs::RegisterDesc> host;
   long long max_faces = 1;
+  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
   for (size_t f = 0; f < fine.boxes.size(); ++f)
     for (int side = 0; side < 2; ++side) {
       const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
-      for (size_t c = 0; c < coarse.boxes.size(); ++c) {
-        Box nodes = coarse.boxes[c];
+      for (size_t c = 0; c < coarse.boxes.size(); ++c)
+      for (const std::array<int, 3>& shift : shifts) {
+        // the coarse box, or its image across a periodic boundary
+        const Box image = fvs::shifted(coarse.boxes[c], shift.data());
+        Box nodes = image;
         nodes.hi[dir] += 1;
         const Box faces = fvs::intersect(plane, nodes);
         if (!faces.ok()) continue;
         const int rf = fine.owner[f], rc = coarse.owner[c];
         if (rf != me && rc != me) continue;
-        Patch* fp = local_patch(fine, (int)f);
         Patch* cp = local_patch(coarse, (int)c);
         fvs::ArrayRef flux_ref;
         if (rf == me && rc == me) {
-          flux_ref = array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size());
+          flux_ref = shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), shift);
         } else {
           double* buf = xf.add(rc, rf, (size_t)faces.size() * ncons);
           flux_ref = array_ref(buf, faces, faces.size());
           if (rc == me) {
-            packs.add(flux_ref, array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), faces);
+            packs.add(flux_ref,
+                      shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), shift),
+                      faces);
             continue;
           }
         }
@@ -1299,8 +1330,8 @@ void crse_init(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double mult) {
         d.side = side;
         d.other = flux_ref;
         for (int e = 0; e < 3; ++e) {
-          d.box_lo[e] = coarse.boxes[c].lo[e];
-          d.box_hi[e] = coarse.boxes[c].hi[e];
+          d.box_lo[e] = image.lo[e];
+          d.box_hi[e] = image.hi[e];
           d.lo[e] = faces.lo[e];
           d.len[e] = faces.len(e);
         }
@@ -1324,12 +1355,16 @@ void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
   RegionCopies packs;
   std::vector<fvs::RegisterDesc> host;
   long long max_faces = 1;
+  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
   for (size_t f = 0; f < fine.boxes.size(); ++f)
     for (int side = 0; side < 2; ++side) {
       const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
-      for (size_t c = 0; c < coarse.boxes.size(); ++c) {
-        // faces of the plane whose OUTSIDE cell belongs to coarse box c
-        Box cells = coarse.boxes[c];
+      for (size_t c = 0; c < coarse.boxes.size(); ++c)
+      for (const std::array<int, 3>& shift : shifts) {
+        // faces of the plane whose OUTSIDE cell belongs to coarse box c (or to
+        // its image across a periodic boundary)
+        const Box image = fvs::shifted(coarse.boxes[c], shift.data());
+        Box cells = image;
         if (side == 0) {
           cells.lo[dir] += 1;
           cells.hi[dir] += 1;
@@ -1364,10 +1399,10 @@ void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
         d.reg = reg_ref;
         d.open = open;
         d.side = side;
-        d.other = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+        d.other = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
         for (int e = 0; e < 3; ++e) {
-          d.box_lo[e] = coarse.boxes[c].lo[e];
-          d.box_hi[e] = coarse.boxes[c].hi[e];
+          d.box_lo[e] = image.lo[e];
+          d.box_hi[e] = image.hi[e];
           d.lo[e] = faces.lo[e];
           d.len[e] = faces.len(e);
         }
@@ -1441,11 +1476,23 @@ void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
   RegionCopies packs;
   std::vector<fvs::InterpDesc> host;
   long long max_cells = 1;
+  // ghost cells beyond a periodic boundary take their parent from the coarse
+  // level's periodic image (the fill domain is grown in the periodic directions)
+  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
+  Box fill_domain = fine.domain;
+  for (int d = 0; d < ctx->cfg.rank; ++d) {
+    if (fine.periodic[d]) {
+      fill_domain.lo[d] -= fine.scratch_gcw;
+      fill_domain.hi[d] += fine.scratch_gcw;
+    }
+  }
   for (size_t f = 0; f < fine.boxes.size(); ++f) {
     const Box fsbox = fvs::state_box(fine.boxes[f], ctx->cfg.rank, fine.scratch_gcw);
-    for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+    for (size_t c = 0; c < coarse.boxes.size(); ++c)
+    for (const std::array<int, 3>& shift : shifts) {
+      const Box image = fvs::shifted(coarse.boxes[c], shift.data());
       const Box region =
-          fvs::intersect(fvs::intersect(fsbox, refine_box(coarse.boxes[c], ratio)), fine.domain);
+          fvs::intersect(fvs::intersect(fsbox, refine_box(image, ratio)), fill_domain);
       if (!region.ok()) continue;
       const int rf = fine.owner[f], rc = coarse.owner[c];
       if (rf != me && rc != me) continue;
@@ -1453,13 +1500,14 @@ void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
       Patch* cp = local_patch(coarse, (int)c);
       fvs::ArrayRef source;
       if (rf == me && rc == me) {
-        source = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+        source = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
       } else {
         const Box parents = coarsen_box(region, ratio);
         double* buf = xf.add(rc, rf, (size_t)parents.size() * ncomp);
         source = array_ref(buf, parents, parents.size());
         if (rc == me) {
-          packs.add(source, array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), parents);
+          packs.add(source, shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift),
+                    parents);
           continue;
         }
       }

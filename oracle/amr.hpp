@@ -48,6 +48,18 @@ struct FluxRegisterFab {
   std::vector<unsigned char> open; // 1 where the outside coarse cell is not covered by a fine box
 };
 
+// amrex::FluxRegister::CrseInit / Reflux copy with geom.periodicity(): the outside
+// cell of a register face on a periodic domain boundary is the cell on the other side
+// of the domain.  Returns the shift (a multiple of the domain length along dir) that
+// takes `cell` into the domain, 0 if the direction is not periodic.
+inline int periodic_shift(const Level& coarse, int dir, int cell) {
+  if (!coarse.periodic[dir]) return 0;
+  const int len = coarse.domain.hi[dir] - coarse.domain.lo[dir] + 1;
+  if (cell < coarse.domain.lo[dir]) return len;
+  if (cell > coarse.domain.hi[dir]) return -len;
+  return 0;
+}
+
 struct CoarseFine {
   int ratio[3]{2, 2, 2};
   std::vector<FluxRegisterFab> regs;
@@ -74,6 +86,7 @@ struct CoarseFine {
               for (int i = fb.lo[0]; i <= fb.hi[0]; ++i, ++n) {
                 int out[3] = {i, j, k};
                 if (side == 0) out[d] -= 1;
+                out[d] += periodic_shift(coarse, d, out[d]);
                 for (size_t g = 0; g < fine.boxes.size(); ++g) {
                   if (coarsen(fine.boxes[g], ratio).contains(out[0], out[1], out[2])) r.open[n] = 0;
                 }
@@ -116,18 +129,21 @@ struct CoarseFine {
       const Box& fb = r.reg.box;
       for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
         const Fab& flux = coarse.fluxes[dir][cbx];
-        const Box faces = intersect(fb, surrounding_nodes(coarse.boxes[cbx], dir));
-        if (!faces.ok()) continue;
         for (int c = 0; c < r.reg.ncomp; ++c)
-          for (int k = faces.lo[2]; k <= faces.hi[2]; ++k)
-            for (int j = faces.lo[1]; j <= faces.hi[1]; ++j)
-              for (int i = faces.lo[0]; i <= faces.hi[0]; ++i) {
+          for (int k = fb.lo[2]; k <= fb.hi[2]; ++k)
+            for (int j = fb.lo[1]; j <= fb.hi[1]; ++j)
+              for (int i = fb.lo[0]; i <= fb.hi[0]; ++i) {
                 // a face shared by two coarse boxes is initialised by the box
-                // that owns the OUTSIDE cell
+                // that owns the OUTSIDE cell (its periodic image on a periodic
+                // boundary; the face then is that box's face on the other side)
                 int out[3] = {i, j, k};
                 if (r.side == 0) out[dir] -= 1;
+                const int shift = periodic_shift(coarse, dir, out[dir]);
+                out[dir] += shift;
                 if (!coarse.boxes[cbx].contains(out[0], out[1], out[2])) continue;
-                r.reg(i, j, k, c) += mult * flux(i, j, k, c);
+                int face[3] = {i, j, k};
+                face[dir] += shift;
+                r.reg(i, j, k, c) += mult * flux(face[0], face[1], face[2], c);
               }
       }
     }
@@ -148,6 +164,7 @@ struct CoarseFine {
               if (!r.open[n]) continue;
               int out[3] = {i, j, k};
               if (r.side == 0) out[dir] -= 1;
+              out[dir] += periodic_shift(coarse, dir, out[dir]);
               if (!coarse.boxes[cbx].contains(out[0], out[1], out[2])) continue;
               for (int c = 0; c < r.reg.ncomp; ++c) {
                 // lower side: the register face is the right face of the cell
@@ -198,23 +215,40 @@ inline void CoarsenConservatively(const Level& fine, Level& coarse, const int ra
 
 // FillPatchTwoLevels with pc_interp: ghost cells inside the domain take the
 // coarse parent unless a fine box (or a periodic image) holds them, then the
-// physical boundary conditions of the fine level.
+// physical boundary conditions of the fine level.  On a periodic domain the
+// ghost cells beyond the periodic boundary take the parent from the coarse
+// level's periodic image (FillPatchTwoLevels works on the domain grown in the
+// periodic directions and gathers the coarse data with geom.periodicity()).
 inline void FillGhostLayerTwoLevels(Level& fine, const Level& coarse, const int ratio[3]) {
+  int r[3];
+  for (int d = 0; d < 3; ++d) r[d] = (d < coarse.rank && coarse.periodic[d]) ? 1 : 0;
+  Box fill_domain = fine.domain; // GrowPeriodicDomain
+  for (int d = 0; d < fine.rank; ++d) {
+    if (fine.periodic[d]) fill_domain = grow(fill_domain, d, fine.scratch_gcw);
+  }
   for (size_t f = 0; f < fine.boxes.size(); ++f) {
     Fab& F = fine.scratch[f];
-    for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx) {
-      const Box region = intersect(intersect(F.box, refine(coarse.boxes[cbx], ratio)), fine.domain);
-      if (!region.ok()) continue;
-      const Fab& Cc = coarse.scratch[cbx];
-      for (int n = 0; n < fine.ncomp(); ++n)
-        for (int k = region.lo[2]; k <= region.hi[2]; ++k)
-          for (int j = region.lo[1]; j <= region.hi[1]; ++j)
-            for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
-              if (fine.boxes[f].contains(i, j, k)) continue;
-              F(i, j, k, n) = Cc(coarsen_index(i, ratio[0]), coarsen_index(j, ratio[1]),
-                                 coarsen_index(k, ratio[2]), n);
-            }
-    }
+    for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx)
+      for (int sz = -r[2]; sz <= r[2]; ++sz)
+        for (int sy = -r[1]; sy <= r[1]; ++sy)
+          for (int sx = -r[0]; sx <= r[0]; ++sx) {
+            // shift of the image in coarse index space
+            const int s[3] = {sx * int(coarse.domain.len(0)), sy * int(coarse.domain.len(1)),
+                              sz * int(coarse.domain.len(2))};
+            Box image = coarse.boxes[cbx];
+            for (int d = 0; d < 3; ++d) image = shift(image, d, s[d]);
+            const Box region = intersect(intersect(F.box, refine(image, ratio)), fill_domain);
+            if (!region.ok()) continue;
+            const Fab& Cc = coarse.scratch[cbx];
+            for (int n = 0; n < fine.ncomp(); ++n)
+              for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+                for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+                  for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+                    if (fine.boxes[f].contains(i, j, k)) continue;
+                    F(i, j, k, n) = Cc(coarsen_index(i, ratio[0]) - s[0], coarsen_index(j, ratio[1]) - s[1],
+                                       coarsen_index(k, ratio[2]) - s[2], n);
+                  }
+          }
   }
   fine.FillGhostLayerSingleLevel();
 }

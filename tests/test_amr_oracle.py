@@ -15,17 +15,24 @@ def oracle():
     return orc
 
 
-@pytest.mark.parametrize("rank", [2, 3])
-def test_composite_conservation(oracle, rank):
+@pytest.mark.parametrize("rank,touching", [(2, False), (3, False), (2, True), (3, True)])
+def test_composite_conservation(oracle, rank, touching):
+    """touching: fine boxes on the periodic domain boundary -- the outside cell of their
+    register faces is the coarse cell on the OTHER side of the domain
+    (amrex::FluxRegister::Reflux copies with geom.periodicity())."""
     orc = oracle
     if rank == 2:
         nc = [32, 24, 1]
         cboxes = [([0, 0, 0], [15, 23, 0]), ([16, 0, 0], [31, 23, 0])]
         fboxes = [([16, 8, 0], [31, 31, 0]), ([32, 8, 0], [47, 23, 0]), ([32, 24, 0], [47, 39, 0])]
+        if touching:  # x low and x high boundary (periodic neighbours of each other), y low
+            fboxes = [([0, 8, 0], [15, 31, 0]), ([48, 8, 0], [63, 23, 0]), ([24, 0, 0], [39, 15, 0])]
     else:
         nc = [16, 12, 12]
         cboxes = [([0, 0, 0], [15, 11, 11])]
         fboxes = [([8, 4, 4], [19, 15, 15]), ([20, 4, 4], [27, 15, 19])]
+        if touching:
+            fboxes = [([0, 4, 4], [11, 15, 15]), ([20, 4, 16], [31, 15, 23])]
     dxc = [1.0 / nc[d] if d < rank else 1.0 for d in range(3)]
     dxf = [0.5 * dxc[d] if d < rank else 1.0 for d in range(3)]
     chi = [nc[d] - 1 if d < rank else 0 for d in range(3)]

@@ -24,28 +24,40 @@ def oracle():
     return orc
 
 
-def two_levels(orc, fvs, rank):
+def two_levels(orc, fvs, rank, periodic=False):
+    """periodic: both levels periodic in every direction and fine boxes ON the
+    periodic boundaries, two of them periodic neighbours of each other (ghost
+    parents, CrseInit faces and Reflux cells come from the coarse level's
+    periodic images; amrex copies with geom.periodicity())."""
     if rank == 2:
         nc = [32, 24, 1]
         cboxes = [([0, 0, 0], [15, 23, 0]), ([16, 0, 0], [31, 23, 0])]
         fboxes = [([16, 8, 0], [31, 31, 0]), ([32, 8, 0], [47, 23, 0]), ([32, 24, 0], [47, 39, 0])]
+        if periodic:
+            fboxes = [([0, 8, 0], [15, 31, 0]), ([48, 8, 0], [63, 23, 0]), ([24, 0, 0], [39, 15, 0])]
     else:
         nc = [16, 12, 12]
         cboxes = [([0, 0, 0], [15, 11, 11])]
         fboxes = [([8, 4, 4], [19, 15, 15]), ([20, 4, 4], [27, 15, 19])]
+        if periodic:
+            fboxes = [([0, 4, 4], [11, 15, 15]), ([20, 4, 16], [31, 15, 23])]
     dxc = [1.0 / nc[d] if d < rank else 1.0 for d in range(3)]
     dxf = [0.5 * dxc[d] if d < rank else 1.0 for d in range(3)]
     chi = [nc[d] - 1 if d < rank else 0 for d in range(3)]
     fhi = [2 * nc[d] - 1 if d < rank else 0 for d in range(3)]
     gcw = (4, 2)
-    ccpu = orc.Level(rank, [0] * 3, chi, dxc, cboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
-    fcpu = orc.Level(rank, [0] * 3, fhi, dxf, fboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
-    cgpu = fvs.Context(rank, [0] * 3, chi, dxc, cboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
-    fgpu = cgpu.define_level(1, [0] * 3, fhi, dxf, fboxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    kw = dict(scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    if periodic:
+        kw["periodic"] = [1 if d < rank else 0 for d in range(3)]
+    ccpu = orc.Level(rank, [0] * 3, chi, dxc, cboxes, **kw)
+    fcpu = orc.Level(rank, [0] * 3, fhi, dxf, fboxes, **kw)
+    cgpu = fvs.Context(rank, [0] * 3, chi, dxc, cboxes, **kw)
+    fgpu = cgpu.define_level(1, [0] * 3, fhi, dxf, fboxes, **kw)
     for lv in (ccpu, fcpu, cgpu, fgpu):
         for d in range(rank):
             for s in (0, 1):
-                lv.add_bc(d, s, 1 if d == 0 else 0)
+                if not periodic:
+                    lv.add_bc(d, s, 1 if d == 0 else 0)
     for cpu, gpu, dx, seed in ((ccpu, cgpu, dxc, 1), (fcpu, fgpu, dxf, 2)):
         for b in range(len(cpu.boxes)):
             arr, lo, hi = cpu.scratch(b)
@@ -60,9 +72,9 @@ def compare(cpu, gpu, what):
         assert_bitwise_equal(gpu.download_state(b), cpu.scratch(b)[0], f"{what} box {b}")
 
 
-@pytest.mark.parametrize("rank", [2, 3])
-def test_fill_ghost_layer_two_levels(oracle, fvs, rank):
-    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank)
+@pytest.mark.parametrize("rank,periodic", [(2, False), (3, False), (2, True), (3, True)])
+def test_fill_ghost_layer_two_levels(oracle, fvs, rank, periodic):
+    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank, periodic)
     ccpu.fill_ghost_layer()
     cgpu.fill_ghost_layer()
     cf.fill_ghost_layer_two_levels()
@@ -82,12 +94,12 @@ def test_coarsen_conservatively(oracle, fvs, rank):
     cgpu.close()
 
 
-@pytest.mark.parametrize("rank", [2, 3])
-def test_flux_register_cycle(oracle, fvs, rank):
+@pytest.mark.parametrize("rank,periodic", [(2, False), (3, False), (2, True), (3, True)])
+def test_flux_register_cycle(oracle, fvs, rank, periodic):
     """One coarse step with two fine subcycles, the order of
     SubcycleFineFirstSolver::AdvanceLevel: reset, fine fluxes accumulated with
     FineAdd, coarse fluxes with CrseInit, Reflux, average_down, complete."""
-    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank)
+    ccpu, fcpu, cgpu, fgpu, cf = two_levels(oracle, fvs, rank, periodic)
     ccpu.fill_ghost_layer()
     cgpu.fill_ghost_layer()
     cf.fill_ghost_layer_two_levels()
