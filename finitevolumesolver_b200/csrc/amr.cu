@@ -2,7 +2,8 @@
 //
 // Reference (paths relative to maikel/FiniteVolumeSolver): the fub side is
 // src/AMReX/IntegratorContext.cpp:380-420 (FillGhostLayerTwoLevels: pc_interp),
-// :451-470 (CoarsenConservatively: amrex::average_down), :472-497
+// :451-470 (CoarsenConservatively: amrex::average_down; cut-cell levels:
+// amrex::EB_average_down, src/AMReX/cutcell/IntegratorContext.cpp:662-677), :472-497
 // (AccumulateCoarseFineFluxes: FluxRegister::FineAdd / CrseInit(ADD)), :499-512
 // (ResetCoarseFineFluxes), :514-531 (ApplyFluxCorrection: FluxRegister::Reflux).
 // The arithmetic itself is AMReX's (unpinned dependency, absent here): restated
@@ -38,6 +39,27 @@ average_down_kernel(const AvgDownDesc* descs, int ncons, Ratio R) {
     const int j = D.lo[1] + (int)((t / D.len[0]) % D.len[1]);
     const int k = D.lo[2] + (int)(t / ((long long)D.len[0] * D.len[1]));
     const long long c_at = at(D.crse, i, j, k);
+    if (D.vfrac) { // amrex_eb_avgdown: src/AMReX/cutcell/IntegratorContext.cpp:662-677
+      for (int n = 0; n < ncons; ++n) {
+        double c = 0.0;
+        double cv = 0.0;
+        for (int kr = 0; kr < R.r[2]; ++kr)
+          for (int jr = 0; jr < R.r[1]; ++jr)
+            for (int ir = 0; ir < R.r[0]; ++ir) {
+              const long long f_at = at(D.fine, i * R.r[0] + ir, j * R.r[1] + jr, k * R.r[2] + kr);
+              const double tmp = D.vfrac[f_at];
+              cv += tmp;
+              c += D.fine.p[f_at + D.fine.sc * n] * tmp;
+            }
+        if (cv > 1.e-30) {
+          c /= cv;
+        } else {
+          c = D.fine.p[at(D.fine, i * R.r[0], j * R.r[1], k * R.r[2]) + D.fine.sc * n];
+        }
+        D.crse.p[c_at + D.crse.sc * n] = c;
+      }
+      continue;
+    }
     for (int n = 0; n < ncons; ++n) {
       double c = 0.0;
       for (int kr = 0; kr < R.r[2]; ++kr)

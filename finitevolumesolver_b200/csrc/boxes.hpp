@@ -234,4 +234,158 @@ inline std::vector<int> distribute_boxes(const std::vector<Box>& boxes, int nran
   return owner;
 }
 
+
+// Load balance of a cut-cell level, cutcell::GriddingAlgorithm::LoadBalance
+// (src/AMReX/cutcell/GriddingAlgorithm.cpp:190-211): every cell of a regular fab
+// weighs 1, every cell of a single-valued (cut) fab `cutcell_weight`
+// (PatchHierarchyOptions::cutcell_load_balance_weight, 6.0), every covered
+// cell 0.001; DistributionMapping::makeKnapSack on the box weights.  The
+// knapsack itself is AMReX's (unpinned): restated as its published greedy
+// first step -- heaviest box first onto the lightest rank, ties to the lower
+// rank -- which is what its swap refinement starts from.
+// fab_type: -1 covered, 0 regular, 1 single valued; covered_cells[i]: number of
+// covered cells of box i (alpha == 0).
+inline std::vector<double> cutcell_box_weights(const std::vector<Box>& boxes, const int* fab_type,
+                                               const long long* covered_cells,
+                                               double cutcell_weight) {
+  std::vector<double> w(boxes.size());
+  for (size_t i = 0; i < boxes.size(); ++i) {
+    const long long cells = boxes[i].size();
+    const long long cov = fab_type[i] < 0 ? cells : (covered_cells ? covered_cells[i] : 0);
+    const double per_cell = fab_type[i] == 1 ? cutcell_weight : 1.0;
+    w[i] = per_cell * (double)(cells - cov) + 0.001 * (double)cov;
+  }
+  return w;
+}
+inline std::vector<int> knapsack(const std::vector<double>& weights, int nranks) {
+  const size_t n = weights.size();
+  std::vector<size_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(),
+                   [&](size_t a, size_t b) { return weights[a] > weights[b]; });
+  std::vector<double> load((size_t)nranks, 0.0);
+  std::vector<int> owner(n, 0);
+  for (size_t k = 0; k < n; ++k) {
+    int best = 0;
+    for (int r = 1; r < nranks; ++r)
+      if (load[(size_t)r] < load[(size_t)best]) best = r;
+    owner[order[k]] = best;
+    load[(size_t)best] += weights[order[k]];
+  }
+  return owner;
+}
+
+// Regrid hand-off: clusters the tags of level l (dense byte map over the level's
+// domain, x fastest; != 0 = tagged) into the boxes of level l + 1.  The
+// reference leaves this to amrex::AmrCore::regrid (Berger-Rigoutsos,
+// src/AMReX/GriddingAlgorithm.cpp:86-110 -- unpinned, absent here); this is a
+// deterministic stand-in with the same contract: boxes are disjoint, cover every
+// tagged cell that may be refined, are aligned to `blocking_factor` fine cells,
+// at most `max_grid_size` fine cells long, and properly nested -- a block is
+// refined only if all of its cells and their `nesting_buffer` neighbourhood lie
+// inside the level's own boxes (or outside the domain).
+// Blocks of blocking_factor / ratio coarse cells are flagged, then merged greedily
+// into rectangles in x, y, z order.  Output boxes are in the index space of level
+// l + 1.
+inline std::vector<Box> cluster_tags(int rank, const Box& domain, const bool periodic[3],
+                                     const std::vector<Box>& level_boxes, const char* tags,
+                                     const int ratio[3], int blocking_factor, int max_grid_size,
+                                     int nesting_buffer) {
+  int bf[3], nb[3], n[3], maxb[3];
+  for (int d = 0; d < 3; ++d) {
+    n[d] = domain.len(d);
+    bf[d] = d < rank ? std::max(blocking_factor / ratio[d], 1) : 1;
+    nb[d] = (n[d] + bf[d] - 1) / bf[d];
+    maxb[d] = d < rank ? std::max(max_grid_size / (bf[d] * ratio[d]), 1) : 1;
+  }
+  const long long ncells = (long long)n[0] * n[1] * n[2];
+  // cells the next level may cover: inside this level's boxes, eroded by the buffer
+  std::vector<unsigned char> covered((size_t)ncells, 0);
+  for (const Box& b : level_boxes) {
+    const Box c = intersect(b, domain);
+    if (!c.ok()) continue;
+    for (int k = c.lo[2]; k <= c.hi[2]; ++k)
+      for (int j = c.lo[1]; j <= c.hi[1]; ++j)
+        for (int i = c.lo[0]; i <= c.hi[0]; ++i)
+          covered[(size_t)((i - domain.lo[0]) + (long long)n[0] * ((j - domain.lo[1]) + (long long)n[1] * (k - domain.lo[2])))] = 1;
+  }
+  auto is_covered = [&](int i, int j, int k) {
+    int p[3] = {i, j, k};
+    for (int d = 0; d < 3; ++d) {
+      if (p[d] < 0 || p[d] >= n[d]) {
+        if (d < rank && periodic[d]) {
+          p[d] = (p[d] % n[d] + n[d]) % n[d];
+        } else {
+          return true; // beyond a physical boundary: no nesting constraint
+        }
+      }
+    }
+    return covered[(size_t)(p[0] + (long long)n[0] * (p[1] + (long long)n[1] * p[2]))] != 0;
+  };
+  const int nbuf[3] = {rank > 0 ? nesting_buffer : 0, rank > 1 ? nesting_buffer : 0,
+                       rank > 2 ? nesting_buffer : 0};
+  std::vector<unsigned char> flagged((size_t)nb[0] * nb[1] * nb[2], 0);
+  for (int bk = 0; bk < nb[2]; ++bk)
+    for (int bj = 0; bj < nb[1]; ++bj)
+      for (int bi = 0; bi < nb[0]; ++bi) {
+        const int lo[3] = {bi * bf[0], bj * bf[1], bk * bf[2]};
+        const int hi[3] = {std::min(lo[0] + bf[0], n[0]) - 1, std::min(lo[1] + bf[1], n[1]) - 1,
+                           std::min(lo[2] + bf[2], n[2]) - 1};
+        bool any = false;
+        for (int k = lo[2]; k <= hi[2] && !any; ++k)
+          for (int j = lo[1]; j <= hi[1] && !any; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i)
+              if (tags[(size_t)(i + (long long)n[0] * (j + (long long)n[1] * k))]) {
+                any = true;
+                break;
+              }
+        if (!any) continue;
+        bool nested = true;
+        for (int k = lo[2] - nbuf[2]; k <= hi[2] + nbuf[2] && nested; ++k)
+          for (int j = lo[1] - nbuf[1]; j <= hi[1] + nbuf[1] && nested; ++j)
+            for (int i = lo[0] - nbuf[0]; i <= hi[0] + nbuf[0]; ++i)
+              if (!is_covered(i, j, k)) {
+                nested = false;
+                break;
+              }
+        if (nested) flagged[(size_t)(bi + (long long)nb[0] * (bj + (long long)nb[1] * bk))] = 1;
+      }
+  auto F = [&](int bi, int bj, int bk) -> unsigned char& {
+    return flagged[(size_t)(bi + (long long)nb[0] * (bj + (long long)nb[1] * bk))];
+  };
+  std::vector<Box> out;
+  for (int bk = 0; bk < nb[2]; ++bk)
+    for (int bj = 0; bj < nb[1]; ++bj)
+      for (int bi = 0; bi < nb[0]; ++bi) {
+        if (F(bi, bj, bk) != 1) continue;
+        int ei = bi, ej = bj, ek = bk;
+        while (ei + 1 < nb[0] && ei + 1 - bi < maxb[0] && F(ei + 1, bj, bk) == 1) ++ei;
+        auto row_ok = [&](int j, int k) {
+          for (int i = bi; i <= ei; ++i)
+            if (F(i, j, k) != 1) return false;
+          return true;
+        };
+        while (ej + 1 < nb[1] && ej + 1 - bj < maxb[1] && row_ok(ej + 1, bk)) ++ej;
+        auto slab_ok = [&](int k) {
+          for (int j = bj; j <= ej; ++j)
+            if (!row_ok(j, k)) return false;
+          return true;
+        };
+        while (ek + 1 < nb[2] && ek + 1 - bk < maxb[2] && slab_ok(ek + 1)) ++ek;
+        for (int k = bk; k <= ek; ++k)
+          for (int j = bj; j <= ej; ++j)
+            for (int i = bi; i <= ei; ++i) F(i, j, k) = 2;
+        Box b;
+        const int blo[3] = {bi, bj, bk}, bhi[3] = {ei, ej, ek};
+        for (int d = 0; d < 3; ++d) {
+          const int clo = domain.lo[d] + blo[d] * bf[d];
+          const int chi = std::min(domain.lo[d] + (bhi[d] + 1) * bf[d], domain.hi[d] + 1) - 1;
+          b.lo[d] = d < rank ? clo * ratio[d] : 0;
+          b.hi[d] = d < rank ? (chi + 1) * ratio[d] - 1 : 0;
+        }
+        out.push_back(b);
+      }
+  return out;
+}
+
 } // namespace fvs

@@ -1415,7 +1415,8 @@ void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
   launch_registers(ctx, host, 2, dir, scale, vol, max_faces, xf);
 }
 
-// amrex::average_down: the owner of the fine box averages, the result travels
+// amrex::average_down (cut-cell levels: amrex::EB_average_down, weighted with the
+// fine volume fractions): the owner of the fine box averages, the result travels
 void average_down(fvs_ctx* ctx, Level& fine, Level& coarse) {
   int ratio[3];
   effective_ratio(ctx, ratio);
@@ -1448,6 +1449,7 @@ void average_down(fvs_ctx* ctx, Level& fine, Level& coarse) {
       fvs::AvgDownDesc d{};
       d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
       d.crse = target;
+      d.vfrac = (fine.has_eb && fp->eb.fab_type == FVS_FAB_SINGLEVALUED) ? fp->eb.alpha : nullptr;
       for (int e = 0; e < 3; ++e) {
         d.lo[e] = region.lo[e];
         d.len[e] = region.len(e);

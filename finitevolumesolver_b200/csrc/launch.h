@@ -152,6 +152,9 @@ struct ArrayRef {
 struct AvgDownDesc { // coarse region <- mean of the fine cells, conservative comps
   ArrayRef fine, crse;
   int lo[3], len[3]; // coarse region
+  // volume fractions on the fine array's box: amrex::EB_average_down of a
+  // single-valued fab (sum(fine * vfrac) / sum(vfrac)); nullptr = plain mean
+  const double* vfrac;
 };
 struct InterpDesc { // fine ghost region <- coarse parent (pc_interp)
   ArrayRef fine, crse;

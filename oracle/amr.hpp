@@ -187,7 +187,16 @@ inline void AccumulateCoarseFineFluxes(CoarseFine* to_coarser, const Level& leve
   if (to_finer) to_finer->CrseInit(level, dir, -vol_dt_over_dx);
 }
 
-// amrex::average_down on the conservative components
+// amrex::average_down on the conservative components.  Cut-cell levels
+// (src/AMReX/cutcell/IntegratorContext.cpp:662-677) call amrex::EB_average_down
+// (S_fine, S_crse, first, size, 2) instead: fabs whose flag type is regular or
+// covered take the plain average, single-valued fabs weight every fine cell with
+// its volume fraction, crse = sum(fine * vfrac) / sum(vfrac), and fall back to
+// the lower-left fine cell where sum(vfrac) <= 1e-30 (a covered coarse cell).
+// PARITY UNPINNED like the rest of this file (AMReX's amrex_eb_avgdown restated
+// from the published algorithm; AMReX decides per tile box, not per fab -- the two
+// formulas agree to the bit wherever every fine cell has vfrac == 1 and wherever
+// all fine data are zero, so the granularity does not show).
 inline void CoarsenConservatively(const Level& fine, Level& coarse, const int ratio[3]) {
   const double volfrac = 1.0 / double(ratio[0] * ratio[1] * ratio[2]);
   for (size_t f = 0; f < fine.boxes.size(); ++f) {
@@ -197,6 +206,31 @@ inline void CoarsenConservatively(const Level& fine, Level& coarse, const int ra
       if (!region.ok()) continue;
       const Fab& F = fine.scratch[f];
       Fab& Cc = coarse.scratch[cbx];
+      if (fine.has_eb && fine.eb[f].fab_type == kFabSingleValued) {
+        const Fab& vf = fine.eb[f].alpha;
+        for (int n = 0; n < fine.ncons(); ++n)
+          for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+            for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+              for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+                double c = 0.0;
+                double cv = 0.0;
+                for (int kr = 0; kr < ratio[2]; ++kr)
+                  for (int jr = 0; jr < ratio[1]; ++jr)
+                    for (int ir = 0; ir < ratio[0]; ++ir) {
+                      const int fi = i * ratio[0] + ir, fj = j * ratio[1] + jr, fk = k * ratio[2] + kr;
+                      const double tmp = vf(fi, fj, fk, 0);
+                      cv += tmp;
+                      c += F(fi, fj, fk, n) * tmp;
+                    }
+                if (cv > 1.e-30) {
+                  c /= cv;
+                } else {
+                  c = F(i * ratio[0], j * ratio[1], k * ratio[2], n);
+                }
+                Cc(i, j, k, n) = c;
+              }
+        continue;
+      }
       for (int n = 0; n < fine.ncons(); ++n)
         for (int k = region.lo[2]; k <= region.hi[2]; ++k)
           for (int j = region.lo[1]; j <= region.hi[1]; ++j)

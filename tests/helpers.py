@@ -224,3 +224,76 @@ def sphere_phi(center, radius, inside_fluid=False):
         r = np.sqrt((x - center[0]) ** 2 + (y - center[1]) ** 2 + (z - center[2]) ** 2)
         return (radius - r) if inside_fluid else (r - radius)
     return phi
+
+
+WEDGE = [(0.02, 0.05), (0.05, 0.0655), (0.05, 0.0345)]
+
+
+def eb_two_level_wedge(orc, fvs=None, n0=(48, 32), gcw=(8, 6), method=(0, 1, 2), at_rest=True,
+                       p_ratio=5.0, phi=None, x_shock=0.015):
+    """The Schardin wedge (examples/AMReX/EB/2D/Schardin.cpp:87-130) on a static
+    two-level cut-cell hierarchy: the fine level (ratio 2) covers the whole body
+    plus a margin of regular cells, so every coarse-fine face is a regular face.
+    Same geometry arrays (per level, from the same level set) on the oracle and,
+    if `fvs` is given, on the device.  Returns (cpu levels, gpu levels, ctx,
+    geometries[level][box])."""
+    rank = 2
+    extent = (0.15, 0.10)
+    phi = phi or polygon_phi(WEDGE)
+    level_boxes = [
+        [([0, 0, 0], [n0[0] // 2 - 1, n0[1] - 1, 0]), ([n0[0] // 2, 0, 0], [n0[0] - 1, n0[1] - 1, 0])],
+        # body: x in [0.02, 0.05], y in [0.0345, 0.0655] -> coarse cells [6..16] x [11..20] at 48 x 32
+        [([8, 16, 0], [23, 31, 0]), ([24, 16, 0], [39, 31, 0]), ([8, 32, 0], [39, 47, 0])],
+    ]
+    cpus, gpus, geoms = [], [], []
+    ctx = None
+    for l, boxes in enumerate(level_boxes):
+        f = 2 ** l
+        hi = [n0[0] * f - 1, n0[1] * f - 1, 0]
+        dx = [extent[0] / (n0[0] * f), extent[1] / (n0[1] * f), 1.0]
+        cpu = orc.Level(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+        cpu.set_method(*method)
+        cpu.enable_eb()
+        gpu = None
+        if fvs is not None:
+            if l == 0:
+                ctx = fvs.Context(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1],
+                                  base=method[0], recon=method[1], limiter=method[2])
+                gpu = ctx
+            else:
+                gpu = ctx.define_level(l, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+            gpu.enable_eb()
+        for lv in (cpu, gpu):
+            if lv is None:
+                continue
+            for d in range(rank):
+                for s in (0, 1):
+                    lv.add_bc(d, s, 0)
+        lg = []
+        for b in range(len(boxes)):
+            arr, lo, hi_b = cpu.scratch(b)
+            g = eb_geometry(rank, lo, hi_b, dx, [0.0] * 3, phi)
+            t = eb_fab_type(g)
+            cpu.set_eb(b, g, t)
+            if gpu is not None:
+                gpu.set_eb(b, g, t)
+            x = (np.arange(lo[0], hi_b[0] + 1) + 0.5) * dx[0]
+            y = (np.arange(lo[1], hi_b[1] + 1) + 0.5) * dx[1]
+            shape = arr.shape[1:]
+            rho = 1.0 + np.zeros(shape)
+            if not at_rest:
+                rho = rho + 0.05 * np.sin(40 * x)[None, None, :] * np.cos(30 * y)[None, :, None]
+            p = np.where(x < x_shock, p_ratio * 101325.0, 101325.0)[None, None, :] + np.zeros(shape)
+            vel = [np.zeros(shape), np.zeros(shape)]
+            if not at_rest:
+                vel = [5.0 * np.cos(25 * y)[None, :, None] + np.zeros(shape),
+                       -3.0 * np.sin(35 * x)[None, None, :] + np.zeros(shape)]
+            st = complete_from_prim(rank, rho, vel, p) * (g["alpha"][0] > 0)
+            arr[...] = st
+            if gpu is not None:
+                gpu.upload_state(b, st)
+            lg.append(g)
+        cpus.append(cpu)
+        gpus.append(gpu)
+        geoms.append(lg)
+    return cpus, gpus, ctx, geoms

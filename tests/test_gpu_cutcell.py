@@ -250,3 +250,42 @@ def test_tagging_bitwise(oracle, fvs):
     t2 = rng.integers(0, 4, size=(1, 23, 17)).astype(np.int8)
     assert np.array_equal(pair.gpu.tag_buffer(t2.copy(), 2, 3), oracle.tag_buffer(t2.copy(), 2, 3))
     pair.close()
+
+
+@pytest.mark.parametrize("split,method", [(1, (0, 1, 2)), (0, (2, 1, 1))])
+def test_eb_two_level_hierarchy_bitwise(oracle, fvs, split, method):
+    """Cut-cell levels inside a hierarchy (src/AMReX/cutcell/IntegratorContext.cpp:596-747):
+    SubcycleFineFirstSolver over two EB levels of the Schardin wedge -- pc_interp ghost fill,
+    FineAdd / CrseInit / Reflux of the unshielded fluxes, volume-fraction weighted
+    EB_average_down, masked CompleteFromCons -- bit-identical states on both levels,
+    identical per-sweep dts and step dt."""
+    from helpers import eb_two_level_wedge
+    cpus, gpus, ctx, geoms = eb_two_level_wedge(oracle, fvs, method=method, at_rest=False)
+    hier = oracle.Hierarchy(cpus)
+    cf = oracle.CoarseFine(cpus[1], cpus[0])
+    cf.coarsen_conservatively()
+    ctx.coarsen_conservatively(1, 0)
+    for l in range(2):
+        for b in range(len(cpus[l].boxes)):
+            assert_bitwise_equal(gpus[l].download_state(b), cpus[l].scratch(b)[0], f"avg down {l} {b}")
+    cpus[0].complete_from_cons()
+    gpus[0].complete_from_cons()
+    cpus[0].fill_ghost_layer()
+    gpus[0].fill_ghost_layer()
+    cf.fill_ghost_layer_two_levels()
+    ctx.fill_ghost_layer_two_levels(1, 0)
+    for step in range(4):
+        dt_c = hier.compute_stable_dt()
+        dt_g = ctx.compute_stable_dt_hierarchy()
+        assert dt_c == dt_g, (step, dt_c, dt_g)
+        ok_c, _, dts_c = hier.advance_hierarchy(0.4 * dt_c, split)
+        ok_g, _, dts_g = ctx.advance_hierarchy(0.4 * dt_g, split)
+        assert ok_c and ok_g and dts_c == dts_g, (step, dts_c, dts_g)
+        for l in range(2):
+            for b in range(len(cpus[l].boxes)):
+                assert_bitwise_equal(gpus[l].download_state(b), cpus[l].scratch(b)[0],
+                                     f"step {step} level {l} box {b}")
+    # the body is inside the fine level and the average really used the volume fractions
+    cut = sum(int(((g["alpha"] > 0) & (g["alpha"] < 1)).sum()) for g in geoms[1])
+    assert cut > 40
+    ctx.close()
