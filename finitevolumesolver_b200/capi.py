@@ -39,6 +39,7 @@ SYMBOLS = [
     "fvs_run", "fvs_set_regrid_frequency", "fvs_set_cycles", "fvs_cycles", "fvs_time_point",
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
+    "fvs_distribute_boxes_cutcell", "fvs_cluster_tags", "fvs_regrid_level",
     "fvs_set_dt_hints", "fvs_dt_hint_redos", "fvs_download_state_region",
     "fvs_enable_timing", "fvs_sweep_time_ms",
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
@@ -81,6 +82,7 @@ def lib():
         L.fvs_time_point.restype = C.c_double
         L.fvs_run.restype = C.c_long
         L.fvs_halo_plan.restype = C.c_long
+        L.fvs_cluster_tags.restype = C.c_long
         L.fvs_kernel_launches.restype = C.c_long
         L.fvs_dt_hint_redos.restype = C.c_long
         L.fvs_cut_cell_flags.restype = C.c_long
@@ -134,10 +136,10 @@ def halo_plan(rank, domain_lo, domain_hi, periodic, boxes, owner, scratch_gcw):
     lo, hi = _boxes(boxes)
     own = (C.c_int * len(boxes))(*[int(o) for o in owner])
     n = _check(lib().fvs_halo_plan(rank, _i3(domain_lo), _i3(domain_hi), _i3(periodic),
-                                   len(boxes), lo, hi, own, scratch_gcw, None, 0))
+                                   len(boxes), lo, hi, own, scratch_gcw, None, C.c_long(0)))
     buf = (HaloCopy * max(n, 1))()
     _check(lib().fvs_halo_plan(rank, _i3(domain_lo), _i3(domain_hi), _i3(periodic),
-                               len(boxes), lo, hi, own, scratch_gcw, buf, n))
+                               len(boxes), lo, hi, own, scratch_gcw, buf, C.c_long(n)))
     return [dict(dst_box=c.dst_box, src_box=c.src_box, dst_owner=c.dst_owner,
                  src_owner=c.src_owner, lo=list(c.lo), hi=list(c.hi), shift=list(c.shift))
             for c in buf[:n]]
@@ -157,6 +159,35 @@ def distribute_boxes(rank, boxes, nranks):
     out = (C.c_int * len(boxes))()
     _check(lib().fvs_distribute_boxes(rank, len(boxes), lo, hi, nranks, out))
     return list(out)
+
+
+def distribute_boxes_cutcell(rank, boxes, fab_types, covered_cells, nranks, cutcell_weight=6.0):
+    """cutcell::GriddingAlgorithm::LoadBalance: knapsack over cut-cell weighted boxes."""
+    lo, hi = _boxes(boxes)
+    ft = (C.c_int * len(boxes))(*[int(t) for t in fab_types])
+    cov = (C.c_longlong * len(boxes))(*[int(c) for c in covered_cells])
+    out = (C.c_int * len(boxes))()
+    _check(lib().fvs_distribute_boxes_cutcell(rank, len(boxes), lo, hi, ft, cov,
+                                              C.c_double(cutcell_weight), nranks, out))
+    return list(out)
+
+
+def cluster_tags(rank, domain_lo, domain_hi, periodic, boxes, tags, ratio=(2, 2, 2),
+                 blocking_factor=8, max_grid_size=128, nesting_buffer=1):
+    """tags: int8 array [z, y, x] over the level's domain.  Returns the boxes of the next
+    finer level as [(lo, hi), ...]."""
+    lo, hi = _boxes(boxes)
+    tags = np.ascontiguousarray(tags, dtype=np.int8)
+    r = [ratio[d] if d < rank else 1 for d in range(3)]
+    args = (rank, _i3(domain_lo), _i3(domain_hi), _i3(periodic), len(boxes), lo, hi,
+            tags.ctypes.data_as(C.c_char_p), _i3(r, 1), blocking_factor, max_grid_size, nesting_buffer)
+    n = lib().fvs_cluster_tags(*args, None, None, C.c_long(0))
+    if n < 0:
+        raise RuntimeError(lib().fvs_last_error().decode())
+    out_lo = ((C.c_int * 3) * max(n, 1))()
+    out_hi = ((C.c_int * 3) * max(n, 1))()
+    lib().fvs_cluster_tags(*args, out_lo, out_hi, C.c_long(n))
+    return [(list(out_lo[i]), list(out_hi[i])) for i in range(n)]
 
 
 def comm_unique_id():
@@ -211,6 +242,21 @@ class Context:
         _check(lib().fvs_level_define(self.h, level, _i3(domain_lo), _i3(domain_hi), _d3(dx),
                                       _i3(periodic), len(boxes), lo, hi, own, scratch_gcw,
                                       flux_gcw))
+        return v
+
+    def regrid_level(self, level, boxes, owner=None):
+        """fvs_regrid_level: new boxes for `level` (>= 1), data from the old level where it
+        exists and from the coarse parent elsewhere.  Returns a view addressing the level."""
+        import copy
+        v = copy.copy(self)
+        v._owns = False
+        v.level = level
+        v.boxes = [(list(lo) + [0] * (3 - len(lo)), list(hi) + [0] * (3 - len(hi)))
+                   for lo, hi in boxes]
+        v.owner = list(owner) if owner is not None else [self.comm_rank] * len(boxes)
+        lo, hi = _boxes(v.boxes)
+        own = (C.c_int * len(boxes))(*v.owner)
+        _check(lib().fvs_regrid_level(self.h, level, len(boxes), lo, hi, own))
         return v
 
     # ---- coarse-fine (two levels) ---------------------------------------------

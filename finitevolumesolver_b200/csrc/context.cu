@@ -1469,7 +1469,7 @@ void average_down(fvs_ctx* ctx, Level& fine, Level& coarse) {
 
 // FillPatchTwoLevels with pc_interp: the coarse parents travel to the owner of
 // the fine box
-void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
+void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse, bool skip_valid = true) {
   int ratio[3];
   effective_ratio(ctx, ratio);
   const int me = ctx->cfg.comm_rank;
@@ -1519,8 +1519,9 @@ void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
       for (int e = 0; e < 3; ++e) {
         d.lo[e] = region.lo[e];
         d.len[e] = region.len(e);
-        d.vlo[e] = fine.boxes[f].lo[e];
-        d.vhi[e] = fine.boxes[f].hi[e];
+        // skip_valid == false (regrid): an empty "own box" -- every cell is filled
+        d.vlo[e] = skip_valid ? fine.boxes[f].lo[e] : 1;
+        d.vhi[e] = skip_valid ? fine.boxes[f].hi[e] : 0;
       }
       max_cells = std::max(max_cells, region.size());
       host.push_back(d);
@@ -1533,6 +1534,47 @@ void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse) {
     ctx->launches += fvs::launch_pc_interp(dev, (int)host.size(), ncomp, ratio, max_cells, ctx->stream);
     FVS_CUDA(cudaGetLastError());
   }
+}
+
+
+// ParallelCopy of the old level's valid cells into the new level's scratch arrays
+// (valid and ghost cells, periodic images included) -- the fine part of the
+// FillPatchTwoLevels behind GriddingAlgorithm::RemakeLevel.
+void copy_from_old_level(fvs_ctx* ctx, Level& L, Level& old) {
+  const int me = ctx->cfg.comm_rank;
+  const int ncomp = ctx->ncomp();
+  Transfers xf(ctx);
+  RegionCopies packs, unpacks, local;
+  const std::vector<std::array<int, 3>> shifts = period_shifts(old, ctx->cfg.rank);
+  for (size_t f = 0; f < L.boxes.size(); ++f) {
+    const Box sbox = fvs::state_box(L.boxes[f], ctx->cfg.rank, L.scratch_gcw);
+    for (size_t o = 0; o < old.boxes.size(); ++o)
+      for (const std::array<int, 3>& shift : shifts) {
+        const Box image = fvs::shifted(old.boxes[o], shift.data());
+        const Box region = fvs::intersect(sbox, image);
+        if (!region.ok()) continue;
+        const int rn = L.owner[f], ro = old.owner[o];
+        if (rn != me && ro != me) continue;
+        Patch* np = local_patch(L, (int)f);
+        Patch* op = local_patch(old, (int)o);
+        if (rn == me && ro == me) {
+          local.add(array_ref(np->buf[L.cur], np->sbox, np->cells),
+                    shifted_ref(array_ref(op->buf[old.cur], op->sbox, op->cells), shift), region);
+          continue;
+        }
+        double* buf = xf.add(ro, rn, (size_t)region.size() * ncomp);
+        const fvs::ArrayRef stage = array_ref(buf, region, region.size());
+        if (ro == me) {
+          packs.add(stage, shifted_ref(array_ref(op->buf[old.cur], op->sbox, op->cells), shift), region);
+        } else {
+          unpacks.add(array_ref(np->buf[L.cur], np->sbox, np->cells), stage, region);
+        }
+      }
+  }
+  local.run(ctx, ncomp, xf);
+  packs.run(ctx, ncomp, xf);
+  xf.run();
+  unpacks.run(ctx, ncomp, xf);
 }
 
 } // namespace
@@ -1658,6 +1700,98 @@ int fvs_set_arithmetic(fvs_ctx* ctx, int arithmetic) {
 
 int fvs_stencil_width(const fvs_ctx* ctx) { return ctx ? ctx->stencil_width() : FVS_ERROR; }
 
+namespace {
+// builds the patches, buffers and halo plan of `L` (an empty Level) on this rank
+void define_level(fvs_ctx* ctx, Level& L, const Box& domain, const double dx[3],
+                  const bool periodic[3], const std::vector<Box>& boxes, const int* owner,
+                  int scratch_gcw, int flux_gcw) {
+  const int rank = ctx->cfg.rank;
+  const int nboxes = (int)boxes.size();
+  L.rank = rank;
+  L.domain = domain;
+  for (int d = 0; d < 3; ++d) {
+    L.dx[d] = dx[d];
+    L.periodic[d] = periodic[d];
+    if (d >= rank && (L.domain.lo[d] != 0 || L.domain.hi[d] != 0)) {
+      throw Error("unused dimensions of the domain must be [0,0]");
+    }
+  }
+  L.scratch_gcw = scratch_gcw;
+  L.flux_gcw = flux_gcw;
+  L.boxes = boxes;
+  L.owner.assign(nboxes, 0);
+  L.local_of_global.assign(nboxes, -1);
+  for (int b = 0; b < nboxes; ++b) {
+    if (!L.boxes[b].ok()) throw Error("empty box");
+    for (int d = rank; d < 3; ++d) {
+      if (L.boxes[b].lo[d] != 0 || L.boxes[b].hi[d] != 0) {
+        throw Error("unused dimensions of a box must be [0,0]");
+      }
+    }
+    if (owner) L.owner[b] = owner[b];
+    if (L.owner[b] < 0 || L.owner[b] >= ctx->cfg.comm_size) throw Error("owner out of range");
+  }
+  for (int d = 0; d < 3; ++d) L.max_n[d] = 1;
+  for (int b = 0; b < nboxes; ++b) {
+    if (L.owner[b] != ctx->cfg.comm_rank) continue;
+    Patch p;
+    p.global_index = b;
+    p.valid = L.boxes[b];
+    p.sbox = fvs::state_box(p.valid, rank, scratch_gcw);
+    for (int d = 0; d < 3; ++d) {
+      p.n[d] = p.sbox.len(d);
+      L.max_n[d] = std::max(L.max_n[d], p.n[d]);
+    }
+    p.cells = p.sbox.size();
+    for (int d = 0; d < rank; ++d) {
+      p.fbox[d] = fvs::flux_box(p.valid, rank, d, scratch_gcw, flux_gcw);
+      for (int w = 1; w <= 2; ++w) {
+        const std::vector<unsigned char> mask =
+            fvs::stable_dt_face_mask(p.valid, scratch_gcw, w, d);
+        FVS_CUDA(cudaMalloc(&p.dtmask[w - 1][d], mask.size()));
+        FVS_CUDA(cudaMemcpy(p.dtmask[w - 1][d], mask.data(), mask.size(),
+                            cudaMemcpyHostToDevice));
+      }
+    }
+    L.local_of_global[b] = (int)L.patches.size();
+    L.patches.push_back(p);
+  }
+  L.defined = true;
+  L.cur = 0;
+  L.keep = -1;
+  ensure_buffer(ctx, L, 0);
+  // halo plan
+  const std::vector<fvs::HaloCopy> plan =
+      fvs::halo_plan(rank, L.domain, L.periodic, L.boxes, scratch_gcw);
+  const int me = ctx->cfg.comm_rank;
+  std::map<int, PeerExchange> peers;
+  for (const fvs::HaloCopy& c : plan) {
+    const int so = L.owner[c.src_box], dow = L.owner[c.dst_box];
+    if (so == me && dow == me) {
+      L.local_copies.push_back(c);
+      L.max_copy_cells = std::max(L.max_copy_cells, c.region.size());
+    } else if (so == me) {
+      PeerExchange& pe = peers[dow];
+      pe.peer = dow;
+      pe.sends.push_back(c);
+      pe.send_elems += c.region.size() * ctx->ncomp();
+    } else if (dow == me) {
+      PeerExchange& pe = peers[so];
+      pe.peer = so;
+      pe.recvs.push_back(c);
+      pe.recv_elems += c.region.size() * ctx->ncomp();
+    }
+  }
+  for (auto& kv : peers) {
+    PeerExchange& pe = kv.second;
+    if (pe.send_elems) FVS_CUDA(cudaMalloc(&pe.sendbuf, pe.send_elems * sizeof(double)));
+    if (pe.recv_elems) FVS_CUDA(cudaMalloc(&pe.recvbuf, pe.recv_elems * sizeof(double)));
+    L.peers.push_back(std::move(pe));
+  }
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+} // namespace
+
 int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int domain_hi[3],
                      const double dx[3], const int periodic[3], int nboxes,
                      const int (*box_lo)[3], const int (*box_hi)[3], const int* owner,
@@ -1674,91 +1808,68 @@ int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int 
     if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
     free_level(ctx->levels[level]);
-    Level& L = ctx->levels[level];
-    const int rank = ctx->cfg.rank;
-    L.rank = rank;
-    L.domain = fvs::make_box(domain_lo, domain_hi);
-    for (int d = 0; d < 3; ++d) {
-      L.dx[d] = dx[d];
-      L.periodic[d] = periodic && periodic[d] != 0;
-      if (d >= rank && (L.domain.lo[d] != 0 || L.domain.hi[d] != 0)) {
-        throw Error("unused dimensions of the domain must be [0,0]");
-      }
-    }
-    L.scratch_gcw = scratch_gcw;
-    L.flux_gcw = flux_gcw;
-    L.boxes.resize(nboxes);
-    L.owner.assign(nboxes, 0);
-    L.local_of_global.assign(nboxes, -1);
-    for (int b = 0; b < nboxes; ++b) {
-      L.boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
-      if (!L.boxes[b].ok()) throw Error("empty box");
-      for (int d = rank; d < 3; ++d) {
-        if (L.boxes[b].lo[d] != 0 || L.boxes[b].hi[d] != 0) {
-          throw Error("unused dimensions of a box must be [0,0]");
-        }
-      }
-      if (owner) L.owner[b] = owner[b];
-      if (L.owner[b] < 0 || L.owner[b] >= ctx->cfg.comm_size) throw Error("owner out of range");
-    }
-    for (int d = 0; d < 3; ++d) L.max_n[d] = 1;
-    for (int b = 0; b < nboxes; ++b) {
-      if (L.owner[b] != ctx->cfg.comm_rank) continue;
-      Patch p;
-      p.global_index = b;
-      p.valid = L.boxes[b];
-      p.sbox = fvs::state_box(p.valid, rank, scratch_gcw);
-      for (int d = 0; d < 3; ++d) {
-        p.n[d] = p.sbox.len(d);
-        L.max_n[d] = std::max(L.max_n[d], p.n[d]);
-      }
-      p.cells = p.sbox.size();
-      for (int d = 0; d < rank; ++d) {
-        p.fbox[d] = fvs::flux_box(p.valid, rank, d, scratch_gcw, flux_gcw);
-        for (int w = 1; w <= 2; ++w) {
-          const std::vector<unsigned char> mask =
-              fvs::stable_dt_face_mask(p.valid, scratch_gcw, w, d);
-          FVS_CUDA(cudaMalloc(&p.dtmask[w - 1][d], mask.size()));
-          FVS_CUDA(cudaMemcpy(p.dtmask[w - 1][d], mask.data(), mask.size(),
-                              cudaMemcpyHostToDevice));
-        }
-      }
-      L.local_of_global[b] = (int)L.patches.size();
-      L.patches.push_back(p);
-    }
-    L.defined = true;
-    L.cur = 0;
-    L.keep = -1;
-    ensure_buffer(ctx, L, 0);
-    // halo plan
-    const std::vector<fvs::HaloCopy> plan =
-        fvs::halo_plan(rank, L.domain, L.periodic, L.boxes, scratch_gcw);
-    const int me = ctx->cfg.comm_rank;
-    std::map<int, PeerExchange> peers;
-    for (const fvs::HaloCopy& c : plan) {
-      const int so = L.owner[c.src_box], dow = L.owner[c.dst_box];
-      if (so == me && dow == me) {
-        L.local_copies.push_back(c);
-        L.max_copy_cells = std::max(L.max_copy_cells, c.region.size());
-      } else if (so == me) {
-        PeerExchange& pe = peers[dow];
-        pe.peer = dow;
-        pe.sends.push_back(c);
-        pe.send_elems += c.region.size() * ctx->ncomp();
-      } else if (dow == me) {
-        PeerExchange& pe = peers[so];
-        pe.peer = so;
-        pe.recvs.push_back(c);
-        pe.recv_elems += c.region.size() * ctx->ncomp();
-      }
-    }
-    for (auto& kv : peers) {
-      PeerExchange& pe = kv.second;
-      if (pe.send_elems) FVS_CUDA(cudaMalloc(&pe.sendbuf, pe.send_elems * sizeof(double)));
-      if (pe.recv_elems) FVS_CUDA(cudaMalloc(&pe.recvbuf, pe.recv_elems * sizeof(double)));
-      L.peers.push_back(std::move(pe));
-    }
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    bool per[3];
+    for (int d = 0; d < 3; ++d) per[d] = periodic && periodic[d] != 0;
+    define_level(ctx, ctx->levels[level], fvs::make_box(domain_lo, domain_hi), dx, per, boxes, owner,
+                 scratch_gcw, flux_gcw);
+    return (int)FVS_OK;
+  });
+}
+
+// GriddingAlgorithm::RemakeLevel / MakeNewLevelFromCoarse followed by
+// IntegratorContext::CopyDataToScratch (src/AMReX/GriddingAlgorithm.cpp:217-260,
+// src/AMReX/IntegratorContext.cpp:629-638): the level gets new boxes; every cell of
+// the new scratch arrays inside the domain takes the old level's valid data where
+// an old box holds it and the coarse parent (pc_interp) elsewhere, then the
+// level's own ghost fill (fine-fine copies, periodic images, physical boundaries).
+int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3],
+                     const int (*box_hi)[3], const int* owner) {
+  return guarded([&] {
+    if (!ctx) throw Error("null context");
+    if (level < 1) throw Error("only levels above the base level are regridded");
+    if (nboxes < 0) throw Error("negative box count");
+    ctx->use_device();
+    if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
+    Level& coarse = ctx->level(level - 1);
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nboxes == 0) { // GriddingAlgorithm::ClearLevel: the level and everything finer goes
+      for (int l = level; l < (int)ctx->levels.size(); ++l) free_level(ctx->levels[l]);
+      return (int)FVS_OK;
+    }
+    int ratio[3];
+    effective_ratio(ctx, ratio);
+    const bool had_old = ctx->levels[level].defined;
+    Level old = std::move(ctx->levels[level]);
+    ctx->levels[level] = Level();
+    Level& L = ctx->levels[level];
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    try {
+      if (had_old) {
+        define_level(ctx, L, old.domain, old.dx, old.periodic, boxes, owner, old.scratch_gcw,
+                     old.flux_gcw);
+        L.bcs = old.bcs;
+      } else {
+        double dx[3];
+        for (int d = 0; d < 3; ++d) dx[d] = coarse.dx[d] / ratio[d];
+        define_level(ctx, L, refine_box(coarse.domain, ratio), dx, coarse.periodic, boxes, owner,
+                     coarse.scratch_gcw, coarse.flux_gcw);
+        L.bcs = coarse.bcs;
+      }
+      pc_interp(ctx, L, coarse, /*skip_valid=*/false);
+      if (had_old) copy_from_old_level(ctx, L, old);
+      fill_ghost_layer(ctx, L);
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+      free_level(old);
+      throw;
+    }
+    free_level(old);
+    // the register of a finer level refers to this level's boxes only through the
+    // coarse index space: it stays valid; this level's own register is rebuilt by
+    // the next fvs_reset_coarse_fine_fluxes
     return (int)FVS_OK;
   });
 }
@@ -2603,6 +2714,56 @@ int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3], const int
     for (int b = 0; b < nboxes; ++b) owner_out[b] = owner[b];
     return (int)FVS_OK;
   });
+}
+
+int fvs_distribute_boxes_cutcell(int rank, int nboxes, const int (*box_lo)[3],
+                                 const int (*box_hi)[3], const int* fab_type,
+                                 const long long* covered_cells, double cutcell_weight, int nranks,
+                                 int* owner_out) {
+  return guarded([&] {
+    (void)rank;
+    if (nranks < 1 || !owner_out || !fab_type) throw Error("invalid argument");
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    const std::vector<int> owner = fvs::knapsack(
+        fvs::cutcell_box_weights(boxes, fab_type, covered_cells, cutcell_weight), nranks);
+    for (int b = 0; b < nboxes; ++b) owner_out[b] = owner[b];
+    return (int)FVS_OK;
+  });
+}
+
+long fvs_cluster_tags(int rank, const int domain_lo[3], const int domain_hi[3],
+                      const int periodic[3], int nboxes, const int (*box_lo)[3],
+                      const int (*box_hi)[3], const char* tags, const int ratio[3],
+                      int blocking_factor, int max_grid_size, int nesting_buffer,
+                      int (*out_lo)[3], int (*out_hi)[3], long capacity) {
+  long count = 0;
+  const int rc = guarded([&] {
+    if (rank < 1 || rank > 3 || !tags || !ratio) throw Error("invalid argument");
+    if (blocking_factor < 1 || max_grid_size < blocking_factor) {
+      throw Error("need 1 <= blocking_factor <= max_grid_size");
+    }
+    for (int d = 0; d < rank; ++d) {
+      if (ratio[d] < 1 || blocking_factor % ratio[d] != 0) {
+        throw Error("blocking_factor must be a multiple of the refinement ratio");
+      }
+    }
+    std::vector<Box> boxes(nboxes);
+    for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
+    bool per[3];
+    for (int d = 0; d < 3; ++d) per[d] = periodic && periodic[d] != 0;
+    const std::vector<Box> out =
+        fvs::cluster_tags(rank, fvs::make_box(domain_lo, domain_hi), per, boxes, tags, ratio,
+                          blocking_factor, max_grid_size, nesting_buffer);
+    count = (long)out.size();
+    for (long i = 0; i < count && i < capacity; ++i)
+      for (int d = 0; d < 3; ++d) {
+        out_lo[i][d] = out[(size_t)i].lo[d];
+        out_hi[i][d] = out[(size_t)i].hi[d];
+      }
+    return (int)FVS_OK;
+  });
+  return rc == FVS_OK ? count : (long)FVS_ERROR;
 }
 
 // ---- embedded boundary ---------------------------------------------------------

@@ -291,6 +291,52 @@ int fvs_stable_dt_face_mask(int rank, const int box_lo[3], const int box_hi[3],
 int fvs_distribute_boxes(int rank, int nboxes, const int (*box_lo)[3],
                          const int (*box_hi)[3], int nranks, int* owner_out);
 
+/* Host-only: load balance of a cut-cell level,
+ * cutcell::GriddingAlgorithm::LoadBalance
+ * (src/AMReX/cutcell/GriddingAlgorithm.cpp:190-211): cells of regular fabs
+ * weigh 1, cells of single-valued fabs `cutcell_weight`
+ * (PatchHierarchyOptions::cutcell_load_balance_weight, 6.0 upstream), covered
+ * cells 0.001; knapsack over the box weights (heaviest box first onto the
+ * lightest rank).  fab_type[i]: FVS_FAB_*; covered_cells[i]: cells of box i
+ * with alpha == 0 (may be NULL).  Covered boxes are dropped by the caller
+ * beforehand (PostProcessBaseGrids, :310-330: keep boxes whose fab_type is not
+ * FVS_FAB_COVERED). */
+int fvs_distribute_boxes_cutcell(int rank, int nboxes, const int (*box_lo)[3],
+                                 const int (*box_hi)[3], const int* fab_type,
+                                 const long long* covered_cells, double cutcell_weight,
+                                 int nranks, int* owner_out);
+
+/* ---- regrid hand-off -------------------------------------------------------- */
+/* Host-only: clusters the tags of level l into boxes of level l + 1 -- the
+ * hand-off between the device tagging kernels below and fvs_regrid_level.
+ * Upstream this is amrex::AmrCore::regrid behind
+ * GriddingAlgorithm::RegridAllFinerlevels (src/AMReX/GriddingAlgorithm.cpp:86-110),
+ * Berger-Rigoutsos clustering from an unpinned dependency; this stand-in keeps
+ * its contract (disjoint boxes covering every refinable tagged cell, aligned to
+ * `blocking_factor` fine cells, at most `max_grid_size` fine cells long,
+ * properly nested with `nesting_buffer` coarse cells inside the boxes of level
+ * l) with a deterministic greedy merge of flagged blocks.
+ * tags: one byte per cell of the level-l DOMAIN (x fastest), != 0 = tagged.
+ * box_lo/hi: the boxes of level l.  Returns the number of boxes (the first
+ * `capacity` are written, in the index space of level l + 1), < 0 on error. */
+long fvs_cluster_tags(int rank, const int domain_lo[3], const int domain_hi[3],
+                      const int periodic[3], int nboxes, const int (*box_lo)[3],
+                      const int (*box_hi)[3], const char* tags, const int ratio[3],
+                      int blocking_factor, int max_grid_size, int nesting_buffer,
+                      int (*out_lo)[3], int (*out_hi)[3], long capacity);
+/* GriddingAlgorithm::RemakeLevel / MakeNewLevelFromCoarse + CopyDataToScratch
+ * (src/AMReX/GriddingAlgorithm.cpp:217-260, src/AMReX/IntegratorContext.cpp:
+ * 601-638): gives level >= 1 new boxes.  Every cell of the new scratch arrays
+ * inside the domain takes the old level's valid data where an old box holds it
+ * and the coarse parent (pc_interp) elsewhere; then the level's ghost fill.
+ * Domain, cell size, ghost widths and boundary conditions are kept (taken from
+ * the coarser level if the level did not exist).  Collective over the ranks of
+ * the context.  EB geometry of the new boxes must be set again
+ * (fvs_level_set_eb).  nboxes == 0 removes the level and every finer one
+ * (GriddingAlgorithm::ClearLevel). */
+int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3],
+                     const int (*box_hi)[3], const int* owner);
+
 /* ---- embedded boundary: Klein-2009 KbnCutCellMethod ------------------------ */
 /* Hands the EB geometry of one box to the library and turns the level into a
  * cut-cell level: replaces cutcell::PatchHierarchy::GetCutCellData

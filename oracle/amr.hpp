@@ -287,6 +287,68 @@ inline void FillGhostLayerTwoLevels(Level& fine, const Level& coarse, const int 
   fine.FillGhostLayerSingleLevel();
 }
 
+// GriddingAlgorithm::RemakeLevel / MakeNewLevelFromCoarse followed by
+// IntegratorContext::CopyDataToScratch (src/AMReX/GriddingAlgorithm.cpp:217-260,
+// src/AMReX/IntegratorContext.cpp:601-638): `fresh` is the level on its new boxes.
+// FillPatchTwoLevels onto the new layout: every cell of the new scratch arrays inside
+// the (periodically grown) domain takes the old level's valid data where an old box
+// holds it, the coarse parent (pc_interp) elsewhere; then the physical boundaries.
+// `old` may be null (the level did not exist).
+inline void RegridFill(Level& fresh, const Level* old, const Level& coarse, const int ratio[3]) {
+  int r[3];
+  for (int d = 0; d < 3; ++d) r[d] = (d < coarse.rank && coarse.periodic[d]) ? 1 : 0;
+  Box fill_domain = fresh.domain;
+  for (int d = 0; d < fresh.rank; ++d) {
+    if (fresh.periodic[d]) fill_domain = grow(fill_domain, d, fresh.scratch_gcw);
+  }
+  for (size_t f = 0; f < fresh.boxes.size(); ++f) {
+    Fab& F = fresh.scratch[f];
+    for (size_t cbx = 0; cbx < coarse.boxes.size(); ++cbx)
+      for (int sz = -r[2]; sz <= r[2]; ++sz)
+        for (int sy = -r[1]; sy <= r[1]; ++sy)
+          for (int sx = -r[0]; sx <= r[0]; ++sx) {
+            const int s[3] = {sx * int(coarse.domain.len(0)), sy * int(coarse.domain.len(1)),
+                              sz * int(coarse.domain.len(2))};
+            Box image = coarse.boxes[cbx];
+            for (int d = 0; d < 3; ++d) image = shift(image, d, s[d]);
+            const Box region = intersect(intersect(F.box, refine(image, ratio)), fill_domain);
+            if (!region.ok()) continue;
+            const Fab& Cc = coarse.scratch[cbx];
+            for (int n = 0; n < fresh.ncomp(); ++n)
+              for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+                for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+                  for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+                    F(i, j, k, n) = Cc(coarsen_index(i, ratio[0]) - s[0], coarsen_index(j, ratio[1]) - s[1],
+                                       coarsen_index(k, ratio[2]) - s[2], n);
+                  }
+          }
+    if (!old) continue;
+    for (size_t o = 0; o < old->boxes.size(); ++o)
+      for (int sz = -r[2]; sz <= r[2]; ++sz)
+        for (int sy = -r[1]; sy <= r[1]; ++sy)
+          for (int sx = -r[0]; sx <= r[0]; ++sx) {
+            const int s[3] = {sx * int(old->domain.len(0)), sy * int(old->domain.len(1)),
+                              sz * int(old->domain.len(2))};
+            Box image = old->boxes[o];
+            for (int d = 0; d < 3; ++d) image = shift(image, d, s[d]);
+            const Box region = intersect(F.box, image);
+            if (!region.ok()) continue;
+            const Fab& O = old->scratch[o];
+            for (int n = 0; n < fresh.ncomp(); ++n)
+              for (int k = region.lo[2]; k <= region.hi[2]; ++k)
+                for (int j = region.lo[1]; j <= region.hi[1]; ++j)
+                  for (int i = region.lo[0]; i <= region.hi[0]; ++i) {
+                    F(i, j, k, n) = O(i - s[0], j - s[1], k - s[2], n);
+                  }
+          }
+  }
+  if (old) {
+    fresh.cycles = old->cycles;
+    fresh.time_point = old->time_point;
+  }
+  fresh.FillGhostLayerSingleLevel();
+}
+
 // ---------------------------------------------------------------------------
 // include/fub/solver/SubcycleFineFirstSolver.hpp:100-193 for a static
 // hierarchy (no regridding) held by one process.

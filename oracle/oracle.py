@@ -293,6 +293,13 @@ class CoarseFine:
         _check(lib().fvso_cf_fill_ghost_layer_two_levels(self.h, self.fine.h, self.coarse.h))
 
 
+def regrid_fill(fresh, old, coarse, ratio=(2, 2, 2)):
+    """GriddingAlgorithm::RemakeLevel + CopyDataToScratch: fills the level `fresh` (already
+    defined on its new boxes) from the old level (may be None) and the coarse level."""
+    r = [ratio[d] if d < fresh.rank else 1 for d in range(3)]
+    _check(lib().fvso_regrid_fill(fresh.h, old.h if old is not None else None, coarse.h, _ia(r)))
+
+
 class Hierarchy:
     """Static multi-level hierarchy with fine-first subcycling (oracle/amr.hpp)."""
 

@@ -323,6 +323,13 @@ int fvso_cf_fill_ghost_layer_two_levels(void* cf, void* fine, void* coarse) {
   });
 }
 
+int fvso_regrid_fill(void* fresh, void* old, void* coarse, const int* ratio) {
+  return guarded([&] {
+    RegridFill(*static_cast<Level*>(fresh), static_cast<const Level*>(old),
+               *static_cast<Level*>(coarse), ratio);
+  });
+}
+
 // --------------------------------------------------------------- hierarchy
 void* fvso_hierarchy_create(int nlevels, void** levels, const int* ratio) {
   Hierarchy* H = new Hierarchy;

@@ -140,3 +140,85 @@ def test_distribute_boxes_balances_and_keeps_neighbours(fvs):
         assert counts.min() == counts.max() == 8 // nranks
     owner = fvs.distribute_boxes(3, boxes, 3)
     assert sorted(set(owner)) == [0, 1, 2]
+
+
+def _cells(boxes):
+    s = set()
+    for lo, hi in boxes:
+        for k in range(lo[2], hi[2] + 1):
+            for j in range(lo[1], hi[1] + 1):
+                for i in range(lo[0], hi[0] + 1):
+                    s.add((i, j, k))
+    return s
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_cluster_tags_contract(fvs, rank):
+    """The regrid hand-off (stand-in for AmrCore::regrid behind
+    src/AMReX/GriddingAlgorithm.cpp:86-110): boxes are disjoint, aligned to the blocking
+    factor, at most max_grid_size long, properly nested, and cover every tagged cell that
+    can be refined."""
+    rng = np.random.default_rng(5)
+    n = [32, 24, 16 if rank == 3 else 1]
+    hi = [n[0] - 1, n[1] - 1, n[2] - 1]
+    # level boxes: an L-shaped part of the domain
+    boxes = [([0, 0, 0], [15, hi[1], hi[2]]), ([16, 8, 0], [31, hi[1], hi[2]])]
+    tags = (rng.random((n[2], n[1], n[0])) < 0.02).astype(np.int8)
+    bf, mg, nest = 8, 16, 1
+    out = fvs.cluster_tags(rank, [0, 0, 0], hi, [0, 0, 0], boxes, tags, blocking_factor=bf,
+                           max_grid_size=mg, nesting_buffer=nest)
+    assert len(out) > 1
+    total = 0
+    for lo, h in out:
+        for d in range(rank):
+            assert lo[d] % bf == 0 and (h[d] + 1) % bf == 0
+            assert h[d] - lo[d] + 1 <= mg
+        for d in range(rank, 3):
+            assert lo[d] == 0 and h[d] == 0
+        total += np.prod([h[d] - lo[d] + 1 for d in range(3)])
+    fine_cells = _cells(out)
+    assert len(fine_cells) == total, "boxes overlap"
+    level_cells = _cells(boxes)
+    r = [2 if d < rank else 1 for d in range(3)]
+    refined_parents = {(i // r[0], j // r[1], k // r[2]) for (i, j, k) in fine_cells}
+    rng_nb = [range(-nest, nest + 1) if d < rank else range(1) for d in range(3)]
+    for (i, j, k) in refined_parents:  # proper nesting
+        for dk in rng_nb[2]:
+            for dj in rng_nb[1]:
+                for di in rng_nb[0]:
+                    q = (i + di, j + dj, k + dk)
+                    inside_domain = all(0 <= q[d] <= hi[d] for d in range(3))
+                    assert (not inside_domain) or q in level_cells
+    bc = bf // 2
+    for k, j, i in zip(*np.nonzero(tags)):
+        blk = [(i // bc) * bc, (j // bc) * bc, (k // bc) * bc if rank == 3 else 0]
+        nestable = True
+        for kk in range(blk[2] - (nest if rank == 3 else 0), blk[2] + (bc if rank == 3 else 1) + (nest if rank == 3 else 0)):
+            for jj in range(blk[1] - nest, blk[1] + bc + nest):
+                for ii in range(blk[0] - nest, blk[0] + bc + nest):
+                    q = (ii, jj, kk)
+                    if all(0 <= q[d] <= hi[d] for d in range(3)) and q not in level_cells:
+                        nestable = False
+        assert ((i, j, k) in refined_parents) == nestable, (i, j, k)
+    # deterministic
+    assert out == fvs.cluster_tags(rank, [0, 0, 0], hi, [0, 0, 0], boxes, tags, blocking_factor=bf,
+                                   max_grid_size=mg, nesting_buffer=nest)
+    # no tags, no boxes
+    assert fvs.cluster_tags(rank, [0, 0, 0], hi, [0, 0, 0], boxes, 0 * tags) == []
+
+
+def test_cutcell_load_balance_weights(fvs):
+    """cutcell::GriddingAlgorithm::LoadBalance (src/AMReX/cutcell/GriddingAlgorithm.cpp:190-211):
+    regular cells weigh 1, cells of single-valued fabs 6, covered cells 0.001; knapsack."""
+    boxes = [([8 * i, 0, 0], [8 * i + 7, 7, 0]) for i in range(8)]
+    fab = [0, 1, 0, -1, 0, 1, 0, 0]          # weights 64, 6*54+0.01=324.01, 64, 0.064, 64, 384, 64, 64
+    cov = [0, 10, 0, 64, 0, 0, 0, 0]
+    owner = fvs.distribute_boxes_cutcell(2, boxes, fab, cov, 2)
+    w = [64, 6 * 54 + 0.001 * 10, 64, 0.001 * 64, 64, 6 * 64, 64, 64]
+    load = [sum(w[i] for i in range(8) if owner[i] == r) for r in range(2)]
+    assert owner[1] != owner[5], "the two cut fabs go to different ranks"
+    assert abs(load[0] - load[1]) <= 64.0
+    # equal-count assignment would put boxes 0-3 on rank 0: 388 vs 640 -- the weights matter
+    assert max(load) < 560
+    # a single rank takes everything
+    assert fvs.distribute_boxes_cutcell(2, boxes, fab, cov, 1) == [0] * 8
