@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <limits>
 #include <map>
+#include <set>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -191,6 +192,8 @@ struct Level {
   std::vector<PeerExchange> peers;
   // descriptor caches, keyed by (kind, dir, src buffer, dst buffer, width)
   std::map<std::tuple<int, int, int, int, int>, std::unique_ptr<DeviceArray<BoxDesc>>> box_cache;
+  // register planes (fused sweeps on AMR levels), keyed by (dir, src buffer): descriptors + count
+  std::map<std::tuple<int, int>, std::pair<std::unique_ptr<DeviceArray<BoxDesc>>, int>> plane_cache;
   std::map<int, std::unique_ptr<DeviceArray<fvs::CopyDesc>>> copy_cache;
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::BcDesc>>> bc_cache;
   std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceArray<fvs::PackDesc>>> pack_cache;
@@ -250,6 +253,13 @@ struct fvs_ctx {
   long sweep_count{0};
   // comm
   Nccl::comm_t comm{nullptr};
+  // descriptor staging: a mapped pinned ring the kernels read their descriptor
+  // arrays from directly, so building one costs a memcpy on the host and no
+  // transfer or synchronisation; rewound whenever the stream is known to be idle
+  unsigned char* ring{nullptr};
+  unsigned char* ring_dev{nullptr};
+  size_t ring_size{0}, ring_used{0};
+  std::vector<unsigned char*> ring_retired; // full rings still referenced by queued kernels
 
   int stencil_width() const { return method.recon == fvs::kReconFirstOrder ? 1 : 2; }
   int ncomp() const { return cfg.rank + 4; }
@@ -316,6 +326,7 @@ void ensure_buffer(fvs_ctx* ctx, Level& L, int b) {
   }
   L.have_buf[b] = true;
   L.box_cache.clear();
+  L.plane_cache.clear();
 }
 
 void ensure_fluxes(fvs_ctx* ctx, Level& L, int dir) {
@@ -328,7 +339,10 @@ void ensure_fluxes(fvs_ctx* ctx, Level& L, int dir) {
       changed = true;
     }
   }
-  if (changed) L.box_cache.clear();
+  if (changed) {
+    L.box_cache.clear();
+    L.plane_cache.clear();
+  }
 }
 
 // a buffer index different from `a` and `b` (and from the kept backup)
@@ -452,6 +466,33 @@ void check_launch(int rc) {
   FVS_CUDA(cudaGetLastError());
 }
 
+// the stream is idle: nothing refers to staged descriptors any more
+void rewind_ring(fvs_ctx* ctx) {
+  ctx->ring_used = 0;
+  for (unsigned char* r : ctx->ring_retired) cudaFreeHost(r);
+  ctx->ring_retired.clear();
+}
+// Copies `bytes` into the descriptor ring and returns their device address.
+const void* stage_bytes(fvs_ctx* ctx, const void* data, size_t bytes) {
+  const size_t aligned = (std::max<size_t>(bytes, 1) + 255) & ~size_t(255);
+  if (ctx->ring_used + aligned > ctx->ring_size) {
+    // descriptors staged so far may not have been consumed yet (or not even been
+    // handed to a kernel): the full ring is retired, not overwritten
+    ctx->ring_retired.push_back(ctx->ring);
+    ctx->ring_size = std::max(ctx->ring_size, 2 * aligned);
+    FVS_CUDA(cudaHostAlloc(&ctx->ring, ctx->ring_size, cudaHostAllocMapped));
+    FVS_CUDA(cudaHostGetDevicePointer(&ctx->ring_dev, ctx->ring, 0));
+    ctx->ring_used = 0;
+  }
+  std::memcpy(ctx->ring + ctx->ring_used, data, bytes);
+  const void* dev = ctx->ring_dev + ctx->ring_used;
+  ctx->ring_used += aligned;
+  return dev;
+}
+template <typename Desc> const Desc* stage_descs(fvs_ctx* ctx, const std::vector<Desc>& host) {
+  return static_cast<const Desc*>(stage_bytes(ctx, host.data(), host.size() * sizeof(Desc)));
+}
+
 // Copies the accumulators and the failure flag into mapped pinned host memory
 // with plain stores from an SM.  A cudaMemcpyAsync would queue behind whatever
 // the device-to-host copy engine is busy with -- a 7.5 GB download of another
@@ -495,6 +536,7 @@ void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out, int* fails = nu
   FVS_CUDA(cudaGetLastError());
   ctx->launches += 1;
   FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  rewind_ring(ctx);
   const bool general = ctx->h_fail[kDtSlots] != 0;
   if (general) {
     FVS_CUDA(cudaMemsetAsync(ctx->d_fail + kDtSlots, 0, sizeof(int), ctx->stream));
@@ -553,7 +595,8 @@ void drain_events(fvs_ctx* ctx) {
 
 // launches the fused sweep cur -> free buffer; does NOT flip.  `hint`: see
 // SweepArgs::sig_hint -- the caller verifies it against the fetched result.
-int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, double hint = 0.0) {
+int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, double hint = 0.0,
+                 bool force_ieee = false) {
   const int src = L.cur;
   const int dst = free_buffer(L, src);
   ensure_buffer(ctx, L, dst);
@@ -562,7 +605,7 @@ int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, doubl
   fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot, hint);
   if (!L.patches.empty()) {
     EventTimer t(ctx);
-    const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
+    const int rc = (ctx->arithmetic == FVS_ARITH_TOLERANCE && !force_ieee)
                        ? fvs::launch_fused_sweep_tolerance(ctx->method, dir, A, ctx->stream)
                        : fvs::launch_fused_sweep(ctx->method, dir, A, ctx->stream);
     check_launch(rc);
@@ -1090,12 +1133,12 @@ struct Transfers {
   explicit Transfers(fvs_ctx* c) : ctx(c) {}
   Transfers(const Transfers&) = delete;
   ~Transfers() {
-    cudaStreamSynchronize(ctx->stream);
-    for (double* p : owned) cudaFree(p);
+    // stream ordered: the memory is recycled once the work queued so far is done
+    for (double* p : owned) cudaFreeAsync(p, ctx->stream);
   }
   double* buffer(size_t count) {
     double* p = nullptr;
-    FVS_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(double)));
+    FVS_CUDA(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(double), ctx->stream));
     owned.push_back(p);
     return p;
   }
@@ -1143,25 +1186,15 @@ struct RegionCopies {
     max_cells = std::max(max_cells, region.size());
     descs.push_back(d);
   }
-  void run(fvs_ctx* ctx, int ncomp, Transfers& keep_alive) {
+  void run(fvs_ctx* ctx, int ncomp, Transfers&) {
     if (descs.empty()) return;
-    fvs::CopyDesc* dev = nullptr;
-    FVS_CUDA(cudaMalloc(&dev, descs.size() * sizeof(fvs::CopyDesc)));
-    keep_alive.owned.push_back(reinterpret_cast<double*>(dev));
-    FVS_CUDA(cudaMemcpyAsync(dev, descs.data(), descs.size() * sizeof(fvs::CopyDesc),
-                             cudaMemcpyHostToDevice, ctx->stream));
-    FVS_CUDA(cudaStreamSynchronize(ctx->stream)); // descs is a host temporary
+    const fvs::CopyDesc* dev = stage_descs(ctx, descs);
     ctx->launches += fvs::launch_copy_regions(dev, (int)descs.size(), ncomp, max_cells, ctx->stream);
   }
 };
-template <typename Desc> Desc* upload_descs(fvs_ctx* ctx, const std::vector<Desc>& host, Transfers& keep) {
-  Desc* dev = nullptr;
-  FVS_CUDA(cudaMalloc(&dev, std::max<size_t>(host.size(), 1) * sizeof(Desc)));
-  keep.owned.push_back(reinterpret_cast<double*>(dev));
-  FVS_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(Desc), cudaMemcpyHostToDevice,
-                           ctx->stream));
-  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-  return dev;
+template <typename Desc>
+const Desc* upload_descs(fvs_ctx* ctx, const std::vector<Desc>& host, Transfers&) {
+  return stage_descs(ctx, host);
 }
 
 // plane of coarse faces of one side of a fine box, and its Reflux mask
@@ -1391,9 +1424,7 @@ void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
             continue;
           }
           const std::vector<unsigned char> mask = register_open(fine, coarse, ratio, faces, dir, side);
-          unsigned char* dmask = reinterpret_cast<unsigned char*>(xf.buffer((mask.size() + 7) / 8 + 1));
-          FVS_CUDA(cudaMemcpy(dmask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
-          open = dmask;
+          open = static_cast<const unsigned char*>(stage_bytes(ctx, mask.data(), mask.size()));
         }
         fvs::RegisterDesc d{};
         d.reg = reg_ref;
@@ -1625,6 +1656,15 @@ int fvs_create(const fvs_config* config, fvs_ctx** out) {
     FVS_CUDA(cudaHostAlloc(&ctx->h_fail, sizeof(int) * (kDtSlots + 1), cudaHostAllocMapped));
     FVS_CUDA(cudaHostGetDevicePointer(&ctx->h_fail_dev, ctx->h_fail, 0));
     std::memset(ctx->h_fail, 0, sizeof(int) * (kDtSlots + 1));
+    ctx->ring_size = size_t(8) << 20;
+    FVS_CUDA(cudaHostAlloc(&ctx->ring, ctx->ring_size, cudaHostAllocMapped));
+    FVS_CUDA(cudaHostGetDevicePointer(&ctx->ring_dev, ctx->ring, 0));
+    { // temporaries come from the stream-ordered allocator: keep its memory across syncs
+      cudaMemPool_t pool;
+      FVS_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+      unsigned long long keep = ~0ull;
+      FVS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     fvs_ctx* raw = ctx.release();
     *out = raw;
     const int rc = fvs_set_method(raw, config->base_method, config->reconstruction, config->limiter);
@@ -1655,6 +1695,8 @@ void fvs_destroy(fvs_ctx* ctx) {
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
   if (ctx->d_fail) cudaFree(ctx->d_fail);
   if (ctx->h_fail) cudaFreeHost(ctx->h_fail);
+  if (ctx->ring) cudaFreeHost(ctx->ring);
+  for (unsigned char* r : ctx->ring_retired) cudaFreeHost(r);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1814,6 +1856,7 @@ int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int 
     for (int d = 0; d < 3; ++d) per[d] = periodic && periodic[d] != 0;
     define_level(ctx, ctx->levels[level], fvs::make_box(domain_lo, domain_hi), dx, per, boxes, owner,
                  scratch_gcw, flux_gcw);
+    if (level > 0) ctx->levels[level - 1].plane_cache.clear();
     return (int)FVS_OK;
   });
 }
@@ -1834,6 +1877,7 @@ int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3]
     if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
     Level& coarse = ctx->level(level - 1);
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    coarse.plane_cache.clear(); // its CrseInit planes follow the boxes of this level
     if (nboxes == 0) { // GriddingAlgorithm::ClearLevel: the level and everything finer goes
       for (int l = level; l < (int)ctx->levels.size(); ++l) free_level(ctx->levels[l]);
       return (int)FVS_OK;
@@ -2328,12 +2372,152 @@ struct TooLarge {
 };
 
 // SubcycleFineFirstSolver::AdvanceLevel (include/fub/solver/SubcycleFineFirstSolver.hpp:114-175)
-// for a static hierarchy on one rank: finer levels first, `ratio` subcycles
-// each, flux registers, flux correction, conservative coarsening.  Works in
-// place through the per-policy entry points (the registers need the flux
-// arrays); throws TooLarge on a CFL violation.
-void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_kind,
-                   std::vector<double>& sweep_dts) {
+// for a hierarchy: finer levels first, `ratio` subcycles each, flux registers, flux
+// correction, conservative coarsening -- speculative like the single-level step: every
+// sweep also evaluates the stable dt of its input state into an accumulator slot, the
+// slots are read back with ONE synchronisation per coarse step (or when they run out)
+// and checked in execution order, so the outcome (TimeStepTooLarge with the dt of the
+// first failing check, the list of dts up to it, untouched state) is the reference's
+// check-before-sweep.  Regular levels run the fused sweep; the fluxes the registers need
+// -- the boundary planes of the level's own boxes (FineAdd) and of the finer level's
+// boxes (CrseInit) -- are evaluated from the sweep's input buffer on those planes only.
+// Cut-cell levels run the cut-cell policies in place.
+struct PendingSweep {
+  int slot, level, dir;
+  double split_dt, hint;
+};
+struct HintRedo {};
+struct AmrStep {
+  std::vector<PendingSweep> pending; // execution order; slots are consecutive
+  std::vector<double> dts;           // checked per-sweep dts
+  bool use_hints{true};
+};
+
+// reads the pending accumulators back and applies the reference's checks in order
+void flush_pending(fvs_ctx* ctx, AmrStep& st) {
+  if (st.pending.empty()) return;
+  const int count = (int)st.pending.size();
+  std::vector<double> sig((size_t)count);
+  std::vector<int> fails((size_t)count);
+  fetch_slots(ctx, st.pending.front().slot, count, sig.data(), fails.data());
+  std::vector<PendingSweep> pending;
+  pending.swap(st.pending);
+  for (int i = 0; i < count; ++i) {
+    const PendingSweep& ps = pending[(size_t)i];
+    Level& L = ctx->levels[(size_t)ps.level];
+    if (!verify_hint(ps.hint, sig[(size_t)i])) throw HintRedo{};
+    L.last_sig[ps.dir] = sig[(size_t)i];
+    const double level_dt = dt_from_signal(L.dx[ps.dir], sig[(size_t)i]);
+    st.dts.push_back(level_dt);
+    if (level_dt < ps.split_dt) throw TooLarge{level_dt * total_ratio(ctx, ps.level)};
+    if (fails[(size_t)i]) throw_newton();
+  }
+}
+
+// descriptors of the register planes of direction dir of level `level`, reading `src`
+const BoxDesc* plane_descs(fvs_ctx* ctx, Level& L, int level, int dir, int src, int* count) {
+  auto key = std::make_tuple(dir, src);
+  auto it = L.plane_cache.find(key);
+  if (it != L.plane_cache.end()) {
+    *count = it->second.second;
+    return it->second.first->ptr;
+  }
+  const int w = ctx->stencil_width();
+  int ratio[3];
+  effective_ratio(ctx, ratio);
+  const bool feeds_coarser = level > 0 && L.cf_coarse >= 0;
+  Level* finer = (level + 1 < (int)ctx->levels.size() && ctx->levels[(size_t)level + 1].defined &&
+                  ctx->levels[(size_t)level + 1].cf_coarse == level)
+                     ? &ctx->levels[(size_t)level + 1]
+                     : nullptr;
+  const std::vector<std::array<int, 3>> shifts = period_shifts(L, ctx->cfg.rank);
+  std::vector<BoxDesc> host;
+  for (Patch& p : L.patches) {
+    std::set<int> planes; // face index = index of the cell to its right
+    if (feeds_coarser) {
+      planes.insert(p.valid.lo[dir]);
+      planes.insert(p.valid.hi[dir] + 1);
+    }
+    if (finer) {
+      for (const Box& g : finer->boxes) {
+        const Box cg = coarsen_box(g, ratio);
+        for (const std::array<int, 3>& sh : shifts) {
+          // the coarse box's image holds the register faces <=> in the box's own index
+          // space the plane sits at P - shift and the fine box at cg - shift
+          Box local = cg;
+          for (int e = 0; e < 3; ++e) {
+            local.lo[e] -= sh[(size_t)e];
+            local.hi[e] -= sh[(size_t)e];
+          }
+          Box nodes = p.valid;
+          nodes.hi[dir] += 1;
+          for (int side = 0; side < 2; ++side) {
+            Box plane = local;
+            plane.lo[dir] = plane.hi[dir] = side == 0 ? local.lo[dir] : local.hi[dir] + 1;
+            if (fvs::intersect(plane, nodes).ok()) planes.insert(plane.lo[dir]);
+          }
+        }
+      }
+    }
+    for (int P : planes) {
+      BoxDesc d{};
+      d.src = p.buf[src];
+      d.dst = p.buf[src];
+      d.flux = p.flux[dir];
+      for (int e = 0; e < 3; ++e) {
+        d.n[e] = p.n[e];
+        d.fn[e] = p.fbox[dir].len(e);
+        d.foff[e] = p.fbox[dir].lo[e] - p.sbox.lo[e];
+      }
+      d.sc = p.cells;
+      d.fsc = p.fbox[dir].size();
+      int ulo, uhi, flo, fhi;
+      fvs::update_cell_range(p.valid, dir, L.flux_gcw, ulo, uhi);
+      fvs::flux_face_range(p.valid, dir, L.scratch_gcw, L.flux_gcw, w, flo, fhi);
+      if (P < flo || P > fhi) continue;
+      d.ulo = ulo - p.sbox.lo[dir];
+      d.uhi = uhi - p.sbox.lo[dir];
+      d.flo = d.fhi = P - p.sbox.lo[dir];
+      d.dtmask = p.dtmask[w - 1][dir];
+      d.fab_type = FVS_FAB_REGULAR;
+      host.push_back(d);
+    }
+  }
+  auto arr = std::make_unique<DeviceArray<BoxDesc>>();
+  if (!host.empty()) arr->upload(host);
+  const BoxDesc* ptr = host.empty() ? nullptr : arr->ptr;
+  *count = (int)host.size();
+  L.plane_cache[key] = std::make_pair(std::move(arr), *count);
+  return ptr;
+}
+
+// numeric fluxes of the sweep (dir, dt) on the register planes, from buffer `src`
+void plane_fluxes(fvs_ctx* ctx, Level& L, int level, int dir, double dt, int src) {
+  ensure_fluxes(ctx, L, dir);
+  int count = 0;
+  const BoxDesc* descs = plane_descs(ctx, L, level, dir, src, &count);
+  if (count == 0) return;
+  fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, descs, -1);
+  A.nboxes = count;
+  A.max_n[dir] = 1; // one plane of faces per descriptor
+  const int rc = fvs::launch_numeric_fluxes(ctx->method, dir, A, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+}
+
+void accumulate_coarse_fine(fvs_ctx* ctx, int level, double scale, int dir) {
+  Level& L = ctx->level(level);
+  ensure_fluxes(ctx, L, dir);
+  const double vol = cell_volume(ctx, L);
+  const double vol_dt_over_dx = vol * scale / L.dx[dir];
+  if (level > 0 && L.cf_coarse >= 0) fine_add(ctx, L, dir, vol_dt_over_dx);
+  if (level + 1 < (int)ctx->levels.size() && ctx->levels[(size_t)level + 1].defined &&
+      ctx->levels[(size_t)level + 1].cf_coarse == level) {
+    crse_init(ctx, ctx->levels[(size_t)level + 1], L, dir, -vol_dt_over_dx);
+  }
+}
+
+void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_kind, AmrStep& st) {
   Level& L = ctx->level(level);
   const int rank = ctx->cfg.rank;
   cc_pre_advance(ctx, L); // PreAdvanceLevel
@@ -2342,8 +2526,9 @@ void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_
   if (has_next) {
     call(fvs_reset_coarse_fine_fluxes(ctx, next, level));
     const int r = max_ratio(ctx);
-    for (int i = 0; i < r; ++i) advance_level(ctx, next, dt / r, i, split_kind, sweep_dts);
+    for (int i = 0; i < r; ++i) advance_level(ctx, next, dt / r, i, split_kind, st);
   }
+  const bool feeds = has_next || (level > 0 && L.cf_coarse >= 0);
   // AdvanceLevelNonRecursively; MakeSplitDirections uses the cycles of level 0
   const bool is_odd = ((ctx->cycles % 2) + sub_first) % 2 != 0;
   int dirs[3];
@@ -2354,14 +2539,27 @@ void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_
     const int dir = dirs[e.slot];
     if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir);
     counts[e.slot] += 1;
-    double level_dt = 0.0;
-    call(fvs_compute_stable_dt(ctx, level, dir, &level_dt));
-    sweep_dts.push_back(level_dt);
-    if (level_dt < e.dt) throw TooLarge{level_dt * total_ratio(ctx, level)};
-    call(fvs_compute_numeric_fluxes(ctx, level, e.dt, dir));
-    call(fvs_update_conservatively(ctx, level, e.dt, dir));
-    call(fvs_complete_from_cons(ctx, level));
-    call(fvs_accumulate_coarse_fine_fluxes(ctx, level, e.dt, dir));
+    if (ctx->next_slot + 1 > kDtSlots) { // out of accumulators: check what is pending
+      flush_pending(ctx, st);
+      ctx->next_slot = 0;
+    }
+    if (L.has_eb) {
+      const int slot = take_slot(ctx);
+      cc_stable_dt(ctx, L, dir, slot);
+      cc_numeric_fluxes(ctx, L, e.dt, dir);
+      cc_update(ctx, L, e.dt, dir);
+      cc_complete(ctx, L);
+      st.pending.push_back({slot, level, dir, e.dt, 0.0});
+    } else {
+      const double hint = st.use_hints ? dt_hint(ctx, L, dir) : 0.0;
+      const int src = L.cur;
+      int dst;
+      const int slot = launch_sweep(ctx, L, e.dt, dir, &dst, hint, /*force_ieee=*/true);
+      st.pending.push_back({slot, level, dir, e.dt, hint});
+      if (feeds) plane_fluxes(ctx, L, level, dir, e.dt, src);
+      L.cur = dst;
+    }
+    if (feeds) accumulate_coarse_fine(ctx, level, e.dt, dir);
   }
   if (has_next) {
     call(fvs_apply_flux_correction(ctx, next, level, dt));
@@ -2374,37 +2572,67 @@ int advance_hierarchy_multilevel(fvs_ctx* ctx, double dt, int split_kind, double
                                  double* sweep_dts, int* n_sweep_dts) {
   const int nl = num_levels(ctx);
   std::vector<int> entry(nl);
-  for (int l = 0; l < nl; ++l) {
-    Level& L = ctx->levels[l];
-    entry[l] = L.cur;
-    L.keep = -1;
-    const int work = free_buffer(L, L.cur);
-    ensure_buffer(ctx, L, work);
-    for (Patch& p : L.patches) {
-      FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[L.cur],
-                               (size_t)p.cells * ctx->ncomp() * sizeof(double),
-                               cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int l = 0; l < nl; ++l) entry[l] = ctx->levels[l].cur;
+  auto roll_back = [&] {
+    for (int l = 0; l < nl; ++l) {
+      ctx->levels[l].cur = entry[l];
+      ctx->levels[l].keep = -1;
     }
-    L.cur = work;
-  }
-  std::vector<double> dts;
+  };
+  AmrStep st;
   int status = FVS_OK;
-  try {
-    advance_level(ctx, 0, dt, 0, split_kind, dts);
-  } catch (const TooLarge& e) {
-    if (failure_dt) *failure_dt = e.dt;
-    status = FVS_TIME_STEP_TOO_LARGE;
-  } catch (...) {
-    for (int l = 0; l < nl; ++l) ctx->levels[l].cur = entry[l];
-    throw;
+  for (int attempt = 0;; ++attempt) {
+    st = AmrStep();
+    st.use_hints = attempt == 0;
+    ctx->next_slot = 0;
+    for (int l = 0; l < nl; ++l) {
+      Level& L = ctx->levels[l];
+      L.cur = entry[l];
+      if (L.has_eb) {
+        // cut-cell levels work in place on a copy of the entry state
+        L.keep = -1;
+        const int work = free_buffer(L, L.cur);
+        ensure_buffer(ctx, L, work);
+        for (Patch& p : L.patches) {
+          FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[L.cur],
+                                   (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        L.keep = entry[l];
+        L.cur = work;
+      } else {
+        L.keep = entry[l]; // the fused sweeps ping-pong between the other two buffers
+      }
+    }
+    try {
+      advance_level(ctx, 0, dt, 0, split_kind, st);
+      flush_pending(ctx, st);
+    } catch (const TooLarge& e) {
+      if (failure_dt) *failure_dt = e.dt;
+      status = FVS_TIME_STEP_TOO_LARGE;
+    } catch (const HintRedo&) {
+      // a stale lazy-dt hint: the sweeps behind it are void, repeat without hints
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+      ctx->hint_redos += 1;
+      roll_back();
+      continue;
+    } catch (...) {
+      cudaStreamSynchronize(ctx->stream);
+      roll_back();
+      throw;
+    }
+    break;
   }
+  const std::vector<double>& dts = st.dts;
   const int cap = (sweep_dts && n_sweep_dts) ? *n_sweep_dts : 0;
   for (int i = 0; i < (int)dts.size() && i < cap; ++i) sweep_dts[i] = dts[(size_t)i];
   if (n_sweep_dts) *n_sweep_dts = (int)dts.size();
   if (status != FVS_OK) {
-    for (int l = 0; l < nl; ++l) ctx->levels[l].cur = entry[l]; // roll back every level
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream)); // work queued behind the failing check
+    roll_back(); // every level: the entry buffers were never written
     return status;
   }
+  for (int l = 0; l < nl; ++l) ctx->levels[l].keep = -1;
   ctx->cycles += 1;
   ctx->time_point = ctx->time_point + dt;
   if (ctx->cycles % ctx->regrid_frequency == 0) { // SubcycleFineFirstSolver.hpp:177-192
