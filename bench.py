@@ -494,6 +494,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the AMR (W3) and cut-cell (W4) sub-records of the N=1 line")
     ap.add_argument("--arithmetic", default="ieee", choices=["ieee", "tolerance"],
                     help="arithmetic of the fused sweep for the headline numbers: ieee = "
                          "bit-identical to the oracle (default); tolerance = within 1e-12 per step "
@@ -694,6 +696,16 @@ def main():
         }
         sjob.close()
 
+    # ---- secondary workloads (N = 1 only): AMR hierarchy (W3) and cut-cell level (W4) ----
+    secondary = {}
+    if n_gpus == 1 and not args.no_secondary:
+        import bench_secondary
+        for name, fn in (("amr", bench_secondary.amr_record), ("eb", bench_secondary.eb_record)):
+            try:
+                secondary[name] = fn(capi, torch, peak)
+            except Exception as e:  # a sub-record must not take the headline down
+                secondary[name] = {"error": f"{type(e).__name__}: {e}"}
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -723,6 +735,7 @@ def main():
     }
     if strong_rec is not None:
         line["strong"] = strong_rec
+    line.update(secondary)
     print(json.dumps(line))
     return 0
 

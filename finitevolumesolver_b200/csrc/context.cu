@@ -42,6 +42,12 @@ struct Error : std::runtime_error {
     }                                                                                         \
   } while (0)
 
+// errors of kernels launched earlier surface at the next check: say which one
+inline void check_last(const char* where) {
+  const cudaError_t e_ = cudaGetLastError();
+  if (e_ != cudaSuccess) throw Error(std::string(where) + ": " + cudaGetErrorString(e_));
+}
+
 template <typename F> int guarded(F&& f) {
   try {
     return f();
@@ -145,6 +151,17 @@ struct BoundaryCondition {
   int dir, side, kind;
 };
 
+// cudaMemcpy from pageable host memory returns once the data sit in the driver's
+// staging buffer; the DMA to the device is ordered on the legacy default stream, which
+// the contexts' non-blocking streams do not wait for -- a kernel launched right after
+// could read the destination before the data arrive.  Every host-to-device upload of a
+// descriptor / mask array therefore waits for the legacy stream.
+inline cudaError_t upload_sync(void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 template <typename T> struct DeviceArray {
   T* ptr{nullptr};
   size_t count{0};
@@ -160,7 +177,7 @@ template <typename T> struct DeviceArray {
     count = host.size();
     if (count == 0) return;
     FVS_CUDA(cudaMalloc(&ptr, count * sizeof(T)));
-    FVS_CUDA(cudaMemcpy(ptr, host.data(), count * sizeof(T), cudaMemcpyHostToDevice));
+    FVS_CUDA(upload_sync(ptr, host.data(), count * sizeof(T)));
   }
 };
 
@@ -170,6 +187,32 @@ struct PeerExchange {
   long long send_elems{0}, recv_elems{0};
   double* sendbuf{nullptr};
   double* recvbuf{nullptr};
+};
+
+// One coarse-fine operation between two levels in executable form: descriptor
+// arrays and staging buffers live on the device until the hierarchy changes.
+struct CfXfer {
+  int src, dst;
+  size_t count;
+  double* ptr; // the local end (send buffer on src, receive buffer on dst)
+};
+struct CfPlan {
+  std::vector<CfXfer> xfers;
+  std::vector<void*> owned; // cudaMalloc'ed: staging buffers, descriptor arrays, masks
+  const void* packs{nullptr};
+  int n_packs{0};
+  long long packs_max{1};
+  const void* unpacks{nullptr};
+  int n_unpacks{0};
+  long long unpacks_max{1};
+  const void* main{nullptr};
+  int n_main{0};
+  long long main_max{1};
+  CfPlan() = default;
+  CfPlan(const CfPlan&) = delete;
+  ~CfPlan() {
+    for (void* q : owned) cudaFree(q);
+  }
 };
 
 struct Level {
@@ -207,6 +250,9 @@ struct Level {
   };
   std::vector<CfRegister> cf_regs;
   int cf_coarse{-1};
+  // coarse-fine operations towards the coarser level, built once per hierarchy
+  // configuration: key (operation, dir, buffer of this level, buffer of the coarser level)
+  std::map<std::tuple<int, int, int, int>, std::shared_ptr<CfPlan>> cf_plans;
   // embedded boundary
   bool has_eb{false};
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::EbDesc>>> eb_cache;
@@ -325,6 +371,8 @@ void ensure_buffer(fvs_ctx* ctx, Level& L, int b) {
     FVS_CUDA(cudaMemsetAsync(p.buf[b], 0, bytes, ctx->stream));
   }
   L.have_buf[b] = true;
+  // descriptor arrays are freed only while the stream is idle (kernels in flight read them)
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
   L.box_cache.clear();
   L.plane_cache.clear();
 }
@@ -340,6 +388,7 @@ void ensure_fluxes(fvs_ctx* ctx, Level& L, int dir) {
     }
   }
   if (changed) {
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
     L.box_cache.clear();
     L.plane_cache.clear();
   }
@@ -463,7 +512,7 @@ void check_dir(const fvs_ctx* ctx, int dir) {
 
 void check_launch(int rc) {
   if (rc < 0) throw Error("method / dimension combination is not compiled in");
-  FVS_CUDA(cudaGetLastError());
+  check_last("launch check #1");
 }
 
 // the stream is idle: nothing refers to staged descriptors any more
@@ -533,7 +582,7 @@ void fetch_slots(fvs_ctx* ctx, int slot, int count, double* out, int* fails = nu
   publish_results_kernel<<<1, 32, 0, ctx->stream>>>(
       ctx->d_slots + slot, ctx->h_slots_dev + slot, count, ctx->d_fail + slot,
       ctx->h_fail_dev + slot, ctx->d_fail + kDtSlots, ctx->h_fail_dev + kDtSlots);
-  FVS_CUDA(cudaGetLastError());
+  check_last("launch check #2");
   ctx->launches += 1;
   FVS_CUDA(cudaStreamSynchronize(ctx->stream));
   rewind_ring(ctx);
@@ -716,7 +765,7 @@ void fill_boundary(fvs_ctx* ctx, Level& L) {
     ctx->launches += fvs::launch_pack(pd, n_regions, ctx->ncomp(), L.peers[i].recvbuf, max_cells,
                                       1, ctx->stream);
   }
-  FVS_CUDA(cudaGetLastError());
+  check_last("launch check #3");
 }
 
 void apply_bc(fvs_ctx* ctx, Level& L, int bc_index) {
@@ -758,7 +807,7 @@ void apply_bc(fvs_ctx* ctx, Level& L, int bc_index) {
   for (Patch& p : L.patches) max_cells = std::max(max_cells, p.cells);
   ctx->launches += fvs::launch_boundary(arr.ptr, (int)arr.count, ctx->ncomp(), bc.dir, bc.kind,
                                         max_cells, ctx->stream);
-  FVS_CUDA(cudaGetLastError());
+  check_last("launch check #4");
 }
 
 void apply_boundary_condition(fvs_ctx* ctx, Level& L, int dir) {
@@ -879,6 +928,7 @@ void enable_eb(fvs_ctx* ctx, Level& L) {
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   L.has_eb = true;
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
   L.box_cache.clear();
   L.eb_cache.clear();
 }
@@ -1120,17 +1170,15 @@ Patch* local_patch(Level& L, int global_box) {
   return loc < 0 ? nullptr : &L.patches[(size_t)loc];
 }
 
-// staging buffers and the transfers of one coarse-fine call
+// staging buffers and the transfers of one coarse-fine call.  With a plan the
+// buffers are persistent (owned by the plan) and the transfer list is recorded in it;
+// without one they are stream-ordered temporaries of this call.
 struct Transfers {
   fvs_ctx* ctx;
-  struct X {
-    int src, dst;
-    size_t count;
-    double* ptr; // the local end (send buffer on src, receive buffer on dst)
-  };
-  std::vector<X> list;
+  CfPlan* plan;
+  std::vector<CfXfer> list;
   std::vector<double*> owned;
-  explicit Transfers(fvs_ctx* c) : ctx(c) {}
+  explicit Transfers(fvs_ctx* c, CfPlan* p = nullptr) : ctx(c), plan(p) {}
   Transfers(const Transfers&) = delete;
   ~Transfers() {
     // stream ordered: the memory is recycled once the work queued so far is done
@@ -1138,23 +1186,31 @@ struct Transfers {
   }
   double* buffer(size_t count) {
     double* p = nullptr;
-    FVS_CUDA(cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(double), ctx->stream));
-    owned.push_back(p);
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(double);
+    if (plan) {
+      FVS_CUDA(cudaMalloc(&p, bytes));
+      plan->owned.push_back(p);
+    } else {
+      FVS_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
+      owned.push_back(p);
+    }
     return p;
   }
   // registers a transfer this rank takes part in; returns its local buffer
   double* add(int src, int dst, size_t count) {
     double* p = buffer(count);
     list.push_back({src, dst, count, p});
+    if (plan) plan->xfers.push_back({src, dst, count, p});
     return p;
   }
-  void run() {
+  void run() { run_transfers(ctx, list); }
+  static void run_transfers(fvs_ctx* ctx, const std::vector<CfXfer>& list) {
     if (list.empty()) return;
     if (!ctx->comm) throw Error("levels span several ranks but fvs_comm_init was not called");
     Nccl& n = Nccl::get();
     const int me = ctx->cfg.comm_rank;
     n.check(n.GroupStart(), "ncclGroupStart");
-    for (const X& x : list) {
+    for (const CfXfer& x : list) {
       if (x.src == me) {
         n.check(n.Send(x.ptr, x.count, Nccl::kDouble, x.dst, ctx->comm, ctx->stream), "ncclSend");
       } else {
@@ -1164,6 +1220,16 @@ struct Transfers {
     n.check(n.GroupEnd(), "ncclGroupEnd");
   }
 };
+
+// descriptor array of a plan: persistent device copy
+template <typename Desc> const Desc* persist_descs(CfPlan& plan, const std::vector<Desc>& host) {
+  if (host.empty()) return nullptr;
+  Desc* dev = nullptr;
+  FVS_CUDA(cudaMalloc(&dev, host.size() * sizeof(Desc)));
+  plan.owned.push_back(dev);
+  FVS_CUDA(upload_sync(dev, host.data(), host.size() * sizeof(Desc)));
+  return dev;
+}
 
 // copies `region` (ncomp components) between two arrays; used to pack a region
 // into a staging buffer (whose box is the region itself) and to unpack it
@@ -1191,10 +1257,35 @@ struct RegionCopies {
     const fvs::CopyDesc* dev = stage_descs(ctx, descs);
     ctx->launches += fvs::launch_copy_regions(dev, (int)descs.size(), ncomp, max_cells, ctx->stream);
   }
+  void persist_packs(CfPlan& plan) {
+    plan.packs = persist_descs(plan, descs);
+    plan.n_packs = (int)descs.size();
+    plan.packs_max = max_cells;
+  }
+  void persist_unpacks(CfPlan& plan) {
+    plan.unpacks = persist_descs(plan, descs);
+    plan.n_unpacks = (int)descs.size();
+    plan.unpacks_max = max_cells;
+  }
 };
+void run_copies(fvs_ctx* ctx, const void* descs, int n, long long max_cells, int ncomp) {
+  if (n == 0) return;
+  ctx->launches += fvs::launch_copy_regions(static_cast<const fvs::CopyDesc*>(descs), n, ncomp,
+                                            max_cells, ctx->stream);
+}
 template <typename Desc>
 const Desc* upload_descs(fvs_ctx* ctx, const std::vector<Desc>& host, Transfers&) {
   return stage_descs(ctx, host);
+}
+CfPlan* find_plan(Level& fine, int op, int dir, int fine_buf, int coarse_buf) {
+  auto it = fine.cf_plans.find(std::make_tuple(op, dir, fine_buf, coarse_buf));
+  return it == fine.cf_plans.end() ? nullptr : it->second.get();
+}
+CfPlan* new_plan(Level& fine, int op, int dir, int fine_buf, int coarse_buf) {
+  auto plan = std::make_shared<CfPlan>();
+  CfPlan* raw = plan.get();
+  fine.cf_plans[std::make_tuple(op, dir, fine_buf, coarse_buf)] = std::move(plan);
+  return raw;
 }
 
 // plane of coarse faces of one side of a fine box, and its Reflux mask
@@ -1250,11 +1341,13 @@ std::vector<unsigned char> register_open(const Level& fine, const Level& coarse,
 // FluxRegister of `fine` towards `coarse`: one plane per side of every OWNED
 // fine box
 void define_flux_register(fvs_ctx* ctx, Level& fine, Level& coarse, int coarse_index) {
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream)); // registers and plans may still be in use
   for (Level::CfRegister& r : fine.cf_regs) {
     if (r.reg) cudaFree(r.reg);
     if (r.open) cudaFree(r.open);
   }
   fine.cf_regs.clear();
+  fine.cf_plans.clear();
   int ratio[3];
   effective_ratio(ctx, ratio);
   const int rank = ctx->cfg.rank;
@@ -1269,7 +1362,7 @@ void define_flux_register(fvs_ctx* ctx, Level& fine, Level& coarse, int coarse_i
         const std::vector<unsigned char> open = register_open(fine, coarse, ratio, r.plane, d, side);
         r.reg = device_alloc_zero<double>(ctx, open.size() * ctx->ncons());
         FVS_CUDA(cudaMalloc(&r.open, open.size()));
-        FVS_CUDA(cudaMemcpy(r.open, open.data(), open.size(), cudaMemcpyHostToDevice));
+        FVS_CUDA(upload_sync(r.open, open.data(), open.size()));
         fine.cf_regs.push_back(r);
       }
   }
@@ -1282,291 +1375,335 @@ Level::CfRegister* find_register(Level& fine, int local_patch_index, int dir, in
   return nullptr;
 }
 
-void launch_registers(fvs_ctx* ctx, const std::vector<fvs::RegisterDesc>& host, int op, int dir,
-                      double mult, double vol, long long max_faces, Transfers& keep) {
-  if (host.empty()) return;
+void run_registers(fvs_ctx* ctx, const CfPlan& plan, int op, int dir, double mult, double vol) {
+  if (plan.n_main == 0) return;
   int ratio[3];
   effective_ratio(ctx, ratio);
-  const fvs::RegisterDesc* dev = upload_descs(ctx, host, keep);
-  ctx->launches += fvs::launch_flux_register(dev, (int)host.size(), op, ctx->ncons(), dir, ratio,
-                                             mult, vol, max_faces, ctx->stream);
-  FVS_CUDA(cudaGetLastError());
+  ctx->launches += fvs::launch_flux_register(static_cast<const fvs::RegisterDesc*>(plan.main),
+                                             plan.n_main, op, ctx->ncons(), dir, ratio, mult, vol,
+                                             plan.main_max, ctx->stream);
+  check_last("launch check #5");
 }
+void set_main(CfPlan& plan, const std::vector<fvs::RegisterDesc>& host, long long max_faces) {
+  plan.main = persist_descs(plan, host);
+  plan.n_main = (int)host.size();
+  plan.main_max = max_faces;
+}
+enum CfOp { kOpFineAdd = 0, kOpCrseInit = 1, kOpReflux = 2, kOpAverageDown = 3, kOpInterp = 4 };
 
 // FineAdd: registers and fine fluxes are both local to the owner of the fine box
 void fine_add(fvs_ctx* ctx, Level& fine, int dir, double mult) {
-  Transfers keep(ctx);
-  std::vector<fvs::RegisterDesc> host;
-  long long max_faces = 1;
-  for (const Level::CfRegister& r : fine.cf_regs) {
-    if (r.dir != dir) continue;
-    Patch& p = fine.patches[(size_t)r.patch];
-    fvs::RegisterDesc d{};
-    d.reg = array_ref(r.reg, r.plane, r.plane.size());
-    d.open = r.open;
-    d.side = r.side;
-    d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
-    for (int e = 0; e < 3; ++e) {
-      d.lo[e] = r.plane.lo[e];
-      d.len[e] = r.plane.len(e);
+  CfPlan* plan = find_plan(fine, kOpFineAdd, dir, 0, 0);
+  if (!plan) {
+    plan = new_plan(fine, kOpFineAdd, dir, 0, 0);
+    std::vector<fvs::RegisterDesc> host;
+    long long max_faces = 1;
+    for (const Level::CfRegister& r : fine.cf_regs) {
+      if (r.dir != dir) continue;
+      Patch& p = fine.patches[(size_t)r.patch];
+      fvs::RegisterDesc d{};
+      d.reg = array_ref(r.reg, r.plane, r.plane.size());
+      d.open = r.open;
+      d.side = r.side;
+      d.other = array_ref(p.flux[dir], p.fbox[dir], p.fbox[dir].size());
+      for (int e = 0; e < 3; ++e) {
+        d.lo[e] = r.plane.lo[e];
+        d.len[e] = r.plane.len(e);
+      }
+      max_faces = std::max(max_faces, r.plane.size());
+      host.push_back(d);
     }
-    max_faces = std::max(max_faces, r.plane.size());
-    host.push_back(d);
+    set_main(*plan, host, max_faces);
   }
-  launch_registers(ctx, host, 0, dir, mult, 1.0, max_faces, keep);
+  run_registers(ctx, *plan, 0, dir, mult, 1.0);
 }
 
 // CrseInit(ADD): the coarse fluxes on the register planes travel to the owner
 // of the fine box
 void crse_init(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double mult) {
-  int ratio[3];
-  effective_ratio(ctx, ratio);
-  const int me = ctx->cfg.comm_rank;
   const int ncons = ctx->ncons();
-  Transfers xf(ctx);
-  RegionCopies packs;
-  std::vector<fvs::RegisterDesc> host;
-  long long max_faces = 1;
-  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
-  for (size_t f = 0; f < fine.boxes.size(); ++f)
-    for (int side = 0; side < 2; ++side) {
-      const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
-      for (size_t c = 0; c < coarse.boxes.size(); ++c)
-      for (const std::array<int, 3>& shift : shifts) {
-        // the coarse box, or its image across a periodic boundary
-        const Box image = fvs::shifted(coarse.boxes[c], shift.data());
-        Box nodes = image;
-        nodes.hi[dir] += 1;
-        const Box faces = fvs::intersect(plane, nodes);
-        if (!faces.ok()) continue;
-        const int rf = fine.owner[f], rc = coarse.owner[c];
-        if (rf != me && rc != me) continue;
-        Patch* cp = local_patch(coarse, (int)c);
-        fvs::ArrayRef flux_ref;
-        if (rf == me && rc == me) {
-          flux_ref = shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), shift);
-        } else {
-          double* buf = xf.add(rc, rf, (size_t)faces.size() * ncons);
-          flux_ref = array_ref(buf, faces, faces.size());
-          if (rc == me) {
-            packs.add(flux_ref,
-                      shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), shift),
-                      faces);
-            continue;
+  CfPlan* plan = find_plan(fine, kOpCrseInit, dir, 0, 0);
+  if (!plan) {
+    plan = new_plan(fine, kOpCrseInit, dir, 0, 0);
+    int ratio[3];
+    effective_ratio(ctx, ratio);
+    const int me = ctx->cfg.comm_rank;
+    Transfers xf(ctx, plan);
+    RegionCopies packs;
+    std::vector<fvs::RegisterDesc> host;
+    long long max_faces = 1;
+    const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
+    for (size_t f = 0; f < fine.boxes.size(); ++f)
+      for (int side = 0; side < 2; ++side) {
+        const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
+        for (size_t c = 0; c < coarse.boxes.size(); ++c)
+          for (const std::array<int, 3>& shift : shifts) {
+            // the coarse box, or its image across a periodic boundary
+            const Box image = fvs::shifted(coarse.boxes[c], shift.data());
+            Box nodes = image;
+            nodes.hi[dir] += 1;
+            const Box faces = fvs::intersect(plane, nodes);
+            if (!faces.ok()) continue;
+            const int rf = fine.owner[f], rc = coarse.owner[c];
+            if (rf != me && rc != me) continue;
+            Patch* cp = local_patch(coarse, (int)c);
+            fvs::ArrayRef flux_ref;
+            if (rf == me && rc == me) {
+              flux_ref =
+                  shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()), shift);
+            } else {
+              double* buf = xf.add(rc, rf, (size_t)faces.size() * ncons);
+              flux_ref = array_ref(buf, faces, faces.size());
+              if (rc == me) {
+                packs.add(flux_ref,
+                          shifted_ref(array_ref(cp->flux[dir], cp->fbox[dir], cp->fbox[dir].size()),
+                                      shift),
+                          faces);
+                continue;
+              }
+            }
+            Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+            if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+            fvs::RegisterDesc d{};
+            d.reg = array_ref(r->reg, r->plane, r->plane.size());
+            d.open = r->open;
+            d.side = side;
+            d.other = flux_ref;
+            for (int e = 0; e < 3; ++e) {
+              d.box_lo[e] = image.lo[e];
+              d.box_hi[e] = image.hi[e];
+              d.lo[e] = faces.lo[e];
+              d.len[e] = faces.len(e);
+            }
+            max_faces = std::max(max_faces, faces.size());
+            host.push_back(d);
           }
-        }
-        Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
-        if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
-        fvs::RegisterDesc d{};
-        d.reg = array_ref(r->reg, r->plane, r->plane.size());
-        d.open = r->open;
-        d.side = side;
-        d.other = flux_ref;
-        for (int e = 0; e < 3; ++e) {
-          d.box_lo[e] = image.lo[e];
-          d.box_hi[e] = image.hi[e];
-          d.lo[e] = faces.lo[e];
-          d.len[e] = faces.len(e);
-        }
-        max_faces = std::max(max_faces, faces.size());
-        host.push_back(d);
       }
-    }
-  packs.run(ctx, ncons, xf);
-  xf.run();
-  launch_registers(ctx, host, 1, dir, mult, 1.0, max_faces, xf);
+    packs.persist_packs(*plan);
+    set_main(*plan, host, max_faces);
+  }
+  run_copies(ctx, plan->packs, plan->n_packs, plan->packs_max, ncons);
+  Transfers::run_transfers(ctx, plan->xfers);
+  run_registers(ctx, *plan, 1, dir, mult, 1.0);
 }
 
 // Reflux: the registers travel to the owners of the coarse boxes
 void reflux(fvs_ctx* ctx, Level& fine, Level& coarse, int dir, double scale) {
-  int ratio[3];
-  effective_ratio(ctx, ratio);
-  const int me = ctx->cfg.comm_rank;
   const int ncons = ctx->ncons();
   const double vol = cell_volume(ctx, coarse);
-  Transfers xf(ctx);
-  RegionCopies packs;
-  std::vector<fvs::RegisterDesc> host;
-  long long max_faces = 1;
-  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
-  for (size_t f = 0; f < fine.boxes.size(); ++f)
-    for (int side = 0; side < 2; ++side) {
-      const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
-      for (size_t c = 0; c < coarse.boxes.size(); ++c)
-      for (const std::array<int, 3>& shift : shifts) {
-        // faces of the plane whose OUTSIDE cell belongs to coarse box c (or to
-        // its image across a periodic boundary)
-        const Box image = fvs::shifted(coarse.boxes[c], shift.data());
-        Box cells = image;
-        if (side == 0) {
-          cells.lo[dir] += 1;
-          cells.hi[dir] += 1;
-        }
-        const Box faces = fvs::intersect(plane, cells);
-        if (!faces.ok()) continue;
-        const int rf = fine.owner[f], rc = coarse.owner[c];
-        if (rf != me && rc != me) continue;
-        Patch* cp = local_patch(coarse, (int)c);
-        fvs::ArrayRef reg_ref;
-        const unsigned char* open = nullptr;
-        if (rf == me && rc == me) {
-          Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
-          if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
-          reg_ref = array_ref(r->reg, r->plane, r->plane.size());
-          open = r->open;
-        } else {
-          double* buf = xf.add(rf, rc, (size_t)faces.size() * ncons);
-          reg_ref = array_ref(buf, faces, faces.size());
-          if (rf == me) {
-            Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
-            if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
-            packs.add(reg_ref, array_ref(r->reg, r->plane, r->plane.size()), faces);
-            continue;
+  CfPlan* plan = find_plan(fine, kOpReflux, dir, 0, coarse.cur);
+  if (!plan) {
+    plan = new_plan(fine, kOpReflux, dir, 0, coarse.cur);
+    int ratio[3];
+    effective_ratio(ctx, ratio);
+    const int me = ctx->cfg.comm_rank;
+    Transfers xf(ctx, plan);
+    RegionCopies packs;
+    std::vector<fvs::RegisterDesc> host;
+    long long max_faces = 1;
+    const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
+    for (size_t f = 0; f < fine.boxes.size(); ++f)
+      for (int side = 0; side < 2; ++side) {
+        const Box plane = register_plane(fine.boxes[f], ratio, dir, side);
+        for (size_t c = 0; c < coarse.boxes.size(); ++c)
+          for (const std::array<int, 3>& shift : shifts) {
+            // faces of the plane whose OUTSIDE cell belongs to coarse box c (or to
+            // its image across a periodic boundary)
+            const Box image = fvs::shifted(coarse.boxes[c], shift.data());
+            Box cells = image;
+            if (side == 0) {
+              cells.lo[dir] += 1;
+              cells.hi[dir] += 1;
+            }
+            const Box faces = fvs::intersect(plane, cells);
+            if (!faces.ok()) continue;
+            const int rf = fine.owner[f], rc = coarse.owner[c];
+            if (rf != me && rc != me) continue;
+            Patch* cp = local_patch(coarse, (int)c);
+            fvs::ArrayRef reg_ref;
+            const unsigned char* open = nullptr;
+            if (rf == me && rc == me) {
+              Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+              if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+              reg_ref = array_ref(r->reg, r->plane, r->plane.size());
+              open = r->open;
+            } else {
+              double* buf = xf.add(rf, rc, (size_t)faces.size() * ncons);
+              reg_ref = array_ref(buf, faces, faces.size());
+              if (rf == me) {
+                Level::CfRegister* r = find_register(fine, fine.local_of_global[f], dir, side);
+                if (!r) throw Error("flux register is not defined (fvs_reset_coarse_fine_fluxes)");
+                packs.add(reg_ref, array_ref(r->reg, r->plane, r->plane.size()), faces);
+                continue;
+              }
+              const std::vector<unsigned char> mask =
+                  register_open(fine, coarse, ratio, faces, dir, side);
+              unsigned char* dmask = nullptr;
+              FVS_CUDA(cudaMalloc(&dmask, std::max<size_t>(mask.size(), 1)));
+              plan->owned.push_back(dmask);
+              FVS_CUDA(upload_sync(dmask, mask.data(), mask.size()));
+              open = dmask;
+            }
+            fvs::RegisterDesc d{};
+            d.reg = reg_ref;
+            d.open = open;
+            d.side = side;
+            d.other = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
+            for (int e = 0; e < 3; ++e) {
+              d.box_lo[e] = image.lo[e];
+              d.box_hi[e] = image.hi[e];
+              d.lo[e] = faces.lo[e];
+              d.len[e] = faces.len(e);
+            }
+            max_faces = std::max(max_faces, faces.size());
+            host.push_back(d);
           }
-          const std::vector<unsigned char> mask = register_open(fine, coarse, ratio, faces, dir, side);
-          open = static_cast<const unsigned char*>(stage_bytes(ctx, mask.data(), mask.size()));
-        }
-        fvs::RegisterDesc d{};
-        d.reg = reg_ref;
-        d.open = open;
-        d.side = side;
-        d.other = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
-        for (int e = 0; e < 3; ++e) {
-          d.box_lo[e] = image.lo[e];
-          d.box_hi[e] = image.hi[e];
-          d.lo[e] = faces.lo[e];
-          d.len[e] = faces.len(e);
-        }
-        max_faces = std::max(max_faces, faces.size());
-        host.push_back(d);
       }
-    }
-  packs.run(ctx, ncons, xf);
-  xf.run();
-  launch_registers(ctx, host, 2, dir, scale, vol, max_faces, xf);
+    packs.persist_packs(*plan);
+    set_main(*plan, host, max_faces);
+  }
+  run_copies(ctx, plan->packs, plan->n_packs, plan->packs_max, ncons);
+  Transfers::run_transfers(ctx, plan->xfers);
+  run_registers(ctx, *plan, 2, dir, scale, vol);
 }
 
 // amrex::average_down (cut-cell levels: amrex::EB_average_down, weighted with the
 // fine volume fractions): the owner of the fine box averages, the result travels
 void average_down(fvs_ctx* ctx, Level& fine, Level& coarse) {
+  const int ncons = ctx->ncons();
   int ratio[3];
   effective_ratio(ctx, ratio);
-  const int me = ctx->cfg.comm_rank;
-  const int ncons = ctx->ncons();
-  Transfers xf(ctx);
-  RegionCopies unpacks;
-  std::vector<fvs::AvgDownDesc> host;
-  long long max_cells = 1;
-  for (size_t f = 0; f < fine.boxes.size(); ++f) {
-    const Box cf = coarsen_box(fine.boxes[f], ratio);
-    for (size_t c = 0; c < coarse.boxes.size(); ++c) {
-      const Box region = fvs::intersect(cf, coarse.boxes[c]);
-      if (!region.ok()) continue;
-      const int rf = fine.owner[f], rc = coarse.owner[c];
-      if (rf != me && rc != me) continue;
-      Patch* fp = local_patch(fine, (int)f);
-      Patch* cp = local_patch(coarse, (int)c);
-      fvs::ArrayRef target;
-      if (rf == me && rc == me) {
-        target = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
-      } else {
-        double* buf = xf.add(rf, rc, (size_t)region.size() * ncons);
-        target = array_ref(buf, region, region.size());
-        if (rc == me) {
-          unpacks.add(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), target, region);
-          continue;
+  CfPlan* plan = find_plan(fine, kOpAverageDown, 0, fine.cur, coarse.cur);
+  if (!plan) {
+    plan = new_plan(fine, kOpAverageDown, 0, fine.cur, coarse.cur);
+    const int me = ctx->cfg.comm_rank;
+    Transfers xf(ctx, plan);
+    RegionCopies unpacks;
+    std::vector<fvs::AvgDownDesc> host;
+    long long max_cells = 1;
+    for (size_t f = 0; f < fine.boxes.size(); ++f) {
+      const Box cf = coarsen_box(fine.boxes[f], ratio);
+      for (size_t c = 0; c < coarse.boxes.size(); ++c) {
+        const Box region = fvs::intersect(cf, coarse.boxes[c]);
+        if (!region.ok()) continue;
+        const int rf = fine.owner[f], rc = coarse.owner[c];
+        if (rf != me && rc != me) continue;
+        Patch* fp = local_patch(fine, (int)f);
+        Patch* cp = local_patch(coarse, (int)c);
+        fvs::ArrayRef target;
+        if (rf == me && rc == me) {
+          target = array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells);
+        } else {
+          double* buf = xf.add(rf, rc, (size_t)region.size() * ncons);
+          target = array_ref(buf, region, region.size());
+          if (rc == me) {
+            unpacks.add(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), target, region);
+            continue;
+          }
         }
+        fvs::AvgDownDesc d{};
+        d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
+        d.crse = target;
+        d.vfrac = (fine.has_eb && fp->eb.fab_type == FVS_FAB_SINGLEVALUED) ? fp->eb.alpha : nullptr;
+        for (int e = 0; e < 3; ++e) {
+          d.lo[e] = region.lo[e];
+          d.len[e] = region.len(e);
+        }
+        max_cells = std::max(max_cells, region.size());
+        host.push_back(d);
       }
-      fvs::AvgDownDesc d{};
-      d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
-      d.crse = target;
-      d.vfrac = (fine.has_eb && fp->eb.fab_type == FVS_FAB_SINGLEVALUED) ? fp->eb.alpha : nullptr;
-      for (int e = 0; e < 3; ++e) {
-        d.lo[e] = region.lo[e];
-        d.len[e] = region.len(e);
-      }
-      max_cells = std::max(max_cells, region.size());
-      host.push_back(d);
     }
+    plan->main = persist_descs(*plan, host);
+    plan->n_main = (int)host.size();
+    plan->main_max = max_cells;
+    unpacks.persist_unpacks(*plan);
   }
-  if (!host.empty()) {
-    const fvs::AvgDownDesc* dev = upload_descs(ctx, host, xf);
-    ctx->launches += fvs::launch_average_down(dev, (int)host.size(), ncons, ratio, max_cells, ctx->stream);
-    FVS_CUDA(cudaGetLastError());
+  if (plan->n_main > 0) {
+    ctx->launches += fvs::launch_average_down(static_cast<const fvs::AvgDownDesc*>(plan->main),
+                                              plan->n_main, ncons, ratio, plan->main_max, ctx->stream);
+    check_last("launch check #6");
   }
-  xf.run();
-  unpacks.run(ctx, ncons, xf);
+  Transfers::run_transfers(ctx, plan->xfers);
+  run_copies(ctx, plan->unpacks, plan->n_unpacks, plan->unpacks_max, ncons);
 }
 
 // FillPatchTwoLevels with pc_interp: the coarse parents travel to the owner of
 // the fine box
 void pc_interp(fvs_ctx* ctx, Level& fine, Level& coarse, bool skip_valid = true) {
+  const int ncomp = ctx->ncomp();
   int ratio[3];
   effective_ratio(ctx, ratio);
-  const int me = ctx->cfg.comm_rank;
-  const int ncomp = ctx->ncomp();
-  Transfers xf(ctx);
-  RegionCopies packs;
-  std::vector<fvs::InterpDesc> host;
-  long long max_cells = 1;
-  // ghost cells beyond a periodic boundary take their parent from the coarse
-  // level's periodic image (the fill domain is grown in the periodic directions)
-  const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
-  Box fill_domain = fine.domain;
-  for (int d = 0; d < ctx->cfg.rank; ++d) {
-    if (fine.periodic[d]) {
-      fill_domain.lo[d] -= fine.scratch_gcw;
-      fill_domain.hi[d] += fine.scratch_gcw;
+  CfPlan* plan = find_plan(fine, kOpInterp, skip_valid ? 1 : 0, fine.cur, coarse.cur);
+  if (!plan) {
+    plan = new_plan(fine, kOpInterp, skip_valid ? 1 : 0, fine.cur, coarse.cur);
+    const int me = ctx->cfg.comm_rank;
+    Transfers xf(ctx, plan);
+    RegionCopies packs;
+    std::vector<fvs::InterpDesc> host;
+    long long max_cells = 1;
+    // ghost cells beyond a periodic boundary take their parent from the coarse
+    // level's periodic image (the fill domain is grown in the periodic directions)
+    const std::vector<std::array<int, 3>> shifts = period_shifts(coarse, ctx->cfg.rank);
+    Box fill_domain = fine.domain;
+    for (int d = 0; d < ctx->cfg.rank; ++d) {
+      if (fine.periodic[d]) {
+        fill_domain.lo[d] -= fine.scratch_gcw;
+        fill_domain.hi[d] += fine.scratch_gcw;
+      }
     }
-  }
-  for (size_t f = 0; f < fine.boxes.size(); ++f) {
-    const Box fsbox = fvs::state_box(fine.boxes[f], ctx->cfg.rank, fine.scratch_gcw);
-    for (size_t c = 0; c < coarse.boxes.size(); ++c)
-    for (const std::array<int, 3>& shift : shifts) {
-      const Box image = fvs::shifted(coarse.boxes[c], shift.data());
-      const Box region =
-          fvs::intersect(fvs::intersect(fsbox, refine_box(image, ratio)), fill_domain);
-      if (!region.ok()) continue;
-      const int rf = fine.owner[f], rc = coarse.owner[c];
-      if (rf != me && rc != me) continue;
-      Patch* fp = local_patch(fine, (int)f);
-      Patch* cp = local_patch(coarse, (int)c);
-      fvs::ArrayRef source;
-      if (rf == me && rc == me) {
-        source = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
-      } else {
-        const Box parents = coarsen_box(region, ratio);
-        double* buf = xf.add(rc, rf, (size_t)parents.size() * ncomp);
-        source = array_ref(buf, parents, parents.size());
-        if (rc == me) {
-          packs.add(source, shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift),
-                    parents);
-          continue;
+    for (size_t f = 0; f < fine.boxes.size(); ++f) {
+      const Box fsbox = fvs::state_box(fine.boxes[f], ctx->cfg.rank, fine.scratch_gcw);
+      for (size_t c = 0; c < coarse.boxes.size(); ++c)
+        for (const std::array<int, 3>& shift : shifts) {
+          const Box image = fvs::shifted(coarse.boxes[c], shift.data());
+          const Box region =
+              fvs::intersect(fvs::intersect(fsbox, refine_box(image, ratio)), fill_domain);
+          if (!region.ok()) continue;
+          const int rf = fine.owner[f], rc = coarse.owner[c];
+          if (rf != me && rc != me) continue;
+          Patch* fp = local_patch(fine, (int)f);
+          Patch* cp = local_patch(coarse, (int)c);
+          fvs::ArrayRef source;
+          if (rf == me && rc == me) {
+            source = shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift);
+          } else {
+            const Box parents = coarsen_box(region, ratio);
+            double* buf = xf.add(rc, rf, (size_t)parents.size() * ncomp);
+            source = array_ref(buf, parents, parents.size());
+            if (rc == me) {
+              packs.add(source,
+                        shifted_ref(array_ref(cp->buf[coarse.cur], cp->sbox, cp->cells), shift),
+                        parents);
+              continue;
+            }
+          }
+          fvs::InterpDesc d{};
+          d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
+          d.crse = source;
+          for (int e = 0; e < 3; ++e) {
+            d.lo[e] = region.lo[e];
+            d.len[e] = region.len(e);
+            // skip_valid == false (regrid): an empty "own box" -- every cell is filled
+            d.vlo[e] = skip_valid ? fine.boxes[f].lo[e] : 1;
+            d.vhi[e] = skip_valid ? fine.boxes[f].hi[e] : 0;
+          }
+          max_cells = std::max(max_cells, region.size());
+          host.push_back(d);
         }
-      }
-      fvs::InterpDesc d{};
-      d.fine = array_ref(fp->buf[fine.cur], fp->sbox, fp->cells);
-      d.crse = source;
-      for (int e = 0; e < 3; ++e) {
-        d.lo[e] = region.lo[e];
-        d.len[e] = region.len(e);
-        // skip_valid == false (regrid): an empty "own box" -- every cell is filled
-        d.vlo[e] = skip_valid ? fine.boxes[f].lo[e] : 1;
-        d.vhi[e] = skip_valid ? fine.boxes[f].hi[e] : 0;
-      }
-      max_cells = std::max(max_cells, region.size());
-      host.push_back(d);
     }
+    packs.persist_packs(*plan);
+    plan->main = persist_descs(*plan, host);
+    plan->n_main = (int)host.size();
+    plan->main_max = max_cells;
   }
-  packs.run(ctx, ncomp, xf);
-  xf.run();
-  if (!host.empty()) {
-    const fvs::InterpDesc* dev = upload_descs(ctx, host, xf);
-    ctx->launches += fvs::launch_pc_interp(dev, (int)host.size(), ncomp, ratio, max_cells, ctx->stream);
-    FVS_CUDA(cudaGetLastError());
+  run_copies(ctx, plan->packs, plan->n_packs, plan->packs_max, ncomp);
+  Transfers::run_transfers(ctx, plan->xfers);
+  if (plan->n_main > 0) {
+    ctx->launches += fvs::launch_pc_interp(static_cast<const fvs::InterpDesc*>(plan->main),
+                                           plan->n_main, ncomp, ratio, plan->main_max, ctx->stream);
+    check_last("launch check #7");
   }
 }
-
 
 // ParallelCopy of the old level's valid cells into the new level's scratch arrays
 // (valid and ghost cells, periodic images included) -- the fine part of the
@@ -1791,8 +1928,7 @@ void define_level(fvs_ctx* ctx, Level& L, const Box& domain, const double dx[3],
         const std::vector<unsigned char> mask =
             fvs::stable_dt_face_mask(p.valid, scratch_gcw, w, d);
         FVS_CUDA(cudaMalloc(&p.dtmask[w - 1][d], mask.size()));
-        FVS_CUDA(cudaMemcpy(p.dtmask[w - 1][d], mask.data(), mask.size(),
-                            cudaMemcpyHostToDevice));
+        FVS_CUDA(upload_sync(p.dtmask[w - 1][d], mask.data(), mask.size()));
       }
     }
     L.local_of_global[b] = (int)L.patches.size();
@@ -1857,6 +1993,7 @@ int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int 
     define_level(ctx, ctx->levels[level], fvs::make_box(domain_lo, domain_hi), dx, per, boxes, owner,
                  scratch_gcw, flux_gcw);
     if (level > 0) ctx->levels[level - 1].plane_cache.clear();
+    if (level + 1 < (int)ctx->levels.size()) ctx->levels[level + 1].cf_plans.clear();
     return (int)FVS_OK;
   });
 }
@@ -1877,7 +2014,7 @@ int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3]
     if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
     Level& coarse = ctx->level(level - 1);
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-    coarse.plane_cache.clear(); // its CrseInit planes follow the boxes of this level
+    coarse.plane_cache.clear(); // its CrseInit planes follow the boxes of this level (stream idle)
     if (nboxes == 0) { // GriddingAlgorithm::ClearLevel: the level and everything finer goes
       for (int l = level; l < (int)ctx->levels.size(); ++l) free_level(ctx->levels[l]);
       return (int)FVS_OK;
@@ -1905,7 +2042,11 @@ int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3]
       pc_interp(ctx, L, coarse, /*skip_valid=*/false);
       if (had_old) copy_from_old_level(ctx, L, old);
       fill_ghost_layer(ctx, L);
+      // plans are freed only while the stream is idle: queued kernels read their
+      // descriptor arrays, and cudaFree does not wait for a non-blocking stream
       FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+      L.cf_plans.clear(); // the fill above was a one-off
+      if (level + 1 < (int)ctx->levels.size()) ctx->levels[level + 1].cf_plans.clear();
     } catch (...) {
       free_level(old);
       throw;
@@ -2297,53 +2438,73 @@ int fvs_apply_boundary_condition(fvs_ctx* ctx, int level, int dir) {
   });
 }
 
+namespace {
+// DimensionalSplitLevelIntegrator::ComputeStableDt of one level, enqueued: the max
+// signal speeds of the `rank` directions go to three consecutive accumulator slots.
+struct DtAllLaunch {
+  int slot;
+  double hints[3];
+};
+DtAllLaunch launch_dt_all(fvs_ctx* ctx, Level& L, bool use_hints) {
+  const int rank = ctx->cfg.rank;
+  DtAllLaunch out{};
+  out.slot = take_slot(ctx, 3);
+  for (int d = 0; d < 3; ++d) out.hints[d] = 0.0;
+  if (L.has_eb) {
+    for (int d = 0; d < rank; ++d) cc_stable_dt(ctx, L, d, out.slot + d);
+    return out;
+  }
+  fvs::DtAllArgs A{};
+  A.eq = ctx->eq;
+  for (int d = 0; d < 3; ++d) {
+    A.boxes[d] = box_descs(ctx, L, d < rank ? d : 0, L.cur, L.cur, false);
+    A.max_n[d] = L.max_n[d];
+  }
+  A.nboxes = (int)L.patches.size();
+  A.max_signal = ctx->d_slots + out.slot;
+  A.fail_flag = ctx->d_fail + out.slot;
+  for (int d = 0; d < 3; ++d) {
+    out.hints[d] = use_hints && d < rank ? dt_hint(ctx, L, d) : 0.0;
+    A.sig_hint[d] = out.hints[d];
+  }
+  if (!L.patches.empty()) {
+    const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
+                       ? fvs::launch_stable_dt_all_tolerance(ctx->method, A, ctx->stream)
+                       : fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
+    check_launch(rc);
+    ctx->launches += rc;
+  }
+  return out;
+}
+// true if the hints held; then the level's dt (DimensionalSplitLevelIntegrator.hpp:204-219)
+bool finish_dt_all(fvs_ctx* ctx, Level& L, const DtAllLaunch& launch, const double sig[3],
+                   double* dt_out) {
+  const int rank = ctx->cfg.rank;
+  for (int d = 0; d < rank; ++d)
+    if (!verify_hint(launch.hints[d], sig[d])) return false;
+  double min_dt = std::numeric_limits<double>::max();
+  for (int d = 0; d < rank; ++d) {
+    if (!L.has_eb) L.last_sig[d] = sig[d];
+    min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
+  }
+  *dt_out = min_dt;
+  return true;
+}
+} // namespace
+
 int fvs_compute_stable_dt_all(fvs_ctx* ctx, int level, double* dt_out) {
   return guarded([&] {
     if (!ctx || !dt_out) throw Error("null argument");
     ctx->use_device();
     Level& L = ctx->level(level);
-    const int rank = ctx->cfg.rank;
-    if (L.has_eb) {
-      const int slot = take_slot(ctx, 3);
-      for (int d = 0; d < rank; ++d) cc_stable_dt(ctx, L, d, slot + d);
+    for (int attempt = 0;; ++attempt) {
+      const DtAllLaunch launch = launch_dt_all(ctx, L, attempt == 0);
       double sig[3];
-      fetch_slots(ctx, slot, 3, sig);
-      double min_dt = std::numeric_limits<double>::max();
-      for (int d = 0; d < rank; ++d) min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
-      *dt_out = min_dt;
-      return (int)FVS_OK;
-    }
-    fvs::DtAllArgs A{};
-    A.eq = ctx->eq;
-    for (int d = 0; d < 3; ++d) {
-      A.boxes[d] = box_descs(ctx, L, d < rank ? d : 0, L.cur, L.cur, false);
-      A.max_n[d] = L.max_n[d];
-    }
-    A.nboxes = (int)L.patches.size();
-    double sig[3];
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      const int slot = take_slot(ctx, 3);
-      A.max_signal = ctx->d_slots + slot;
-      A.fail_flag = ctx->d_fail + slot;
-      for (int d = 0; d < 3; ++d) A.sig_hint[d] = attempt == 0 && d < rank ? dt_hint(ctx, L, d) : 0.0;
-      if (!L.patches.empty()) {
-        const int rc = ctx->arithmetic == FVS_ARITH_TOLERANCE
-                           ? fvs::launch_stable_dt_all_tolerance(ctx->method, A, ctx->stream)
-                           : fvs::launch_stable_dt_all(ctx->method, A, ctx->stream);
-        check_launch(rc);
-        ctx->launches += rc;
-      }
-      fetch_slots(ctx, slot, 3, sig);
-      bool ok = true;
-      for (int d = 0; d < rank; ++d) ok = ok && verify_hint(A.sig_hint[d], sig[d]);
-      if (ok) break;
+      fetch_slots(ctx, launch.slot, 3, sig);
+      if (finish_dt_all(ctx, L, launch, sig, dt_out)) break;
       ctx->hint_redos += 1;
+      if (attempt > 0) throw Error("stable dt evaluation without hints failed its own check");
     }
-    for (int d = 0; d < rank; ++d) L.last_sig[d] = sig[d];
-    // DimensionalSplitLevelIntegrator.hpp:204-219
-    double min_dt = std::numeric_limits<double>::max();
-    for (int d = 0; d < rank; ++d) min_dt = std::min(min_dt, dt_from_signal(L.dx[d], sig[d]));
-    *dt_out = min_dt;
     return (int)FVS_OK;
   });
 }
@@ -2646,10 +2807,29 @@ int advance_hierarchy_multilevel(fvs_ctx* ctx, double dt, int split_kind, double
 int fvs_compute_stable_dt_hierarchy(fvs_ctx* ctx, double* dt_out) {
   return guarded([&] {
     if (!ctx || !dt_out) throw Error("null argument");
+    ctx->use_device();
+    // SubcycleFineFirstSolver::ComputeStableDt (SubcycleFineFirstSolver.hpp:100-112); the
+    // passes of all levels are enqueued back to back and read with one synchronisation
+    const int nl = num_levels(ctx);
+    if (3 * nl > kDtSlots) throw Error("too many levels");
+    ctx->next_slot = 0;
+    std::vector<DtAllLaunch> launches((size_t)nl);
+    for (int l = 0; l < nl; ++l) launches[(size_t)l] = launch_dt_all(ctx, ctx->levels[(size_t)l], true);
+    std::vector<double> sig((size_t)(3 * nl));
+    fetch_slots(ctx, 0, 3 * nl, sig.data());
     double min_dt = std::numeric_limits<double>::max();
-    for (int l = 0; l < num_levels(ctx); ++l) {
+    for (int l = 0; l < nl; ++l) {
+      Level& L = ctx->levels[(size_t)l];
       double d = 0.0;
-      call(fvs_compute_stable_dt_all(ctx, l, &d));
+      if (!finish_dt_all(ctx, L, launches[(size_t)l], sig.data() + 3 * l, &d)) {
+        ctx->hint_redos += 1; // a stale hint on this level: once more without
+        const DtAllLaunch again = launch_dt_all(ctx, L, false);
+        double s3[3];
+        fetch_slots(ctx, again.slot, 3, s3);
+        if (!finish_dt_all(ctx, L, again, s3, &d)) {
+          throw Error("stable dt evaluation without hints failed its own check");
+        }
+      }
       min_dt = std::min(min_dt, total_ratio(ctx, l) * d);
     }
     *dt_out = min_dt;
@@ -3030,7 +3210,7 @@ int fvs_level_set_eb(fvs_ctx* ctx, int level, int box, const double* alpha,
     std::vector<unsigned char> flags(cells);
     FVS_CUDA(cudaMemcpyAsync(flags.data(), e.flags, cells, cudaMemcpyDeviceToHost, ctx->stream));
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
-    FVS_CUDA(cudaGetLastError());
+    check_last("launch check #8");
     std::vector<long long> list;
     for (size_t c = 0; c < cells; ++c)
       if (flags[c]) list.push_back((long long)c);
@@ -3039,11 +3219,11 @@ int fvs_level_set_eb(fvs_ctx* ctx, int level, int box, const double* alpha,
     e.n_cut = (int)list.size();
     if (!list.empty()) {
       FVS_CUDA(cudaMalloc(&e.cut_cells, list.size() * sizeof(long long)));
-      FVS_CUDA(cudaMemcpy(e.cut_cells, list.data(), list.size() * sizeof(long long),
-                          cudaMemcpyHostToDevice));
+      FVS_CUDA(upload_sync(e.cut_cells, list.data(), list.size() * sizeof(long long)));
     }
     const std::vector<unsigned char> mode = complete_modes(rank, L, p, alpha, beta);
-    FVS_CUDA(cudaMemcpy(e.complete_mode, mode.data(), cells, cudaMemcpyHostToDevice));
+    FVS_CUDA(upload_sync(e.complete_mode, mode.data(), cells));
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
     L.box_cache.clear();
     L.eb_cache.clear();
     return (int)FVS_OK;
@@ -3068,7 +3248,7 @@ int fvs_pre_advance_hierarchy(fvs_ctx* ctx) {
     for (Level& L : ctx->levels) {
       if (L.defined) cc_pre_advance(ctx, L);
     }
-    FVS_CUDA(cudaGetLastError());
+    check_last("launch check #9");
     return (int)FVS_OK;
   });
 }

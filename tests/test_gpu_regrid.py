@@ -119,7 +119,7 @@ def compare(cpus, gpus, what):
             assert_bitwise_equal(g.download_state(b), c.scratch(b)[0], f"{what} level {l} box {b}")
 
 
-@pytest.mark.parametrize("steps", [100])
+@pytest.mark.parametrize("steps", [int(__import__("os").environ.get("FVS_REGRID_STEPS", "100"))])
 def test_tag_regrid_step_bitwise(oracle, fvs, steps):
     orc = oracle
     hi0, dx0 = level_geometry(0)
