@@ -68,14 +68,9 @@ class AmrRun:
         lv.fill_ghost_layer()
 
     def tags(self, l):
-        lv = self.levels[l]
         hi, _ = self.geom(l)
-        dense = np.zeros((1, hi[1] + 1, hi[0] + 1), dtype=np.int8)
-        for b, (lo, h) in enumerate(lv.boxes):
-            t = lv.tag_gradient(b, [(0, 1e-2)])
-            dense[0, lo[1]:h[1] + 1, lo[0]:h[0] + 1] |= t[0]
-        lv.tag_buffer(dense, 2, self.BUFFER)
-        return dense
+        return self.levels[l].tag_level([hi[0] + 1, hi[1] + 1, 1], [(0, 1e-2)],
+                                        buffer_width=self.BUFFER)
 
     def regrid(self, init=False):
         l = 0

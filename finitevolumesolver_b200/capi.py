@@ -39,7 +39,7 @@ SYMBOLS = [
     "fvs_run", "fvs_set_regrid_frequency", "fvs_set_cycles", "fvs_cycles", "fvs_time_point",
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
-    "fvs_distribute_boxes_cutcell", "fvs_cluster_tags", "fvs_regrid_level",
+    "fvs_distribute_boxes_cutcell", "fvs_cluster_tags", "fvs_regrid_level", "fvs_tag_level",
     "fvs_set_dt_hints", "fvs_dt_hint_redos", "fvs_download_state_region",
     "fvs_enable_timing", "fvs_sweep_time_ms",
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
@@ -348,6 +348,18 @@ class Context:
         tols = (C.c_double * len(conditions))(*[t for _, t in conditions])
         _check(lib().fvs_tag_gradient(self.h, self.level, box, len(conditions), comps, tols,
                                       1 if use_alpha else 0, tags.ctypes.data_as(C.c_char_p)))
+        return tags
+
+    def tag_level(self, domain_n, conditions=(), use_alpha=False, cutcells=False, buffer_width=0,
+                  tags=None):
+        """Dense [z, y, x] int8 tag map of this level (fvs_tag_level)."""
+        if tags is None:
+            tags = np.zeros((domain_n[2], domain_n[1], domain_n[0]), dtype=np.int8)
+        comps = (C.c_int * max(len(conditions), 1))(*[c for c, _ in conditions])
+        tols = (C.c_double * max(len(conditions), 1))(*[t for _, t in conditions])
+        _check(lib().fvs_tag_level(self.h, self.level, len(conditions), comps, tols,
+                                   1 if use_alpha else 0, 1 if cutcells else 0, buffer_width,
+                                   tags.ctypes.data_as(C.c_char_p)))
         return tags
 
     def tag_cutcells(self, box, tags=None):

@@ -144,6 +144,9 @@ struct Patch {
   double* flux[3]{nullptr, nullptr, nullptr};
   Box fbox[3];
   unsigned char* dtmask[2][3]{{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  // cut-cell adapter: the stable dt runs over every face of the flux box
+  // (include/fub/AMReX/cutcell/FluxMethod.hpp:262-289), not over the tiled stencil set
+  unsigned char* dtmask_eb[3]{nullptr, nullptr, nullptr};
   EbPatch eb;
 };
 
@@ -339,6 +342,7 @@ void free_level(Level& L) {
       if (p.flux[d]) cudaFree(p.flux[d]);
       for (int w = 0; w < 2; ++w)
         if (p.dtmask[w][d]) cudaFree(p.dtmask[w][d]);
+      if (p.dtmask_eb[d]) cudaFree(p.dtmask_eb[d]);
     }
     EbPatch& e = p.eb;
     void* single[] = {e.alpha, e.bcent, e.bnorm, e.reference, e.boundary_flux, e.cut_cells,
@@ -404,13 +408,30 @@ int free_buffer(const Level& L, int a) {
 
 enum DescKind { kDescSweep = 0 };
 
-const BoxDesc* box_descs(fvs_ctx* ctx, Level& L, int dir, int src, int dst, bool with_flux) {
+// Patches of a cut-cell level by the flag type of their fab: regular fabs take the
+// fused sweep, single-valued (cut) fabs the cut-cell kernels, covered fabs nothing.
+enum PatchGroup { kGroupAll = 0, kGroupRegular = 1, kGroupCut = 2 };
+bool in_group(const Level& L, const Patch& p, int group) {
+  if (group == kGroupAll) return true;
+  if (!L.has_eb) return group == kGroupRegular;
+  return group == kGroupRegular ? p.eb.fab_type == FVS_FAB_REGULAR
+                                : p.eb.fab_type == FVS_FAB_SINGLEVALUED;
+}
+int group_size(const Level& L, int group) {
+  int n = 0;
+  for (const Patch& p : L.patches) n += in_group(L, p, group) ? 1 : 0;
+  return n;
+}
+
+const BoxDesc* box_descs(fvs_ctx* ctx, Level& L, int dir, int src, int dst, bool with_flux,
+                         int group = kGroupAll) {
   const int w = ctx->stencil_width();
-  auto key = std::make_tuple(with_flux ? 1 : 0, dir, src, dst, w);
+  auto key = std::make_tuple((with_flux ? 1 : 0) + 2 * group, dir, src, dst, w);
   auto it = L.box_cache.find(key);
   if (it != L.box_cache.end()) return it->second->ptr;
   std::vector<BoxDesc> host;
   for (Patch& p : L.patches) {
+    if (!in_group(L, p, group)) continue;
     BoxDesc d{};
     d.src = p.buf[src];
     d.dst = p.buf[dst];
@@ -430,6 +451,17 @@ const BoxDesc* box_descs(fvs_ctx* ctx, Level& L, int dir, int src, int dst, bool
     d.flo = flo - p.sbox.lo[dir];
     d.fhi = fhi - p.sbox.lo[dir];
     d.dtmask = p.dtmask[w - 1][dir];
+    if (L.has_eb && group == kGroupRegular) {
+      // the fused sweep of a regular fab of a cut-cell level: same formulas, but the
+      // stable dt covers the faces flo .. fhi (mask index = left cell of the face)
+      if (!p.dtmask_eb[dir]) {
+        std::vector<unsigned char> mask((size_t)p.n[dir], 0);
+        for (int f = d.flo; f <= d.fhi; ++f) mask[(size_t)(f - 1)] = 1;
+        FVS_CUDA(cudaMalloc(&p.dtmask_eb[dir], mask.size()));
+        FVS_CUDA(upload_sync(p.dtmask_eb[dir], mask.data(), mask.size()));
+      }
+      d.dtmask = p.dtmask_eb[dir];
+    }
     d.alpha = p.eb.alpha;
     d.beta = p.eb.beta[dir];
     d.fab_type = p.eb.fab_type;
@@ -645,14 +677,15 @@ void drain_events(fvs_ctx* ctx) {
 // launches the fused sweep cur -> free buffer; does NOT flip.  `hint`: see
 // SweepArgs::sig_hint -- the caller verifies it against the fetched result.
 int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, double hint = 0.0,
-                 bool force_ieee = false) {
+                 bool force_ieee = false, int group = kGroupAll) {
   const int src = L.cur;
   const int dst = free_buffer(L, src);
   ensure_buffer(ctx, L, dst);
-  const BoxDesc* boxes = box_descs(ctx, L, dir, src, dst, false);
+  const BoxDesc* boxes = box_descs(ctx, L, dir, src, dst, false, group);
   const int slot = take_slot(ctx);
   fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, slot, hint);
-  if (!L.patches.empty()) {
+  A.nboxes = group_size(L, group);
+  if (A.nboxes > 0) {
     EventTimer t(ctx);
     const int rc = (ctx->arithmetic == FVS_ARITH_TOLERANCE && !force_ieee)
                        ? fvs::launch_fused_sweep_tolerance(ctx->method, dir, A, ctx->stream)
@@ -661,6 +694,35 @@ int launch_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out, doubl
     ctx->launches += rc;
     t.stop();
   }
+  *dst_out = dst;
+  return slot;
+}
+
+// One directional sweep of a cut-cell level, L.cur -> a free buffer (returned in
+// *dst_out, not flipped): the regular fabs take the fused sweep (same formulas as on a
+// regular level; the stable dt over the cut-cell adapter's face set), the cut fabs are
+// copied and then run the cut-cell policies in place on the copy, covered fabs are
+// copied.  The stable dt of the level's input state accumulates in the returned slot.
+void cc_stable_dt(fvs_ctx*, Level&, int, int, int);
+void cc_numeric_fluxes(fvs_ctx*, Level&, double, int, int);
+void cc_update(fvs_ctx*, Level&, double, int, int);
+void cc_complete(fvs_ctx*, Level&, int);
+int eb_sweep(fvs_ctx* ctx, Level& L, double dt, int dir, int* dst_out) {
+  const int src = L.cur;
+  int dst;
+  // cut-cell levels stay in IEEE arithmetic
+  const int slot = launch_sweep(ctx, L, dt, dir, &dst, 0.0, /*force_ieee=*/true, kGroupRegular);
+  for (Patch& p : L.patches) {
+    if (in_group(L, p, kGroupRegular)) continue;
+    FVS_CUDA(cudaMemcpyAsync(p.buf[dst], p.buf[src], (size_t)p.cells * ctx->ncomp() * sizeof(double),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  L.cur = dst; // the cut-cell kernels work in place on the copy
+  cc_stable_dt(ctx, L, dir, slot, kGroupCut);
+  cc_numeric_fluxes(ctx, L, dt, dir, kGroupCut);
+  cc_update(ctx, L, dt, dir, kGroupCut);
+  cc_complete(ctx, L, kGroupCut);
+  L.cur = src;
   *dst_out = dst;
   return slot;
 }
@@ -995,13 +1057,14 @@ std::vector<unsigned char> complete_modes(int rank, const Level& L, const Patch&
   return mode;
 }
 
-const fvs::EbDesc* eb_descs(fvs_ctx* ctx, Level& L, int dir, int buf) {
-  auto key = std::make_tuple(dir, buf);
+const fvs::EbDesc* eb_descs(fvs_ctx* ctx, Level& L, int dir, int buf, int group = kGroupAll) {
+  auto key = std::make_tuple(dir, buf + 8 * group);
   auto it = L.eb_cache.find(key);
   if (it != L.eb_cache.end()) return it->second->ptr;
   const int w = ctx->stencil_width();
   std::vector<fvs::EbDesc> host;
   for (Patch& p : L.patches) {
+    if (!in_group(L, p, group)) continue;
     fvs::EbDesc d{};
     const EbPatch& e = p.eb;
     d.fab_type = e.fab_type;
@@ -1048,11 +1111,11 @@ const fvs::EbDesc* eb_descs(fvs_ctx* ctx, Level& L, int dir, int buf) {
   return ptr;
 }
 
-fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt) {
+fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt, int group = kGroupAll) {
   fvs::EbArgs A{};
   A.eq = ctx->eq;
-  A.boxes = eb_descs(ctx, L, dir, L.cur);
-  A.nboxes = (int)L.patches.size();
+  A.boxes = eb_descs(ctx, L, dir, L.cur, group);
+  A.nboxes = group_size(L, group);
   A.rank = ctx->cfg.rank;
   A.dir = dir;
   A.riemann = ctx->cutcell_riemann;
@@ -1060,6 +1123,7 @@ fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt) {
   A.max_cells = 0;
   A.max_cut = 0;
   for (const Patch& p : L.patches) {
+    if (!in_group(L, p, group)) continue;
     // one more plane along dir for the face-centred kernels
     A.max_cells = std::max(A.max_cells, p.cells + p.cells / p.n[dir]);
     A.max_cut = std::max(A.max_cut, p.eb.n_cut);
@@ -1069,28 +1133,33 @@ fvs::EbArgs eb_args(fvs_ctx* ctx, Level& L, int dir, double dt) {
 }
 
 // cutcell::FluxMethod::ComputeStableDt into accumulator `slot`
-void cc_stable_dt(fvs_ctx* ctx, Level& L, int dir, int slot) {
-  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+void cc_stable_dt(fvs_ctx* ctx, Level& L, int dir, int slot, int group = kGroupAll) {
+  const int n = group_size(L, group);
+  if (n == 0) return;
+  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true, group);
   fvs::SweepArgs A = sweep_args(ctx, L, dir, 0.0, boxes, slot);
-  if (L.patches.empty()) return;
+  A.nboxes = n;
   const int rc = fvs::launch_cc_stable_dt(ctx->method, dir, A, ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
 }
 // cutcell::FluxMethod::ComputeNumericFluxes: boundary fluxes, (masked) regular
 // fluxes, stabilised fluxes
-void cc_numeric_fluxes(fvs_ctx* ctx, Level& L, double dt, int dir) {
-  if (L.patches.empty()) return;
+void cc_numeric_fluxes(fvs_ctx* ctx, Level& L, double dt, int dir, int group = kGroupAll) {
+  const int n = group_size(L, group);
+  if (n == 0) return;
   for (Patch& p : L.patches) { // boundary_fluxes.setVal(0.0), FluxMethod.hpp:173
+    if (!in_group(L, p, group)) continue;
     FVS_CUDA(cudaMemsetAsync(p.eb.boundary_flux, 0,
                              (size_t)p.cells * ctx->ncons() * sizeof(double), ctx->stream));
   }
-  const fvs::EbArgs E = eb_args(ctx, L, dir, dt);
+  const fvs::EbArgs E = eb_args(ctx, L, dir, dt, group);
   int rc = fvs::launch_cc_boundary_fluxes(E, ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
-  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true);
+  const BoxDesc* boxes = box_descs(ctx, L, dir, L.cur, L.cur, true, group);
   fvs::SweepArgs A = sweep_args(ctx, L, dir, dt, boxes, -1);
+  A.nboxes = n;
   rc = fvs::launch_cc_numeric_fluxes(ctx->method, dir, A, ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
@@ -1098,21 +1167,22 @@ void cc_numeric_fluxes(fvs_ctx* ctx, Level& L, double dt, int dir) {
   check_launch(rc);
   ctx->launches += rc;
 }
-void cc_update(fvs_ctx* ctx, Level& L, double dt, int dir) {
-  if (L.patches.empty()) return;
-  const int rc = fvs::launch_cc_update(eb_args(ctx, L, dir, dt), ctx->stream);
+void cc_update(fvs_ctx* ctx, Level& L, double dt, int dir, int group = kGroupAll) {
+  if (group_size(L, group) == 0) return;
+  const int rc = fvs::launch_cc_update(eb_args(ctx, L, dir, dt, group), ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
 }
-void cc_complete(fvs_ctx* ctx, Level& L) {
-  if (L.patches.empty()) return;
-  const int rc = fvs::launch_cc_complete(eb_args(ctx, L, 0, 0.0), ctx->stream);
+void cc_complete(fvs_ctx* ctx, Level& L, int group = kGroupAll) {
+  if (group_size(L, group) == 0) return;
+  const int rc = fvs::launch_cc_complete(eb_args(ctx, L, 0, 0.0, group), ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
 }
 void cc_pre_advance(fvs_ctx* ctx, Level& L) {
-  if (!L.has_eb || L.patches.empty()) return;
-  const int rc = fvs::launch_cc_reference_states(eb_args(ctx, L, 0, 0.0), ctx->stream);
+  if (!L.has_eb || group_size(L, kGroupCut) == 0) return;
+  const int rc =
+      fvs::launch_cc_reference_states(eb_args(ctx, L, 0, 0.0, kGroupCut), ctx->stream);
   check_launch(rc);
   ctx->launches += rc;
 }
@@ -2594,6 +2664,7 @@ const BoxDesc* plane_descs(fvs_ctx* ctx, Level& L, int level, int dir, int src, 
   const std::vector<std::array<int, 3>> shifts = period_shifts(L, ctx->cfg.rank);
   std::vector<BoxDesc> host;
   for (Patch& p : L.patches) {
+    if (!in_group(L, p, kGroupRegular)) continue; // cut fabs: cc_numeric_fluxes fills the array
     std::set<int> planes; // face index = index of the cell to its right
     if (feeds_coarser) {
       planes.insert(p.valid.lo[dir]);
@@ -2705,12 +2776,14 @@ void advance_level(fvs_ctx* ctx, int level, double dt, int sub_first, int split_
       ctx->next_slot = 0;
     }
     if (L.has_eb) {
-      const int slot = take_slot(ctx);
-      cc_stable_dt(ctx, L, dir, slot);
-      cc_numeric_fluxes(ctx, L, e.dt, dir);
-      cc_update(ctx, L, e.dt, dir);
-      cc_complete(ctx, L);
+      const int src = L.cur;
+      int dst;
+      const int slot = eb_sweep(ctx, L, e.dt, dir, &dst);
       st.pending.push_back({slot, level, dir, e.dt, 0.0});
+      // regular fabs: register-plane fluxes from the input buffer; cut fabs: the
+      // cut-cell kernels have written the whole (unshielded) flux array
+      if (feeds) plane_fluxes(ctx, L, level, dir, e.dt, src);
+      L.cur = dst;
     } else {
       const double hint = st.use_hints ? dt_hint(ctx, L, dir) : 0.0;
       const int src = L.cur;
@@ -2749,21 +2822,7 @@ int advance_hierarchy_multilevel(fvs_ctx* ctx, double dt, int split_kind, double
     for (int l = 0; l < nl; ++l) {
       Level& L = ctx->levels[l];
       L.cur = entry[l];
-      if (L.has_eb) {
-        // cut-cell levels work in place on a copy of the entry state
-        L.keep = -1;
-        const int work = free_buffer(L, L.cur);
-        ensure_buffer(ctx, L, work);
-        for (Patch& p : L.patches) {
-          FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[L.cur],
-                                   (size_t)p.cells * ctx->ncomp() * sizeof(double),
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        L.keep = entry[l];
-        L.cur = work;
-      } else {
-        L.keep = entry[l]; // the fused sweeps ping-pong between the other two buffers
-      }
+      L.keep = entry[l]; // the sweeps ping-pong between the other two buffers
     }
     try {
       advance_level(ctx, 0, dt, 0, split_kind, st);
@@ -2872,30 +2931,17 @@ int fvs_advance_hierarchy(fvs_ctx* ctx, double dt, int split_kind, double* failu
       std::vector<double> hints;
       ctx->next_slot = 0;
       try {
-        if (L.has_eb) {
-          // cut-cell levels work in place on a copy of the entry state
-          const int work = free_buffer(L, entry);
-          ensure_buffer(ctx, L, work);
-          for (Patch& p : L.patches) {
-            FVS_CUDA(cudaMemcpyAsync(p.buf[work], p.buf[entry],
-                                     (size_t)p.cells * ctx->ncomp() * sizeof(double),
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
-          }
-          L.cur = work;
-          cc_pre_advance(ctx, L); // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
-        }
+        // cutcell::IntegratorContext::PreAdvanceLevel, :802-806
+        if (L.has_eb) cc_pre_advance(ctx, L);
         for (const SweepPlanEntry& e : plan) {
           const int dir = dirs[e.slot];
           if (counts[e.slot] > 0) apply_boundary_condition(ctx, L, dir); // :228-234
           counts[e.slot] += 1;
           if (L.has_eb) {
-            const int slot = take_slot(ctx);
-            cc_stable_dt(ctx, L, dir, slot);
-            cc_numeric_fluxes(ctx, L, e.dt, dir);
-            cc_update(ctx, L, e.dt, dir);
-            cc_complete(ctx, L);
-            slots.push_back(slot);
+            int dst;
+            slots.push_back(eb_sweep(ctx, L, e.dt, dir, &dst));
             hints.push_back(0.0);
+            L.cur = dst;
             continue;
           }
           int dst;
@@ -3425,6 +3471,18 @@ struct DeviceTags {
     if (ptr) cudaFree(ptr);
   }
 };
+void call_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width) {
+  int nn[3] = {n[0], rank >= 2 ? n[1] : 1, rank >= 3 ? n[2] : 1};
+  const size_t total = (size_t)nn[0] * nn[1] * nn[2];
+  if (total == 0) return;
+  DeviceTags dt(total), scratch(total);
+  FVS_CUDA(cudaMemcpyAsync(dt.ptr, tags, total, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = fvs::launch_tag_buffer(dt.ptr, scratch.ptr, rank, nn, width, ctx->stream);
+  check_launch(rc);
+  ctx->launches += rc;
+  FVS_CUDA(cudaMemcpyAsync(tags, dt.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+}
 } // namespace
 
 int fvs_tag_gradient(fvs_ctx* ctx, int level, int box, int ncond, const int* comps,
@@ -3458,6 +3516,77 @@ int fvs_tag_gradient(fvs_ctx* ctx, int level, int box, int ncond, const int* com
   });
 }
 
+// The tags of a whole level in one go (the regrid hand-off): GradientDetector on every
+// owned box, one read-back, scattered into a dense byte map of the level's domain, then
+// TagBuffer on that map.  tags is OR-ed into; on several ranks every rank fills the
+// cells of its own boxes (the caller combines the maps).
+int fvs_tag_level(fvs_ctx* ctx, int level, int ncond, const int* comps, const double* tols,
+                  int use_alpha, int tag_cutcells, int buffer_width, char* tags) {
+  return guarded([&] {
+    if (!ctx || !tags || (ncond > 0 && (!comps || !tols))) throw Error("null argument");
+    if (ncond < 0 || ncond > 8) throw Error("at most 8 tagging conditions");
+    for (int c = 0; c < ncond; ++c)
+      if (comps[c] < 0 || comps[c] >= ctx->ncomp()) throw Error("component out of range");
+    ctx->use_device();
+    Level& L = ctx->level(level);
+    if (ncond > 0 && L.scratch_gcw < 1) throw Error("gradient tagging needs one ghost cell");
+    if ((use_alpha || tag_cutcells) && !L.has_eb) {
+      throw Error("level has no embedded boundary (fvs_level_set_eb)");
+    }
+    size_t total = 0;
+    std::vector<size_t> offset;
+    for (const Patch& p : L.patches) {
+      offset.push_back(total);
+      total += (size_t)p.valid.size();
+    }
+    std::vector<char> host(total);
+    if (total > 0) {
+      DeviceTags dt(total);
+      FVS_CUDA(cudaMemsetAsync(dt.ptr, 0, total, ctx->stream));
+      for (size_t i = 0; i < L.patches.size(); ++i) {
+        Patch& p = L.patches[i];
+        int lo[3], len[3];
+        for (int d = 0; d < 3; ++d) {
+          lo[d] = p.valid.lo[d] - p.sbox.lo[d];
+          len[d] = p.valid.len(d);
+        }
+        if (ncond > 0) {
+          const int rc = fvs::launch_tag_gradient(p.buf[L.cur], p.cells, p.n,
+                                                  use_alpha ? p.eb.alpha : nullptr, ctx->cfg.rank, lo,
+                                                  len, ncond, comps, tols, dt.ptr + offset[i],
+                                                  ctx->stream);
+          check_launch(rc);
+          ctx->launches += rc;
+        }
+        if (tag_cutcells) {
+          const int rc = fvs::launch_tag_cutcells(p.eb.alpha, p.n, lo, len, dt.ptr + offset[i],
+                                                  ctx->stream);
+          check_launch(rc);
+          ctx->launches += rc;
+        }
+      }
+      FVS_CUDA(cudaMemcpyAsync(host.data(), dt.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
+      FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const long long nx = L.domain.len(0), ny = L.domain.len(1);
+    for (size_t i = 0; i < L.patches.size(); ++i) {
+      const Patch& p = L.patches[i];
+      const char* src = host.data() + offset[i];
+      for (int k = p.valid.lo[2]; k <= p.valid.hi[2]; ++k)
+        for (int j = p.valid.lo[1]; j <= p.valid.hi[1]; ++j) {
+          char* dst = tags + (p.valid.lo[0] - L.domain.lo[0]) +
+                      nx * ((j - L.domain.lo[1]) + ny * (long long)(k - L.domain.lo[2]));
+          for (int x = 0; x < p.valid.len(0); ++x) dst[x] |= *src++;
+        }
+    }
+    if (buffer_width > 0) {
+      const int n[3] = {L.domain.len(0), L.domain.len(1), L.domain.len(2)};
+      call_tag_buffer(ctx, ctx->cfg.rank, tags, n, buffer_width);
+    }
+    return (int)FVS_OK;
+  });
+}
+
 int fvs_tag_cutcells(fvs_ctx* ctx, int level, int box, char* tags) {
   return guarded([&] {
     if (!ctx || !tags) throw Error("null argument");
@@ -3487,16 +3616,7 @@ int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width
     if (!ctx || !tags || !n) throw Error("null argument");
     if (rank < 1 || rank > 3 || width < 0) throw Error("invalid argument");
     ctx->use_device();
-    int nn[3] = {n[0], rank >= 2 ? n[1] : 1, rank >= 3 ? n[2] : 1};
-    const size_t total = (size_t)nn[0] * nn[1] * nn[2];
-    if (total == 0) return (int)FVS_OK;
-    DeviceTags dt(total), scratch(total);
-    FVS_CUDA(cudaMemcpyAsync(dt.ptr, tags, total, cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = fvs::launch_tag_buffer(dt.ptr, scratch.ptr, rank, nn, width, ctx->stream);
-    check_launch(rc);
-    ctx->launches += rc;
-    FVS_CUDA(cudaMemcpyAsync(tags, dt.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
-    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    call_tag_buffer(ctx, rank, tags, n, width);
     return (int)FVS_OK;
   });
 }

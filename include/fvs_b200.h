@@ -415,6 +415,14 @@ int fvs_compute_stable_dt_hierarchy(fvs_ctx* ctx, double* dt_out);
  * x fastest) is OR-ed into. */
 int fvs_tag_gradient(fvs_ctx* ctx, int level, int box, int ncond, const int* comps,
                      const double* tols, int use_alpha, char* tags);
+/* The tags of a whole level for the regrid hand-off (what
+ * GriddingAlgorithm::ErrorEst, src/AMReX/GriddingAlgorithm.cpp:177-183, collects
+ * through AnyTaggingMethod): GradientDetector conditions (ncond may be 0) and /
+ * or TagCutCells on every box this rank owns, then TagBuffer(buffer_width) on
+ * the level's map.  tags: one byte per cell of the level's DOMAIN (x fastest),
+ * OR-ed into.  One device synchronisation for the whole level. */
+int fvs_tag_level(fvs_ctx* ctx, int level, int ncond, const int* comps, const double* tols,
+                  int use_alpha, int tag_cutcells, int buffer_width, char* tags);
 /* fub::TagCutCells (src/tagging_method/TagCutCells.cpp:27-35) */
 int fvs_tag_cutcells(fvs_ctx* ctx, int level, int box, char* tags);
 /* fub::TagBuffer (src/tagging_method/TagBuffer.cpp:27-86) on a dense view of

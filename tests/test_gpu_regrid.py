@@ -74,6 +74,9 @@ def level_tags(fvs, orc, l, cpu, gpu):
     ref = dense.copy()
     orc.tag_buffer(ref, RANK, BUFFER)
     assert np.array_equal(buffered, ref)
+    # the level-wide entry point gives the same map with one synchronisation
+    whole = gpu.tag_level([hi[0] + 1, hi[1] + 1, 1], [(0, 1e-2)], buffer_width=BUFFER)
+    assert np.array_equal(whole, ref)
     return buffered
 
 
