@@ -1267,7 +1267,19 @@ template <int D> struct MusclHancockPrim {
   void ComputeNumericFlux(Cons<T, D>& flux, const T& face_fractions, const Complete<T, D>* st,
                           const T* volume_fractions, double dt, double dx, int dir) const {
     const M8 mask = face_fractions > 0.0;
-    if (!any(mask)) return; // the reference leaves `flux` untouched
+    if (!any(mask)) {
+      // The reference returns here and leaves `flux` -- the method's zero-initialised
+      // member array, KbnStabilisation.hpp:399-407 -- holding the fluxes of whichever chunk
+      // this thread computed last; they are stored into faces whose face fraction is 0 and
+      // every later use multiplies them by a zero fraction.  Which values end up there
+      // depends on the OpenMP schedule, so there is nothing to reproduce: a face of a chunk
+      // without any open face gets 0, like the closed faces of every other chunk (:1082-1083
+      // of HllemMethod.hpp).  DESIGN.md section 7, "Deliberate restrictions".
+      flux.rho = T(0.0);
+      for (int i = 0; i < D; ++i) flux.mom[i] = T(0.0);
+      flux.E = T(0.0);
+      return;
+    }
     const M8 left_mask = volume_fractions[0] > 0.0;
     const M8 right_mask = volume_fractions[3] > 0.0;
     const T rho_l = select(mask, st[1].rho, 1.0);

@@ -124,6 +124,18 @@ def eb_geometry(rank, lo, hi, dx, origin, phi, nsub=8):
         sl_hi[ax] = slice(0, -1)     # faces 0..n-1 have a right cell 0..n-1
         beta[d][tuple(sl_lo)] = np.where(covered, 0.0, beta[d][tuple(sl_lo)])
         beta[d][tuple(sl_hi)] = np.where(covered, 0.0, beta[d][tuple(sl_hi)])
+    # a cell with a partly closed face is a cut cell (EB2 consistency: the body that
+    # covers part of a face reaches into both of its cells); the volume sampling can miss
+    # a thin sliver, so such a "full" cell gets the smallest cut the sampling resolves
+    partial = np.zeros(alpha.shape, dtype=bool)
+    for d in range(rank):
+        ax = 3 - d
+        lo_f = [slice(None)] * 4
+        hi_f = [slice(None)] * 4
+        lo_f[ax] = slice(0, -1)
+        hi_f[ax] = slice(1, None)
+        partial |= (beta[d][tuple(lo_f)] < 1.0) | (beta[d][tuple(hi_f)] < 1.0)
+    alpha = np.where(partial & (alpha == 1.0), 1.0 - 0.5 / nsub ** rank, alpha)
     cc = [coords(d, False, False)[:, 0] for d in range(3)]
     X, Y, Z = cc[0][None, None, :], cc[1][None, :, None], cc[2][:, None, None]
     p0 = phi(X, Y, Z) + np.zeros((n[2], n[1], n[0]))
@@ -297,3 +309,101 @@ def eb_two_level_wedge(orc, fvs=None, n0=(48, 32), gcw=(8, 6), method=(0, 1, 2),
         gpus.append(gpu)
         geoms.append(lg)
     return cpus, gpus, ctx, geoms
+
+
+def nozzle_phi(r_tube=0.015, height=2.0, center=(0.0, 0.0)):
+    """Level set (> 0 in the fluid) of examples/AMReX/EB/2D/ConvergentNozzle.cpp:164-185:
+    the plenum half-space x > center_x united with the inlet tube, a polygon of half-height
+    r_tube that converges to r_tube / 2 over the last 4 r_tube before the plenum.  (AMReX
+    states it as the intersection of the two BODIES, PlaneIF(..., false) and the inverted
+    polygon.)"""
+    cx, cy = center
+    xlo, xhi = cx - height, cx
+    r, r2 = r_tube, 0.5 * r_tube
+    xdiv = xhi - 4.0 * r
+    outside = polygon_phi([(xlo, cy + r), (xdiv, cy + r), (xhi, cy + r2), (xhi, cy - r2),
+                           (xdiv, cy - r), (xlo, cy - r)])
+
+    def phi(x, y, z):
+        return np.maximum(x - cx + 0 * y, -outside(x, y, z)) + 0 * z
+    return phi
+
+
+def plenum_phi(r_tube=0.015, r_inner=0.065, r_outer=0.1925, n_tubes=6):
+    """Level set (> 0 in the fluid) of the annular plenum with its tube stubs,
+    examples/AMReX/EB/3D/MultiTube_PerfectGas.cpp:48-83 (.py:25-30): the outer cylinder
+    (axis x, 0 <= x <= 1) united with n_tubes tubes of radius r_tube on the circle of radius
+    (r_inner + r_outer) / 2 (-2.05 <= x <= 0.05), minus the inner cylinder (-0.25 <= x <= 0.75)."""
+    r_c = 0.5 * r_inner + 0.5 * r_outer
+    alpha = 2.0 * np.pi / n_tubes
+
+    def cyl(radius, length, cx, cy, cz):
+        def f(x, y, z):
+            rho = np.sqrt((y - cy) ** 2 + (z - cz) ** 2)
+            return np.minimum(radius - rho, 0.5 * length - np.abs(x - cx))
+        return f
+    outer = cyl(r_outer, 1.0, 0.5, 0.0, 0.0)
+    inner = cyl(r_inner, 1.0, 0.25, 0.0, 0.0)
+    tubes = [cyl(r_tube, 2.1, -1.0, r_c * np.cos(i * alpha), r_c * np.sin(i * alpha))
+             for i in range(n_tubes)]
+
+    def phi(x, y, z):
+        fluid = outer(x, y, z)
+        for t in tubes:
+            fluid = np.maximum(fluid, t(x, y, z))
+        return np.minimum(fluid, -inner(x, y, z))
+    return phi
+
+
+def eb_shock_pair(orc, fvs, rank, n, origin, extent, phi, method, gcw, boxes=None, shock_x=0.0,
+                  p_ratio=5.0, rho0=1.22, nsub=4, riemann=0):
+    """A single cut-cell level with the geometry `phi` on the oracle and (if fvs is given) on the
+    device: gas at rest, pressure p_ratio * 101325 left of shock_x.  Returns (cpu, gpu, geoms)."""
+    dx = [extent[d] / n[d] for d in range(rank)] + [1.0] * (3 - rank)
+    hi = [n[d] - 1 if d < rank else 0 for d in range(3)]
+    boxes = boxes or [([0] * 3, hi)]
+    cpu = orc.Level(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1])
+    cpu.set_method(*method)
+    cpu.enable_eb(riemann)
+    gpu = None
+    if fvs is not None:
+        gpu = fvs.Context(rank, [0] * 3, hi, dx, boxes, scratch_gcw=gcw[0], flux_gcw=gcw[1],
+                          base=method[0], recon=method[1], limiter=method[2])
+        gpu.enable_eb(riemann)
+    for lv in (cpu, gpu):
+        if lv is not None:
+            for d in range(rank):
+                for s in (0, 1):
+                    lv.add_bc(d, s, 0)
+    geoms = []
+    for b in range(len(boxes)):
+        arr, lo, h = cpu.scratch(b)
+        g = eb_geometry(rank, lo, h, dx, origin, phi, nsub=nsub)
+        t = eb_fab_type(g)
+        cpu.set_eb(b, g, t)
+        x = origin[0] + (np.arange(lo[0], h[0] + 1) + 0.5) * dx[0]
+        shape = arr.shape[1:]
+        rho = rho0 + np.zeros(shape)
+        p = np.where(x < shock_x, p_ratio * 101325.0, 101325.0)[None, None, :] + np.zeros(shape)
+        st = complete_from_prim(rank, rho, [np.zeros(shape)] * rank, p) * (g["alpha"][0] > 0)
+        arr[...] = st
+        if gpu is not None:
+            gpu.set_eb(b, g, t)
+            gpu.upload_state(b, st)
+        geoms.append(g)
+    cpu.fill_ghost_layer()
+    if gpu is not None:
+        gpu.fill_ghost_layer()
+    return cpu, gpu, geoms
+
+
+# BASELINE configs 4 and 5 in small: the geometries of the reference's examples
+NOZZLE_CASE = dict(rank=2, n=(96, 48), origin=[-0.12, -0.0612, 0.0], extent=(0.24, 0.12),
+                   method=(0, 1, 2), gcw=(8, 6), shock_x=-0.08, p_ratio=5.0,
+                   boxes=[([0, 0, 0], [47, 47, 0]), ([48, 0, 0], [95, 47, 0])])
+# (the whole cross-section: the y / z boundaries lie in the covered region outside the outer
+# cylinder and the x boundaries cut walls that are parallel to x, so the transmissive ghost
+# cells agree with the ghost geometry)
+PLENUM_CASE = dict(rank=3, n=(48, 48, 48), origin=[-0.1, -0.2, -0.2], extent=(0.4, 0.4, 0.4),
+                   method=(0, 2, 0), gcw=(4, 2), shock_x=-0.05, p_ratio=3.0,
+                   boxes=[([0, 0, 0], [23, 47, 47]), ([24, 0, 0], [47, 47, 47])])

@@ -7,7 +7,8 @@ FillCutCellData / IsCutCell / TagBuffer."""
 import numpy as np
 import pytest
 
-from helpers import (complete_from_prim, eb_fab_type, eb_geometry, eb_two_level_wedge, polygon_phi,
+from helpers import (NOZZLE_CASE, PLENUM_CASE, complete_from_prim, eb_fab_type, eb_geometry,
+                     eb_shock_pair, eb_two_level_wedge, nozzle_phi, plenum_phi, polygon_phi,
                      sphere_phi)
 
 
@@ -254,3 +255,50 @@ def test_eb_two_level_wedge_steady_state_and_average_down(oracle):
                     else:
                         assert got == u[0, 0]
     assert checked > 10
+
+
+def test_nozzle_and_plenum_level_sets():
+    """The geometries of BASELINE configs 4 and 5 (examples/AMReX/EB/2D/ConvergentNozzle.cpp:164-185,
+    examples/AMReX/EB/3D/MultiTube_PerfectGas.cpp:48-83) as level sets: known points."""
+    noz = nozzle_phi()
+    z = 0.0
+    assert noz(0.05, 0.3, z) > 0          # plenum half-space
+    assert noz(-0.5, 0.0, z) > 0          # inside the tube
+    assert noz(-0.5, 0.0149, z) > 0 and noz(-0.5, 0.0151, z) < 0      # tube wall at r_tube
+    assert noz(-1e-4, 0.0074, z) > 0 and noz(-1e-4, 0.0076, z) < 0    # throat at r_tube / 2
+    assert noz(-0.03, 0.0112, z) > 0 and noz(-0.03, 0.0113, z) < 0    # half way down the convergent part
+    assert noz(-2.5, 0.0, z) < 0          # behind the inlet
+    ple = plenum_phi()
+    r_c = 0.5 * (0.065 + 0.1925)
+    assert ple(0.5, 0.13, 0.0) > 0        # annulus
+    assert ple(0.5, 0.05, 0.0) < 0        # hub
+    assert ple(0.5, 0.2, 0.0) < 0         # outside the outer wall
+    assert ple(0.9, 0.05, 0.0) > 0        # behind the hub (it ends at x = 0.75)
+    for i in range(6):                    # the six tube stubs
+        a = i * np.pi / 3
+        assert ple(-0.5, r_c * np.cos(a), r_c * np.sin(a)) > 0
+        assert ple(-0.5, (r_c + 0.016) * np.cos(a), (r_c + 0.016) * np.sin(a)) < 0
+    assert ple(-0.5, 0.0, 0.0) < 0        # between the tubes
+
+
+@pytest.mark.parametrize("case,phi,split", [(NOZZLE_CASE, nozzle_phi(), 1), (PLENUM_CASE, plenum_phi(), 0)])
+def test_nozzle_and_plenum_runs(oracle, case, phi, split):
+    """Shock running through the inlet into the plenum on the oracle: cut cells exist on both
+    boxes' geometries, the run stays finite and physical, covered cells stay zero."""
+    cpu, _, geoms = eb_shock_pair(oracle, None, phi=phi, **case)
+    rank = case["rank"]
+    cut = sum(int(((g["alpha"] > 0) & (g["alpha"] < 1)).sum()) for g in geoms)
+    assert cut > (100 if rank == 2 else 1000)
+    for _ in range(6):
+        dt = 0.4 * min(cpu.compute_stable_dt(d) for d in range(rank))
+        ok, _, _ = cpu.advance_hierarchy(dt, split)
+        assert ok
+    gw = case["gcw"][0]
+    inner = (slice(gw, -gw) if rank == 3 else slice(None), slice(gw, -gw), slice(gw, -gw))
+    for b, g in enumerate(geoms):
+        arr = cpu.scratch(b)[0]
+        assert not np.isnan(arr).any()
+        fluid = (g["alpha"][0] > 0)[inner]     # valid cells (ghost cells may copy covered ones)
+        rho = arr[0][inner]
+        assert rho[fluid].min() > 0.3 and rho[fluid].max() < 4.0
+        assert np.all(arr[:, g["alpha"][0] == 0] == 0.0)
