@@ -40,6 +40,7 @@ SYMBOLS = [
     "fvs_min_all", "fvs_comm_unique_id", "fvs_comm_init", "fvs_halo_plan",
     "fvs_stable_dt_face_mask", "fvs_distribute_boxes", "fvs_kernel_launches", "fvs_stream",
     "fvs_distribute_boxes_cutcell", "fvs_cluster_tags", "fvs_regrid_level", "fvs_tag_level",
+    "fvs_write_checkpoint",
     "fvs_set_dt_hints", "fvs_dt_hint_redos", "fvs_download_state_region",
     "fvs_enable_timing", "fvs_sweep_time_ms",
     "fvs_level_set_eb", "fvs_set_cutcell_riemann_solver", "fvs_pre_advance_hierarchy",
@@ -243,6 +244,9 @@ class Context:
                                       _i3(periodic), len(boxes), lo, hi, own, scratch_gcw,
                                       flux_gcw))
         return v
+
+    def write_checkpoint(self, directory):
+        _check(lib().fvs_write_checkpoint(self.h, str(directory).encode()))
 
     def regrid_level(self, level, boxes, owner=None):
         """fvs_regrid_level: new boxes for `level` (>= 1), data from the old level where it

@@ -14,6 +14,10 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <fstream>
+#include <sys/stat.h>
+#include <cerrno>
+#include <algorithm>
 #include <limits>
 #include <map>
 #include <set>
@@ -3617,6 +3621,149 @@ int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width
     if (rank < 1 || rank > 3 || width < 0) throw Error("invalid argument");
     ctx->use_device();
     call_tag_buffer(ctx, rank, tags, n, width);
+    return (int)FVS_OK;
+  });
+}
+
+// ---- checkpoint output --------------------------------------------------------------
+namespace {
+std::string box_text(const Box& b, int rank) {
+  auto tuple = [rank](const int v[3]) {
+    std::string t = "(";
+    for (int d = 0; d < rank; ++d) t += (d ? "," : "") + std::to_string(v[d]);
+    return t + ")";
+  };
+  const int zero[3] = {0, 0, 0};
+  return "(" + tuple(b.lo) + " " + tuple(b.hi) + " " + tuple(zero) + ")";
+}
+std::string boxarray_text(const std::vector<Box>& boxes, int rank) { // BoxArray::writeOn
+  std::string t = "(" + std::to_string(boxes.size()) + " 0\n";
+  for (const Box& b : boxes) t += box_text(b, rank) + "\n";
+  return t + ")";
+}
+// header line of one FAB on disk: native little-endian IEEE doubles (RealDescriptor)
+std::string fab_header(const Box& b, int rank, int ncomp) {
+  return "FAB ((8, (64 11 52 0 1 12 0 1023)),(8, (8 7 6 5 4 3 2 1)))" + box_text(b, rank) + " " +
+         std::to_string(ncomp) + "\n";
+}
+void make_dir(const std::string& path) {
+  if (::mkdir(path.c_str(), 0755) != 0 && errno != EEXIST) {
+    throw Error("cannot create directory " + path);
+  }
+}
+std::string five(int n) {
+  char buf[16];
+  std::snprintf(buf, sizeof buf, "%05d", n);
+  return buf;
+}
+} // namespace
+
+int fvs_write_checkpoint(fvs_ctx* ctx, const char* directory) {
+  return guarded([&] {
+    if (!ctx || !directory) throw Error("null argument");
+    ctx->use_device();
+    const int rank = ctx->cfg.rank;
+    const int ncomp = ctx->ncomp();
+    const int nl = num_levels(ctx);
+    const int me = ctx->cfg.comm_rank;
+    const std::string root(directory);
+    // PreBuildDirectorHierarchy: every rank may arrive first
+    make_dir(root);
+    for (int l = 0; l < nl; ++l) make_dir(root + "/Level_" + std::to_string(l));
+    if (me == 0) { // PatchHierarchy.cpp:324-355
+      std::ofstream h(root + "/Header", std::ios::out | std::ios::trunc | std::ios::binary);
+      if (!h.good()) throw Error("cannot open " + root + "/Header");
+      h.precision(17);
+      h << "Checkpoint File\n" << nl - 1 << '\n';
+      for (int l = 0; l < nl; ++l) h << ctx->cycles * total_ratio(ctx, l) << ' ';
+      h << '\n';
+      for (int l = 0; l < nl; ++l) h << ctx->time_point << ' ';
+      h << '\n';
+      for (int l = 0; l < nl; ++l) h << boxarray_text(ctx->levels[(size_t)l].boxes, rank) << '\n';
+    }
+    // VisMF::Write of the level data (valid cells, no ghost cells): one data file per rank,
+    // the FABs of the rank's boxes in box order; rank 0 writes the VisMF header, whose
+    // offsets follow from the (deterministic) FAB header lengths
+    for (int l = 0; l < nl; ++l) {
+      Level& L = ctx->levels[(size_t)l];
+      const std::string prefix = root + "/Level_" + std::to_string(l) + "/data";
+      std::vector<std::vector<double>> mins(L.boxes.size()), maxs(L.boxes.size());
+      if (!L.patches.empty()) {
+        std::ofstream out(prefix + "_D_" + five(me), std::ios::out | std::ios::trunc | std::ios::binary);
+        if (!out.good()) throw Error("cannot open " + prefix + "_D_" + five(me));
+        std::vector<double> host;
+        for (Patch& p : L.patches) {
+          const size_t cells = (size_t)p.valid.size();
+          host.resize(cells * (size_t)ncomp);
+          copy_valid(ctx, L, p, host.data(), false);
+          FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+          const std::string fh = fab_header(p.valid, rank, ncomp);
+          out.write(fh.data(), (std::streamsize)fh.size());
+          out.write(reinterpret_cast<const char*>(host.data()), (std::streamsize)(host.size() * sizeof(double)));
+          std::vector<double>& mn = mins[(size_t)p.global_index];
+          std::vector<double>& mx = maxs[(size_t)p.global_index];
+          for (int c = 0; c < ncomp; ++c) {
+            const double* v = host.data() + cells * (size_t)c;
+            mn.push_back(*std::min_element(v, v + cells));
+            mx.push_back(*std::max_element(v, v + cells));
+          }
+        }
+      }
+      // the min / max tables of the header need every rank's values
+      if (ctx->cfg.comm_size > 1) {
+        std::vector<double> table(L.boxes.size() * (size_t)ncomp * 2, -std::numeric_limits<double>::max());
+        for (size_t b = 0; b < L.boxes.size(); ++b)
+          for (int c = 0; c < ncomp && !mins[b].empty(); ++c) {
+            table[(b * (size_t)ncomp + (size_t)c) * 2] = -mins[b][(size_t)c];
+            table[(b * (size_t)ncomp + (size_t)c) * 2 + 1] = maxs[b][(size_t)c];
+          }
+        double* dev = nullptr;
+        FVS_CUDA(cudaMalloc(&dev, table.size() * sizeof(double)));
+        FVS_CUDA(upload_sync(dev, table.data(), table.size() * sizeof(double)));
+        Nccl& n = Nccl::get();
+        if (!ctx->comm) throw Error("levels span several ranks but fvs_comm_init was not called");
+        n.check(n.AllReduce(dev, dev, table.size(), Nccl::kDouble, Nccl::kMax, ctx->comm, ctx->stream),
+                "ncclAllReduce(checkpoint min/max)");
+        FVS_CUDA(cudaMemcpyAsync(table.data(), dev, table.size() * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dev);
+        for (size_t b = 0; b < L.boxes.size(); ++b) {
+          mins[b].assign((size_t)ncomp, 0.0);
+          maxs[b].assign((size_t)ncomp, 0.0);
+          for (int c = 0; c < ncomp; ++c) {
+            mins[b][(size_t)c] = -table[(b * (size_t)ncomp + (size_t)c) * 2];
+            maxs[b][(size_t)c] = table[(b * (size_t)ncomp + (size_t)c) * 2 + 1];
+          }
+        }
+      }
+      if (me != 0) continue;
+      std::ofstream h(prefix + "_H", std::ios::out | std::ios::trunc | std::ios::binary);
+      if (!h.good()) throw Error("cannot open " + prefix + "_H");
+      h.precision(17);
+      std::string ngrow = "(";
+      for (int d = 0; d < rank; ++d) ngrow += d ? ",0" : "0";
+      ngrow += ")";
+      h << 1 << '\n' << 1 << '\n' << ncomp << '\n' << ngrow << '\n';
+      h << boxarray_text(L.boxes, rank) << '\n' << L.boxes.size() << '\n';
+      std::vector<long long> offset((size_t)ctx->cfg.comm_size, 0);
+      for (size_t b = 0; b < L.boxes.size(); ++b) {
+        const int r = L.owner[b];
+        h << "FabOnDisk: data_D_" << five(r) << ' ' << offset[(size_t)r] << '\n';
+        offset[(size_t)r] += (long long)fab_header(L.boxes[b], rank, ncomp).size() +
+                             L.boxes[b].size() * (long long)ncomp * (long long)sizeof(double);
+      }
+      h << '\n';
+      for (int pass = 0; pass < 2; ++pass) {
+        h << L.boxes.size() << ',' << ncomp << '\n';
+        for (size_t b = 0; b < L.boxes.size(); ++b) {
+          const std::vector<double>& v = pass == 0 ? mins[b] : maxs[b];
+          for (int c = 0; c < ncomp; ++c) h << v[(size_t)c] << ',';
+          h << '\n';
+        }
+        h << '\n';
+      }
+    }
     return (int)FVS_OK;
   });
 }

@@ -429,6 +429,19 @@ int fvs_tag_cutcells(fvs_ctx* ctx, int level, int box, char* tags);
  * extents n[] (x fastest), in place. */
 int fvs_tag_buffer(fvs_ctx* ctx, int rank, char* tags, const int n[3], int width);
 
+/* ---- output -------------------------------------------------------------- */
+/* fub::amrex::WriteCheckpointFile (src/AMReX/PatchHierarchy.cpp:320-371) for
+ * the device-resident hierarchy: <directory>/Header ("Checkpoint File", finest
+ * level, cycles and time points per level, the BoxArray of every level) and
+ * per level the VisMF pair Level_<l>/data_H + Level_<l>/data_D_<rank> holding
+ * the level data (valid cells, all rank+4 components, FAB order, native
+ * doubles).  Collective over the ranks of the context; every rank writes the
+ * FABs of its own boxes, rank 0 the headers.  The on-disk layout restates
+ * AMReX's published VisMF format (version 1, "NFiles"); AMReX is absent here,
+ * so it is checked by a reader written against the same description
+ * (tests/test_gpu_checkpoint.py), not by AMReX itself. */
+int fvs_write_checkpoint(fvs_ctx* ctx, const char* directory);
+
 /* ---- statistics ---------------------------------------------------------- */
 /* Number of kernels this context has launched so far. */
 long fvs_kernel_launches(const fvs_ctx* ctx);
