@@ -17,6 +17,10 @@ LIB_PATH = os.environ.get("FVS_B200_LIB") or os.path.join(_HERE, "libfvs_b200.so
 BASE_HLLEM_LARROUTUROU, BASE_HLLEM, BASE_HLL_EINFELDT, BASE_GODUNOV_EXACT = 0, 1, 2, 3
 RECON_FIRST_ORDER, RECON_MUSCL_HANCOCK, RECON_MUSCL_HANCOCK_PRIM, RECON_MUSCL_HANCOCK_CHAR = 0, 1, 2, 3
 LIMITER_NONE, LIMITER_MINMOD, LIMITER_VANLEER = 0, 1, 2
+# MusclHancock2<Gradient, Reconstruction, Base> (MusclHancockMethod2.hpp) and the limiters of
+# CentralDifferenceGradient (Gradient.hpp:31-59), passed in place of LIMITER_*
+RECON_MH2_CONSERVATIVE, RECON_MH2_PRIMITIVE, RECON_MH2_CHARACTERISTICS = 4, 5, 6
+LIMITER2_NONE, LIMITER2_UPWIND, LIMITER2_MINMOD, LIMITER2_VANLEER = 0, 1, 2, 3
 BC_TRANSMISSIVE, BC_REFLECTIVE = 0, 1
 SPLIT_GODUNOV, SPLIT_STRANG, SPLIT_STRANG_LUMPED = 0, 1, 2
 OK, ERROR, TIME_STEP_TOO_LARGE = 0, -1, 1

@@ -12,6 +12,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <fstream>
@@ -520,6 +521,8 @@ fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxD
                           int slot, double hint = 0.0) {
   fvs::SweepArgs A{};
   A.eq = ctx->eq;
+  A.eq.dx = L.dx[dir];
+  A.eq.limiter2 = ctx->method.limiter;
   A.lambda = dt / L.dx[dir];
   A.lambda_half = 0.5 * dt / L.dx[dir];
   A.boxes = boxes;
@@ -794,8 +797,43 @@ const fvs::PackDesc* pack_descs(fvs_ctx* ctx, Level& L, int peer_index, int buf,
   return ptr;
 }
 
+// FVS_HALO_TRACE=1: per-phase device times of the halo exchange on stderr (events and a
+// synchronisation per phase: a diagnosis switch, never on in a timed run)
+struct HaloTrace {
+  bool on;
+  cudaEvent_t ev[4];
+  double ms[3] = {0, 0, 0};
+  long calls = 0;
+  HaloTrace() : on(std::getenv("FVS_HALO_TRACE") != nullptr) {}
+  void mark(int i, cudaStream_t s) {
+    if (!on) return;
+    if (calls == 0 && i == 0) {
+      for (cudaEvent_t& e : ev) cudaEventCreate(&e);
+    }
+    cudaEventRecord(ev[i], s);
+  }
+  void done(cudaStream_t s, int rank) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    for (int i = 0; i < 3; ++i) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms[i] += t;
+    }
+    calls += 1;
+    if (calls % 8 == 0) {
+      std::fprintf(stderr,
+                   "[fvs halo trace] rank %d, %ld exchanges: pack %.3f ms, send/recv %.3f ms, "
+                   "local copies + unpack %.3f ms (means)\n",
+                   rank, calls, ms[0] / calls, ms[1] / calls, ms[2] / calls);
+    }
+  }
+};
+
 void fill_boundary(fvs_ctx* ctx, Level& L) {
+  static thread_local HaloTrace trace;
   const int buf = L.cur;
+  trace.mark(0, ctx->stream);
   // remote part first so that the transfers overlap the local copies
   if (!L.peers.empty()) {
     if (!ctx->comm) throw Error("level has boxes on other ranks but fvs_comm_init was not called");
@@ -807,6 +845,7 @@ void fill_boundary(fvs_ctx* ctx, Level& L) {
       ctx->launches += fvs::launch_pack(descs, count, ctx->ncomp(), L.peers[i].sendbuf,
                                         max_cells, 0, ctx->stream);
     }
+    trace.mark(1, ctx->stream);
     n.check(n.GroupStart(), "ncclGroupStart");
     for (PeerExchange& pe : L.peers) {
       if (pe.send_elems)
@@ -819,7 +858,10 @@ void fill_boundary(fvs_ctx* ctx, Level& L) {
                 "ncclRecv");
     }
     n.check(n.GroupEnd(), "ncclGroupEnd");
+  } else {
+    trace.mark(1, ctx->stream);
   }
+  trace.mark(2, ctx->stream);
   int count;
   const fvs::CopyDesc* descs = copy_descs(ctx, L, buf, &count);
   ctx->launches +=
@@ -832,6 +874,8 @@ void fill_boundary(fvs_ctx* ctx, Level& L) {
                                       1, ctx->stream);
   }
   check_last("launch check #3");
+  trace.mark(3, ctx->stream);
+  trace.done(ctx->stream, ctx->cfg.comm_rank);
 }
 
 void apply_bc(fvs_ctx* ctx, Level& L, int bc_index) {
@@ -1916,15 +1960,23 @@ int fvs_set_method(fvs_ctx* ctx, int base_method, int reconstruction, int limite
   return guarded([&] {
     if (!ctx) throw Error("null context");
     if (base_method < 0 || base_method > 3) throw Error("unknown base method");
-    if (reconstruction < 0 || reconstruction > 3) throw Error("unknown reconstruction");
-    if (reconstruction >= FVS_RECON_MUSCL_HANCOCK_PRIM && base_method != FVS_BASE_HLLEM_LARROUTUROU) {
+    if (reconstruction < 0 || reconstruction > FVS_RECON_MH2_CHARACTERISTICS) {
+      throw Error("unknown reconstruction");
+    }
+    const bool mh2 = reconstruction >= FVS_RECON_MH2_CONSERVATIVE;
+    if (!mh2 && reconstruction >= FVS_RECON_MUSCL_HANCOCK_PRIM &&
+        base_method != FVS_BASE_HLLEM_LARROUTUROU) {
       // src/equations/perfect_gas/MusclHancockPrimMethod.hpp:175,
       // include/fub/equations/perfect_gas/MusclHancockCharactersticMethod.hpp:174
       throw Error("MusclHancockPrim / MusclHancockChar are defined over HLLEM (Larrouturou) only");
     }
-    if (limiter < 0 || limiter > 2) throw Error("unknown limiter");
+    // MusclHancock2 takes the limiters of include/fub/flux_method/Gradient.hpp:31-59
+    if (limiter < 0 || limiter > (mh2 ? FVS_LIMITER2_VANLEER : 2)) throw Error("unknown limiter");
     if (ctx->arithmetic == FVS_ARITH_TOLERANCE && base_method == FVS_BASE_GODUNOV_EXACT) {
       throw Error("the exact Riemann solver has no tolerance-arithmetic build");
+    }
+    if (ctx->arithmetic == FVS_ARITH_TOLERANCE && mh2) {
+      throw Error("MusclHancock2 has no tolerance-arithmetic build");
     }
     const int w = reconstruction == FVS_RECON_FIRST_ORDER ? 1 : 2;
     for (Level& L : ctx->levels) {
@@ -1945,6 +1997,9 @@ int fvs_set_arithmetic(fvs_ctx* ctx, int arithmetic) {
     }
     if (arithmetic == FVS_ARITH_TOLERANCE && ctx->method.base == FVS_BASE_GODUNOV_EXACT) {
       throw Error("the exact Riemann solver has no tolerance-arithmetic build");
+    }
+    if (arithmetic == FVS_ARITH_TOLERANCE && ctx->method.recon >= FVS_RECON_MH2_CONSERVATIVE) {
+      throw Error("MusclHancock2 has no tolerance-arithmetic build");
     }
     ctx->arithmetic = arithmetic;
     return (int)FVS_OK;
@@ -2452,12 +2507,28 @@ int fvs_complete_from_cons(fvs_ctx* ctx, int level) {
   });
 }
 
+namespace {
+void plane_fluxes(fvs_ctx* ctx, Level& L, int level, int dir, double dt, int src);
+void accumulate_coarse_fine(fvs_ctx* ctx, int level, double scale, int dir);
+// does a sweep on `level` feed a flux register (as the fine or as the coarse side)?
+bool feeds_register(fvs_ctx* ctx, int level) {
+  const Level& L = ctx->level(level);
+  if (level > 0 && L.cf_coarse >= 0) return true;
+  return level + 1 < (int)ctx->levels.size() && ctx->levels[(size_t)level + 1].defined &&
+         ctx->levels[(size_t)level + 1].cf_coarse == level;
+}
+} // namespace
+
 int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out) {
   return guarded([&] {
     if (!ctx) throw Error("null context");
     ctx->use_device();
     Level& L = ctx->level(level);
     check_dir(ctx, dir);
+    // DimensionalSplitLevelIntegrator.hpp:262-264: AccumulateCoarseFineFluxes follows the
+    // sweep; the fused kernel keeps no flux array, so the register planes are evaluated
+    // from the sweep's input buffer
+    const bool feeds = feeds_register(ctx, level);
     if (L.has_eb) {
       // cut-cell levels: the unfused sequence, in place; the dt check comes
       // first so that a rejected sweep leaves the state untouched
@@ -2471,8 +2542,10 @@ int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out)
       cc_numeric_fluxes(ctx, L, dt, dir);
       cc_update(ctx, L, dt, dir);
       cc_complete(ctx, L);
+      if (feeds) accumulate_coarse_fine(ctx, level, dt, dir);
       return (int)FVS_OK;
     }
+    const int src = L.cur;
     int dst;
     double hint = dt_hint(ctx, L, dir);
     int slot = launch_sweep(ctx, L, dt, dir, &dst, hint);
@@ -2489,6 +2562,10 @@ int fvs_sweep(fvs_ctx* ctx, int level, double dt, int dir, double* level_dt_out)
     // DimensionalSplitLevelIntegrator.hpp:243-245
     if (level_dt < dt) return (int)FVS_TIME_STEP_TOO_LARGE;
     L.cur = dst;
+    if (feeds) {
+      plane_fluxes(ctx, L, level, dir, dt, src);
+      accumulate_coarse_fine(ctx, level, dt, dir);
+    }
     return (int)FVS_OK;
   });
 }

@@ -27,9 +27,19 @@ enum : int {
   kReconFirstOrder = 0,
   kReconMusclHancock = 1,
   kReconMusclHancockPrim = 2,
-  kReconMusclHancockChar = 3
+  kReconMusclHancockChar = 3,
+  // MusclHancock2<Equation, Gradient, Reconstruction, Base>
+  // (include/fub/flux_method/MusclHancockMethod2.hpp:35-239): gradient and reconstruction
+  // in conservative, primitive or characteristic variables; the limiter of the
+  // CentralDifferenceGradient is a run-time value (EqConst::limiter2)
+  kReconMh2Conservative = 4,
+  kReconMh2Primitive = 5,
+  kReconMh2Characteristics = 6
 };
 enum : int { kLimiterNone = 0, kLimiterMinMod = 1, kLimiterVanLeer = 2 };
+// include/fub/flux_method/Gradient.hpp:31-59
+enum : int { kLimiter2None = 0, kLimiter2Upwind = 1, kLimiter2MinMod = 2, kLimiter2VanLeer = 3 };
+__host__ __device__ constexpr bool is_mh2(int recon) { return recon >= kReconMh2Conservative; }
 
 // PerfectGas equation constants (include/fub/equations/PerfectGas.hpp:216-219):
 // gamma_minus_1_inv = 1.0 / (gamma - 1.0) evaluated in fp64 on the host.
@@ -37,6 +47,9 @@ struct EqConst {
   double gamma;
   double gamma_minus_1_inv;
   double gamma_minus_1; // gamma - 1.0
+  // per launch, read by MusclHancock2 only: cell size along the sweep and the limiter
+  double dx;
+  int limiter2;
 };
 
 template <int D> struct Cons {
@@ -1085,6 +1098,238 @@ FVS_DEV double godunov_exact_max_signal(const EqConst& eq, const SL& left, const
   m = fmax(m, fabs(s0));
   m = fmax(m, fabs(s1));
   return m;
+}
+
+// ---------------------------------------------------------------------------
+// MusclHancock2 (include/fub/flux_method/MusclHancockMethod2.hpp:35-239, array path):
+// ComputeGradient of the cell from its two neighbours (Gradient.hpp), Reconstruct at the
+// lower and the upper face (Reconstruct.hpp), the base method between the edge states of
+// two cells.  One call evaluates the cell's gradient once and both of its edge states.
+// CentralDifferenceGradient<Limiter>::ComputeGradient, Gradient.hpp:211-217:
+//   mask = sL sR > 0;  R = sR / sL;  mask.select(0.5 limiter(R) (sL + sR), 0)
+template <class M> FVS_DEV double mh2_central(double sL, double sR, int limiter, Flag& fl) {
+  const bool mask = sL * sR > 0.0;
+  double lim;
+  if (limiter == kLimiter2None) {
+    lim = 1.0;
+  } else if (limiter == kLimiter2Upwind) {
+    lim = 0.0;
+  } else {
+    const double R = M::div(sR, sL, fl, mask);
+    if (limiter == kLimiter2MinMod) { // :41-50
+      const double two = M::div(2.0, 1.0 + R, fl, mask);
+      lim = vmin(two, R * two);
+    } else { // VanLeerLimiter :52-59
+      lim = M::div(4.0 * R, (1.0 + R) * (1.0 + R), fl, mask);
+    }
+  }
+  const double g = 0.5 * lim * (sL + sR);
+  return mask ? g : 0.0;
+}
+
+// (b - a) / dx for a difference that may be zero; rdx from M::rcp(dx), window-checked
+template <class M> FVS_DEV double mh2_slope(double a, double b, const Rcp& rdx, Flag& fl) {
+  return M::divz(b - a, rdx, fl);
+}
+
+// PerfectGas::CompleteFromPrim (array), src/equations/PerfectGas.cpp:160-174
+template <class M, int D>
+FVS_DEV void mh2_complete_from_prim(const EqM& eq, Edge<D>& out, double rho, const double (&u)[D],
+                                    double p, Flag& fl) {
+  out.q.rho = rho;
+#pragma unroll
+  for (int d = 0; d < D; ++d) out.q.mom[d] = rho * u[d];
+  out.q.p = p;
+  out.rc = M::rcp(rho);
+  M::check_window(out.rc, fl);
+  const double e_kin = M::divz(0.5 * squared_norm<D>(out.q.mom), out.rc, fl);
+  out.q.E = e_kin + p * eq.gm1_inv.b;
+  out.q.a = M::sqrt(M::div(eq.gamma * p, out.rc, fl), fl);
+}
+
+// ConservativeGradient + ConservativeReconstruction (Gradient.hpp:247-270,
+// Reconstruct.hpp:188-214)
+template <class M, int D, int DIR, typename S0, typename S1, typename S2>
+FVS_DEV void mh2_cons_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp, double dx,
+                              int limiter, double lambda_half, Edge<D>& recL, Edge<D>& recR,
+                              Flag& fl, bool slope_ok = true) {
+  const Rcp rdx = M::rcp(dx);
+  M::check_window(rdx, fl);
+  const double half_dx = 0.5 * dx;
+  Complete<D> qL, qR;
+  auto split = [&](double um, double u, double up, double& l, double& r) {
+    double g = mh2_central<M>(mh2_slope<M>(um, u, rdx, fl), mh2_slope<M>(u, up, rdx, fl), limiter, fl);
+    g = slope_ok ? g : 0.0; // MusclHancockMethod2.hpp:200-213
+    const double du = half_dx * g;
+    l = u - du;
+    r = u + du;
+  };
+  split(qm.rho, q0.rho, qp.rho, qL.rho, qR.rho);
+#pragma unroll
+  for (int d = 0; d < D; ++d) split(qm.mom[d], q0.mom[d], qp.mom[d], qL.mom[d], qR.mom[d]);
+  split(qm.E, q0.E, qp.E, qL.E, qR.E);
+  Rcp rcL = M::rcp(qL.rho);
+  Rcp rcR = M::rcp(qR.rho);
+  complete_edge<M, D, false, false>(eq, qL, rcL, fl);
+  complete_edge<M, D, false, false>(eq, qR, rcR, fl);
+  Cons<D> fL, fR;
+  euler_flux_v<D, DIR>(fL, qL, M::divz(qL.mom[DIR], rcL, fl));
+  euler_flux_v<D, DIR>(fR, qR, M::divz(qR.mom[DIR], rcR, fl));
+  {
+    const double c = lambda_half * (fL.rho - fR.rho);
+    recL.q.rho = qL.rho + c;
+    recR.q.rho = qR.rho + c;
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double c = lambda_half * (fL.mom[d] - fR.mom[d]);
+    recL.q.mom[d] = qL.mom[d] + c;
+    recR.q.mom[d] = qR.mom[d] + c;
+  }
+  {
+    const double c = lambda_half * (fL.E - fR.E);
+    recL.q.E = qL.E + c;
+    recR.q.E = qR.E + c;
+  }
+  recL.rc = M::rcp(recL.q.rho);
+  recR.rc = M::rcp(recR.q.rho);
+  complete_edge<M, D, false>(eq, recL.q, recL.rc, fl);
+  complete_edge<M, D, false>(eq, recR.q, recR.rc, fl);
+}
+
+// PrimitiveGradient + PrimitiveReconstruction (Gradient.hpp:287-302, Reconstruct.hpp:343-388)
+template <class M, int D, int DIR, typename S0, typename S1, typename S2>
+FVS_DEV void mh2_prim_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp, double dx,
+                              int limiter, double lambda, Edge<D>& recL, Edge<D>& recR, Flag& fl,
+                              bool slope_ok = true) {
+  PrimCell<D> m, c, p;
+  prim_cell<M, D>(m, qm, fl);
+  prim_cell<M, D>(c, q0, fl);
+  prim_cell<M, D>(p, qp, fl);
+  const Rcp rdx = M::rcp(dx);
+  M::check_window(rdx, fl);
+  auto grad = [&](double a, double b, double cc) {
+    const double g =
+        mh2_central<M>(mh2_slope<M>(a, b, rdx, fl), mh2_slope<M>(b, cc, rdx, fl), limiter, fl);
+    return slope_ok ? g : 0.0;
+  };
+  const double drho = grad(m.rho, c.rho, p.rho);
+  const double dp = grad(m.p, c.p, p.p);
+  double du[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) du[i] = grad(m.u[i], c.u[i], p.u[i]);
+  const double u = c.u[DIR];
+  const double rho = q0.rho;
+  const double a2 = q0.a * q0.a;
+  const double rho_a2 = rho * a2;
+  const Rcp rcc = M::rcp(rho);
+  M::check_window(rcc, fl);
+  const double dp_over_rho = M::divz(dp, rcc, fl);
+  auto edge = [&](double sign, Edge<D>& out) {
+    const double lam = sign * lambda;
+    const double dx_half = sign * (0.5 * dx);
+    const double rec_rho = c.rho + dx_half * (drho - lam * (u * drho + rho * du[DIR]));
+    const double rec_p = c.p + dx_half * (dp - lam * (rho_a2 * du[DIR] + u * dp));
+    double rec_u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i == DIR) {
+        rec_u[i] = c.u[i] + dx_half * (du[i] - lam * (u * du[i] + dp_over_rho));
+      } else {
+        rec_u[i] = c.u[i] + dx_half * (du[i] - lam * u * du[i]);
+      }
+    }
+    mh2_complete_from_prim<M, D>(eq, out, rec_rho, rec_u, rec_p, fl);
+  };
+  edge(-1.0, recL);
+  edge(+1.0, recR);
+}
+
+// CharacteristicsGradient + CharacteristicsReconstruction (Gradient.hpp:354-368 with
+// ComputeAmplitudes :322-352, Reconstruct.hpp:458-516)
+template <class M, int D, int DIR, typename S0, typename S1, typename S2>
+FVS_DEV void mh2_char_predict(const EqM& eq, const S0& qm, const S1& q0, const S2& qp, double dx,
+                              int limiter, double lambda, Edge<D>& recL, Edge<D>& recR, Flag& fl,
+                              bool slope_ok = true) {
+  PrimCell<D> m, c, p;
+  prim_cell<M, D>(m, qm, fl);
+  prim_cell<M, D>(c, q0, fl);
+  prim_cell<M, D>(p, qp, fl);
+  const Rcp rdx = M::rcp(dx);
+  M::check_window(rdx, fl);
+  const double cs = q0.a;
+  const double ooc2 = M::div(1.0, cs * cs, fl);
+  const double rhoc = q0.rho * cs;
+  // amplitudes: minus, plus, zero[0] (entropy), zero[1..] (transverse velocities)
+  struct Amp {
+    double minus, plus, zero[D];
+  };
+  auto amplitudes = [&](const PrimCell<D>& l, const PrimCell<D>& r, Amp& a) {
+    const double dpx = mh2_slope<M>(l.p, r.p, rdx, fl);
+    const double dux = mh2_slope<M>(l.u[DIR], r.u[DIR], rdx, fl);
+    const double drx = mh2_slope<M>(l.rho, r.rho, rdx, fl);
+    a.minus = dpx - (1.0 * rhoc) * dux;
+    a.plus = dpx + (1.0 * rhoc) * dux;
+    a.zero[0] = drx - ooc2 * dpx;
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+      const int iy = (DIR + i) % D;
+      a.zero[i] = mh2_slope<M>(l.u[iy], r.u[iy], rdx, fl);
+    }
+  };
+  Amp aL, aR, g;
+  amplitudes(m, c, aL);
+  amplitudes(c, p, aR);
+  auto lim = [&](double sl, double sr) {
+    const double v = mh2_central<M>(sl, sr, limiter, fl);
+    return slope_ok ? v : 0.0;
+  };
+  g.minus = lim(aL.minus, aR.minus);
+  g.plus = lim(aL.plus, aR.plus);
+#pragma unroll
+  for (int i = 0; i < D; ++i) g.zero[i] = lim(aL.zero[i], aR.zero[i]);
+  const double u = c.u[DIR];
+  const double c2 = cs * cs;
+  const Rcp rc2 = M::rcp(c2);
+  M::check_window(rc2, fl);
+  const Rcp rrhoc = M::rcp(rhoc);
+  M::check_window(rrhoc, fl);
+  auto edge = [&](double sign, Edge<D>& out) {
+    const double lam = sign * lambda;
+    const double dx_half = sign * (0.5 * dx);
+    const double kminus = dx_half * g.minus * (1.0 - lam * (u - cs));
+    const double kplus = dx_half * g.plus * (1.0 - lam * (u + cs));
+    double kzero[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) kzero[i] = dx_half * g.zero[i] * (1.0 - lam * u);
+    const double dwp = 0.5 * (kminus + kplus);
+    const double dwrho = M::divz(dwp, rc2, fl) + kzero[0];
+    double dwu[D];
+    dwu[DIR] = M::divz(0.5 * (kplus - kminus), rrhoc, fl);
+#pragma unroll
+    for (int i = 1; i < D; ++i) dwu[(DIR + i) % D] = kzero[i];
+    double rec_u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) rec_u[i] = c.u[i] + dwu[i];
+    mh2_complete_from_prim<M, D>(eq, out, c.rho + dwrho, rec_u, c.p + dwp, fl);
+  };
+  edge(-1.0, recL);
+  edge(+1.0, recR);
+}
+
+template <class M, int D, int DIR, int RECON, typename S0, typename S1, typename S2>
+FVS_DEV void mh2_predict(const EqM& eq, const EqConst& c, const S0& qm, const S1& q0, const S2& qp,
+                         double lambda_half, Edge<D>& recL, Edge<D>& recR, Flag& fl,
+                         bool slope_ok = true) {
+  if constexpr (RECON == kReconMh2Conservative) {
+    mh2_cons_predict<M, D, DIR>(eq, qm, q0, qp, c.dx, c.limiter2, lambda_half, recL, recR, fl, slope_ok);
+  } else if constexpr (RECON == kReconMh2Primitive) {
+    mh2_prim_predict<M, D, DIR>(eq, qm, q0, qp, c.dx, c.limiter2, 2.0 * lambda_half, recL, recR, fl,
+                                slope_ok);
+  } else {
+    mh2_char_predict<M, D, DIR>(eq, qm, q0, qp, c.dx, c.limiter2, 2.0 * lambda_half, recL, recR, fl,
+                                slope_ok);
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #define FVS_SWEEP_SMEM 1
 #endif
 #include <algorithm>
+#include <type_traits>
 #ifndef FVS_INST_D
 #error "define FVS_INST_D"
 #endif
@@ -113,6 +114,17 @@ int by_recon(const MethodKey& k, F0 fo, F1 none, F2 minmod, F3 vanleer, F4 prim,
   return -1;
 }
 
+// MusclHancock2: the gradient / reconstruction variables are a template argument, the
+// limiter of the CentralDifferenceGradient a run-time value (EqConst::limiter2)
+template <typename F> int by_mh2(const MethodKey& k, F f) {
+  switch (k.recon) {
+  case kReconMh2Conservative: return f(std::integral_constant<int, kReconMh2Conservative>{});
+  case kReconMh2Primitive: return f(std::integral_constant<int, kReconMh2Primitive>{});
+  case kReconMh2Characteristics: return f(std::integral_constant<int, kReconMh2Characteristics>{});
+  }
+  return -1;
+}
+
 template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStream_t s) {
 #ifdef FVS_INST_MINIMAL
   // tuning builds (tools/build_variant.py --minimal, tools/count_steady.sh): only the
@@ -122,6 +134,13 @@ template <int DIR> int fused_dir(const MethodKey& k, const SweepArgs& A, cudaStr
   }
   return -1;
 #else
+  if (is_mh2(k.recon)) {
+#ifdef FVS_TOLERANCE_UNIT
+    return -1; // no tolerance-arithmetic build of MusclHancock2
+#else
+    return by_mh2(k, [&](auto R) { return fused<DIR, decltype(R)::value, kLimiterNone>(A, s); });
+#endif
+  }
   return by_recon<DIR>(
       k, [&] { return fused<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fused<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
@@ -150,6 +169,9 @@ template <int DIR> int fluxes_dir(const MethodKey& k, const SweepArgs& A, cudaSt
 #ifdef FVS_INST_MINIMAL
   return -1;
 #else
+  if (is_mh2(k.recon)) {
+    return by_mh2(k, [&](auto R) { return fluxes<DIR, decltype(R)::value, kLimiterNone>(A, s); });
+  }
   return by_recon<DIR>(
       k, [&] { return fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },
@@ -178,6 +200,9 @@ template <int DIR> int cc_fluxes_dir(const MethodKey& k, const SweepArgs& A, cud
 #ifdef FVS_INST_MINIMAL
   return -1;
 #else
+  if (is_mh2(k.recon)) {
+    return by_mh2(k, [&](auto R) { return cc_fluxes<DIR, decltype(R)::value, kLimiterNone>(A, s); });
+  }
   return by_recon<DIR>(
       k, [&] { return cc_fluxes<DIR, kReconFirstOrder, kLimiterNone>(A, s); },
       [&] { return cc_fluxes<DIR, kReconMusclHancock, kLimiterNone>(A, s); },

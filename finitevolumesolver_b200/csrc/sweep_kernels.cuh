@@ -110,6 +110,10 @@ FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const S1& q0, const S2& 
     with_fallback([&](auto M, Flag& fl) {
       muscl_char_predict<decltype(M), D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
     });
+  } else if constexpr (is_mh2(RECON)) {
+    with_fallback([&](auto M, Flag& fl) {
+      mh2_predict<decltype(M), D, DIR, RECON>(eq.m, eq.c, qm, q0, qp, lambda_half, recL, recR, fl);
+    });
   } else {
     recL.q = q0;
     recL.rc = FastMath::rcp(q0.rho);
@@ -285,6 +289,8 @@ fused_sweep_yz_kernel(const SweepArgs A) {
             muscl_prim_predict<MM, D, DIR>(eq.m, q2, q1, q0, A.lambda, recL, recR, fl);
           } else if constexpr (RECON == kReconMusclHancockChar) {
             muscl_char_predict<MM, D, DIR>(eq.m, q2, q1, q0, A.lambda, recL, recR, fl);
+          } else if constexpr (is_mh2(RECON)) {
+            mh2_predict<MM, D, DIR, RECON>(eq.m, eq.c, q2, q1, q0, A.lambda_half, recL, recR, fl);
           } else {
             recL.q = q1;
             recL.rc = MM::rcp(q1.rho);
@@ -1097,6 +1103,25 @@ __global__ void __launch_bounds__(128) cc_numeric_flux_kernel(const SweepArgs A)
           muscl_char_predict<SafeMath, D, DIR>(eq.m, s0, s1, s2, A.lambda, unused, left, fl);
           muscl_char_predict<SafeMath, D, DIR>(eq.m, s1, s2, s3, A.lambda, right, unused, fl);
         }
+      } else if constexpr (is_mh2(RECON)) {
+        // MusclHancockMethod2.hpp:193-216: only the gradients are masked
+        Complete<D> s0, s1, s2, s3;
+        load_complete<D>(s0, p - 2 * stride, B.sc);
+        load_complete<D>(s1, p - stride, B.sc);
+        load_complete<D>(s2, p, B.sc);
+        load_complete<D>(s3, p + stride, B.sc);
+        bool okL = true, okR = true;
+        if (single) {
+          const double* al = B.alpha + cell;
+          const bool a0 = al[-2 * stride] > 0.0, a1 = al[-stride] > 0.0, a2 = al[0] > 0.0,
+                     a3 = al[stride] > 0.0;
+          okL = a0 && a1 && a2;
+          okR = a1 && a2 && a3;
+        }
+        mh2_predict<SafeMath, D, DIR, RECON>(eq.m, eq.c, s0, s1, s2, A.lambda_half, unused, left, fl,
+                                             okL);
+        mh2_predict<SafeMath, D, DIR, RECON>(eq.m, eq.c, s1, s2, s3, A.lambda_half, right, unused,
+                                             fl, okR);
       } else if constexpr (RECON == kReconMusclHancock) {
         Complete<D> s0, s1, s2, s3;
         load_complete<D>(s0, p - 2 * stride, B.sc);

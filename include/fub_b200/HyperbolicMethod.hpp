@@ -82,7 +82,21 @@ enum class BaseMethod : int {
 };
 enum class Reconstruct : int {
   FirstOrder = FVS_RECON_FIRST_ORDER,
-  MusclHancock = FVS_RECON_MUSCL_HANCOCK ///< MusclHancockMethod<Eq, Base, Limiter>
+  MusclHancock = FVS_RECON_MUSCL_HANCOCK, ///< MusclHancockMethod<Eq, Base, Limiter>
+  MusclHancockPrim = FVS_RECON_MUSCL_HANCOCK_PRIM, ///< perfect_gas::MusclHancockPrim<Rank>
+  MusclHancockChar = FVS_RECON_MUSCL_HANCOCK_CHAR, ///< perfect_gas::MusclHancockCharacteristic<Rank>
+  /// MusclHancock2<Eq, XGradient<Eq, CentralDifferenceGradient<L>>, XReconstruction<Eq>, Base>
+  /// (include/fub/flux_method/MusclHancockMethod2.hpp); the limiter is a Limiter2 value
+  Mh2Conservative = FVS_RECON_MH2_CONSERVATIVE,
+  Mh2Primitive = FVS_RECON_MH2_PRIMITIVE,
+  Mh2Characteristics = FVS_RECON_MH2_CHARACTERISTICS
+};
+/// include/fub/flux_method/Gradient.hpp:31-59
+enum class Limiter2 : int {
+  None = FVS_LIMITER2_NONE,
+  Upwind = FVS_LIMITER2_UPWIND,
+  MinMod = FVS_LIMITER2_MINMOD,
+  VanLeer = FVS_LIMITER2_VANLEER
 };
 enum class Limiter : int {
   None = FVS_LIMITER_NONE,
@@ -411,6 +425,9 @@ public:
         m.flux_method.ComputeNumericFluxes(ctx, level, split_dt, dir);
         m.time_integrator.UpdateConservatively(ctx, level, split_dt, dir);
         m.reconstruction.CompleteFromCons(ctx, level, split_dt);
+        // DimensionalSplitLevelIntegrator.hpp:262-264 (a no-op on a level without registers;
+        // fvs_sweep does the same for the fused path)
+        ctx.AccumulateCoarseFineFluxes(level, split_dt.count(), dir);
         return std::nullopt;
       }
     };

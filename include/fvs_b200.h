@@ -51,7 +51,23 @@ enum {
   FVS_RECON_FIRST_ORDER = 0,
   FVS_RECON_MUSCL_HANCOCK = 1,
   FVS_RECON_MUSCL_HANCOCK_PRIM = 2,
-  FVS_RECON_MUSCL_HANCOCK_CHAR = 3
+  FVS_RECON_MUSCL_HANCOCK_CHAR = 3,
+  /* include/fub/flux_method/MusclHancockMethod2.hpp:35-239 MusclHancock2<Equation, Gradient,
+   * Reconstruction, Base> with the gradient and the reconstruction in the same variables
+   * (include/fub/flux_method/Gradient.hpp, Reconstruct.hpp; the three combinations of
+   * include/fub/AMReX/FluxMethodFactory.hpp:161-176); `limiter` is then a FVS_LIMITER2_*
+   * value, any base method */
+  FVS_RECON_MH2_CONSERVATIVE = 4,
+  FVS_RECON_MH2_PRIMITIVE = 5,
+  FVS_RECON_MH2_CHARACTERISTICS = 6
+};
+/* limiters of CentralDifferenceGradient<Limiter>, include/fub/flux_method/Gradient.hpp:31-59
+ * (NoLimiter2, UpwindLimiter, MinModLimiter, VanLeerLimiter) */
+enum {
+  FVS_LIMITER2_NONE = 0,
+  FVS_LIMITER2_UPWIND = 1,
+  FVS_LIMITER2_MINMOD = 2,
+  FVS_LIMITER2_VANLEER = 3
 };
 /* include/fub/flux_method/MusclHancockMethod.hpp:31-187 */
 enum { FVS_LIMITER_NONE = 0, FVS_LIMITER_MINMOD = 1, FVS_LIMITER_VANLEER = 2 };
@@ -108,7 +124,7 @@ typedef struct fvs_config {
   double gamma;       /* PerfectGas::gamma, include/fub/equations/PerfectGas.hpp:216-219 */
   int base_method;    /* FVS_BASE_* */
   int reconstruction; /* FVS_RECON_* */
-  int limiter;        /* FVS_LIMITER_* (ignored for first order) */
+  int limiter;        /* FVS_LIMITER_* (ignored for first order); FVS_LIMITER2_* for FVS_RECON_MH2_* */
   int device;         /* CUDA device ordinal, -1 = current device */
   int comm_rank;      /* this process' index among the ranks sharing the level (0 if single) */
   int comm_size;      /* number of ranks (1 if single) */

@@ -18,7 +18,16 @@
 namespace fvso {
 
 enum BaseKind { kHllemLarrouturou = 0, kHllem = 1, kHllEinfeldt = 2, kGodunovExact = 3 };
-enum ReconKind { kFirstOrder = 0, kMusclHancock = 1, kMusclHancockPrim = 2, kMusclHancockChar = 3 };
+enum ReconKind {
+  kFirstOrder = 0,
+  kMusclHancock = 1,
+  kMusclHancockPrim = 2,
+  kMusclHancockChar = 3,
+  // MusclHancock2 (MusclHancockMethod2.hpp); `limiter` is then a Limiter2Kind
+  kMh2ConservativeRecon = 4,
+  kMh2PrimitiveRecon = 5,
+  kMh2CharacteristicsRecon = 6
+};
 enum LimiterKind { kNoLimiter = 0, kMinMod = 1, kVanLeer = 2 };
 enum BcKind { kTransmissive = 0, kReflective = 1 };
 enum SplitKind { kGodunovSplitting = 0, kStrangSplitting = 1, kStrangSplittingLumped = 2 };
@@ -55,6 +64,18 @@ void with_method(const MethodSpec& ms, const PerfectGasEq& eq, F&& f) {
     f(MusclHancockPrim<D>(eq));
   } else if (ms.recon == kMusclHancockChar) {
     f(MusclHancockChar<D>(eq));
+  } else if (ms.recon >= kMh2ConservativeRecon) {
+    with_base([&](auto base) {
+      using Base = decltype(base);
+      switch (ms.recon) {
+      case kMh2ConservativeRecon: f(MusclHancock2<Base, kMh2Conservative>(eq, ms.limiter)); break;
+      case kMh2PrimitiveRecon: f(MusclHancock2<Base, kMh2Primitive>(eq, ms.limiter)); break;
+      case kMh2CharacteristicsRecon:
+        f(MusclHancock2<Base, kMh2Characteristics>(eq, ms.limiter));
+        break;
+      default: throw std::runtime_error("unknown reconstruction");
+      }
+    });
   } else if (ms.recon == kFirstOrder) {
     with_base([&](auto base) { f(base); });
   } else {

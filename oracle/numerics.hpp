@@ -1453,4 +1453,232 @@ template <int D> struct MusclHancockChar {
   }
 };
 
+// ---------------------------------------------------------------------------
+// MusclHancock2<Equation, Gradient, Reconstruction, Base>
+// include/fub/flux_method/MusclHancockMethod2.hpp:35-239 (array path), with
+//   include/fub/flux_method/Gradient.hpp     (limiters :31-59, CentralDifferenceGradient
+//       :211-217, Conservative/Primitive/CharacteristicsGradient :247-302, :322-368)
+//   include/fub/flux_method/Reconstruct.hpp  (Conservative :188-214, Primitive :343-388,
+//       Characteristics :458-516)
+// KIND selects the variables of both the gradient and the reconstruction (the three
+// pairings of include/fub/AMReX/FluxMethodFactory.hpp:161-176); the limiter of the
+// CentralDifferenceGradient is a run-time value here.
+enum Mh2Kind { kMh2Conservative = 0, kMh2Primitive = 1, kMh2Characteristics = 2 };
+enum Limiter2Kind { kLimiter2None = 0, kLimiter2Upwind = 1, kLimiter2MinMod = 2, kLimiter2VanLeer = 3 };
+
+template <typename Base, int KIND> struct MusclHancock2 {
+  static constexpr int kWidth = 2;
+  static constexpr int kDim = Base::kDim;
+  static constexpr int D = Base::kDim;
+  using T = A8;
+  using Lane = A8;
+  PerfectGasEq eq;
+  Base base;
+  int limiter;
+  MusclHancock2(const PerfectGasEq& e, int lim) : eq(e), base(e), limiter(lim) {}
+
+  // Gradient.hpp:31-59
+  T limit(const T& R) const {
+    switch (limiter) {
+    case kLimiter2None: return T(1.0);
+    case kLimiter2Upwind: return T(0.0);
+    case kLimiter2MinMod: {
+      const T two_over_one_plus_R = 2.0 / (1.0 + R);
+      return vmin(two_over_one_plus_R, R * two_over_one_plus_R);
+    }
+    default: return 4.0 * R / ((1.0 + R) * (1.0 + R));
+    }
+  }
+  // CentralDifferenceGradient::ComputeGradient(Array1d, Array1d), Gradient.hpp:211-217
+  T central(const T& sL, const T& sR) const {
+    const M8 mask = (sL * sR) > 0.0;
+    const T R = sR / sL;
+    return select(mask, 0.5 * limit(R) * (sL + sR), 0.0);
+  }
+
+  // gradient variables: Conservative -> (rho, mom, E); Primitive -> (rho, u, p);
+  // Characteristics -> (minus, zero[0..D-1], plus) stored as g[0], g[1..D], g[D+1]
+  struct Grad {
+    T g[D + 2];
+  };
+  struct Prim {
+    T rho, p;
+    T u[D];
+  };
+  static Prim prim_of(const Complete<T, D>& q) { // PrimFromComplete, PerfectGas.hpp:339-347
+    Prim w;
+    w.rho = q.rho;
+    w.p = q.p;
+    for (int i = 0; i < D; ++i) w.u[i] = q.mom[i] / q.rho;
+    return w;
+  }
+
+  void ComputeGradient(Grad& out, const Complete<T, D>* q, double dx, int dir) const {
+    if constexpr (KIND == kMh2Conservative) { // Gradient.hpp:259-270
+      auto one = [&](const T& uL, const T& uM, const T& uR) {
+        return central((uM - uL) / dx, (uR - uM) / dx);
+      };
+      out.g[0] = one(q[0].rho, q[1].rho, q[2].rho);
+      for (int i = 0; i < D; ++i) out.g[1 + i] = one(q[0].mom[i], q[1].mom[i], q[2].mom[i]);
+      out.g[D + 1] = one(q[0].E, q[1].E, q[2].E);
+    } else if constexpr (KIND == kMh2Primitive) { // :287-302
+      const Prim wL = prim_of(q[0]), wM = prim_of(q[1]), wR = prim_of(q[2]);
+      auto one = [&](const T& a, const T& b, const T& c) {
+        return central((b - a) / dx, (c - b) / dx);
+      };
+      out.g[0] = one(wL.rho, wM.rho, wR.rho);
+      for (int i = 0; i < D; ++i) out.g[1 + i] = one(wL.u[i], wM.u[i], wR.u[i]);
+      out.g[D + 1] = one(wL.p, wM.p, wR.p);
+    } else { // :354-368 with ComputeAmplitudes :322-352 (MaSq == 1 for PerfectGas)
+      const Prim wL = prim_of(q[0]), wM = prim_of(q[1]), wR = prim_of(q[2]);
+      const T rho = q[1].rho;
+      const T c = q[1].a;
+      const T ooc2 = 1.0 / (c * c);
+      const T rhoc = rho * c;
+      auto amplitudes = [&](Grad& a, const Prim& left, const Prim& right) {
+        const T Ma(std::sqrt(1.0));
+        const T dp = (right.p - left.p) / dx;
+        const T du = (right.u[dir] - left.u[dir]) / dx;
+        const T drho = (right.rho - left.rho) / dx;
+        a.g[0] = dp - Ma * rhoc * du;     // minus
+        a.g[D + 1] = dp + Ma * rhoc * du; // plus
+        a.g[1] = drho - ooc2 * dp;        // zero[0]
+        for (int i = 1; i < D; ++i) {
+          const int iy = (dir + i) % D;
+          a.g[1 + i] = (right.u[iy] - left.u[iy]) / dx; // zero[i]
+        }
+      };
+      Grad aL, aR;
+      amplitudes(aL, wL, wM);
+      amplitudes(aR, wM, wR);
+      for (int k = 0; k < D + 2; ++k) out.g[k] = central(aL.g[k], aR.g[k]);
+    }
+  }
+
+  // side: -1 = Side::Lower, +1 = Side::Upper
+  void Reconstruct(Complete<T, D>& rec, const Complete<T, D>& q0, const Grad& grad, double dt,
+                   double dx, int dir, int sign) const {
+    if constexpr (KIND == kMh2Conservative) { // Reconstruct.hpp:188-214
+      Complete<T, D> qL, qR;
+      auto split = [&](T& uL, T& uR, const T& u, const T& du_dx) {
+        const T du = (0.5 * dx) * du_dx;
+        uL = u - du;
+        uR = u + du;
+      };
+      split(qL.rho, qR.rho, q0.rho, grad.g[0]);
+      for (int i = 0; i < D; ++i) split(qL.mom[i], qR.mom[i], q0.mom[i], grad.g[1 + i]);
+      split(qL.E, qR.E, q0.E, grad.g[D + 1]);
+      CompleteFromCons<T, D>(eq, qL, qL);
+      CompleteFromCons<T, D>(eq, qR, qR);
+      Cons<T, D> fL, fR;
+      Flux<T, D>(eq, fL, qL, dir);
+      Flux<T, D>(eq, fR, qR, dir);
+      const double lambda_half = 0.5 * dt / dx;
+      const Complete<T, D>& q = sign < 0 ? qL : qR;
+      auto add = [&](T& r, const T& u, const T& fl, const T& fr) {
+        const T dF = fl - fr;
+        const T dU = lambda_half * dF;
+        r = u + dU;
+      };
+      add(rec.rho, q.rho, fL.rho, fR.rho);
+      for (int i = 0; i < D; ++i) add(rec.mom[i], q.mom[i], fL.mom[i], fR.mom[i]);
+      add(rec.E, q.E, fL.E, fR.E);
+      CompleteFromCons<T, D>(eq, rec, rec);
+    } else if constexpr (KIND == kMh2Primitive) { // :343-388
+      const Prim w = prim_of(q0);
+      const T lambda(sign * dt / dx);
+      const T dx_half(sign * 0.5 * dx);
+      const T u = w.u[dir];
+      const T rho = q0.rho;
+      const T a = q0.a;
+      const T a2 = a * a;
+      const T rho_a2 = rho * a2;
+      const T& d_rho = grad.g[0];
+      const T& d_p = grad.g[D + 1];
+      const T* d_u = &grad.g[1];
+      Prim r;
+      r.rho = w.rho + dx_half * (d_rho - lambda * (u * d_rho + rho * d_u[dir]));
+      r.p = w.p + dx_half * (d_p - lambda * (rho_a2 * d_u[dir] + u * d_p));
+      r.u[dir] = w.u[dir] + dx_half * (d_u[dir] - lambda * (u * d_u[dir] + d_p / rho));
+      for (int i = 1; i < D; ++i) {
+        const int iy = (dir + i) % D;
+        r.u[iy] = w.u[iy] + dx_half * (d_u[iy] - lambda * u * d_u[iy]);
+      }
+      from_prim(rec, r);
+    } else { // :458-516
+      Prim w = prim_of(q0);
+      const T u = w.u[dir];
+      const T c = q0.a;
+      const T lambda(sign * dt / dx);
+      const T dx_half(sign * 0.5 * dx);
+      const T one(1.0);
+      Grad k;
+      k.g[0] = dx_half * grad.g[0] * (one - lambda * (u - c));         // minus
+      k.g[D + 1] = dx_half * grad.g[D + 1] * (one - lambda * (u + c)); // plus
+      for (int i = 0; i < D; ++i) k.g[1 + i] = dx_half * grad.g[1 + i] * (one - lambda * u);
+      const T rho = w.rho;
+      const T rhoc = rho * c;
+      const T c2 = c * c;
+      Prim dw;
+      dw.p = 0.5 * (k.g[0] + k.g[D + 1]);
+      dw.rho = dw.p / c2 + k.g[1];
+      dw.u[dir] = 0.5 * (k.g[D + 1] - k.g[0]) / rhoc;
+      for (int i = 1; i < D; ++i) {
+        const int iy = (dir + i) % D;
+        dw.u[iy] = k.g[1 + i];
+      }
+      w.rho = w.rho + dw.rho;
+      w.p = w.p + dw.p;
+      for (int i = 0; i < D; ++i) w.u[i] = w.u[i] + dw.u[i];
+      from_prim(rec, w);
+    }
+  }
+  // PerfectGas::CompleteFromPrim (array), src/equations/PerfectGas.cpp:160-174
+  void from_prim(Complete<T, D>& q, const Prim& w) const {
+    q.rho = w.rho;
+    for (int i = 0; i < D; ++i) q.mom[i] = w.rho * w.u[i];
+    q.p = w.p;
+    const T e_kin = KineticEnergy<T, D>(q.rho, q.mom);
+    q.E = e_kin + w.p * eq.gamma_minus_1_inv;
+    q.a = vsqrt(eq.gamma * q.p / q.rho);
+  }
+
+  // MusclHancockMethod2.hpp:55-75
+  T ComputeStableDt(const Complete<T, D>* states, double dx, int dir) const {
+    return base.ComputeStableDt(states + 1, dx, dir);
+  }
+  T ComputeStableDt(const Complete<T, D>* states, const T& face_fraction, const T* vols,
+                    double dx, int dir) const {
+    return base.ComputeStableDt(states + 1, face_fraction, vols + 1, dx, dir);
+  }
+  // :164-191
+  void ComputeNumericFlux(Cons<T, D>& flux, const Complete<T, D>* st, double dt, double dx,
+                          int dir) const {
+    Grad grad[2];
+    ComputeGradient(grad[0], st, dx, dir);
+    ComputeGradient(grad[1], st + 1, dx, dir);
+    Complete<T, D> rec[2];
+    Reconstruct(rec[0], st[1], grad[0], dt, dx, dir, +1);
+    Reconstruct(rec[1], st[2], grad[1], dt, dx, dir, -1);
+    base.ComputeNumericFlux(flux, rec, dt, dx, dir);
+  }
+  // :193-239 (masked: only the gradients see the volume fractions)
+  void ComputeNumericFlux(Cons<T, D>& flux, const T& face_fractions, const Complete<T, D>* st,
+                          const T* vols, double dt, double dx, int dir) const {
+    Grad grad[2];
+    ComputeGradient(grad[0], st, dx, dir);
+    ComputeGradient(grad[1], st + 1, dx, dir);
+    const M8 left_mask = (vols[0] > 0.0) && (vols[1] > 0.0) && (vols[2] > 0.0);
+    const M8 right_mask = (vols[1] > 0.0) && (vols[2] > 0.0) && (vols[3] > 0.0);
+    for (int k = 0; k < D + 2; ++k) {
+      grad[0].g[k] = select(left_mask, grad[0].g[k], 0.0);
+      grad[1].g[k] = select(right_mask, grad[1].g[k], 0.0);
+    }
+    Complete<T, D> rec[2];
+    Reconstruct(rec[0], st[1], grad[0], dt, dx, dir, +1);
+    Reconstruct(rec[1], st[2], grad[1], dt, dx, dir, -1);
+    base.ComputeNumericFlux(flux, face_fractions, rec, vols + 1, dt, dx, dir);
+  }
+};
+
 } // namespace fvso

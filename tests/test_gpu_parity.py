@@ -31,6 +31,12 @@ BITWISE_METHODS = [
     (2, 1, 1), (2, 1, 2), (2, 0, 0),
     (0, 2, 0),  # perfect_gas::MusclHancockPrim (over HLLEM Larrouturou)
     (0, 3, 2),  # perfect_gas::MusclHancockCharacteristic (VanLeer, HLLEM Larrouturou)
+    # MusclHancock2<Gradient, Reconstruction, Base> (MusclHancockMethod2.hpp): recon 4 / 5 / 6 =
+    # conservative / primitive / characteristic variables, limiter = Gradient.hpp's
+    # NoLimiter2 (0), Upwind (1), MinMod (2), VanLeer (3)
+    (1, 4, 3), (0, 4, 2), (0, 4, 1),
+    (1, 5, 3), (0, 5, 0), (2, 5, 2),
+    (1, 6, 3), (0, 6, 2), (2, 6, 3),
 ]
 
 

@@ -230,6 +230,66 @@ def test_muscl_hancock_prim_and_char_sod_star_state(oracle, recon):
     assert abs(r[x > 0.5].mean() - 0.125) < 1e-12
 
 
+@_pytest.mark.parametrize("recon", [4, 5, 6])
+@_pytest.mark.parametrize("limiter", [2, 3])
+@_pytest.mark.parametrize("base", [0, 1, 2])
+def test_muscl_hancock2_sod_star_state(oracle, recon, limiter, base):
+    """MusclHancock2<Gradient, Reconstruction, Base> (MusclHancockMethod2.hpp; upstream only
+    constructs it, tests/test.NewStates.cpp): conservative / primitive / characteristic
+    variables with the MinMod and VanLeer limiters of Gradient.hpp must resolve the Sod
+    problem (Toro, section 4.3.3: star density 0.42632, post-contact density 0.26557)."""
+    import numpy as np
+    from helpers import complete_from_prim
+    n = 400
+    dx = [2.0 / n]
+    lvl = oracle.Level(1, [0], [n - 1], dx, [([0], [n - 1])], scratch_gcw=2, flux_gcw=0)
+    lvl.set_method(base, recon, limiter)
+    lvl.add_bc(0, 0, oracle.BC_TRANSMISSIVE)
+    lvl.add_bc(0, 1, oracle.BC_TRANSMISSIVE)
+    arr, lo, hi = lvl.scratch(0)
+    x = -1.0 + (np.arange(lo[0], hi[0] + 1) + 0.5) * dx[0]
+    rho = np.where(x < 0.0, 1.0, 0.125)[None, None, :]
+    p = np.where(x < 0.0, 1.0, 0.1)[None, None, :]
+    arr[...] = complete_from_prim(1, rho, [np.zeros_like(rho)], p)
+    lvl.fill_ghost_layer()
+    lvl.run(0.5, 0.25, -1, oracle.SPLIT_GODUNOV)
+    r = arr[0, 0, 0]
+    assert not np.isnan(arr).any()
+    star = r[(x > 0.08) & (x < 0.20)]
+    assert abs(star.mean() - 0.42632) < 3e-3
+    post_shock = r[(x > 0.27) & (x < 0.41)]
+    assert abs(post_shock.mean() - 0.26557) < 3e-3
+    assert abs(r[x > 0.5].mean() - 0.125) < 1e-12
+
+
+@_pytest.mark.parametrize("recon", [4, 5, 6])
+def test_muscl_hancock2_limiters_on_known_stencils(oracle, recon):
+    """Gradient.hpp:31-59, :211-217 through the flux of a four-cell stencil: (a) a uniform
+    stencil gives the physical flux for every limiter; (b) the upwind limiter (zero gradient)
+    gives exactly the flux of the base method on the two inner cells; (c) across an extremum
+    (sL sR <= 0 in every variable) every limiter agrees with upwind."""
+    import numpy as np
+    rank = 1
+    q = lambda rho, u, p: complete(oracle, rank, rho, [rho * u], p / (GAMMA - 1.0) + 0.5 * rho * u * u)
+    dt, dx = 0.01, 0.1
+    uniform = np.concatenate([q(1.3, 0.4, 0.9)] * 4)
+    f_phys = np.array([1.3 * 0.4, 1.3 * 0.4 * 0.4 + 0.9,
+                       0.4 * (0.9 / (GAMMA - 1.0) + 0.5 * 1.3 * 0.16 + 0.9)])
+    for lim in range(4):
+        f = oracle.numeric_flux(rank, 0, recon, lim, uniform, dt, dx, 0)
+        assert np.allclose(f, f_phys, rtol=1e-14, atol=0)
+    st = np.concatenate([q(1.0, 0.1, 1.0), q(1.2, 0.3, 1.4), q(0.9, 0.2, 0.8), q(1.1, 0.5, 1.0)])
+    first_order = oracle.numeric_flux(rank, 0, 0, 0, st[5:15], dt, dx, 0)
+    upwind = oracle.numeric_flux(rank, 0, recon, 1, st, dt, dx, 0)
+    assert np.allclose(upwind, first_order, rtol=1e-14, atol=0)
+    if recon == 4:
+        # zig-zag in rho, rho u and E alike: every central gradient is masked out
+        zig = np.concatenate([q(1.0, 0.0, 1.0), q(2.0, 0.0, 2.0), q(1.0, 0.0, 1.0), q(2.0, 0.0, 2.0)])
+        ref = oracle.numeric_flux(rank, 0, recon, 1, zig, dt, dx, 0)
+        for lim in (0, 2, 3):
+            assert np.array_equal(oracle.numeric_flux(rank, 0, recon, lim, zig, dt, dx, 0), ref)
+
+
 # --- HLLEM: the reference's two code paths against each other ---------------------
 # The reference cross-checks its scalar and array paths for HLL only
 # (tests/test.simd_FluxMethod.cpp:54-105).  oracle/scalar_hllem.hpp restates the
