@@ -87,21 +87,44 @@ def grid_of_boxes(n_gpus, size, strong=False):
     return [parts[d] * box_n[d] for d in range(3)], boxes, parts, box_n
 
 
-def geometry(domain_n):
-    dx = [2.0 / domain_n[0]] * 3
-    origin = [-1.0, -1.0 * domain_n[1] / domain_n[0], -1.0 * domain_n[2] / domain_n[0]]
+def geometry(domain_n, size):
+    """The size^3 problem spans [-1, 1]^3 (dx = 2 / size); the domain is centred at 0."""
+    dx = [2.0 / size] * 3
+    origin = [-0.5 * domain_n[d] * dx[d] for d in range(3)]
     return dx, origin
 
 
-def box_state(lo, hi, dx, origin, out=None):
-    """Spherical Riemann problem (r < 0.4: rho = p = 1, else 0.125 / 0.1, at
-    rest) on the fab box [lo, hi]; built plane by plane to bound host memory."""
-    from helpers import riemann_state
+def lattice_state(lo, hi, dx, origin, period):
+    """Spherical Riemann problem (r < 0.4: rho = p = 1, else 0.125 / 0.1, at rest) on the fab
+    box [lo, hi].  period[d] = 0: one sphere at the centre of the domain (1 GPU, and the strong-
+    scaling decomposition).  period[d] = 2 (weak scaling, directions cut into boxes): the sphere
+    repeats with the box size, centred ON the box interfaces -- every box holds the same amount of
+    sphere and of wave front as the 1-GPU problem (per-GPU work really is fixed; with one sphere
+    scaled to the grown domain the lazy stable dt and the zero-slope fast paths see different data
+    and the sweeps of a 2-GPU run are 2 % slower for that reason alone), and the front crosses
+    the rank boundaries, which is where the parity check looks."""
+    from helpers import cell_centers, complete_from_prim
+    z, y, x = cell_centers(lo, hi, dx, origin)
+    shape = (hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
+    r2 = np.zeros(shape)
+    for c, per in zip((x, y, z), period):
+        if per:
+            c = np.mod(c + 0.5 * per, per) - 0.5 * per
+        r2 = r2 + c * c
+    inside = r2 < 0.4 * 0.4
+    rho = np.where(inside, 1.0, 0.125)
+    p = np.where(inside, 1.0, 0.1)
+    zero = np.zeros(shape)
+    return complete_from_prim(3, rho, [zero] * 3, p)
+
+
+def box_state(lo, hi, dx, origin, period, out=None):
+    """lattice_state built plane by plane to bound host memory."""
     shape = (7, hi[2] - lo[2] + 1, hi[1] - lo[1] + 1, hi[0] - lo[0] + 1)
     if out is None:
         out = np.empty(shape)
     for k in range(lo[2], hi[2] + 1):
-        out[:, k - lo[2]] = riemann_state(3, [lo[0], lo[1], k], [hi[0], hi[1], k], dx, origin)[:, 0]
+        out[:, k - lo[2]] = lattice_state([lo[0], lo[1], k], [hi[0], hi[1], k], dx, origin, period)[:, 0]
     return out
 
 
@@ -261,11 +284,13 @@ def cpu_reference_run(steps, warmup, size=REFERENCE_SIZE, budget_s=30.0):
 class Job:
     """One decomposition of the workload on the ranks of this run."""
 
-    def __init__(self, env, domain_n, boxes, parts, box_n, arithmetic):
+    def __init__(self, env, domain_n, boxes, parts, box_n, arithmetic, size, strong=False):
         capi, torch, dist = env["capi"], env["torch"], env["dist"]
         rank, world, local_rank = env["rank"], env["world"], env["local_rank"]
         self.env, self.domain_n, self.boxes, self.parts, self.box_n = env, domain_n, boxes, parts, box_n
-        self.dx, self.origin = geometry(domain_n)
+        self.dx, self.origin = geometry(domain_n, size)
+        # weak scaling: the sphere repeats with the box size along the cut directions
+        self.period = [0.0 if strong or parts[d] == 1 else 2.0 for d in range(3)]
         self.owner = list(range(len(boxes))) if world > 1 else [0] * len(boxes)
         self.arithmetic = arithmetic
         self.ctx = self.new_context()
@@ -298,7 +323,7 @@ class Job:
         for b in self.my_boxes:
             lo, hi, _ = self.ctx.state_box(b)
             t = torch.empty(self.ctx.state_shape(b), dtype=torch.float64, pin_memory=True)
-            box_state(lo, hi, self.dx, self.origin, out=t.numpy())
+            box_state(lo, hi, self.dx, self.origin, self.period, out=t.numpy())
             self.ctx.upload_state(b, t.numpy())
             if keep_host:
                 host[b] = t
@@ -358,7 +383,6 @@ class Job:
         device state bit for bit (the wide-halo cadence makes a box independent of its
         neighbours within one step: tests/test_gpu_fullsize.py)."""
         from oracle import oracle as orc
-        from helpers import riemann_state
         torch, dist = self.env["torch"], self.env["dist"]
         orc.build()
         orc.set_num_threads(min(host_cores(), 8))
@@ -377,7 +401,7 @@ class Job:
                         scratch_gcw=GCW[0], flux_gcw=GCW[1])
         lvl.set_method(orc.BASE_HLLEM_LARROUTUROU, orc.RECON_MUSCL_HANCOCK, orc.LIMITER_VANLEER)
         arr, slo, shi = lvl.scratch(0)
-        arr[...] = riemann_state(3, slo, shi, self.dx, self.origin)
+        arr[...] = lattice_state(slo, shi, self.dx, self.origin, self.period)
         ok, _, _ = lvl.advance_hierarchy(dt, orc.SPLIT_STRANG)
         g = GCW[0]
         ref = arr[(slice(None),) + (slice(g, -g),) * 3]
@@ -513,7 +537,10 @@ def main():
     workload = (f"3D spherical Riemann problem, PerfectGas gamma=1.4, "
                 f"MUSCL-Hancock<HLLEM-Larrouturou,VanLeer>, Strang split sweeps, "
                 f"{domain_n[0]}x{domain_n[1]}x{domain_n[2]} cells = {n_gpus} box(es) of "
-                f"{box_n[0]}x{box_n[1]}x{box_n[2]}, gcw {GCW[0]}/{GCW[1]}, transmissive, CFL {CFL}")
+                f"{box_n[0]}x{box_n[1]}x{box_n[2]}"
+                + (", the sphere repeated with the box size and centred on the box interfaces"
+                   if n_gpus > 1 and not strong else "")
+                + f", gcw {GCW[0]}/{GCW[1]}, transmissive, CFL {CFL}")
     config = {
         "workload": workload,
         "cells_per_gpu": box_n[0] * box_n[1] * box_n[2], "sweeps_per_step": SWEEPS_PER_STEP,
@@ -571,7 +598,7 @@ def main():
         "tolerance: reciprocal-multiply quotients + FMA contraction, within 1e-12 relative per "
         "step of the CPU oracle (tests/test_gpu_tolerance_arithmetic.py)")
 
-    job = Job(env, domain_n, boxes, parts, box_n, arith[args.arithmetic])
+    job = Job(env, domain_n, boxes, parts, box_n, arith[args.arithmetic], args.size, strong)
     host = job.fill(keep_host=True)
     my_boxes = job.my_boxes
     ctx = job.ctx
@@ -671,7 +698,7 @@ def main():
     strong_rec = None
     if not strong and n_gpus > 1 and not args.no_strong:
         sdom, sboxes, sparts, sbox_n = grid_of_boxes(n_gpus, args.size, True)
-        sjob = Job(env, sdom, sboxes, sparts, sbox_n, arith[args.arithmetic])
+        sjob = Job(env, sdom, sboxes, sparts, sbox_n, arith[args.arithmetic], args.size, True)
         sjob.fill()
         sparity = None
         if not args.no_parity_check and min(sbox_n) >= 64:

@@ -47,6 +47,27 @@ template <int D> FVS_DEV void prefetch_complete(const double* p, long long sc) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p + sc * c));
   }
 }
+// cp.async (LDGSTS) of the D + 4 component values of one cell into a lane-private
+// shared-memory column: the load of the NEXT chunk is in flight during a whole chunk of
+// arithmetic and costs no registers
+template <int D> FVS_DEV void stage_complete_async(double* smem_col, int stride, const double* p,
+                                                   long long sc) {
+#pragma unroll
+  for (int c = 0; c < D + 4; ++c) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_col + c * stride);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p + sc * c)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int D> FVS_DEV void staged_complete(Complete<D>& q, const double* smem_col, int stride) {
+  q.rho = smem_col[0];
+#pragma unroll
+  for (int d = 0; d < D; ++d) q.mom[d] = smem_col[(1 + d) * stride];
+  q.E = smem_col[(1 + D) * stride];
+  q.p = smem_col[(2 + D) * stride];
+  q.a = smem_col[(3 + D) * stride];
+}
 template <int D> FVS_DEV void store_complete(double* p, long long sc, const Complete<D>& q) {
   p[0] = q.rho;
 #pragma unroll
@@ -377,8 +398,16 @@ template <typename T> struct Slot<T, false> {
 
 // 0: none, 1: cell j+1 held in registers, 2: prefetch.global.L1 of cell
 // j + FVS_SWEEP_PREFETCH_DIST
+// 3 = cp.async staging of cell j + 1 through a thread-private shared-memory column (no
+// registers held across the step; measured best for the bit-exact arithmetic: 6.67 -> 6.47 ms
+// per 512^3 sweep together with the x kernel's staging), 1 = register prefetch (measured
+// best for the tolerance arithmetic), 2 = prefetch.global.L1
 #ifndef FVS_SWEEP_PREFETCH
+#ifdef FVS_TOLERANCE_UNIT
 #define FVS_SWEEP_PREFETCH 1
+#else
+#define FVS_SWEEP_PREFETCH 3
+#endif
 #endif
 #ifndef FVS_SWEEP_PREFETCH_DIST
 #define FVS_SWEEP_PREFETCH_DIST 1
@@ -396,6 +425,14 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
   __shared__ Slot<Cons<D>> s_F[kSweepThreads];      // flux through face j-2
   // eager stable dt (exact Riemann solver): dt data of cell j-1
   __shared__ Slot<DtData<D, BASE>> s_dt[kLazyDt<BASE> ? 1 : kSweepThreads];
+  // the eager stable dt (exact Riemann solver) needs the shared memory for its dt data
+  constexpr int kPrefetch = (FVS_SWEEP_PREFETCH == 3 && !kLazyDt<BASE>) ? 1 : FVS_SWEEP_PREFETCH;
+  constexpr bool kStaged = kPrefetch == 3;
+  // cell j+1, staged by cp.async while cell j is being worked on: [component][thread].  One
+  // buffer (static shared memory ends at 48 KB): the slot is thread-private, the thread has read
+  // cell j out of it (LDS, in program order through the same load/store unit) before it
+  // issues the copy of cell j+1, whose write happens a global-memory latency later
+  __shared__ double s_in[kStaged ? D + 4 : 1][kStaged ? kSweepThreads : 1];
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
   const long long nlines = (long long)n0 * ((DIR == 1) ? B.n[2] : B.n[1]);
@@ -424,18 +461,16 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
     const unsigned char* dtmask = B.dtmask;
 
     Complete<D> q0; // cell j
-#if FVS_SWEEP_PREFETCH == 1
-    Complete<D> qn; // prefetched cell j+1
-#endif
+    Complete<D> qn; // prefetched cell j+1 (kPrefetch == 1 only)
     DtData<D, BASE> dt_cur;
     SigBound sb_prev{0, 0}, sb_cur{0, 0};
     double thr = A.sig_hint * kLazyKeep;
     const int jstart = max(o_first - 2, 0);
     load_complete<D>(q0, src + stride * jstart, sc);
-#if FVS_SWEEP_PREFETCH == 1
-    qn = q0;
-    if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
-#endif
+    if constexpr (kPrefetch == 1) {
+      qn = q0;
+      if (jstart + 1 < nd) load_complete<D>(qn, src + stride * (jstart + 1), sc);
+    } // staged: the first pass of the loop stages cell jstart + 1
     {
       Cons<D> c0;
       copy_cons<D>(c0, q0);
@@ -468,11 +503,16 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 #pragma unroll 1
     for (int j = jstart; j <= jend; ++j) {
       if (j > jstart) {
-#if FVS_SWEEP_PREFETCH == 1
-        q0 = qn;
-#else
-        if (j < nd) load_complete<D>(q0, src + stride * j, sc);
-#endif
+        if constexpr (kPrefetch == 1) {
+          q0 = qn;
+        } else if constexpr (kStaged) {
+          if (j < nd) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            staged_complete<D>(q0, &s_in[0][tid], kSweepThreads);
+          }
+        } else {
+          if (j < nd) load_complete<D>(q0, src + stride * j, sc);
+        }
         if (j < nd) {
           if constexpr (kLazyDt<BASE>) {
             sb_prev = sb_cur;
@@ -482,13 +522,17 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
           }
         }
       }
-#if FVS_SWEEP_PREFETCH == 1
-      if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
-#elif FVS_SWEEP_PREFETCH == 2
-      if (j + FVS_SWEEP_PREFETCH_DIST < nd) {
-        prefetch_complete<D>(src + stride * (j + FVS_SWEEP_PREFETCH_DIST), sc);
+      if constexpr (kPrefetch == 1) {
+        if (j + 1 < nd) load_complete<D>(qn, src + stride * (j + 1), sc); // prefetch
+      } else if constexpr (kPrefetch == 2) {
+        if (j + FVS_SWEEP_PREFETCH_DIST < nd) {
+          prefetch_complete<D>(src + stride * (j + FVS_SWEEP_PREFETCH_DIST), sc);
+        }
+      } else if constexpr (kStaged) {
+        if (j + 1 < nd) {
+          stage_complete_async<D>(&s_in[0][tid], kSweepThreads, src + stride * (j + 1), sc);
+        }
       }
-#endif
       const int i1 = m3 == 0 ? 2 : m3 - 1;  // (j - 1) % 3
       const int i2 = i1 == 0 ? 2 : i1 - 1;  // (j - 2) % 3
       const int cr = j & 1;
@@ -602,8 +646,11 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 #ifndef FVS_SWEEP_XS_MIN_BLOCKS
 #define FVS_SWEEP_XS_MIN_BLOCKS 4
 #endif
+// 3 = the next chunk's cells staged by cp.async (hides the global-load latency that was
+// 12.6 % of the kernel's stall samples), 2 = held in registers one chunk ahead (tolerance
+// units, build.py), 1 = prefetch.global.L1
 #ifndef FVS_SWEEP_XS_PREFETCH
-#define FVS_SWEEP_XS_PREFETCH 1
+#define FVS_SWEEP_XS_PREFETCH 3
 #endif
 template <int D, int BASE, int RECON, int LIM>
 __global__ void __launch_bounds__(kSweepThreads, FVS_SWEEP_XS_MIN_BLOCKS)
@@ -616,6 +663,10 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
   __shared__ Slot<Cons<D>> s_F[kWarps][33];         // slot i + 1 <- flux of lane i (face c - 1)
   // eager stable dt (exact Riemann solver): slot i + 1 <- dt data of lane i's cell
   __shared__ Slot<DtData<D, BASE>> s_dt[kLazyDt<BASE> ? 1 : kWarps][kLazyDt<BASE> ? 1 : 33];
+#if FVS_SWEEP_XS_PREFETCH == 3
+  // next chunk's cells, staged by cp.async: [warp][buffer][component][lane]
+  __shared__ double s_in[kWarps][2][D + 4][32];
+#endif
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
   const long long nrows = (long long)B.n[1] * B.n[2];
@@ -644,6 +695,13 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     Complete<D> qn;
     load_complete<D>(qn, src + min(max(o_first - 2 + lane, 0), n0 - 1), sc);
 #endif
+#if FVS_SWEEP_XS_PREFETCH == 3
+    int stage_buf = 0;
+    stage_complete_async<D>(&s_in[warp][0][0][lane], 32,
+                            src + min(max(o_first - 2 + lane, 0), n0 - 1), sc);
+    // the stable-dt mask byte of the face (c-1 | c), fetched one chunk ahead as well
+    unsigned char mask_next = dtmask[min(max(o_first - 3 + lane, 0), n0 - 1)];
+#endif
     for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
       const int c = c0 + lane;
       const int cl = min(max(c, 0), n0 - 1);
@@ -653,6 +711,16 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       q0 = qn;
       (void)cl;
       if (c0 + 32 - 2 <= o_last) load_complete<D>(qn, src + min(c + 32, n0 - 1), sc);
+#elif FVS_SWEEP_XS_PREFETCH == 3
+      (void)cl;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      staged_complete<D>(q0, &s_in[warp][stage_buf][0][lane], 32);
+      const unsigned char mask_cur = mask_next;
+      if (c0 + 32 - 2 <= o_last) {
+        stage_buf ^= 1;
+        stage_complete_async<D>(&s_in[warp][stage_buf][0][lane], 32, src + min(c + 32, n0 - 1), sc);
+        mask_next = dtmask[min(max(c + 31, 0), n0 - 1)];
+      }
 #else
       load_complete<D>(q0, src + cl, sc);
 #endif
@@ -718,13 +786,23 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
         }
         carry_u = __shfl_sync(0xffffffffu, sb.u, 31);
         carry_c = __shfl_sync(0xffffffffu, sb.c, 31);
-        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+#if FVS_SWEEP_XS_PREFETCH == 3
+        const bool in_dt = mask_cur != 0;
+#else
+        const bool in_dt = c - 1 >= 0 && c < n0 && dtmask[c - 1];
+#endif
+        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && in_dt) {
           if (sig_bound_exceeds(lu, lc, sb.u, sb.c, thr)) {
             stage_dt_exact<D, DIR, BASE>(eq, src + (c - 1), src + c, sc, maxsig, thr, failed);
           }
         }
       } else {
-        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && dtmask[c - 1]) {
+#if FVS_SWEEP_XS_PREFETCH == 3
+        const bool in_dt = mask_cur != 0;
+#else
+        const bool in_dt = c - 1 >= 0 && c < n0 && dtmask[c - 1];
+#endif
+        if ((!first || lane >= 1) && c - 1 >= 0 && c < n0 && in_dt) {
           const double sgn = stage_dt_face<D, DIR, BASE>(eq, s_dt[warp][lane].v, dt_cur, failed);
           maxsig = sgn > maxsig ? sgn : maxsig;
         }
