@@ -1885,6 +1885,10 @@ int fvs_create(const fvs_config* config, fvs_ctx** out) {
     if (!config || !out) throw Error("null argument");
     if (config->rank < 1 || config->rank > 3) throw Error("rank must be 1, 2 or 3");
     if (!(config->gamma > 1.0)) throw Error("gamma must be > 1");
+    // 1 / (gamma - 1) is a windowed divisor of the branch-free divisions (fastmath.cuh, divw)
+    if (!(config->gamma - 1.0 >= 0x1p-60 && config->gamma <= 0x1p60)) {
+      throw Error("gamma - 1 must lie in [2^-60, 2^60]");
+    }
     if (fvs_device_count() == 0) {
       throw Error("no CUDA device: libfvs_b200 has no CPU fallback");
     }

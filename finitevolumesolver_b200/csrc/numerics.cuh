@@ -113,8 +113,8 @@ template <class M, int D>
 FVS_DEV void complete_from_cons(const EqM& eq, Complete<D>& q, const Rcp& rc, Flag& fl) {
   const double e_kin = M::divz(0.5 * squared_norm<D>(q.mom), rc, fl);
   const double e_int = q.E - e_kin;
-  q.p = M::div(e_int, eq.gm1_inv, fl);
-  q.a = M::sqrt(M::div(eq.gamma * q.p, rc, fl), fl);
+  q.p = M::divw(e_int, eq.gm1_inv, fl); // 2^-60 <= gamma - 1 <= 2^60, checked by the host
+  q.a = M::sqrt(M::divw(eq.gamma * q.p, rc, fl), fl);
 }
 
 // ---------------------------------------------------------------------------
@@ -175,7 +175,7 @@ FVS_DEV void complete_edge(const EqM& eq, Complete<D>& q, Rcp& rc, Flag& fl) {
   } else {
     const double e_kin = M::divz(0.5 * squared_norm<D>(q.mom), rc, fl);
     const double e_int = q.E - e_kin;
-    q.p = M::div(e_int, eq.gm1_inv, fl);
+    q.p = M::divw(e_int, eq.gm1_inv, fl);
     q.a = 0.0;
   }
 }
@@ -518,15 +518,15 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   const double rhoER = right.E;
   const double pL = left.p;
   const double pR = right.p;
-  const double hL = M::div(rhoEL + pL, rcL, fl);
-  const double hR = M::div(rhoER + pR, rcR, fl);
+  const double hL = M::divw(rhoEL + pL, rcL, fl);
+  const double hR = M::divw(rhoER + pR, rcR, fl);
   const double sqRhoL = M::sqrt(rhoL, fl);
   const double sqRhoR = M::sqrt(rhoR, fl);
   const double sqRhoSum = sqRhoL + sqRhoR;
   const Rcp rcSum = M::rcp(sqRhoSum);
-  M::check(rcSum, fl);
-  const double sqRhoL_over_Sum = M::div(sqRhoL, rcSum, fl);
-  const double sqRhoR_over_Sum = M::div(sqRhoR, rcSum, fl);
+  M::check_window(rcSum, fl);
+  const double sqRhoL_over_Sum = M::divw(sqRhoL, rcSum, fl);
+  const double sqRhoR_over_Sum = M::divw(sqRhoR, rcSum, fl);
   double roeU[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) {
@@ -548,7 +548,7 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   // (sqrt(rhoL) gamma + sqrt(rhoR) gamma) / (sqrt(rhoL) + sqrt(rhoR)) is gamma up to rounding
   double gm1;
   if constexpr (M::kExact) {
-    const double roeGamma = M::div(sqRhoL * eq.gamma + sqRhoR * eq.gamma, rcSum, fl);
+    const double roeGamma = M::divw(sqRhoL * eq.gamma + sqRhoR * eq.gamma, rcSum, fl);
     gm1 = roeGamma - 1.0;
   } else {
     gm1 = eq.gamma_minus_1;
@@ -586,7 +586,7 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
     } else {
       const double num =
           bR * fluxL.mom[d] - bL * fluxR.mom[d] + bLbR * (right.mom[d] - left.mom[d]);
-      hlle.mom[d] = d == DIR ? M::div(num, rcDb, fl) : M::divz(num, rcDb, fl);
+      hlle.mom[d] = d == DIR ? M::divw(num, rcDb, fl) : M::divz(num, rcDb, fl);
     }
   }
   hlle.E = M::divz(bR * fluxL.E - bL * fluxR.E + bLbR * (right.E - left.E), rcDb, fl);
@@ -594,14 +594,18 @@ FVS_DEV void hllem_flux(const EqM& eq, Cons<D>& flux, const Edge<D>& eL, const E
   // :813-823
   const double u_bar = 0.5 * (sR + sL);
   const double u_bar_abs = fabs(u_bar);
-  const double delta = M::div(roeA, roeA + u_bar_abs, fl);
+  const Rcp rcDelta = M::rcp(roeA + u_bar_abs);
+  M::check_window(rcDelta, fl);
+  const double delta = M::divw(roeA, rcDelta, fl);
   const double b = M::divz(bLbR, rcDb, fl);
   const double deltaRho = rhoR - rhoL;
   double deltaRhoU[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) deltaRhoU[i] = right.mom[i] - left.mom[i];
   const double deltaRhoE = rhoER - rhoEL;
-  const double gm1_over_roeA2 = M::div(gm1, roeA2, fl);
+  const Rcp rcA2 = M::rcp(roeA2);
+  M::check_window(rcA2, fl);
+  const double gm1_over_roeA2 = M::divw(gm1, rcA2, fl);
   const double l21 = gm1_over_roeA2 * (roeH - squaredNormRoeU);
 
   if constexpr (D == 1) {
@@ -1392,6 +1396,9 @@ FVS_DEV double base_max_signal(const Eqs& eq, const DtData<D, BASE>& left,
 #ifndef FVS_FASTMATH
 #define FVS_FASTMATH 1
 #endif
+#ifdef FVS_EXPERIMENT_NO_FALLBACK
+__device__ int g_experiment_sink;
+#endif
 template <typename F> FVS_DEV void with_fallback(F&& f) {
 #if FVS_FASTMATH
   Flag fl;
@@ -1400,14 +1407,30 @@ template <typename F> FVS_DEV void with_fallback(F&& f) {
 #else
   f(FastMath{}, fl);
 #endif
+#ifdef FVS_EXPERIMENT_NO_FALLBACK
+  // measurement only (tools/ab.sh): the tests are evaluated, the recompute is not compiled in
+  if (fl.any()) atomicAdd(&g_experiment_sink, 1);
+#else
   if (fl.any()) {
     Flag unused;
     f(SafeMath{}, unused);
   }
+#endif
 #else
   Flag unused;
   f(SafeMath{}, unused);
 #endif
 }
+
+// Fast path only, validity accumulated into the caller's flag (the fused y/z sweep tests it
+// once per line segment and redoes the segment with the checked stages if it is not clean).
+#if FVS_FASTMATH == 2
+using FastPolicy = ToleranceMath;
+#elif FVS_FASTMATH
+using FastPolicy = FastMath;
+#else
+using FastPolicy = SafeMath;
+#endif
+template <typename F> FVS_DEV void fast_only(F&& f, Flag& fl) { f(FastPolicy{}, fl); }
 
 } // namespace fvs

@@ -413,6 +413,81 @@ template <typename T> struct Slot<T, false> {
 #define FVS_SWEEP_PREFETCH_DIST 1
 #endif
 
+// Stages A, B, C of one steady step of the y/z march under the math policy MM:
+// predictor of cell j-1 (from cells j-2, j-1, j), flux through face j-1, update of cell j-2.
+template <class MM, int D, int DIR, int BASE, int RECON, int LIM, typename QT, typename Q0>
+FVS_DEV void steady_stages(const Eqs& eq, const QT& q2, const QT& q1, const Q0& q0,
+                           const Edge<D>& recR_prev, Edge<D>& recR_out, const Cons<D>& F_prev,
+                           Cons<D>& F, Complete<D>& out, double lambda, double lambda_half,
+                           Flag& fl, int& failed) {
+  Edge<D> recL;
+  {
+    Edge<D> recR;
+    if constexpr (RECON == kReconMusclHancock) {
+      muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, lambda_half, recL, recR, fl);
+    } else {
+      recL.q = q1;
+      recL.rc = MM::rcp(q1.rho);
+      recR = recL;
+    }
+    recR_out = recR;
+  }
+  FVS_STAGE_BARRIER();
+  base_flux<MM, D, DIR, BASE>(eq, F, recR_prev, recL, fl, failed);
+  FVS_STAGE_BARRIER();
+  out.rho = q2.rho + lambda * (F_prev.rho - F.rho);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    out.mom[d] = q2.mom[d] + lambda * (F_prev.mom[d] - F.mom[d]);
+  }
+  out.E = q2.E + lambda * (F_prev.E - F.E);
+  const Rcp rc = MM::rcp(out.rho);
+  MM::check_window(rc, fl);
+  complete_from_cons<MM, D>(eq.m, out, rc, fl);
+}
+
+// Mark and repair.  The y/z march never branches on the validity of its fast paths: a warp
+// that did would have to drain the longest dependency chain of the step (update -> 1 / rho ->
+// p -> a) before it could issue anything else, once per cell.  Instead every steady step stores
+// its results unconditionally and a step whose fast paths left their domain (vacuum, tiny or
+// denormal momenta, ...) is entered into a short per-thread list.  Such a step j can only have
+// spoiled
+//   the updated cell j-2, the flux through face j-1 (cells j-2, j-1) and the upper edge state of
+//   cell j-1 (flux through face j, cells j-1 and j),
+// everything later is computed from the cell states again -- the pipeline heals itself.  After
+// the march the listed steps have their cells j-2 .. j recomputed from global memory (`src` is
+// never written by the sweep) with the checked, unfused stage functions, out of line.  A list
+// that overflows turns into "everything from here on".  Returns the Newton failure flag of the
+// exact Riemann solver.
+constexpr int kMaxMarked = 24;
+template <int D, int DIR, int BASE, int RECON, int LIM>
+__device__ __noinline__ int repair_cells(EqConst eqc, const double* src, double* dst,
+                                         long long stride, long long sc, int nd, int c_lo,
+                                         int c_hi, double lambda, double lambda_half) {
+  const Eqs eq(eqc);
+  int failed = 0;
+#pragma unroll 1
+  for (int c = c_lo; c <= c_hi; ++c) {
+    Complete<D> q[5]; // cells c-2 .. c+2
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      load_complete<D>(q[k], src + stride * min(max(c - 2 + k, 0), nd - 1), sc);
+    }
+    Edge<D> eL[3], eR[3]; // edge states of cells c-1, c, c+1
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      stage_predict<D, DIR, RECON, LIM>(eq, q[k], q[k + 1], q[k + 2], lambda_half, eL[k], eR[k]);
+    }
+    Cons<D> Flo, Fhi;
+    stage_flux<D, DIR, BASE>(eq, Flo, eR[0], eL[1], failed);
+    stage_flux<D, DIR, BASE>(eq, Fhi, eR[1], eL[2], failed);
+    Complete<D> out;
+    stage_update<D>(eq, out, q[2], Flo, Fhi, lambda, true);
+    store_complete<D>(dst + stride * c, sc, out);
+  }
+  return failed;
+}
+
 template <int D, int DIR, int BASE, int RECON, int LIM>
 __global__ void FVS_SWEEP_BOUNDS
 fused_sweep_yz_smem_kernel(const SweepArgs A) {
@@ -500,6 +575,8 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
     const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
     const int je = min(min(uhi + 2, nd - 1), jend); // inclusive
     int m3 = jstart % 3; // j % 3
+    int marked[kMaxMarked]; // steady steps whose fast paths left their domain (local memory)
+    int n_marked = 0;
 #pragma unroll 1
     for (int j = jstart; j <= jend; ++j) {
       if (j > jstart) {
@@ -543,35 +620,22 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       Cons<D>& F_prev = s_F[tid].v;
       Edge<D> recL;
       Cons<D> F;
-      if (j >= js && j <= je) {
-        // steady state: stages A, B, C share one fast-path validity flag
+      const bool steady = j >= js && j <= je;
+      if (steady) {
+        // steady state: stages A, B, C, fast paths only; results are stored unconditionally and
+        // the step is marked if a fast path left its domain (repair_marked_steps)
         Complete<D> out;
-        with_fallback([&](auto M, Flag& fl) {
-          using MM = decltype(M);
-          {
-            Edge<D> recR;
-            if constexpr (RECON == kReconMusclHancock) {
-              muscl_predict<MM, D, DIR, LIM>(eq.m, q2, q1, q0, A.lambda_half, recL, recR, fl);
-            } else {
-              recL.q = q1;
-              recL.rc = MM::rcp(q1.rho);
-              recR = recL;
-            }
-            recR_out = recR;
-          }
-          FVS_STAGE_BARRIER();
-          base_flux<MM, D, DIR, BASE>(eq, F, recR_prev, recL, fl, failed);
-          FVS_STAGE_BARRIER();
-          out.rho = q2.rho + A.lambda * (F_prev.rho - F.rho);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            out.mom[d] = q2.mom[d] + A.lambda * (F_prev.mom[d] - F.mom[d]);
-          }
-          out.E = q2.E + A.lambda * (F_prev.E - F.E);
-          const Rcp rc = MM::rcp(out.rho);
-          MM::check_window(rc, fl);
-          complete_from_cons<MM, D>(eq.m, out, rc, fl);
-        });
+        Flag fl;
+        int newton = 0;
+        steady_stages<FastPolicy, D, DIR, BASE, RECON, LIM>(eq, q2, q1, q0, recR_prev, recR_out,
+                                                            F_prev, F, out, A.lambda,
+                                                            A.lambda_half, fl, newton);
+        const bool bad = FastPolicy::kFast && fl.any();
+        if (bad) {
+          if (n_marked < kMaxMarked) marked[n_marked] = j;
+          ++n_marked;
+        }
+        failed |= bad ? 0 : newton;
         store_complete<D>(dst + stride * (j - 2), sc, out);
       } else {
         // stage A: cell j-1
@@ -629,6 +693,22 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       if constexpr (!kLazyDt<BASE>) s_dt[tid].v = dt_cur;
       FVS_STAGE_BARRIER();
       m3 = m3 == 2 ? 0 : m3 + 1;
+    }
+    if (n_marked) {
+      const int c_max = min(uhi, o_last);
+      int next = 0; // first cell not yet repaired
+#pragma unroll 1
+      for (int i = 0; i < min(n_marked, kMaxMarked); ++i) {
+        const int jj = marked[i];
+        // the last entry of a list that overflowed stands for every later step
+        const int hi = (i == kMaxMarked - 1 && n_marked > kMaxMarked) ? c_max : min(jj, c_max);
+        const int lo = max(jj - 2, next);
+        if (lo <= hi) {
+          failed |= repair_cells<D, DIR, BASE, RECON, LIM>(A.eq, src, dst, stride, sc, nd, lo, hi,
+                                                           A.lambda, A.lambda_half);
+        }
+        next = max(next, hi + 1);
+      }
     }
   }
   reduce_max_signal(maxsig, A.max_signal);

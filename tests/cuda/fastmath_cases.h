@@ -140,6 +140,36 @@ FM_FN void run_cases(unsigned long long seed, int iters, Counters& c) {
         c.fl_divz++;
       }
     }
+    // division over a windowed divisor with only the quotient tested (divw), the
+    // two-argument form, and the `used` overloads (an unused operation never flags)
+    {
+      const double bw = fabs(b);
+      Flag f;
+      const Rcp rc = FastMath::rcp(bw);
+      FastMath::check_window(rc, f);
+      const double q = FastMath::divw(a, rc, f);
+      if (!f.any()) {
+        c.bad_div += !same_bits(q, a / bw);
+      } else {
+        c.fl_div++;
+      }
+      Flag g2;
+      const double q2 = FastMath::div(a, b, g2);
+      if (!g2.any()) c.bad_div += !same_bits(q2, a / b);
+      Flag g3;
+      const bool used = (it & 8) != 0;
+      const double q3 = FastMath::div(a, b, g3, used);
+      const double s3 = FastMath::sqrt(a2, g3, used);
+      const Rcp rc3 = FastMath::rcp(a2);
+      FastMath::check(rc3, g3, used);
+      const double q4 = FastMath::div(a, rc3, g3, used);
+      if (!used) {
+        c.bad_div += g3.any();
+      } else if (!g3.any()) {
+        c.bad_div += !same_bits(q3, a / b) + !same_bits(q4, a / a2);
+        c.bad_sqrt += !same_bits(s3, sqrt(a2));
+      }
+    }
     {
       Flag g;
       const double x = fabs(a);
