@@ -141,6 +141,24 @@ FVS_DEV void stage_predict(const Eqs& eq, const S0& qm, const S1& q0, const S2& 
     recR = recL;
   }
 }
+// the same under the math policy M with the caller's validity flag (mark and repair)
+template <class M, int D, int DIR, int RECON, int LIM, typename S0, typename S1, typename S2>
+FVS_DEV void predict_with(const Eqs& eq, const S0& qm, const S1& q0, const S2& qp,
+                          double lambda_half, Edge<D>& recL, Edge<D>& recR, Flag& fl) {
+  if constexpr (RECON == kReconMusclHancock) {
+    muscl_predict<M, D, DIR, LIM>(eq.m, qm, q0, qp, lambda_half, recL, recR, fl);
+  } else if constexpr (RECON == kReconMusclHancockPrim) {
+    muscl_prim_predict<M, D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
+  } else if constexpr (RECON == kReconMusclHancockChar) {
+    muscl_char_predict<M, D, DIR>(eq.m, qm, q0, qp, 2.0 * lambda_half, recL, recR, fl);
+  } else if constexpr (is_mh2(RECON)) {
+    mh2_predict<M, D, DIR, RECON>(eq.m, eq.c, qm, q0, qp, lambda_half, recL, recR, fl);
+  } else {
+    recL.q = q0;
+    recL.rc = M::rcp(q0.rho);
+    recR = recL;
+  }
+}
 // stage B: base flux through the face between two edge states
 template <int D, int DIR, int BASE>
 FVS_DEV void stage_flux(const Eqs& eq, Cons<D>& F, const Edge<D>& left, const Edge<D>& right,
@@ -463,7 +481,8 @@ constexpr int kMaxMarked = 24;
 template <int D, int DIR, int BASE, int RECON, int LIM>
 __device__ __noinline__ int repair_cells(EqConst eqc, const double* src, double* dst,
                                          long long stride, long long sc, int nd, int c_lo,
-                                         int c_hi, double lambda, double lambda_half) {
+                                         int c_hi, int ulo, int uhi, double lambda,
+                                         double lambda_half) {
   const Eqs eq(eqc);
   int failed = 0;
 #pragma unroll 1
@@ -482,7 +501,7 @@ __device__ __noinline__ int repair_cells(EqConst eqc, const double* src, double*
     stage_flux<D, DIR, BASE>(eq, Flo, eR[0], eL[1], failed);
     stage_flux<D, DIR, BASE>(eq, Fhi, eR[1], eL[2], failed);
     Complete<D> out;
-    stage_update<D>(eq, out, q[2], Flo, Fhi, lambda, true);
+    stage_update<D>(eq, out, q[2], Flo, Fhi, lambda, c >= ulo && c <= uhi);
     store_complete<D>(dst + stride * c, sc, out);
   }
   return failed;
@@ -705,7 +724,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
         const int lo = max(jj - 2, next);
         if (lo <= hi) {
           failed |= repair_cells<D, DIR, BASE, RECON, LIM>(A.eq, src, dst, stride, sc, nd, lo, hi,
-                                                           A.lambda, A.lambda_half);
+                                                           ulo, uhi, A.lambda, A.lambda_half);
         }
         next = max(next, hi + 1);
       }
@@ -723,8 +742,10 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 // lane i, slot 0 carries lane 31 of the previous 32-cell chunk (two carry slots
 // for the cell states): no shuffle / select carry logic, and -- as in the y/z
 // kernel -- a register budget of one stage instead of the whole pipeline.
+// 3 resident blocks (168 registers): with the three stages on one validity flag (mark and
+// repair) the kernel spills 112 B at 4 blocks / 128 registers (6.48 vs 6.45 ms mean sweep)
 #ifndef FVS_SWEEP_XS_MIN_BLOCKS
-#define FVS_SWEEP_XS_MIN_BLOCKS 4
+#define FVS_SWEEP_XS_MIN_BLOCKS 3
 #endif
 // 3 = the next chunk's cells staged by cp.async (hides the global-load latency that was
 // 12.6 % of the kernel's stall samples), 2 = held in registers one chunk ahead (tolerance
@@ -768,6 +789,8 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
+    int marked[kMaxMarked]; // this lane's cells whose fast paths left their domain
+    int n_marked = 0;
     double thr = A.sig_hint * kLazyKeep;
     int carry_u = 0, carry_c = 0; // signal bound of lane 31 of the previous chunk
 #if FVS_SWEEP_XS_PREFETCH == 2
@@ -832,19 +855,24 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
         }
       }
       __syncwarp();
+      // Stages A to C run the branch-free fast paths only and share one validity flag; a lane
+      // whose flag is not clean enters its cell into the repair list (mark and repair, see
+      // repair_cells: the spoiled cells are c-2 .. c here as well)
+      Flag fl;
+      int newton = 0;
       // ---- stage A: cell c-1 from cells c-2, c-1, c
       Edge<D> recL;
       {
         Edge<D> recR;
-        stage_predict<D, DIR, RECON, LIM>(eq, s_q[warp][lane].v, s_q[warp][lane + 1].v, q0,
-                                          A.lambda_half, recL, recR);
+        predict_with<FastPolicy, D, DIR, RECON, LIM>(eq, s_q[warp][lane].v, s_q[warp][lane + 1].v,
+                                                     q0, A.lambda_half, recL, recR, fl);
         s_rec[warp][lane + 1].v = recR;
         if (first && lane == 0) s_rec[warp][0].v = recR;
       }
       __syncwarp();
       // ---- stage B: face c-1 = (c-2 | c-1)
       Cons<D> F;
-      stage_flux<D, DIR, BASE>(eq, F, s_rec[warp][lane].v, recL, failed);
+      base_flux<FastPolicy, D, DIR, BASE>(eq, F, s_rec[warp][lane].v, recL, fl, newton);
       s_F[warp][lane + 1].v = F;
       if (first && lane == 0) s_F[warp][0].v = F;
       __syncwarp();
@@ -852,9 +880,31 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       const int o = c - 2;
       if ((!first || lane >= 4) && o >= o_first && o <= o_last) {
         Complete<D> out;
-        stage_update<D>(eq, out, s_q[warp][lane].v, s_F[warp][lane].v, F, A.lambda,
-                        o >= ulo && o <= uhi);
+        const QT& qo = s_q[warp][lane].v;
+        const Cons<D>& Fl = s_F[warp][lane].v;
+        if (o >= ulo && o <= uhi) {
+          out.rho = qo.rho + A.lambda * (Fl.rho - F.rho);
+#pragma unroll
+          for (int d = 0; d < D; ++d) out.mom[d] = qo.mom[d] + A.lambda * (Fl.mom[d] - F.mom[d]);
+          out.E = qo.E + A.lambda * (Fl.E - F.E);
+        } else {
+          out.rho = qo.rho;
+#pragma unroll
+          for (int d = 0; d < D; ++d) out.mom[d] = qo.mom[d];
+          out.E = qo.E;
+        }
+        const Rcp rc = FastPolicy::rcp(out.rho);
+        FastPolicy::check_window(rc, fl);
+        complete_from_cons<FastPolicy, D>(eq.m, out, rc, fl);
         store_complete<D>(dst + o, sc, out);
+      }
+      {
+        const bool bad = FastPolicy::kFast && fl.any();
+        if (bad) {
+          if (n_marked < kMaxMarked) marked[n_marked] = c;
+          ++n_marked;
+        }
+        failed |= bad ? 0 : newton;
       }
       // ---- stage D: face (c-1 | c) of the stored states
       if constexpr (kLazyDt<BASE>) {
@@ -897,6 +947,21 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       }
       __syncwarp();
       first = false;
+    }
+    if (n_marked) {
+      int next = o_first; // first cell not yet repaired
+#pragma unroll 1
+      for (int i = 0; i < min(n_marked, kMaxMarked); ++i) {
+        const int cc = marked[i];
+        // the last entry of a list that overflowed stands for every later cell of the segment
+        const int hi = (i == kMaxMarked - 1 && n_marked > kMaxMarked) ? o_last : min(cc, o_last);
+        const int lo = max(cc - 2, next);
+        if (lo <= hi) {
+          failed |= repair_cells<D, DIR, BASE, RECON, LIM>(A.eq, src, dst, 1, sc, n0, lo, hi, ulo,
+                                                           uhi, A.lambda, A.lambda_half);
+        }
+        next = max(next, hi + 1);
+      }
     }
   }
   reduce_max_signal(maxsig, A.max_signal);
