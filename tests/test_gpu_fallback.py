@@ -113,3 +113,31 @@ def test_fused_sweeps_bitwise_on_states_outside_the_fast_path_domain(oracle, fvs
             has_nan = bool(np.isnan(pair.cpu.scratch(0)[0]).any())
             compare(pair, f"{kind}, direction {d}")
     pair.close()
+
+
+@pytest.mark.parametrize("rank,n", [(2, (900, 6)), (2, (6, 300))])
+@pytest.mark.parametrize("kind", ["tiny_everything", "tiny_momentum"])
+def test_repair_list_overflow(oracle, fvs, rank, n, kind):
+    """More marked steps per thread than the repair list holds (24): with every cell outside
+    the fast-path domain a lane of the x sweep marks one cell per 32-cell chunk of its row
+    (900 cells: 29 chunks) and a thread of the y sweep every step of its line (300 cells);
+    the overflowing list must turn into `every later cell`."""
+    pair, dx = make_pair(oracle, fvs, rank, n)
+    pair.gpu.set_dt_hints(0)
+
+    def fill(l, h):
+        out = extreme_state(rank, dx, "tiny_everything", seed=3)(l, h)
+        if kind == "tiny_momentum":
+            out = extreme_state(rank, dx, "at_rest", seed=3)(l, h)
+            out[1] = np.where((np.indices(out[1].shape).sum(axis=0) % 2) == 0, 3e-300, -2e-295)
+        return out
+
+    pair.fill(fill)
+    with np.errstate(all="ignore"):
+        for d in range(rank):
+            dt_ref = pair.cpu.compute_stable_dt(d)
+            pair.cpu.sweep(0.3 * dt_ref, d)
+            rc, level_dt = pair.gpu.sweep(0.3 * dt_ref, d)
+            assert rc == fvs.OK and level_dt == dt_ref, (kind, d, rc, level_dt, dt_ref)
+            compare(pair, f"{kind}, direction {d}")
+    pair.close()
