@@ -249,6 +249,15 @@ struct Level {
   std::map<std::tuple<int, int>, std::unique_ptr<DeviceArray<fvs::BcDesc>>> bc_cache;
   std::map<std::tuple<int, int, int>, std::unique_ptr<DeviceArray<fvs::PackDesc>>> pack_cache;
   long long max_copy_cells{0};
+  // halo exchange over peer memory (p2p_*, below): the peers' state arrays of buffer b, opened
+  // through CUDA IPC (indexed by global box, nullptr where not needed), and the region copies
+  // from this rank's boxes straight into them
+  std::vector<double*> remote_buf[kNumBuffers];
+  bool have_remote[kNumBuffers]{false, false, false};
+  std::map<int, std::unique_ptr<DeviceArray<fvs::CopyDesc>>> p2p_cache;
+  int p2p_count{0};
+  long long p2p_max_cells{0};
+  bool halo_crosses_ranks{false}; // some halo copy of the level has its ends on different ranks
   // coarse-fine: the flux register this level holds towards its coarser level
   struct CfRegister {
     int patch, dir, side;
@@ -307,6 +316,10 @@ struct fvs_ctx {
   long sweep_count{0};
   // comm
   Nccl::comm_t comm{nullptr};
+  // 1: halo exchange by direct stores into the peers' ghost cells (CUDA IPC + NVLink,
+  // FVS_HALO_P2P=1), 0 (default): pack -> grouped ncclSend / ncclRecv -> unpack
+  int halo_p2p{-1};
+  int* d_barrier{nullptr};
   // descriptor staging: a mapped pinned ring the kernels read their descriptor
   // arrays from directly, so building one costs a memcpy on the host and no
   // transfer or synchronisation; rewound whenever the stream is known to be idle
@@ -340,6 +353,12 @@ struct fvs_ctx {
 namespace {
 
 void free_level(Level& L) {
+  for (int b = 0; b < kNumBuffers; ++b) {
+    for (double* q : L.remote_buf[b])
+      if (q) cudaIpcCloseMemHandle(q);
+    L.remote_buf[b].clear();
+    L.have_remote[b] = false;
+  }
   for (Patch& p : L.patches) {
     for (int b = 0; b < kNumBuffers; ++b)
       if (p.buf[b]) cudaFree(p.buf[b]);
@@ -830,10 +849,188 @@ struct HaloTrace {
   }
 };
 
+// ---- halo exchange over peer memory -------------------------------------------------------
+// One process per GPU, every GPU of the node reaches every other through NVLink / NVSwitch: a
+// rank can store its boundary cells straight into the ghost cells of its neighbours' state
+// arrays.  The arrays are plain cudaMalloc allocations, exported with cudaIpcGetMemHandle; the
+// handles of buffer b travel once per level configuration in one all-reduce (every rank fills
+// the slots of its own boxes, the rest is zero).  An exchange is then
+//   barrier (every rank has finished the kernels that write its state / read its old ghosts)
+//   ONE copy_regions launch: this rank's send regions -> the peers' arrays
+//   barrier (the neighbours' stores into this rank's ghost cells have landed)
+// where a barrier is a one-word ncclAllReduce on the stream: no pack / unpack kernels, no
+// staging buffers, no second pass over the halo through NCCL's FIFOs.
+bool p2p_enabled(fvs_ctx* ctx) {
+  if (ctx->halo_p2p < 0) {
+    // opt-in: with the general region-copy kernel the direct stores move a 125 MB face in
+    // 1.9 ms, NCCL's pipelined send / recv in 0.4 ms (profiles/r02_tuning.md) -- the path is
+    // kept bit-identical and tested (tests/test_gpu_multirank.py) for a wide, vectorised
+    // copy kernel to take over
+    const char* e = std::getenv("FVS_HALO_P2P");
+    ctx->halo_p2p = (e && e[0] == '1') ? 1 : 0;
+  }
+  return ctx->halo_p2p == 1;
+}
+
+void stream_barrier(fvs_ctx* ctx) {
+  Nccl& n = Nccl::get();
+  if (!ctx->d_barrier) {
+    FVS_CUDA(cudaMalloc(&ctx->d_barrier, sizeof(int)));
+    FVS_CUDA(cudaMemset(ctx->d_barrier, 0, sizeof(int)));
+  }
+  n.check(n.AllReduce(ctx->d_barrier, ctx->d_barrier, 1, 2 /* ncclInt32 */, Nccl::kMax, ctx->comm,
+                      ctx->stream),
+          "ncclAllReduce(barrier)");
+}
+
+// Collective over the communicator: opens the peers' arrays of buffer `buf` that this rank
+// sends to.  Returns false (on every rank alike) if any rank could not open a handle; the
+// caller then falls back to the NCCL exchange for good.
+bool p2p_open(fvs_ctx* ctx, Level& L, int buf) {
+  if (L.have_remote[buf]) return true;
+  Nccl& n = Nccl::get();
+  const int nb = (int)L.boxes.size();
+  constexpr int kWords = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(int));
+  // last words: failures, and the buffer index (the ranks march in lockstep: all of them are
+  // about to exchange the same buffer)
+  std::vector<int> table((size_t)nb * kWords + 2, 0);
+  table[(size_t)nb * kWords + 1] = buf;
+  for (Patch& p : L.patches) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p.buf[buf]) != cudaSuccess) {
+      cudaGetLastError();
+      table[(size_t)nb * kWords] = 1;
+      continue;
+    }
+    std::memcpy(&table[(size_t)p.global_index * kWords], &h, sizeof(h));
+  }
+  int* dev = nullptr;
+  FVS_CUDA(cudaMalloc(&dev, table.size() * sizeof(int)));
+  FVS_CUDA(cudaMemcpyAsync(dev, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  n.check(n.AllReduce(dev, dev, table.size(), 2 /* ncclInt32 */, 0 /* ncclSum */, ctx->comm,
+                      ctx->stream),
+          "ncclAllReduce(ipc handles)");
+  FVS_CUDA(cudaMemcpyAsync(table.data(), dev, table.size() * sizeof(int), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int failures = table[(size_t)nb * kWords];
+  if (table[(size_t)nb * kWords + 1] != buf * ctx->cfg.comm_size) failures = 1;
+  L.remote_buf[buf].assign(nb, nullptr);
+  if (failures == 0) {
+    for (PeerExchange& pe : L.peers) {
+      for (const fvs::HaloCopy& c : pe.sends) {
+        if (L.remote_buf[buf][c.dst_box]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, &table[(size_t)c.dst_box * kWords], sizeof(h));
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          failures = 1;
+          break;
+        }
+        L.remote_buf[buf][c.dst_box] = (double*)q;
+      }
+      if (failures) break;
+    }
+  }
+  // the decision must be the same everywhere
+  FVS_CUDA(cudaMemcpyAsync(dev, &failures, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  n.check(n.AllReduce(dev, dev, 1, 2 /* ncclInt32 */, Nccl::kMax, ctx->comm, ctx->stream),
+          "ncclAllReduce(ipc status)");
+  FVS_CUDA(cudaMemcpyAsync(&failures, dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dev);
+  if (failures) {
+    for (double*& q : L.remote_buf[buf]) {
+      if (q) cudaIpcCloseMemHandle(q);
+      q = nullptr;
+    }
+    return false;
+  }
+  L.have_remote[buf] = true;
+  return true;
+}
+
+const fvs::CopyDesc* p2p_descs(fvs_ctx* ctx, Level& L, int buf) {
+  auto it = L.p2p_cache.find(buf);
+  if (it != L.p2p_cache.end()) return it->second->ptr;
+  std::vector<fvs::CopyDesc> host;
+  L.p2p_max_cells = 0;
+  for (PeerExchange& pe : L.peers) {
+    for (const fvs::HaloCopy& c : pe.sends) {
+      Patch& sp = ctx->patch(L, c.src_box);
+      const Box dbox = fvs::state_box(L.boxes[c.dst_box], L.rank, L.scratch_gcw);
+      fvs::CopyDesc d{};
+      d.src = sp.buf[buf];
+      d.dst = L.remote_buf[buf][c.dst_box];
+      for (int e = 0; e < 3; ++e) {
+        d.sn[e] = sp.n[e];
+        d.dn[e] = dbox.len(e);
+        d.dlo[e] = c.region.lo[e] - dbox.lo[e];
+        d.slo[e] = c.region.lo[e] - c.shift[e] - sp.sbox.lo[e];
+        d.len[e] = c.region.len(e);
+      }
+      d.ssc = sp.cells;
+      d.dsc = dbox.size();
+      L.p2p_max_cells = std::max(L.p2p_max_cells, c.region.size());
+      host.push_back(d);
+    }
+  }
+  L.p2p_count = (int)host.size();
+  auto arr = std::make_unique<DeviceArray<fvs::CopyDesc>>();
+  arr->upload(host);
+  const fvs::CopyDesc* ptr = arr->ptr;
+  L.p2p_cache[buf] = std::move(arr);
+  return ptr;
+}
+
+// Collective: closes the peers' arrays and waits until every rank has done so -- an exported
+// allocation must not be freed while a peer still has it open.
+void p2p_release(fvs_ctx* ctx, Level& L) {
+  bool any = false;
+  for (int b = 0; b < kNumBuffers; ++b) {
+    any = any || L.have_remote[b];
+    for (double* q : L.remote_buf[b])
+      if (q) cudaIpcCloseMemHandle(q);
+    L.remote_buf[b].clear();
+    L.have_remote[b] = false;
+  }
+  L.p2p_cache.clear();
+  if (any && ctx->comm) {
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    stream_barrier(ctx);
+    FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+}
+
 void fill_boundary(fvs_ctx* ctx, Level& L) {
   static thread_local HaloTrace trace;
   const int buf = L.cur;
   trace.mark(0, ctx->stream);
+  // every rank of the communicator takes part (the barriers are collectives), also one whose
+  // own boxes have no remote neighbour
+  if (L.halo_crosses_ranks && ctx->comm && p2p_enabled(ctx)) {
+    if (!p2p_open(ctx, L, buf)) {
+      ctx->halo_p2p = 0; // on every rank alike
+    } else {
+      const fvs::CopyDesc* rd = p2p_descs(ctx, L, buf);
+      stream_barrier(ctx);
+      trace.mark(1, ctx->stream);
+      ctx->launches +=
+          fvs::launch_copy_regions(rd, L.p2p_count, ctx->ncomp(), L.p2p_max_cells, ctx->stream);
+      stream_barrier(ctx);
+      trace.mark(2, ctx->stream);
+      int count;
+      const fvs::CopyDesc* descs = copy_descs(ctx, L, buf, &count);
+      ctx->launches +=
+          fvs::launch_copy_regions(descs, count, ctx->ncomp(), L.max_copy_cells, ctx->stream);
+      check_last("launch check #3 (peer-memory halo)");
+      trace.mark(3, ctx->stream);
+      trace.done(ctx->stream, ctx->cfg.comm_rank);
+      return;
+    }
+  }
   // remote part first so that the transfers overlap the local copies
   if (!L.peers.empty()) {
     if (!ctx->comm) throw Error("level has boxes on other ranks but fvs_comm_init was not called");
@@ -1940,7 +2137,13 @@ void fvs_destroy(fvs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (Level& L : ctx->levels) free_level(L);
+  for (Level& L : ctx->levels) {
+    try {
+      p2p_release(ctx, L);
+    } catch (...) {
+    }
+    free_level(L);
+  }
   for (auto& ev : ctx->pending_events) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
@@ -1953,6 +2156,7 @@ void fvs_destroy(fvs_ctx* ctx) {
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
   if (ctx->d_fail) cudaFree(ctx->d_fail);
+  if (ctx->d_barrier) cudaFree(ctx->d_barrier);
   if (ctx->h_fail) cudaFreeHost(ctx->h_fail);
   if (ctx->ring) cudaFreeHost(ctx->ring);
   for (unsigned char* r : ctx->ring_retired) cudaFreeHost(r);
@@ -2081,6 +2285,9 @@ void define_level(fvs_ctx* ctx, Level& L, const Box& domain, const double dx[3],
     if (so == me && dow == me) {
       L.local_copies.push_back(c);
       L.max_copy_cells = std::max(L.max_copy_cells, c.region.size());
+    }
+    if (so != dow) L.halo_crosses_ranks = true; // the same on every rank (global plan)
+    if (so == me && dow == me) {
     } else if (so == me) {
       PeerExchange& pe = peers[dow];
       pe.peer = dow;
@@ -2118,6 +2325,7 @@ int fvs_level_define(fvs_ctx* ctx, int level, const int domain_lo[3], const int 
     ctx->use_device();
     if ((int)ctx->levels.size() <= level) ctx->levels.resize(level + 1);
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
+    p2p_release(ctx, ctx->levels[level]);
     free_level(ctx->levels[level]);
     std::vector<Box> boxes(nboxes);
     for (int b = 0; b < nboxes; ++b) boxes[b] = fvs::make_box(box_lo[b], box_hi[b]);
@@ -2149,7 +2357,10 @@ int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3]
     FVS_CUDA(cudaStreamSynchronize(ctx->stream));
     coarse.plane_cache.clear(); // its CrseInit planes follow the boxes of this level (stream idle)
     if (nboxes == 0) { // GriddingAlgorithm::ClearLevel: the level and everything finer goes
-      for (int l = level; l < (int)ctx->levels.size(); ++l) free_level(ctx->levels[l]);
+      for (int l = level; l < (int)ctx->levels.size(); ++l) {
+        p2p_release(ctx, ctx->levels[l]);
+        free_level(ctx->levels[l]);
+      }
       return (int)FVS_OK;
     }
     int ratio[3];
@@ -2184,6 +2395,7 @@ int fvs_regrid_level(fvs_ctx* ctx, int level, int nboxes, const int (*box_lo)[3]
       free_level(old);
       throw;
     }
+    p2p_release(ctx, old);
     free_level(old);
     // the register of a finer level refers to this level's boxes only through the
     // coarse index space: it stays valid; this level's own register is rebuilt by

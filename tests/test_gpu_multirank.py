@@ -28,14 +28,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_multirank_halo_dt_amr_eb_bitwise(nranks):
+@pytest.mark.parametrize("nranks,halo", [(2, "nccl"), (2, "p2p"), (4, "nccl"), (8, "nccl")])
+def test_multirank_halo_dt_amr_eb_bitwise(nranks, halo):
+    """halo = p2p: the opt-in exchange by direct stores into the peers' ghost cells (CUDA IPC over
+    NVLink, FVS_HALO_P2P=1) must give the same bits."""
     n = _gpus()
     if n < nranks:
         pytest.skip(f"needs {nranks} GPUs, this box has {n}")
+    env = dict(os.environ, FVS_HALO_P2P="1" if halo == "p2p" else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1", "--master-port",
            str(_free_port()), os.path.join(ROOT, "tests", "multigpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"multigpu_check ok: {nranks} ranks" in r.stdout, r.stdout[-2000:]
