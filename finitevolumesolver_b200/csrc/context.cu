@@ -862,10 +862,11 @@ struct HaloTrace {
 // staging buffers, no second pass over the halo through NCCL's FIFOs.
 bool p2p_enabled(fvs_ctx* ctx) {
   if (ctx->halo_p2p < 0) {
-    // opt-in: with the general region-copy kernel the direct stores move a 125 MB face in
-    // 1.9 ms, NCCL's pipelined send / recv in 0.4 ms (profiles/r02_tuning.md) -- the path is
-    // kept bit-identical and tested (tests/test_gpu_multirank.py) for a wide, vectorised
-    // copy kernel to take over
+    // opt-in: on the measured boxes SM stores through the cudaIpc peer mapping run at about
+    // 60 GB/s (a 125 MB face in 2 ms, whatever the copy kernel does) where NCCL's own peer
+    // mappings reach 312 GB/s (0.4 ms), profiles/r02_tuning.md -- the path is kept
+    // bit-identical and tested (tests/test_gpu_multirank.py) for nodes where peer stores run
+    // at NVLink speed
     const char* e = std::getenv("FVS_HALO_P2P");
     ctx->halo_p2p = (e && e[0] == '1') ? 1 : 0;
   }
@@ -1017,8 +1018,8 @@ void fill_boundary(fvs_ctx* ctx, Level& L) {
       const fvs::CopyDesc* rd = p2p_descs(ctx, L, buf);
       stream_barrier(ctx);
       trace.mark(1, ctx->stream);
-      ctx->launches +=
-          fvs::launch_copy_regions(rd, L.p2p_count, ctx->ncomp(), L.p2p_max_cells, ctx->stream);
+      ctx->launches += fvs::launch_copy_regions_wide(rd, L.p2p_count, ctx->ncomp(),
+                                                     L.p2p_max_cells, ctx->stream);
       stream_barrier(ctx);
       trace.mark(2, ctx->stream);
       int count;

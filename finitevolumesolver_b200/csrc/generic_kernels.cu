@@ -158,6 +158,59 @@ __global__ void __launch_bounds__(256) copy_regions_kernel(const CopyDesc* regio
   }
 }
 
+// The same copy for destinations in a PEER's memory (halo exchange by direct stores over
+// NVLink): remote stores are fire-and-forget, what limits them is how many bytes a thread has
+// in flight.  Every thread moves four independent 16-byte pieces per round (all loads first,
+// then all stores), components and rows flattened into one index so that also an 8-cell wide
+// x slab (64-byte runs) keeps every lane busy.  Falls back to 8-byte pieces where the rows are
+// not 16-byte aligned.
+template <typename V> __device__ __forceinline__ void copy_wide(const CopyDesc& R, int ncomp) {
+  constexpr int W = (int)(sizeof(V) / sizeof(double));
+  const unsigned lx = (unsigned)R.len[0] / W;
+  const unsigned ly = (unsigned)R.len[1];
+  const unsigned per_comp = lx * ly * (unsigned)R.len[2];
+  const unsigned total = per_comp * (unsigned)ncomp;
+  const unsigned nthreads = gridDim.x * blockDim.x;
+  for (unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += 4 * nthreads) {
+    V v[4];
+    long long d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned t = t0 + u * nthreads;
+      d[u] = -1;
+      if (t < total) {
+        const unsigned c = t / per_comp;
+        const unsigned r = t - c * per_comp;
+        const unsigned row = r / lx;
+        const unsigned i = (r - row * lx) * W;
+        const unsigned k = row / ly;
+        const unsigned j = row - k * ly;
+        const long long s = (R.slo[0] + i) + (long long)R.sn[0] * ((R.slo[1] + j) +
+                                                                   (long long)R.sn[1] * (R.slo[2] + k));
+        d[u] = (R.dlo[0] + i) +
+               (long long)R.dn[0] * ((R.dlo[1] + j) + (long long)R.dn[1] * (R.dlo[2] + k)) +
+               R.dsc * c;
+        v[u] = __ldg(reinterpret_cast<const V*>(R.src + s + R.ssc * c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (d[u] >= 0) *reinterpret_cast<V*>(R.dst + d[u]) = v[u];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) copy_regions_wide_kernel(const CopyDesc* regions, int ncomp) {
+  const CopyDesc& R = regions[blockIdx.y];
+  const bool even = (((R.len[0] | R.slo[0] | R.dlo[0] | R.sn[0] | R.dn[0]) & 1) == 0) &&
+                    ((R.ssc | R.dsc) & 1) == 0 &&
+                    ((((unsigned long long)R.src) | ((unsigned long long)R.dst)) & 15) == 0;
+  if (even) {
+    copy_wide<double2>(R, ncomp);
+  } else {
+    copy_wide<double>(R, ncomp);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pack_kernel(const PackDesc* regions, int ncomp, double* buffer, int unpack) {
   const PackDesc& R = regions[blockIdx.y];
@@ -241,6 +294,19 @@ int launch_copy_regions(const CopyDesc* regions, int nregions, int ncomp, long l
   for (int r0 = 0; r0 < nregions; r0 += 65535) {
     dim3 grid(gx, (unsigned)min(nregions - r0, 65535), 1);
     copy_regions_kernel<<<grid, 256, 0, s>>>(regions + r0, ncomp);
+  }
+  return (nregions + 65534) / 65535;
+}
+
+int launch_copy_regions_wide(const CopyDesc* regions, int nregions, int ncomp, long long max_cells,
+                             cudaStream_t s) {
+  if (nregions <= 0) return 0;
+  // enough threads for four 16-byte pieces each, at most 8 blocks per SM of a B200
+  const long long pieces = (max_cells * ncomp + 1) / 2;
+  const unsigned gx = (unsigned)min((long long)cdiv(pieces, 256 * 4), 148LL * 8);
+  for (int r0 = 0; r0 < nregions; r0 += 65535) {
+    dim3 grid(max(gx, 1u), (unsigned)min(nregions - r0, 65535), 1);
+    copy_regions_wide_kernel<<<grid, 256, 0, s>>>(regions + r0, ncomp);
   }
   return (nregions + 65534) / 65535;
 }

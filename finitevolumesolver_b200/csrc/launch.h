@@ -190,6 +190,9 @@ struct CopyDesc {
 };
 int launch_copy_regions(const CopyDesc* regions, int nregions, int ncomp, long long max_cells,
                         cudaStream_t);
+// destinations in a peer's memory: 16-byte pieces, four in flight per thread
+int launch_copy_regions_wide(const CopyDesc* regions, int nregions, int ncomp, long long max_cells,
+                             cudaStream_t);
 // pack / unpack of regions to / from a contiguous buffer (multi-GPU halo)
 struct PackDesc {
   double* array; // state array
