@@ -768,7 +768,6 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
   // next chunk's cells, staged by cp.async: [warp][buffer][component][lane]
   __shared__ double s_in[kWarps][2][D + 4][32];
 #endif
-  __shared__ int s_marked[kMaxMarked][kSweepThreads]; // repair lists, [entry][thread]
   const BoxDesc& B = A.boxes[blockIdx.y];
   const int n0 = B.n[0];
   const long long nrows = (long long)B.n[1] * B.n[2];
@@ -790,7 +789,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
-    int* marked = &s_marked[0][threadIdx.x]; // this lane's cells whose fast paths left their domain
+    int marked[kMaxMarked]; // this lane's cells whose fast paths left their domain
     int n_marked = 0;
     double thr = A.sig_hint * kLazyKeep;
     int carry_u = 0, carry_c = 0; // signal bound of lane 31 of the previous chunk
@@ -902,7 +901,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       {
         const bool bad = FastPolicy::kFast && fl.any();
         if (bad) {
-          if (n_marked < kMaxMarked) marked[n_marked * kSweepThreads] = c;
+          if (n_marked < kMaxMarked) marked[n_marked] = c;
           ++n_marked;
         }
         failed |= bad ? 0 : newton;
@@ -953,7 +952,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       int next = o_first; // first cell not yet repaired
 #pragma unroll 1
       for (int i = 0; i < min(n_marked, kMaxMarked); ++i) {
-        const int cc = marked[i * kSweepThreads];
+        const int cc = marked[i];
         // the last entry of a list that overflowed stands for every later cell of the segment
         const int hi = (i == kMaxMarked - 1 && n_marked > kMaxMarked) ? o_last : min(cc, o_last);
         const int lo = max(cc - 2, next);
