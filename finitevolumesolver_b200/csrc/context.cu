@@ -114,6 +114,7 @@ using fvs::Box;
 using fvs::BoxDesc;
 
 constexpr int kNumBuffers = 3;
+constexpr unsigned kRepairCap = 1u << 18; // repair entries per sweep before "every cell" (6 MB)
 constexpr int kDtSlots = 64;
 
 // Embedded-boundary data of one box (fvs_level_set_eb); CutCellData of
@@ -320,6 +321,10 @@ struct fvs_ctx {
   // FVS_HALO_P2P=1), 0 (default): pack -> grouped ncclSend / ncclRecv -> unpack
   int halo_p2p{-1};
   int* d_barrier{nullptr};
+  // mark and repair (SweepArgs::repair_*)
+  fvs::RepairEntry* d_repair{nullptr};
+  unsigned* d_repair_count{nullptr};
+  unsigned repair_cap{kRepairCap}; // FVS_REPAIR_CAP overrides (tests of the overflow path)
   // descriptor staging: a mapped pinned ring the kernels read their descriptor
   // arrays from directly, so building one costs a memcpy on the host and no
   // transfer or synchronisation; rewound whenever the stream is known to be idle
@@ -552,6 +557,17 @@ fvs::SweepArgs sweep_args(fvs_ctx* ctx, Level& L, int dir, double dt, const BoxD
   A.max_signal = ctx->d_slots + std::max(slot, 0);
   A.fail_flag = ctx->d_fail + (slot >= 0 ? slot : kDtSlots);
   A.sig_hint = hint;
+  if (!ctx->d_repair) {
+    if (const char* e = std::getenv("FVS_REPAIR_CAP")) {
+      ctx->repair_cap = (unsigned)std::max(1L, std::atol(e));
+    }
+    FVS_CUDA(cudaMalloc(&ctx->d_repair, sizeof(fvs::RepairEntry) * ctx->repair_cap));
+    FVS_CUDA(cudaMalloc(&ctx->d_repair_count, 2 * sizeof(unsigned)));
+    FVS_CUDA(cudaMemsetAsync(ctx->d_repair_count, 0, 2 * sizeof(unsigned), ctx->stream));
+  }
+  A.repair_list = ctx->d_repair;
+  A.repair_count = ctx->d_repair_count;
+  A.repair_cap = ctx->repair_cap;
   return A;
 }
 
@@ -2158,6 +2174,8 @@ void fvs_destroy(fvs_ctx* ctx) {
   if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
   if (ctx->d_fail) cudaFree(ctx->d_fail);
   if (ctx->d_barrier) cudaFree(ctx->d_barrier);
+  if (ctx->d_repair) cudaFree(ctx->d_repair);
+  if (ctx->d_repair_count) cudaFree(ctx->d_repair_count);
   if (ctx->h_fail) cudaFreeHost(ctx->h_fail);
   if (ctx->ring) cudaFreeHost(ctx->ring);
   for (unsigned char* r : ctx->ring_retired) cudaFreeHost(r);

@@ -29,6 +29,15 @@ struct BoxDesc {
   int fab_type;        // -1 covered, 0 regular, 1 single valued
 };
 
+// A step of a fused sweep whose branch-free fast paths left their domain: cells lo..hi of the
+// grid line that starts at element offset `line` of box `box` are recomputed by the repair
+// pass that follows the sweep (sweep_kernels.cuh, "Mark and repair").
+struct RepairEntry {
+  long long line;
+  int box;
+  int lo, hi;
+};
+
 struct SweepArgs {
   EqConst eq;
   double lambda;      // dt / dx
@@ -44,6 +53,11 @@ struct SweepArgs {
   // below it are not evaluated.  The caller MUST verify result >= sig_hint
   // afterwards and repeat with 0 otherwise.  0 = no hint.
   double sig_hint;
+  // mark and repair: list of the steps to recompute, its length ([0]; [1] counts the blocks of
+  // the repair pass that are done) and its capacity -- a longer list means "every cell"
+  RepairEntry* repair_list;
+  unsigned* repair_count;
+  unsigned repair_cap;
 };
 
 struct MethodKey {

@@ -47,6 +47,8 @@ int fused(const SweepArgs& A, cudaStream_t s) {
     const int nseg = (A.max_n[0] + A.seg_len - 1) / A.seg_len;
     dim3 grid(cdiv(rows * nseg, kSweepThreads / 32), A.nboxes, 1);
     fused_sweep_x_smem_kernel<D, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+    repair_kernel<D, DIR, BASE, RECON, LIM><<<kRepairBlocks, 128, 0, s>>>(A);
+    return 2;
   } else {
     const long long lines = (long long)A.max_n[0] * (DIR == 1 ? A.max_n[2] : A.max_n[1]);
     const int nseg = (A.max_n[DIR] + A.seg_len - 1) / A.seg_len;
@@ -55,6 +57,8 @@ int fused(const SweepArgs& A, cudaStream_t s) {
     // the 255-register limit: the MUSCL-Hancock variants
     if constexpr (FVS_SWEEP_SMEM != 0 && RECON == kReconMusclHancock) {
       fused_sweep_yz_smem_kernel<D, DIR, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
+      repair_kernel<D, DIR, BASE, RECON, LIM><<<kRepairBlocks, 128, 0, s>>>(A);
+      return 2;
     } else {
       fused_sweep_yz_kernel<D, DIR, BASE, RECON, LIM><<<grid, kSweepThreads, 0, s>>>(A);
     }

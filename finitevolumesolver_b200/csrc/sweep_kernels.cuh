@@ -464,26 +464,25 @@ FVS_DEV void steady_stages(const Eqs& eq, const QT& q2, const QT& q1, const Q0& 
   complete_from_cons<MM, D>(eq.m, out, rc, fl);
 }
 
-// Mark and repair.  The y/z march never branches on the validity of its fast paths: a warp
-// that did would have to drain the longest dependency chain of the step (update -> 1 / rho ->
-// p -> a) before it could issue anything else, once per cell.  Instead every steady step stores
-// its results unconditionally and a step whose fast paths left their domain (vacuum, tiny or
-// denormal momenta, ...) is entered into a short per-thread list.  Such a step j can only have
-// spoiled
+// Mark and repair.  The marches never branch on the validity of their fast paths: a warp that
+// did would have to drain the longest dependency chain of the step (update -> 1 / rho -> p -> a)
+// before it could issue anything else, once per cell.  Instead every steady step stores its
+// results unconditionally and a step whose fast paths left their domain (vacuum, tiny or
+// denormal momenta, ...) is entered into the sweep's repair list (one atomic, predicated).
+// Such a step j can only have spoiled
 //   the updated cell j-2, the flux through face j-1 (cells j-2, j-1) and the upper edge state of
 //   cell j-1 (flux through face j, cells j-1 and j),
-// everything later is computed from the cell states again -- the pipeline heals itself.  After
-// the march the listed steps have their cells j-2 .. j recomputed from global memory (`src` is
-// never written by the sweep) with the checked, unfused stage functions, out of line.  A list
-// that overflows turns into "everything from here on".  Returns the Newton failure flag of the
-// exact Riemann solver.
-constexpr int kMaxMarked = 24;
+// everything later is computed from the cell states again -- the pipeline heals itself.  The
+// repair pass that follows every fused sweep on the stream (repair_kernel; a handful of blocks
+// that return at once when the list is empty) recomputes cells j-2 .. j of the listed steps
+// from global memory (`src` is never written by the sweep) with the checked, unfused stage
+// functions.  A list longer than its capacity means "every cell of the sweep".  Keeping the
+// recompute out of the sweep kernels altogether matters: as an out-of-line call behind the
+// march it made the x sweep spill 112 B at 128 registers (profiles/r02_tuning.md).
 template <int D, int DIR, int BASE, int RECON, int LIM>
-__device__ __noinline__ int repair_cells(EqConst eqc, const double* src, double* dst,
-                                         long long stride, long long sc, int nd, int c_lo,
-                                         int c_hi, int ulo, int uhi, double lambda,
-                                         double lambda_half) {
-  const Eqs eq(eqc);
+FVS_DEV int repair_cells(const Eqs& eq, const double* src, double* dst, long long stride,
+                         long long sc, int nd, int c_lo, int c_hi, int ulo, int uhi,
+                         double lambda, double lambda_half) {
   int failed = 0;
 #pragma unroll 1
   for (int c = c_lo; c <= c_hi; ++c) {
@@ -505,6 +504,77 @@ __device__ __noinline__ int repair_cells(EqConst eqc, const double* src, double*
     store_complete<D>(dst + stride * c, sc, out);
   }
   return failed;
+}
+
+// enters cells lo..hi of the line at element offset `line` of box `box` into the repair list
+FVS_DEV void mark_for_repair(const SweepArgs& A, int box, long long line, int lo, int hi) {
+  if (lo > hi) return;
+  const unsigned i = atomicAdd(A.repair_count, 1u);
+  if (i < A.repair_cap) A.repair_list[i] = RepairEntry{line, box, lo, hi};
+}
+
+// The marches collect the marks of up to 32 steps in a register (no branch per step: the flag of
+// a step is the last thing its dependency chains produce) and enter them here in one go; bit b
+// stands for step j0 + b * jstep.
+FVS_DEV void flush_marks(const SweepArgs& A, unsigned mask, int box, long long line, int j0,
+                         int jstep, int clamp_lo, int clamp_hi) {
+  while (mask) {
+    const int b = __ffs((int)mask) - 1;
+    mask &= mask - 1;
+    const int j = j0 + b * jstep;
+    mark_for_repair(A, box, line, max(j - 2, clamp_lo), min(j, clamp_hi));
+  }
+}
+
+constexpr int kRepairBlocks = 148;
+template <int D, int DIR, int BASE, int RECON, int LIM>
+__global__ void __launch_bounds__(128) repair_kernel(const SweepArgs A) {
+  const unsigned n = *reinterpret_cast<volatile unsigned*>(A.repair_count);
+  if (n == 0) return; // the same on every block: nothing else writes the counter now
+  const Eqs eq(A.eq);
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned nthreads = gridDim.x * blockDim.x;
+  int failed = 0;
+  if (n <= A.repair_cap) {
+    for (unsigned i = tid; i < n; i += nthreads) {
+      const RepairEntry e = A.repair_list[i];
+      const BoxDesc& B = A.boxes[e.box];
+      const long long stride =
+          DIR == 0 ? 1 : DIR == 1 ? (long long)B.n[0] : (long long)B.n[0] * B.n[1];
+      failed |= repair_cells<D, DIR, BASE, RECON, LIM>(eq, B.src + e.line, B.dst + e.line, stride,
+                                                       B.sc, B.n[DIR], e.lo, e.hi, B.ulo, B.uhi,
+                                                       A.lambda, A.lambda_half);
+    }
+  } else {
+    // the list overflowed: every cell of every line of every box
+    for (int b = 0; b < A.nboxes; ++b) {
+      const BoxDesc& B = A.boxes[b];
+      const int n0 = B.n[0], n1 = B.n[1], n2 = B.n[2];
+      const long long stride = DIR == 0 ? 1 : DIR == 1 ? (long long)n0 : (long long)n0 * n1;
+      const long long nlines = DIR == 0 ? (long long)n1 * n2 : DIR == 1 ? (long long)n0 * n2
+                                                                        : (long long)n0 * n1;
+      for (long long l = tid; l < nlines; l += nthreads) {
+        long long line;
+        if (DIR == 0) {
+          line = l * n0;
+        } else if (DIR == 1) {
+          line = (l % n0) + (long long)n0 * n1 * (l / n0);
+        } else {
+          line = l;
+        }
+        failed |= repair_cells<D, DIR, BASE, RECON, LIM>(eq, B.src + line, B.dst + line, stride,
+                                                         B.sc, B.n[DIR], 0, B.n[DIR] - 1, B.ulo,
+                                                         B.uhi, A.lambda, A.lambda_half);
+      }
+    }
+  }
+  if (failed) *A.fail_flag = 1;
+  // the last block to finish empties the list for the next sweep
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(A.repair_count + 1, gridDim.x - 1) == gridDim.x - 1) *A.repair_count = 0u;
+  }
 }
 
 template <int D, int DIR, int BASE, int RECON, int LIM>
@@ -594,10 +664,14 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
     const int js = max(max(jstart + 3, ulo + 2), o_first + 2);
     const int je = min(min(uhi + 2, nd - 1), jend); // inclusive
     int m3 = jstart % 3; // j % 3
-    int marked[kMaxMarked]; // steady steps whose fast paths left their domain (local memory)
-    int n_marked = 0;
+    unsigned marks = 0;  // bit j - jg: steady step j of the current group left the fast-path domain
+    // groups of 32 steps: the marks of a group are entered into the repair list between the
+    // groups, the march itself has no branch on them
 #pragma unroll 1
-    for (int j = jstart; j <= jend; ++j) {
+    for (int jg = jstart; jg <= jend; jg += 32) {
+    const int jg_end = min(jg + 31, jend);
+#pragma unroll 1
+    for (int j = jg; j <= jg_end; ++j) {
       if (j > jstart) {
         if constexpr (kPrefetch == 1) {
           q0 = qn;
@@ -650,10 +724,7 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
                                                             F_prev, F, out, A.lambda,
                                                             A.lambda_half, fl, newton);
         const bool bad = FastPolicy::kFast && fl.any();
-        if (bad) {
-          if (n_marked < kMaxMarked) marked[n_marked] = j;
-          ++n_marked;
-        }
+        marks |= (unsigned)bad << (j - jg);
         failed |= bad ? 0 : newton;
         store_complete<D>(dst + stride * (j - 2), sc, out);
       } else {
@@ -713,21 +784,10 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
       FVS_STAGE_BARRIER();
       m3 = m3 == 2 ? 0 : m3 + 1;
     }
-    if (n_marked) {
-      const int c_max = min(uhi, o_last);
-      int next = 0; // first cell not yet repaired
-#pragma unroll 1
-      for (int i = 0; i < min(n_marked, kMaxMarked); ++i) {
-        const int jj = marked[i];
-        // the last entry of a list that overflowed stands for every later step
-        const int hi = (i == kMaxMarked - 1 && n_marked > kMaxMarked) ? c_max : min(jj, c_max);
-        const int lo = max(jj - 2, next);
-        if (lo <= hi) {
-          failed |= repair_cells<D, DIR, BASE, RECON, LIM>(A.eq, src, dst, stride, sc, nd, lo, hi,
-                                                           ulo, uhi, A.lambda, A.lambda_half);
-        }
-        next = max(next, hi + 1);
-      }
+    if (marks) {
+      flush_marks(A, marks, blockIdx.y, base, jg, 1, o_first, min(uhi, o_last));
+      marks = 0;
+    }
     }
   }
   reduce_max_signal(maxsig, A.max_signal);
@@ -742,10 +802,8 @@ fused_sweep_yz_smem_kernel(const SweepArgs A) {
 // lane i, slot 0 carries lane 31 of the previous 32-cell chunk (two carry slots
 // for the cell states): no shuffle / select carry logic, and -- as in the y/z
 // kernel -- a register budget of one stage instead of the whole pipeline.
-// 3 resident blocks (168 registers): with the three stages on one validity flag (mark and
-// repair) the kernel spills 112 B at 4 blocks / 128 registers (6.48 vs 6.45 ms mean sweep)
 #ifndef FVS_SWEEP_XS_MIN_BLOCKS
-#define FVS_SWEEP_XS_MIN_BLOCKS 3
+#define FVS_SWEEP_XS_MIN_BLOCKS 4
 #endif
 // 3 = the next chunk's cells staged by cp.async (hides the global-load latency that was
 // 12.6 % of the kernel's stall samples), 2 = held in registers one chunk ahead (tolerance
@@ -789,8 +847,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     const int ulo = B.ulo, uhi = B.uhi;
     const unsigned char* dtmask = B.dtmask;
     bool first = true;
-    int marked[kMaxMarked]; // this lane's cells whose fast paths left their domain
-    int n_marked = 0;
+    unsigned marks = 0; // bit b: this lane's step of chunk b of the group left the fast-path domain
     double thr = A.sig_hint * kLazyKeep;
     int carry_u = 0, carry_c = 0; // signal bound of lane 31 of the previous chunk
 #if FVS_SWEEP_XS_PREFETCH == 2
@@ -805,7 +862,12 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
     // the stable-dt mask byte of the face (c-1 | c), fetched one chunk ahead as well
     unsigned char mask_next = dtmask[min(max(o_first - 3 + lane, 0), n0 - 1)];
 #endif
-    for (int c0 = o_first - 2; c0 - 2 <= o_last; c0 += 32) {
+    // groups of 32 chunks: marks entered into the repair list between the groups
+#pragma unroll 1
+    for (int cg = o_first - 2; cg - 2 <= o_last; cg += 32 * 32) {
+    int chunk = 0;
+#pragma unroll 1
+    for (int c0 = cg; c0 - 2 <= o_last && chunk < 32; c0 += 32, ++chunk) {
       const int c = c0 + lane;
       const int cl = min(max(c, 0), n0 - 1);
       // ---- load: cell c, its dt data
@@ -900,10 +962,7 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       }
       {
         const bool bad = FastPolicy::kFast && fl.any();
-        if (bad) {
-          if (n_marked < kMaxMarked) marked[n_marked] = c;
-          ++n_marked;
-        }
+        marks |= (unsigned)bad << chunk;
         failed |= bad ? 0 : newton;
       }
       // ---- stage D: face (c-1 | c) of the stored states
@@ -948,20 +1007,11 @@ fused_sweep_x_smem_kernel(const SweepArgs A) {
       __syncwarp();
       first = false;
     }
-    if (n_marked) {
-      int next = o_first; // first cell not yet repaired
-#pragma unroll 1
-      for (int i = 0; i < min(n_marked, kMaxMarked); ++i) {
-        const int cc = marked[i];
-        // the last entry of a list that overflowed stands for every later cell of the segment
-        const int hi = (i == kMaxMarked - 1 && n_marked > kMaxMarked) ? o_last : min(cc, o_last);
-        const int lo = max(cc - 2, next);
-        if (lo <= hi) {
-          failed |= repair_cells<D, DIR, BASE, RECON, LIM>(A.eq, src, dst, 1, sc, n0, lo, hi, ulo,
-                                                           uhi, A.lambda, A.lambda_half);
-        }
-        next = max(next, hi + 1);
-      }
+    if (marks) {
+      // bit b: this lane's cell of chunk b of the group
+      flush_marks(A, marks, blockIdx.y, row * n0, cg + lane, 32, o_first, o_last);
+      marks = 0;
+    }
     }
   }
   reduce_max_signal(maxsig, A.max_signal);

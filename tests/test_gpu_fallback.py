@@ -115,13 +115,15 @@ def test_fused_sweeps_bitwise_on_states_outside_the_fast_path_domain(oracle, fvs
     pair.close()
 
 
-@pytest.mark.parametrize("rank,n", [(2, (900, 6)), (2, (6, 300))])
+@pytest.mark.parametrize("rank,n", [(2, (900, 6)), (2, (6, 300)), (3, (40, 12, 20))])
 @pytest.mark.parametrize("kind", ["tiny_everything", "tiny_momentum"])
-def test_repair_list_overflow(oracle, fvs, rank, n, kind):
-    """More marked steps per thread than the repair list holds (24): with every cell outside
-    the fast-path domain a lane of the x sweep marks one cell per 32-cell chunk of its row
-    (900 cells: 29 chunks) and a thread of the y sweep every step of its line (300 cells);
-    the overflowing list must turn into `every later cell`."""
+@pytest.mark.parametrize("cap", [None, 5])
+def test_repair_list_overflow(oracle, fvs, rank, n, kind, cap, monkeypatch):
+    """Many marked steps per line, and (cap = 5, FVS_REPAIR_CAP) more marked steps than the
+    repair list of the sweep holds: the repair pass must then recompute every cell of the
+    sweep."""
+    if cap is not None:
+        monkeypatch.setenv("FVS_REPAIR_CAP", str(cap))
     pair, dx = make_pair(oracle, fvs, rank, n)
     pair.gpu.set_dt_hints(0)
 
