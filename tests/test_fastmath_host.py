@@ -21,6 +21,9 @@ def test_fastmath_host_bitwise():
     vals = dict(zip(fields[0::2], map(int, fields[1::2])))
     assert vals["mismatch_div"] == 0 and vals["mismatch_sqrt"] == 0 and vals["mismatch_divz"] == 0
     assert vals["tested"] == 40000000
+    # deterministic sweep over the exponents around the thresholds of the folded tests
+    assert vals["threshold_sweep_mismatch"] == 0
+    assert vals["threshold_sweep_clean"] > 0.1 * vals["threshold_sweep_tested"]
     # the zero numerators are accepted by the fast path, not sent to the fallback
     assert vals["zero_divz"] > 0.2 * vals["tested"]
     # more than a third of the zero-tolerant divisions ran inside the window
